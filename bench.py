@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the SPH sub-step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
+
+One "step" = one sub-step = one simulate_single_frame equivalent (libclsph/sph_simulation.cpp:
+173-344 in the reference). Default workload at N=1: BASELINE config 2 (water dam break in
+box.obj, 1 Mi particles, jittered-lattice state S1). Prints ONE JSON line (rank 0).
+
+  value      device-resident throughput: state in HBM, K sub-steps timed with CUDA events on the
+             library's stream, max over ranks
+  e2e        same metric through clsph_simulate_single_frame with pinned HOST buffers: every
+             step uploads the 80-byte AoS array, steps, and downloads it (the reference's
+             call shape when a callback is installed)
+  roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration, against the
+             measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own kernels (oracle/_ref, built from the reference sources) or the
+             oracle port, on the host cores, on a bounded sample of the same workload
+
+--impl reference times only the CPU side (reference arm of the driver).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle_steps_per_sec"
+UNIT = "particle-steps/s"
+# Algorithmic bytes per particle-step (SURVEY 8d / DESIGN.md): 256 + 16 P, P = radix passes.
+def step_bytes(passes):
+    return 256 + 16 * passes
+# Algorithmic bytes per particle of each kernel as built (DESIGN.md "Kernels"):
+KERNEL_BYTES = {
+    "keys": 20.0,        # read pos 16, write key 4
+    "sort": None,        # 4 + 16 P, filled at run time
+    "reorder": 104.0,    # perm 4 + gather 48 + write 48 + sorted key 4
+    "density": 24.0,     # read pos 16, write rho,p 8
+    "forces": 56.0,      # read pos 16 + vel 16 + rho,p 8, write acceleration 16
+    "integrate": 96.0,   # read pos, ivel, acceleration 48, write pos, vel, ivel 48
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="config2_dambreak_1m")
+    ap.add_argument("--particles", type=int, default=0, help="override the particle count of the config")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=102400)
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def sample_workload(args, n_override=None):
+    """(params, terms, volume, scene_file, state) for the configured workload."""
+    from libclsph_b200 import workloads
+    fluid, n, mass, scene = workloads.CONFIGS[args.config]
+    if args.particles:
+        n = args.particles
+    if n_override:
+        n = n_override
+    p, terms, vol, _ = workloads.make_config(fluid=fluid, particles_count=n, particle_mass=mass)
+    state = workloads.jittered_state(p, vol)
+    return p, terms, vol, scene, state
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the reference's own kernels (oracle/_ref) or the oracle port
+# ------------------------------------------------------------------------------------------------
+def cpu_run(args, n, substeps, warmup):
+    """Times `substeps` sub-steps of n particles on the host cores. Returns (rate, kind, cores)."""
+    from oracle import oracle as O, ref as R
+    p, terms, vol, scene_file, state = sample_workload(args, n_override=n)
+    scene = O.load_obj(os.path.join(ROOT, "scenes", scene_file))
+    if R.available():
+        _, _, secs = R.simulate(p, terms, vol, scene, initial=state, substeps=warmup + substeps, record_all=False)
+        elapsed = float(secs[warmup:].sum())
+        return n * substeps / elapsed, "reference", R.num_threads(), elapsed
+    cur = state
+    po = p.copy()
+    for _ in range(warmup):
+        cur = O.step(cur, po, terms, scene, taps=False).particles
+    t0 = time.perf_counter()
+    for _ in range(substeps):
+        cur = O.step(cur, po, terms, scene, taps=False).particles
+    elapsed = time.perf_counter() - t0
+    return n * substeps / elapsed, "port", O.num_threads(), elapsed
+
+
+def cpu_baseline(args, budget_s=20.0):
+    """Bounded CPU sample: calibrate on 2 sub-steps, then run as many as fit the budget."""
+    n = min(args.cpu_sample, sample_workload(args)[0].particles_count)
+    rate, kind, cores, el = cpu_run(args, n, 2, 1)
+    steps = int(max(2, min(20, budget_s * rate / n)))
+    rate, kind, cores, el = cpu_run(args, n, steps, 1)
+    what = ("reference kernels + host code compiled from the reference sources behind an in-process OpenCL shim "
+            "(oracle/_ref, OpenMP over work-groups; PoCL unavailable)" if kind == "reference"
+            else "CPU restatement of the reference kernels (oracle port, OpenMP; PoCL unavailable)")
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%s at %d particles (state S1), %d sub-steps after 1 warm-up, %.1f s; %s" % (args.config, n, steps, el, what)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    fluid, n_full, mass, scene = __import__("libclsph_b200.workloads", fromlist=["CONFIGS"]).CONFIGS[args.config]
+    n_full = args.particles or n_full
+    # bounded sample: calibrate, then size N so that K+W sub-steps take about two minutes
+    n_cal = min(16384, n_full)
+    rate, kind, cores, _ = cpu_run(args, n_cal, 2, 1)
+    total = max(1, args.steps + args.warmup)
+    n = int(min(n_full, args.cpu_sample, max(4096, rate * 120.0 / total)))
+    n -= n % 4096 if n >= 4096 else 0
+    t_wall = time.perf_counter()
+    rate, kind, cores, elapsed = cpu_run(args, n, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.config, "particles_per_step_sample": n, "particles_full": n_full,
+                   "state": "S1 jittered lattice, seed 20261017", "note": "each step is a bounded sample of the workload (same fluid, same spacing)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d particles x %d sub-steps, %.1f s wall" % (n, args.steps, time.perf_counter() - t_wall)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    from libclsph_b200 import capi, workloads
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    torch.cuda.set_device(local_rank)
+    p, terms, vol, scene_file, state = sample_workload(args)
+    n = state.size
+    normals, vertices, indices = workloads.scene_arrays(scene_file)
+    ctx = capi.Context(n, device=local_rank)
+    ctx.set_scene(normals, vertices, indices)
+    ctx.set_parameters(p, terms)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    # ---- device-resident throughput ("value")
+    ctx.upload(state)
+    ctx.step(args.warmup)
+    ctx.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile_enable(False)  # resets the launch counter
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ctx.step(args.steps)
+    e1.record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.finish()
+    launches = ctx.profile_read()["kernel_launches"]
+    n_total = sum_over_ranks(float(n))
+    value = n_total * args.steps / (ms_total * 1e-3)
+    grid = ctx.parameters()
+    passes = max(1, (int(grid.grid_cell_count - 1).bit_length() + 7) // 8)
+
+    # ---- per-kernel durations over a second timed region (stage events on the same stream)
+    ctx.profile_enable(True)
+    ctx.step(args.steps)
+    stage = ctx.profile_read()
+    ctx.profile_enable(False)
+    per = {k[3:]: stage[k] / max(1, stage["substeps"]) for k in stage if k.startswith("ms_")}
+    kb = dict(KERNEL_BYTES)
+    kb["sort"] = 4.0 + 16.0 * passes
+    dominant = max((k for k in kb), key=lambda k: per.get(k, 0.0))
+    peak, peak_src = measured_peak()
+    achieved = n * kb[dominant] / (per[dominant] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_" + dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": kb[dominant], "ms_per_launch": per[dominant],
+                "whole_step": {"bytes_per_particle_step": step_bytes(passes), "radix_passes": passes,
+                               "achieved": value / world * step_bytes(passes) / 1e9,
+                               "frac": value / world * step_bytes(passes) / 1e9 / peak,
+                               "frac_of_nominal_8TBs": value / world * step_bytes(passes) / 1e9 / 8000.0},
+                "stage_ms": per,
+                "note": "density/force passes are FP32-issue / shared-memory bound at the reference's 2h cell geometry (SURVEY 8d)"}
+
+    # ---- end to end through the reference-shaped call, pinned host buffers
+    host_in = torch.empty(n * 80, dtype=torch.uint8).pin_memory()
+    host_out = torch.empty(n * 80, dtype=torch.uint8).pin_memory()
+    host_in.numpy()[:] = np.frombuffer(state.tobytes(), dtype=np.uint8)
+    import ctypes
+    from libclsph_b200.abi import particle_ptr
+    lib = capi.load_library()
+    p_io = p.copy()
+
+    def e2e_step():
+        rc = lib.clsph_simulate_single_frame(ctx._h, ctypes.c_void_p(host_in.data_ptr()),
+                                             ctypes.c_void_p(host_out.data_ptr()), ctypes.byref(p_io), ctypes.byref(terms))
+        if rc:
+            raise RuntimeError(lib.clsph_last_error(ctx._h).decode())
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 80, "d2h_bytes_per_step": n * 80,
+           "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+           "path": "clsph_simulate_single_frame(host AoS in, host AoS out), pinned buffers"}
+    ctx.close()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.config, "particles_per_gpu": n, "fluid": workloads.CONFIGS[args.config][0],
+                   "scene": scene_file, "state": "S1 jittered lattice, seed 20261017",
+                   "parallelism": "single GPU" if world == 1 else "replicas: one independent fluid block per GPU, no exchange",
+                   "l2": "per-step working set ~%d MB vs 126 MB L2, no flush: sub-steps form a dependent chain" % (n * 200 // (1 << 20)),
+                   "grid": [grid.grid_size_x, grid.grid_size_y, grid.grid_size_z], "grid_cell_count": grid.grid_cell_count},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args)
+        except Exception as exc:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it, one rank per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

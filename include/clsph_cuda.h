@@ -1,0 +1,170 @@
+/*
+ * clsph_cuda.h -- C ABI of the B200 (sm_100a) implementation of libclsph's per-step SPH path.
+ *
+ * This is the whole device boundary. It replaces, in the reference tree,
+ *   util/cl_boilerplate.h:41-43      init_cl_single_device / make_program / readKernelFile
+ *   libclsph/sph_simulation.cpp      every cl::Buffer / cl::Kernel / cl::CommandQueue use:
+ *       :366-380  kernel + buffer creation        -> clsph_create
+ *       :296-319  per-step scene upload           -> clsph_set_scene        (once)
+ *       :283-290, :322-323, :330-333 setArg(params, terms) -> clsph_set_parameters (once)
+ *       :195      enqueueWriteBuffer(particles)   -> clsph_upload_particles
+ *       :199-337  bounds, locate_in_grid, sort_particles, cell table, density_pressure,
+ *                 forces, advection_collision     -> clsph_step             (device resident)
+ *       :339      enqueueReadBuffer(particles)    -> clsph_download_particles
+ *       :173-344  simulate_single_frame(in, out)  -> clsph_simulate_single_frame (host in/out)
+ * and the six OpenCL kernels of libclsph/kernels/ (grid.cl, sort.cl, sph.cl, forces.cl,
+ * smoothing.cl, advection.cl, collisions.cl), which are hand-written CUDA inside the library.
+ *
+ * Conventions
+ *   - plain C: opaque handle, PODs by pointer with the reference's exact layouts
+ *     (include/clsph/clsph_types.h), caller owns every host buffer, the library owns all
+ *     device memory, streams, events and communicators;
+ *   - every function returns 0 on success or a CLSPH_E* code; clsph_last_error() gives the
+ *     message. (The reference prints file:line and exit(-1)s, util/cl_boilerplate.h:28-34; the
+ *     host wrapper in libclsph_b200/host/ keeps that behaviour on top of these codes.)
+ *   - a context is bound to one GPU and one caller thread; clsph_step() only enqueues work,
+ *     the calls documented as "synchronises" wait for it;
+ *   - there is no CPU fallback: without a usable CUDA device clsph_create() fails.
+ */
+#ifndef CLSPH_CUDA_H_
+#define CLSPH_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "clsph/clsph_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct clsph_context clsph_context;
+
+enum {
+  CLSPH_OK = 0,
+  CLSPH_EINVAL = 1,       /* bad argument (null pointer, N < 128, N > capacity, ...)            */
+  CLSPH_ECUDA = 2,        /* a CUDA runtime call failed                                         */
+  CLSPH_EGRID = 3,        /* a grid axis reached 1024 cells (reference: assert, cpp:247-249)    */
+  CLSPH_ESTATE = 4,       /* call order (no particles uploaded, no parameters set, ...)         */
+  CLSPH_ECOMM = 5,        /* NCCL / multi-GPU failure                                           */
+  CLSPH_ENOMEM = 6        /* device or host allocation failed                                   */
+};
+
+/* What clsph_debug_fetch can read back. "sorted" = order of the particle array after the
+ * last sub-step (the reference's output order). Taps other than the first three need
+ * clsph_set_debug(ctx, 1) before the step. */
+enum {
+  CLSPH_TAP_SORTED_KEYS = 0,   /* uint32[N]  Morton cell key per sorted particle               */
+  CLSPH_TAP_PERMUTATION = 1,   /* uint32[N]  sorted r came from pre-step index perm[r]         */
+  CLSPH_TAP_CELL_TABLE = 2,    /* uint32[grid_cell_count] reference form: first idx, key >= c  */
+  CLSPH_TAP_KEYS_INPUT = 3,    /* uint32[N]  key per particle in pre-step order      (debug)   */
+  CLSPH_TAP_CANDIDATE_COUNT = 4, /* uint32[N] sorted: sum over 27 cells of end-start (debug)   */
+  CLSPH_TAP_SUPPORT_COUNT = 5, /* uint32[N]  sorted: candidates with r/h < 1         (debug)   */
+  CLSPH_TAP_DENSITY = 6,       /* float[N]   sorted                                            */
+  CLSPH_TAP_PRESSURE = 7,      /* float[N]   sorted                                            */
+  CLSPH_TAP_ACCELERATION = 8,  /* float[3N]  sorted, after the force pass            (debug)   */
+  CLSPH_TAP_COLLISION_ITERS = 9 /* uint32[N] sorted, advect/collide loop trips       (debug)   */
+};
+
+/* Device time per stage of the step, accumulated while profiling is on. */
+typedef struct clsph_stage_times {
+  double ms_bounds_grid;   /* AABB reduce (first step only) + grid setup                       */
+  double ms_keys;          /* cell keys + radix digit histograms                               */
+  double ms_sort;          /* histogram scan + onesweep passes                                 */
+  double ms_reorder;       /* gather into sorted order + cell start/end table                  */
+  double ms_density;       /* density / pressure pass                                          */
+  double ms_forces;        /* force pass                                                       */
+  double ms_integrate;     /* leapfrog + collisions + next step's AABB                         */
+  double ms_exchange;      /* multi-GPU migration + halo traffic (0 on one GPU)                */
+  uint64_t substeps;       /* sub-steps covered by the sums above                              */
+  uint64_t kernel_launches;/* kernels launched by the library since profiling was enabled      */
+} clsph_stage_times;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* Number of CUDA devices visible to the process (0 if none / no driver). Never fails. */
+int clsph_device_count(void);
+
+/* Creates a context on CUDA device `device` able to hold `max_particles` particles.
+ * `cell_table_capacity` = entries of the dense Morton-indexed cell table (0 = choose from
+ * max_particles); steps whose grid_cell_count exceeds it fall back to binary search over the
+ * sorted keys, with identical results. Replaces sph_simulation.cpp:354-380. */
+int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32_t cell_table_capacity);
+void clsph_destroy(clsph_context* ctx);
+
+/* Message for the last non-zero return on `ctx` (or of clsph_create when ctx is NULL). */
+const char* clsph_last_error(const clsph_context* ctx);
+
+/* ---- inputs ---------------------------------------------------------------------------- */
+
+/* The three scene arrays of libclsph/scene.h:11-14 (normals 3F floats, vertices, indices 3F).
+ * Uploaded once; the reference re-uploads them every sub-step (sph_simulation.cpp:296-319). */
+int clsph_set_scene(clsph_context* ctx, const float* face_normals, const float* vertices,
+                    size_t n_vertex_floats, const uint32_t* indices, uint32_t face_count);
+
+/* Fluid / time-step constants and smoothing terms, as load_settings derives them
+ * (sph_simulation.cpp:405-506). The grid block of `params` is ignored on input. */
+int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params,
+                         const precomputed_kernel_values* terms);
+
+/* Host AoS (80-byte records) -> device SoA. n must be >= 128 (sort.cl:9-20, erratum E8) and
+ * <= max_particles. Replaces sph_simulation.cpp:195. */
+int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n);
+
+/* ---- the step -------------------------------------------------------------------------- */
+
+/* Enqueues `n_substeps` sub-steps, each the equivalent of one simulate_single_frame
+ * (sph_simulation.cpp:173-344): padded AABB + grid sizing, Morton cell keys, stable radix
+ * sort by key, cell start/end table, density + Tait pressure, pressure/viscosity/surface
+ * tension forces over the 27-cell neighbourhood, leapfrog + triangle collisions. State stays
+ * on the device; returns without waiting. */
+int clsph_step(clsph_context* ctx, uint32_t n_substeps);
+
+/* Waits for all enqueued work; reports CLSPH_EGRID if any sub-step overflowed the grid. */
+int clsph_synchronize(clsph_context* ctx);
+
+/* Parameters with the grid block (grid_size_*, grid_cell_count, min_point, max_point) of the
+ * most recent sub-step, as sph_simulation.cpp:229-252 leaves them. Synchronises. */
+int clsph_get_parameters(clsph_context* ctx, simulation_parameters* out);
+
+/* Device SoA -> host AoS in the reference's output order (sorted by cell key, stable):
+ * position, velocity, intermediate_velocity, density, pressure, grid_index as the reference
+ * writes them, acceleration = 0 (sph.cl:97-99). Synchronises. Replaces sph_simulation.cpp:339. */
+int clsph_download_particles(clsph_context* ctx, particle* aos_out);
+
+/* One sub-step with host buffers on both sides, the exact shape of
+ * sph_simulation::simulate_single_frame(in, out): upload, step, download, and the grid
+ * block of *params rewritten. `in` may equal `out`. `terms` may be NULL to keep the ones set. */
+int clsph_simulate_single_frame(clsph_context* ctx, const particle* in, particle* out,
+                                simulation_parameters* params, const precomputed_kernel_values* terms);
+
+/* ---- observation ----------------------------------------------------------------------- */
+
+/* The reference's `advection_collision` kernel on its own (kernels/sph.cl:64-112, argument
+ * order of sph_simulation.cpp:330-333): n records in, each with its own acceleration; out gets
+ * position / velocity / intermediate_velocity advanced by one sub-step with collisions against
+ * the scene set by clsph_set_scene, in the same order (no sort). Exists so the one stage whose
+ * input (the post-force acceleration) the step never exports can be checked in isolation.
+ * Replaces the particles held by the context. Synchronises. */
+int clsph_kernel_advection_collision(clsph_context* ctx, const particle* in, particle* out, uint32_t n);
+
+/* Enables (1) / disables (0) recording of the per-stage taps marked "(debug)" above. */
+int clsph_set_debug(clsph_context* ctx, int enable);
+
+/* Copies tap `what` of the most recent sub-step into dst (bytes = exact size). Synchronises. */
+int clsph_debug_fetch(clsph_context* ctx, int what, void* dst, size_t bytes);
+
+/* Per-stage CUDA-event timing. Enabling resets the sums. Reading synchronises. */
+int clsph_profile_enable(clsph_context* ctx, int enable);
+int clsph_profile_read(clsph_context* ctx, clsph_stage_times* out);
+
+/* Number of particles currently held (after migration on multi-GPU runs this changes). */
+int clsph_particle_count(clsph_context* ctx, uint32_t* n);
+
+/* Raw cudaStream_t the context enqueues on (for callers that time with their own events). */
+void* clsph_stream(clsph_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLSPH_CUDA_H_ */

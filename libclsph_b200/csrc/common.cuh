@@ -1,0 +1,126 @@
+// common.cuh -- shared device-side definitions of the sm_100a SPH step.
+//
+// Data layout in HBM (one set per ping-pong side, all arrays of length N in cell-sorted order):
+//   pos   float4  x y z .          vel   float4  vx vy vz .        ivel  float4  (leapfrog half-step velocity)
+//   aux   float4  rho, p, p/rho^2, m/rho   (written by the density pass, read by the force pass)
+//   skey  uint32  Morton cell key
+// plus the dense cell table cell_start[c], cell_end[c] indexed by Morton key.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace clsph {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// Written by k_grid_setup on the device each sub-step (sph_simulation.cpp:221-252 of the
+// reference), read by every later kernel of the step. Lives in device memory so that a whole
+// run of sub-steps needs no host round trip.
+struct GridState {
+  float min_x, min_y, min_z, cell;   // padded AABB minimum, cell side 2h
+  float max_x, max_y, max_z, pad0;
+  int gx, gy, gz;                    // grid_size_*
+  uint32_t cell_count;               // morton(gx, gy, gz)
+  uint32_t n;                        // particles on this device
+  uint32_t sort_passes;              // ceil(bits(cell_count - 1) / 8), 1..4
+  uint32_t dense;                    // 1: cell_count fits the dense table; 0: binary-search fallback
+  uint32_t error;                    // bit 0: a grid axis reached 1024 cells
+};
+
+// AABB accumulators: floats mapped to order-preserving unsigned so atomicMin/Max apply.
+struct BoundsAcc {
+  uint32_t lo[3];
+  uint32_t hi[3];
+};
+
+// Per-run constants, passed to kernels by value.
+struct SphConst {
+  float h, h2, support_s;      // support_s: smallest s = |d|^2 with sqrt(s)/h >= 1 (exact window test)
+  float mass, rho0, K;
+  float c_poly6, c_spiky, c_visc, c_poly6_grad, c_poly6_lap;
+  float mu, sigma, tension_threshold;
+  float gx, gy, gz;
+  float dt;                    // time_delta * simulation_scale
+  float vmax, restitution;
+  float spiky_degenerate;      // -45 / (pi h^6) as smoothing.cl:24 evaluates it (erratum E3)
+};
+
+__host__ __device__ inline uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float ordered_to_float(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+
+// 10-bit-per-axis Morton code (libclsph/common/util.h:41-62 of the reference).
+__host__ __device__ inline uint32_t spread10(uint32_t v) {
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__host__ __device__ inline uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+  return spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
+}
+// Inverse of spread10 (util.h:4-19 does it bit by bit; this is the log-step form).
+__host__ __device__ inline uint32_t compact10(uint32_t v) {
+  v &= 0x09249249u;
+  v = (v | (v >> 2)) & 0x030C30C3u;
+  v = (v | (v >> 4)) & 0x0300F00Fu;
+  v = (v | (v >> 8)) & 0x030000FFu;
+  v = (v | (v >> 16)) & 0x000003FFu;
+  return v;
+}
+
+// Cell coordinate of a position along one axis, grid.cl:56-61: (uint)((p - min) / (2h)) with a
+// correctly rounded subtract and divide (no reciprocal, no contraction).
+__device__ __forceinline__ uint32_t cell_coord(float p, float mn, float cell) {
+  return __float2uint_rz(__fdiv_rn(__fsub_rn(p, mn), cell));
+}
+
+// Squared distance exactly as the oracle's distance(): d = a - b, s = fma(dz,dz,fma(dy,dy,dx*dx)).
+__device__ __forceinline__ float dist2_contract(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Cell range lookup. Dense: two loads. Fallback (grid larger than the table): lower_bound over
+// the sorted key array, same answer.
+__device__ __forceinline__ uint32_t lower_bound_key(const uint32_t* __restrict__ skey, uint32_t n, uint32_t key) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(skey + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ uint2 cell_range(uint32_t key, const GridState& g, const uint32_t* __restrict__ cell_start,
+                                            const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ skey) {
+  if (key >= g.cell_count) return make_uint2(0u, 0u);
+  if (g.dense) return make_uint2(__ldg(cell_start + key), __ldg(cell_end + key));
+  uint32_t a = lower_bound_key(skey, g.n, key);
+  uint32_t b = lower_bound_key(skey, g.n, key + 1u);
+  return make_uint2(a, b);
+}
+
+}  // namespace clsph

@@ -1,0 +1,606 @@
+// context.cu -- the C ABI of include/clsph_cuda.h: context, device memory, the per-sub-step
+// launch sequence, taps and profiling. No arithmetic of the SPH step lives here; it only
+// orders the kernels of sort.cu / grid.cu / neighbors.cu / integrate.cu on one stream.
+//
+// Sub-step launch sequence (all device resident, no host round trip):
+//   k_grid_setup -> memset(sort scratch) -> k_keys_hist -> k_scan_hist -> k_onesweep x4
+//   -> k_clear_cells -> k_reorder -> k_density -> k_forces -> k_integrate
+// The reference's equivalent is libclsph/sph_simulation.cpp:173-344 with 17 blocking transfers.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "clsph_cuda.h"
+#include "kernels.cuh"
+
+using namespace clsph;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum Stage { kStBounds = 0, kStKeys, kStSort, kStReorder, kStDensity, kStForces, kStIntegrate, kStEnd, kStages = kStEnd };
+
+}  // namespace
+
+struct clsph_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  uint32_t capacity = 0;       // max particles
+  uint32_t cell_capacity = 0;  // dense table entries
+  uint32_t n = 0;              // particles held
+  bool have_particles = false, have_params = false, bounds_valid = false, debug = false;
+
+  simulation_parameters params{};
+  precomputed_kernel_values terms{};
+  SphConst konst{};
+
+  StateArrays state[2]{};
+  int cur = 0;  // which side holds the current particles
+  float4* aux = nullptr;
+  float4* accel = nullptr;
+  uint32_t* skey = nullptr;
+  uint32_t* perm = nullptr;
+  SortBuffers sort{};
+  uint32_t* cell_start = nullptr;
+  uint32_t* cell_end = nullptr;
+  GridState* grid = nullptr;
+  BoundsAcc* bounds = nullptr;
+  void* aos_stage = nullptr;
+
+  Face* faces = nullptr;
+  uint32_t face_count = 0;
+
+  DebugTaps taps{};
+  uint32_t* ref_table = nullptr;
+  size_t ref_table_words = 0;
+
+  bool profiling = false;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  clsph_stage_times times{};
+  uint64_t launches = 0;
+
+  std::string error;
+};
+
+namespace {
+
+int fail(clsph_context* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->error = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CLSPH_CUDA_TRY(ctx, expr)                                                                    \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? CLSPH_ENOMEM : CLSPH_ECUDA, "%s:%d: %s -> %s", \
+                  __FILE__, __LINE__, #expr, cudaGetErrorString(e__));                               \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+// Smallest s with sqrtf(s) / h >= 1: the reference's window 1 - clamp(floor(r/h), 0, 1) is 1
+// exactly when s = |d|^2 is below it (sqrt and divide are monotone), smoothing.cl:2.
+float support_threshold(float h) {
+  uint32_t lo = 0u, hi = 0x7f800000u;
+  while (hi - lo > 1u) {
+    const uint32_t mid = lo + (hi - lo) / 2u;
+    float s;
+    std::memcpy(&s, &mid, 4);
+    volatile float r = sqrtf(s);
+    volatile float q = r / h;
+    if (q >= 1.0f) hi = mid; else lo = mid;
+  }
+  float s;
+  std::memcpy(&s, &hi, 4);
+  return s;
+}
+
+void derive_constants(clsph_context* ctx) {
+  const simulation_parameters& p = ctx->params;
+  const precomputed_kernel_values& t = ctx->terms;
+  SphConst& c = ctx->konst;
+  c.h = p.h;
+  volatile float h2 = p.h * p.h;
+  c.h2 = h2;
+  c.support_s = support_threshold(p.h);
+  c.mass = p.particle_mass;
+  c.rho0 = p.fluid_density;
+  c.K = p.K;
+  c.c_poly6 = t.poly_6;
+  c.c_spiky = t.spiky;
+  c.c_visc = t.viscosity;
+  c.c_poly6_grad = t.poly_6_gradient;
+  c.c_poly6_lap = t.poly_6_laplacian;
+  c.mu = p.dynamic_viscosity;
+  c.sigma = p.surface_tension;
+  c.tension_threshold = p.surface_tension_threshold;
+  c.gx = p.constant_acceleration.s[0];
+  c.gy = p.constant_acceleration.s[1];
+  c.gz = p.constant_acceleration.s[2];
+  volatile float dt = p.time_delta * p.simulation_scale;  // sph.cl:76
+  c.dt = dt;
+  c.vmax = p.max_velocity;
+  c.restitution = p.restitution;
+  volatile float h6 = p.h;  // pown(h, 6) by sequential fp32 multiplies, smoothing.cl:24
+  for (int k = 1; k < 6; ++k) h6 = h6 * p.h;
+  c.spiky_degenerate = -45.f / (float)(3.14159265358979323846 * (double)h6);
+}
+
+cudaEvent_t next_event(clsph_context* ctx) {
+  if (ctx->events_used == ctx->event_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->event_pool.push_back(e);
+  }
+  cudaEvent_t e = ctx->event_pool[ctx->events_used++];
+  cudaEventRecord(e, ctx->stream);
+  return e;
+}
+
+// Folds the recorded stage boundaries into ctx->times. Caller has synchronised the stream.
+void drain_events(clsph_context* ctx) {
+  const size_t per_step = kStages + 1;
+  for (size_t base = 0; base + per_step <= ctx->events_used; base += per_step) {
+    double ms[kStages];
+    for (int s = 0; s < kStages; ++s) {
+      float f = 0.f;
+      cudaEventElapsedTime(&f, ctx->event_pool[base + s], ctx->event_pool[base + s + 1]);
+      ms[s] = f;
+    }
+    ctx->times.ms_bounds_grid += ms[kStBounds];
+    ctx->times.ms_keys += ms[kStKeys];
+    ctx->times.ms_sort += ms[kStSort];
+    ctx->times.ms_reorder += ms[kStReorder];
+    ctx->times.ms_density += ms[kStDensity];
+    ctx->times.ms_forces += ms[kStForces];
+    ctx->times.ms_integrate += ms[kStIntegrate];
+    ctx->times.substeps += 1;
+  }
+  ctx->events_used = 0;
+}
+
+int check_device_flags(clsph_context* ctx) {
+  GridState g;
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&g, ctx->grid, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (g.error & 1u) {
+    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(&ctx->grid->error, 0, sizeof(uint32_t), ctx->stream));
+    return fail(ctx, CLSPH_EGRID, "grid overflow: %d x %d x %d cells, each axis must stay below 1024 "
+                "(10-bit Morton code; the reference asserts at sph_simulation.cpp:247-249)", g.gx, g.gy, g.gz);
+  }
+  return CLSPH_OK;
+}
+
+int ensure_debug_buffers(clsph_context* ctx) {
+  if (ctx->taps.keys_input) return CLSPH_OK;
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->taps.keys_input, ctx->capacity));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->taps.candidate_count, ctx->capacity));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->taps.support_count, ctx->capacity));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->taps.collision_iters, ctx->capacity));
+  return CLSPH_OK;
+}
+
+// One sub-step, enqueued on ctx->stream.
+int enqueue_substep(clsph_context* ctx) {
+  cudaStream_t st = ctx->stream;
+  uint64_t* lc = &ctx->launches;
+  const uint32_t n = ctx->n;
+  const bool prof = ctx->profiling;
+  StateArrays& src = ctx->state[ctx->cur];
+  StateArrays& dst = ctx->state[ctx->cur ^ 1];
+
+  if (prof) next_event(ctx);
+  if (!ctx->bounds_valid) {  // first step after an upload; later steps get the AABB from the integrator
+    launch_bounds_reset(ctx->bounds, st, lc);
+    launch_bounds(src.pos, n, ctx->bounds, ctx->sm_count, st, lc);
+    ctx->bounds_valid = true;
+  }
+  launch_grid_setup(ctx->bounds, ctx->grid, ctx->params.h, n, ctx->cell_capacity, st, lc);
+  if (prof) next_event(ctx);
+
+  launch_sort_keys(ctx->sort, src.pos, ctx->grid, n, ctx->sm_count, ctx->debug ? ctx->taps.keys_input : nullptr, st, lc);
+  if (prof) next_event(ctx);
+  launch_sort_passes(ctx->sort, ctx->grid, n, st, lc);
+  if (prof) next_event(ctx);
+
+  launch_clear_cells(ctx->cell_start, ctx->cell_end, ctx->grid, ctx->cell_capacity, ctx->sm_count, st, lc);
+  launch_reorder(src, dst, ctx->sort, ctx->skey, ctx->perm, ctx->cell_start, ctx->cell_end, ctx->grid, n, st, lc);
+  ctx->cur ^= 1;
+  if (prof) next_event(ctx);
+
+  launch_density(dst.pos, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->aux, ctx->taps,
+                 ctx->debug, n, st, lc);
+  if (prof) next_event(ctx);
+  launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst,
+                ctx->accel, n, st, lc);
+  if (prof) next_event(ctx);
+  if (ctx->debug)  // the integrator consumes the acceleration; keep a copy for the tap
+    CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->taps.acceleration, ctx->accel, sizeof(float4) * n,
+                                        cudaMemcpyDeviceToDevice, st));
+  launch_integrate(dst, ctx->accel, ctx->faces, ctx->face_count, ctx->grid, ctx->konst, ctx->bounds,
+                   ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, lc);
+  if (prof) next_event(ctx);
+  CLSPH_CUDA_TRY(ctx, cudaGetLastError());
+  return CLSPH_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int clsph_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* clsph_last_error(const clsph_context* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32_t cell_table_capacity) {
+  if (!out) return fail(nullptr, CLSPH_EINVAL, "clsph_create: out is null");
+  *out = nullptr;
+  if (max_particles < 128u || max_particles >= (1u << 30))
+    return fail(nullptr, CLSPH_EINVAL, "clsph_create: max_particles must be in [128, 2^30), got %u", max_particles);
+  int count = clsph_device_count();
+  if (count <= 0) return fail(nullptr, CLSPH_ECUDA, "clsph_create: no CUDA device available (there is no CPU fallback)");
+  if (device < 0 || device >= count) return fail(nullptr, CLSPH_EINVAL, "clsph_create: device %d out of range [0, %d)", device, count);
+
+  clsph_context* ctx = new clsph_context();
+  ctx->device = device;
+  ctx->capacity = max_particles;
+  // Morton-indexed tables are 1.1x-6.4x the cell count for compact fluids; 8 entries
+  // per particle with a 4 Mi floor covers every BASELINE config; larger grids use the fallback.
+  ctx->cell_capacity = cell_table_capacity ? cell_table_capacity
+                                           : (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_particles * 8u, 1u << 22), 1u << 28);
+#define CREATE_TRY(expr)                                                                                          \
+  do {                                                                                                            \
+    cudaError_t e__ = (expr);                                                                                     \
+    if (e__ != cudaSuccess) {                                                                                     \
+      int rc__ = fail(nullptr, e__ == cudaErrorMemoryAllocation ? CLSPH_ENOMEM : CLSPH_ECUDA, "clsph_create: %s -> %s", #expr, \
+                      cudaGetErrorString(e__));                                                                   \
+      clsph_destroy(ctx);                                                                                         \
+      return rc__;                                                                                                \
+    }                                                                                                             \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  const size_t cap = max_particles;
+  for (int s = 0; s < 2; ++s) {
+    CREATE_TRY(dev_alloc(&ctx->state[s].pos, cap));
+    CREATE_TRY(dev_alloc(&ctx->state[s].vel, cap));
+    CREATE_TRY(dev_alloc(&ctx->state[s].ivel, cap));
+  }
+  CREATE_TRY(dev_alloc(&ctx->aux, cap));
+  CREATE_TRY(dev_alloc(&ctx->accel, cap));
+  CREATE_TRY(dev_alloc(&ctx->taps.acceleration, cap));
+  CREATE_TRY(dev_alloc(&ctx->skey, cap));
+  CREATE_TRY(dev_alloc(&ctx->perm, cap));
+  CREATE_TRY(dev_alloc(&ctx->sort.keys_a, cap));
+  CREATE_TRY(dev_alloc(&ctx->sort.keys_b, cap));
+  CREATE_TRY(dev_alloc(&ctx->sort.vals_a, cap));
+  CREATE_TRY(dev_alloc(&ctx->sort.vals_b, cap));
+  CREATE_TRY(dev_alloc(&ctx->sort.scratch, sort_scratch_words(max_particles)));
+  CREATE_TRY(dev_alloc(&ctx->cell_start, (size_t)ctx->cell_capacity));
+  CREATE_TRY(dev_alloc(&ctx->cell_end, (size_t)ctx->cell_capacity));
+  CREATE_TRY(dev_alloc(&ctx->grid, 1));
+  CREATE_TRY(dev_alloc(&ctx->bounds, 1));
+  CREATE_TRY(cudaMalloc(&ctx->aos_stage, cap * sizeof(particle)));
+  CREATE_TRY(cudaMemset(ctx->grid, 0, sizeof(GridState)));
+  CREATE_TRY(cudaMemset(ctx->cell_start, 0, sizeof(uint32_t) * ctx->cell_capacity));
+  CREATE_TRY(cudaMemset(ctx->cell_end, 0, sizeof(uint32_t) * ctx->cell_capacity));
+  neighbors_init();
+  CREATE_TRY(cudaGetLastError());
+#undef CREATE_TRY
+  *out = ctx;
+  return CLSPH_OK;
+}
+
+void clsph_destroy(clsph_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(ctx->state[s].pos);
+    cudaFree(ctx->state[s].vel);
+    cudaFree(ctx->state[s].ivel);
+  }
+  cudaFree(ctx->aux);
+  cudaFree(ctx->accel);
+  cudaFree(ctx->skey);
+  cudaFree(ctx->perm);
+  cudaFree(ctx->sort.keys_a);
+  cudaFree(ctx->sort.keys_b);
+  cudaFree(ctx->sort.vals_a);
+  cudaFree(ctx->sort.vals_b);
+  cudaFree(ctx->sort.scratch);
+  cudaFree(ctx->cell_start);
+  cudaFree(ctx->cell_end);
+  cudaFree(ctx->grid);
+  cudaFree(ctx->bounds);
+  cudaFree(ctx->aos_stage);
+  cudaFree(ctx->faces);
+  cudaFree(ctx->taps.keys_input);
+  cudaFree(ctx->taps.candidate_count);
+  cudaFree(ctx->taps.support_count);
+  cudaFree(ctx->taps.acceleration);
+  cudaFree(ctx->taps.collision_iters);
+  cudaFree(ctx->ref_table);
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
+  delete ctx;
+}
+
+int clsph_set_scene(clsph_context* ctx, const float* face_normals, const float* vertices, size_t n_vertex_floats,
+                    const uint32_t* indices, uint32_t face_count) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (face_count && (!face_normals || !vertices || !indices))
+    return fail(ctx, CLSPH_EINVAL, "clsph_set_scene: null array with face_count = %u", face_count);
+  for (size_t k = 0; k < (size_t)face_count * 3; ++k)
+    if ((size_t)indices[k] * 3 + 2 >= n_vertex_floats)
+      return fail(ctx, CLSPH_EINVAL, "clsph_set_scene: index %u out of range (%zu vertex floats)", indices[k], n_vertex_floats);
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->faces);
+  ctx->faces = nullptr;
+  ctx->face_count = face_count;
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->faces, face_count));
+  if (face_count == 0) return CLSPH_OK;
+  float *d_n = nullptr, *d_v = nullptr;
+  uint32_t* d_i = nullptr;
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&d_n, (size_t)face_count * 3));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&d_v, n_vertex_floats));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&d_i, (size_t)face_count * 3));
+  cudaMemcpyAsync(d_n, face_normals, sizeof(float) * face_count * 3, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d_v, vertices, sizeof(float) * n_vertex_floats, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d_i, indices, sizeof(uint32_t) * face_count * 3, cudaMemcpyHostToDevice, ctx->stream);
+  launch_prepare_faces(d_n, d_v, d_i, face_count, ctx->faces, ctx->stream, &ctx->launches);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_n);
+  cudaFree(d_v);
+  cudaFree(d_i);
+  CLSPH_CUDA_TRY(ctx, e);
+  CLSPH_CUDA_TRY(ctx, cudaGetLastError());
+  return CLSPH_OK;
+}
+
+int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params, const precomputed_kernel_values* terms) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (!params) return fail(ctx, CLSPH_EINVAL, "clsph_set_parameters: params is null");
+  if (!terms && !ctx->have_params) return fail(ctx, CLSPH_EINVAL, "clsph_set_parameters: terms is null and none were set before");
+  if (!(params->h > 0.f)) return fail(ctx, CLSPH_EINVAL, "clsph_set_parameters: h must be positive, got %g", (double)params->h);
+  ctx->params = *params;
+  if (terms) ctx->terms = *terms;
+  ctx->have_params = true;
+  derive_constants(ctx);
+  return CLSPH_OK;
+}
+
+int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (!aos) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: aos is null");
+  if (n < 128u) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: need at least 128 particles, got %u (sort.cl:9-20)", n);
+  if (n > ctx->capacity) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: %u particles exceed the capacity %u", n, ctx->capacity);
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, aos, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, n, ctx->stream, &ctx->launches);
+  CLSPH_CUDA_TRY(ctx, cudaGetLastError());
+  ctx->n = n;
+  ctx->have_particles = true;
+  ctx->bounds_valid = false;
+  return CLSPH_OK;
+}
+
+int clsph_step(clsph_context* ctx, uint32_t n_substeps) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (!ctx->have_particles) return fail(ctx, CLSPH_ESTATE, "clsph_step: no particles uploaded");
+  if (!ctx->have_params) return fail(ctx, CLSPH_ESTATE, "clsph_step: parameters not set");
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->debug) {
+    int rc = ensure_debug_buffers(ctx);
+    if (rc) return rc;
+  }
+  for (uint32_t k = 0; k < n_substeps; ++k) {
+    if (ctx->profiling && ctx->events_used + kStages + 1 > 4096) {  // bound the event pool
+      CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      drain_events(ctx);
+    }
+    int rc = enqueue_substep(ctx);
+    if (rc) return rc;
+  }
+  return CLSPH_OK;
+}
+
+int clsph_synchronize(clsph_context* ctx) {
+  if (!ctx) return CLSPH_EINVAL;
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->profiling) drain_events(ctx);
+  return check_device_flags(ctx);
+}
+
+int clsph_get_parameters(clsph_context* ctx, simulation_parameters* out) {
+  if (!ctx || !out) return CLSPH_EINVAL;
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  GridState g;
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&g, ctx->grid, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = ctx->params;
+  out->particles_count = ctx->n;
+  out->grid_size_x = g.gx;
+  out->grid_size_y = g.gy;
+  out->grid_size_z = g.gz;
+  out->grid_cell_count = g.cell_count;
+  out->min_point.s[0] = g.min_x; out->min_point.s[1] = g.min_y; out->min_point.s[2] = g.min_z; out->min_point.s[3] = 0.f;
+  out->max_point.s[0] = g.max_x; out->max_point.s[1] = g.max_y; out->max_point.s[2] = g.max_z; out->max_point.s[3] = 0.f;
+  return CLSPH_OK;
+}
+
+int clsph_download_particles(clsph_context* ctx, particle* aos_out) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (!aos_out) return fail(ctx, CLSPH_EINVAL, "clsph_download_particles: aos_out is null");
+  if (!ctx->have_particles) return fail(ctx, CLSPH_ESTATE, "clsph_download_particles: no particles uploaded");
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  launch_soa_to_aos(ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->aos_stage, ctx->n, ctx->stream, &ctx->launches);
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(aos_out, ctx->aos_stage, sizeof(particle) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  return clsph_synchronize(ctx);
+}
+
+int clsph_simulate_single_frame(clsph_context* ctx, const particle* in, particle* out, simulation_parameters* params,
+                                const precomputed_kernel_values* terms) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (!in || !out || !params) return fail(ctx, CLSPH_EINVAL, "clsph_simulate_single_frame: null argument");
+  int rc = clsph_set_parameters(ctx, params, terms);
+  if (rc) return rc;
+  if ((rc = clsph_upload_particles(ctx, in, params->particles_count))) return rc;
+  if ((rc = clsph_step(ctx, 1))) return rc;
+  if ((rc = clsph_download_particles(ctx, out))) return rc;
+  return clsph_get_parameters(ctx, params);
+}
+
+int clsph_kernel_advection_collision(clsph_context* ctx, const particle* in, particle* out, uint32_t n) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (!in || !out) return fail(ctx, CLSPH_EINVAL, "clsph_kernel_advection_collision: null argument");
+  if (!ctx->have_params) return fail(ctx, CLSPH_ESTATE, "clsph_kernel_advection_collision: parameters not set");
+  if (n == 0 || n > ctx->capacity) return fail(ctx, CLSPH_EINVAL, "clsph_kernel_advection_collision: n = %u out of range", n);
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, in, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, st));
+  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->accel, n, st, &ctx->launches);
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->n, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  launch_bounds_reset(ctx->bounds, st, &ctx->launches);
+  if (ctx->debug) {
+    int rc = ensure_debug_buffers(ctx);
+    if (rc) return rc;
+  }
+  launch_integrate(ctx->state[ctx->cur], ctx->accel, ctx->faces, ctx->face_count, ctx->grid, ctx->konst, ctx->bounds,
+                   ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, &ctx->launches);
+  ctx->n = n;
+  ctx->have_particles = true;
+  ctx->bounds_valid = false;
+  return clsph_download_particles(ctx, out);
+}
+
+int clsph_set_debug(clsph_context* ctx, int enable) {
+  if (!ctx) return CLSPH_EINVAL;
+  ctx->debug = enable != 0;
+  if (ctx->debug) {
+    CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return ensure_debug_buffers(ctx);
+  }
+  return CLSPH_OK;
+}
+
+int clsph_debug_fetch(clsph_context* ctx, int what, void* dst, size_t bytes) {
+  if (!ctx || !dst) return CLSPH_EINVAL;
+  if (!ctx->have_particles) return fail(ctx, CLSPH_ESTATE, "clsph_debug_fetch: no particles uploaded");
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = ctx->n;
+  const void* src = nullptr;
+  size_t need = 0;
+  bool needs_debug = false;
+  std::vector<float> packed;
+  switch (what) {
+    case CLSPH_TAP_SORTED_KEYS: src = ctx->skey; need = 4 * n; break;
+    case CLSPH_TAP_PERMUTATION: src = ctx->perm; need = 4 * n; break;
+    case CLSPH_TAP_KEYS_INPUT: src = ctx->taps.keys_input; need = 4 * n; needs_debug = true; break;
+    case CLSPH_TAP_CANDIDATE_COUNT: src = ctx->taps.candidate_count; need = 4 * n; needs_debug = true; break;
+    case CLSPH_TAP_SUPPORT_COUNT: src = ctx->taps.support_count; need = 4 * n; needs_debug = true; break;
+    case CLSPH_TAP_COLLISION_ITERS: src = ctx->taps.collision_iters; need = 4 * n; needs_debug = true; break;
+    case CLSPH_TAP_CELL_TABLE: {
+      simulation_parameters p;
+      int rc = clsph_get_parameters(ctx, &p);
+      if (rc) return rc;
+      need = 4 * (size_t)p.grid_cell_count;
+      if (bytes != need) return fail(ctx, CLSPH_EINVAL, "clsph_debug_fetch: cell table is %zu bytes, got %zu", need, bytes);
+      if (ctx->ref_table_words < p.grid_cell_count) {
+        cudaFree(ctx->ref_table);
+        ctx->ref_table = nullptr;
+        ctx->ref_table_words = 0;
+        CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->ref_table, (size_t)p.grid_cell_count));
+        ctx->ref_table_words = p.grid_cell_count;
+      }
+      launch_reference_cell_table(ctx->skey, ctx->grid, ctx->ref_table, ctx->n, ctx->stream, &ctx->launches);
+      src = ctx->ref_table;
+      break;
+    }
+    case CLSPH_TAP_DENSITY:
+    case CLSPH_TAP_PRESSURE:
+    case CLSPH_TAP_ACCELERATION: {
+      const bool acc = what == CLSPH_TAP_ACCELERATION;
+      if (acc && !ctx->debug) return fail(ctx, CLSPH_ESTATE, "clsph_debug_fetch: enable clsph_set_debug before the step");
+      need = acc ? 12 * n : 4 * n;
+      if (bytes != need) return fail(ctx, CLSPH_EINVAL, "clsph_debug_fetch: tap %d is %zu bytes, got %zu", what, need, bytes);
+      std::vector<float> host(4 * n);
+      CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), acc ? ctx->taps.acceleration : ctx->aux, 16 * n, cudaMemcpyDeviceToHost, ctx->stream));
+      CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      float* o = static_cast<float*>(dst);
+      for (size_t i = 0; i < n; ++i) {
+        if (acc) { o[3 * i] = host[4 * i]; o[3 * i + 1] = host[4 * i + 1]; o[3 * i + 2] = host[4 * i + 2]; }
+        else o[i] = host[4 * i + (what == CLSPH_TAP_PRESSURE ? 1 : 0)];
+      }
+      return CLSPH_OK;
+    }
+    default:
+      return fail(ctx, CLSPH_EINVAL, "clsph_debug_fetch: unknown tap %d", what);
+  }
+  if (needs_debug && (!ctx->debug || !src)) return fail(ctx, CLSPH_ESTATE, "clsph_debug_fetch: enable clsph_set_debug before the step");
+  if (bytes != need) return fail(ctx, CLSPH_EINVAL, "clsph_debug_fetch: tap %d is %zu bytes, got %zu", what, need, bytes);
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CLSPH_CUDA_TRY(ctx, cudaGetLastError());
+  return CLSPH_OK;
+}
+
+int clsph_profile_enable(clsph_context* ctx, int enable) {
+  if (!ctx) return CLSPH_EINVAL;
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->events_used = 0;
+  ctx->times = clsph_stage_times{};
+  ctx->launches = 0;
+  ctx->profiling = enable != 0;
+  return CLSPH_OK;
+}
+
+int clsph_profile_read(clsph_context* ctx, clsph_stage_times* out) {
+  if (!ctx || !out) return CLSPH_EINVAL;
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  drain_events(ctx);
+  *out = ctx->times;
+  out->kernel_launches = ctx->launches;
+  return CLSPH_OK;
+}
+
+int clsph_particle_count(clsph_context* ctx, uint32_t* n) {
+  if (!ctx || !n) return CLSPH_EINVAL;
+  *n = ctx->n;
+  return CLSPH_OK;
+}
+
+void* clsph_stream(clsph_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// kernels.cuh -- launcher declarations shared by the translation units of libclsph_cuda.so.
+#pragma once
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace clsph {
+
+constexpr int kRadix = 256;
+constexpr int kMaxSortPasses = 4;
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;
+
+// One ping-pong side of the particle state (device pointers, capacity = max_particles).
+struct StateArrays {
+  float4* pos;
+  float4* vel;
+  float4* ivel;
+};
+
+struct SortBuffers {
+  uint32_t* keys_a;   // keys in input order (pass 0 source)
+  uint32_t* keys_b;
+  uint32_t* vals_a;
+  uint32_t* vals_b;
+  uint32_t* scratch;  // sort_scratch_words() words
+};
+
+// Precomputed triangle record for the collision pass (5 x float4).
+struct Face {
+  float nx, ny, nz, nlen;   // scene normal and its length()
+  float ax, ay, az, uv;     // vertex 0, dot(u, v)
+  float ux, uy, uz, uu;     // edge v1 - v0, dot(u, u)
+  float vx, vy, vz, vv;     // edge v2 - v0, dot(v, v)
+  float det, pad0, pad1, pad2;  // uv*uv - uu*vv
+};
+
+struct DebugTaps {           // all nullable; sorted order unless stated
+  uint32_t* keys_input;      // pre-step order
+  uint32_t* candidate_count;
+  uint32_t* support_count;
+  float4* acceleration;      // always allocated (the force pass writes it for the integrator)
+  uint32_t* collision_iters;
+};
+
+// ---- sort.cu
+uint32_t sort_tiles_for(uint32_t n);
+size_t sort_scratch_words(uint32_t max_particles);
+void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* grid, uint32_t n_launch, int sm_count,
+                      uint32_t* keys_tap, cudaStream_t stream, uint64_t* launches);
+void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_launch, cudaStream_t stream,
+                        uint64_t* launches);
+
+// ---- grid.cu
+void launch_bounds_reset(BoundsAcc* acc, cudaStream_t stream, uint64_t* launches);
+void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, cudaStream_t stream, uint64_t* launches);
+void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity,
+                       cudaStream_t stream, uint64_t* launches);
+void launch_clear_cells(uint32_t* cell_start, uint32_t* cell_end, const GridState* grid, uint32_t cell_capacity,
+                        int sm_count, cudaStream_t stream, uint64_t* launches);
+// Gathers `src` into `dst` through the sort permutation, writes sorted keys and the cell table.
+void launch_reorder(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
+                    uint32_t* perm_out, uint32_t* cell_start, uint32_t* cell_end, const GridState* grid,
+                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uint32_t* skey, float4* accel, uint32_t n,
+                       cudaStream_t stream, uint64_t* launches);
+void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, void* aos, uint32_t n,
+                       cudaStream_t stream, uint64_t* launches);
+void launch_reference_cell_table(const uint32_t* skey, const GridState* grid, uint32_t* table, uint32_t n_launch,
+                                 cudaStream_t stream, uint64_t* launches);
+void launch_copy_u32(const uint32_t* src, uint32_t* dst, uint32_t n, cudaStream_t stream, uint64_t* launches);
+
+// ---- neighbors.cu
+void neighbors_init();  // opts the kernels into their dynamic shared memory size
+void launch_density(const float4* pos, const uint32_t* skey, const uint32_t* cell_start, const uint32_t* cell_end,
+                    const GridState* grid, const SphConst& c, float4* aux, const DebugTaps& taps, bool debug,
+                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
+                   const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
+                   float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+
+// ---- integrate.cu
+void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,
+                          Face* faces, cudaStream_t stream, uint64_t* launches);
+void launch_integrate(const StateArrays& s, const float4* accel, const Face* faces, uint32_t face_count,
+                      const GridState* grid, const SphConst& c, BoundsAcc* next_bounds, uint32_t* iters_tap,
+                      uint32_t n_launch, int sm_count, cudaStream_t stream, uint64_t* launches);
+
+}  // namespace clsph
