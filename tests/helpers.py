@@ -28,12 +28,14 @@ def state_s1(p, vol, **kw):
     return workloads.jittered_state(p, vol, **kw)
 
 
-def drop_state(p, vol, scene_floor_y, speed=2.5, seed=7):
-    """A slab of particles just above a floor, moving down fast enough to hit it within one
-    sub-step: exercises detect/respond/time-splitting on most particles."""
+def drop_state(p, vol, scene_floor_y, speed=2.5, seed=7, slab=0.003):
+    """All particles squeezed into a slab `slab` metres thick just above a floor and moving down
+    fast enough to cross it within one sub-step: nearly every particle goes through
+    detect/respond/time-splitting, and the crowded cells (hundreds of particles each) exercise the
+    candidate-list chunking and neighbour-list flushing of the CUDA neighbour kernels."""
     s = workloads.jittered_state(p, vol, seed=seed)
-    ymin = s["position"][:, 1].min()
-    s["position"][:, 1] += np.float32(scene_floor_y + 0.002 - ymin)
+    u = workloads.uniform01(seed + 1, np.arange(s.size, dtype=np.uint64))
+    s["position"][:, 1] = (scene_floor_y + 0.0005 + slab * u).astype(np.float32)
     s["intermediate_velocity"][:, 1] = np.float32(-speed)
     s["velocity"][:, 1] = np.float32(-speed)
     return s

@@ -89,7 +89,7 @@ def test_collision_heavy_step(plane_scene):
     p, terms, vol = H.config("mucus", 8192)
     s = H.drop_state(p, vol, scene_floor_y=-1.0)
     got, taps, want = check_against_oracle(s, p, terms, plane_scene, "drop onto plane")
-    assert (want.collision_iters > 1).mean() > 0.05
+    assert (want.collision_iters > 1).mean() > 0.2
 
 
 def test_labyrinth_scene_many_faces():
@@ -103,7 +103,7 @@ def test_advection_collision_kernel_bit_exact(box_scene):
     """With identical inputs (acceleration included) the integrator is bit-identical to the
     oracle's restatement of kernels/sph.cl:64-112 + collisions.cl."""
     p, terms, vol = H.config("water", 20000)
-    s = H.drop_state(p, vol, scene_floor_y=-2.0, speed=2.9)
+    s = H.drop_state(p, vol, scene_floor_y=-2.0, speed=2.9, slab=0.02)
     rng = np.random.default_rng(11)
     s["acceleration"][:, :3] = rng.normal(0, 30, size=(s.size, 3)).astype(np.float32)
     s["intermediate_velocity"][:, 0] = rng.uniform(-2, 2, s.size).astype(np.float32)
