@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=102400)
+    ap.add_argument("--option", action="append", default=[], help="name=value passed to clsph_set_option (tuning)")
     return ap.parse_args()
 
 
@@ -227,6 +228,9 @@ def run_ours(args, rank, world, local_rank):
     n = state.size
     normals, vertices, indices = workloads.scene_arrays(scene_file)
     ctx = capi.Context(n, device=local_rank)
+    for opt in args.option:
+        k, v = opt.split("=")
+        ctx.set_option(k, int(v))
     ctx.set_scene(normals, vertices, indices)
     ctx.set_parameters(p, terms)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
@@ -311,7 +315,8 @@ def run_ours(args, rank, world, local_rank):
                    "scene": scene_file, "state": "S1 jittered lattice, seed 20261017",
                    "parallelism": "single GPU" if world == 1 else "replicas: one independent fluid block per GPU, no exchange",
                    "l2": "per-step working set ~%d MB vs 126 MB L2, no flush: sub-steps form a dependent chain" % (n * 200 // (1 << 20)),
-                   "grid": [grid.grid_size_x, grid.grid_size_y, grid.grid_size_z], "grid_cell_count": grid.grid_cell_count},
+                   "grid": [grid.grid_size_x, grid.grid_size_y, grid.grid_size_z], "grid_cell_count": grid.grid_cell_count,
+                   "options": args.option},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -107,6 +107,14 @@ int clsph_set_scene(clsph_context* ctx, const float* face_normals, const float* 
 int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params,
                          const precomputed_kernel_values* terms);
 
+/* Tuning knobs; results are the same (to rounding) whatever they are set to.
+ *   "neighbour_lists"  1 (default): the density pass stores per-particle neighbour lists in HBM
+ *                      and the force pass reads them; 0: both passes search on their own.
+ *                      (Environment override at creation: CLSPH_NEIGHBOUR_LISTS=0/1.)
+ *   "list_rows"        list entries kept per particle (0 = derive from the rest density);
+ *                      particles with more neighbours fall back to the searching force kernel. */
+int clsph_set_option(clsph_context* ctx, const char* name, long long value);
+
 /* Host AoS (80-byte records) -> device SoA. n must be >= 128 (sort.cl:9-20, erratum E8) and
  * <= max_particles. Replaces sph_simulation.cpp:195. */
 int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n);

@@ -14,7 +14,7 @@ from .abi import PARTICLE, PrecomputedKernelValues, SimulationParameters, partic
 # every symbol include/clsph_cuda.h declares
 SYMBOLS = [
     "clsph_device_count", "clsph_create", "clsph_destroy", "clsph_last_error", "clsph_set_scene",
-    "clsph_set_parameters", "clsph_upload_particles", "clsph_step", "clsph_synchronize",
+    "clsph_set_parameters", "clsph_set_option", "clsph_upload_particles", "clsph_step", "clsph_synchronize",
     "clsph_get_parameters", "clsph_download_particles", "clsph_simulate_single_frame", "clsph_set_debug",
     "clsph_debug_fetch", "clsph_kernel_advection_collision", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_stream",
 ]
@@ -61,6 +61,7 @@ def load_library(path=None):
     L.clsph_last_error.restype = ctypes.c_char_p
     L.clsph_set_scene.argtypes = [vp, vp, vp, sz, vp, u32]
     L.clsph_set_parameters.argtypes = [vp, vp, vp]
+    L.clsph_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_longlong]
     L.clsph_upload_particles.argtypes = [vp, vp, u32]
     L.clsph_step.argtypes = [vp, u32]
     L.clsph_synchronize.argtypes = [vp]
@@ -121,6 +122,9 @@ class Context:
 
     def set_parameters(self, params, terms):
         self._check(self._lib.clsph_set_parameters(self._h, ctypes.byref(params), ctypes.byref(terms)))
+
+    def set_option(self, name, value):
+        self._check(self._lib.clsph_set_option(self._h, name.encode(), int(value)))
 
     def upload(self, particles):
         self._check(self._lib.clsph_upload_particles(self._h, particle_ptr(particles), particles.size))

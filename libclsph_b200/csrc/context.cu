@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -54,6 +55,12 @@ struct clsph_context {
 
   Face* faces = nullptr;
   uint32_t face_count = 0;
+
+  // list mode (default): the density pass stores neighbour lists, the force pass reads them
+  bool use_lists = true;
+  uint32_t list_rows_override = 0;  // 0 = derive from the rest density
+  NeighbourLists lists{};
+  size_t list_words = 0;            // allocated words of lists.entries
 
   DebugTaps taps{};
   uint32_t* ref_table = nullptr;
@@ -195,6 +202,41 @@ int ensure_debug_buffers(clsph_context* ctx) {
   return CLSPH_OK;
 }
 
+// Rows of the neighbour-list array: about 2.5x the neighbour count at rest density
+// (rho0 / m particles per unit volume times the support sphere), rounded up to 8, in [32, 256].
+uint32_t list_rows_for(const clsph_context* ctx) {
+  if (ctx->list_rows_override) return ctx->list_rows_override;
+  const simulation_parameters& p = ctx->params;
+  const double n_rest = (double)p.fluid_density / (double)p.particle_mass * 4.18879020478639 * (double)p.h * p.h * p.h;
+  double rows = 2.5 * n_rest + 8.0;
+  if (!(rows >= 32.0)) rows = 32.0;
+  if (rows > 256.0) rows = 256.0;
+  return ((uint32_t)rows + 7u) & ~7u;
+}
+
+int ensure_lists(clsph_context* ctx) {
+  if (!ctx->use_lists) {
+    ctx->lists.rows = 0;
+    return CLSPH_OK;
+  }
+  const uint32_t rows = list_rows_for(ctx);
+  const size_t words = (size_t)rows * ctx->capacity;
+  if (words > ctx->list_words) {
+    CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->lists.entries);
+    ctx->lists.entries = nullptr;
+    ctx->list_words = 0;
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->lists.entries, words));
+    ctx->list_words = words;
+  }
+  if (!ctx->lists.count) {
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->lists.count, ctx->capacity));
+    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->lists.count, 0, sizeof(uint32_t) * ctx->capacity, ctx->stream));
+  }
+  ctx->lists.rows = rows;
+  return CLSPH_OK;
+}
+
 // One sub-step, enqueued on ctx->stream.
 int enqueue_substep(clsph_context* ctx) {
   cudaStream_t st = ctx->stream;
@@ -223,11 +265,11 @@ int enqueue_substep(clsph_context* ctx) {
   ctx->cur ^= 1;
   if (prof) next_event(ctx);
 
-  launch_density(dst.pos, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->aux, ctx->taps,
-                 ctx->debug, n, st, lc);
+  launch_density(dst.pos, dst.vel, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
+                 ctx->taps, ctx->debug, n, st, lc);
   if (prof) next_event(ctx);
   launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst,
-                ctx->accel, n, st, lc);
+                ctx->lists, ctx->accel, n, st, lc);
   if (prof) next_event(ctx);
   if (ctx->debug)  // the integrator consumes the acceleration; keep a copy for the tap
     CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->taps.acceleration, ctx->accel, sizeof(float4) * n,
@@ -269,6 +311,7 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
   ctx->capacity = max_particles;
   // Morton-indexed tables are 1.1x-6.4x the cell count for compact fluids; 8 entries
   // per particle with a 4 Mi floor covers every BASELINE config; larger grids use the fallback.
+  if (const char* env = std::getenv("CLSPH_NEIGHBOUR_LISTS")) ctx->use_lists = std::atoi(env) != 0;
   ctx->cell_capacity = cell_table_capacity ? cell_table_capacity
                                            : (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_particles * 8u, 1u << 22), 1u << 28);
 #define CREATE_TRY(expr)                                                                                          \
@@ -347,6 +390,8 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->taps.acceleration);
   cudaFree(ctx->taps.collision_iters);
   cudaFree(ctx->ref_table);
+  cudaFree(ctx->lists.entries);
+  cudaFree(ctx->lists.count);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
@@ -395,7 +440,22 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
   if (terms) ctx->terms = *terms;
   ctx->have_params = true;
   derive_constants(ctx);
-  return CLSPH_OK;
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return ensure_lists(ctx);
+}
+
+int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
+  if (!ctx || !name) return CLSPH_EINVAL;
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!std::strcmp(name, "neighbour_lists")) {
+    ctx->use_lists = value != 0;
+  } else if (!std::strcmp(name, "list_rows")) {
+    if (value < 0 || value > 1024) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: list_rows must be in [0, 1024]");
+    ctx->list_rows_override = (uint32_t)value;
+  } else {
+    return fail(ctx, CLSPH_EINVAL, "clsph_set_option: unknown option \"%s\"", name);
+  }
+  return ctx->have_params ? ensure_lists(ctx) : CLSPH_OK;
 }
 
 int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) {

@@ -72,14 +72,22 @@ void launch_reference_cell_table(const uint32_t* skey, const GridState* grid, ui
                                  cudaStream_t stream, uint64_t* launches);
 void launch_copy_u32(const uint32_t* src, uint32_t* dst, uint32_t n, cudaStream_t stream, uint64_t* launches);
 
+// Per-particle neighbour lists in HBM (list mode). rows == 0 selects the two-pass kernels.
+struct NeighbourLists {
+  uint32_t* entries = nullptr;  // [capacity][rows]: entries[i * rows + e] = e-th neighbour of particle i
+  uint32_t* count = nullptr;    // [capacity]: entries of particle i, 0xFFFFFFFF = more than `rows`
+  uint32_t rows = 0;
+};
+
 // ---- neighbors.cu
 void neighbors_init();  // opts the kernels into their dynamic shared memory size
-void launch_density(const float4* pos, const uint32_t* skey, const uint32_t* cell_start, const uint32_t* cell_end,
-                    const GridState* grid, const SphConst& c, float4* aux, const DebugTaps& taps, bool debug,
-                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+// Also leaves p/rho^2 in pos[].w and m/rho in vel[].w for the force pass.
+void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* cell_start, const uint32_t* cell_end,
+                    const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
+                    const DebugTaps& taps, bool debug, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
-                   float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+                   const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 
 // ---- integrate.cu
 void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,

@@ -6,36 +6,54 @@
 // candidate set, same support test s < support_s <=> sqrt(s)/h < 1, same per-pair formulas), but
 // the work is organised for the SM:
 //
-//   * one warp owns 32 consecutive cell-sorted particles; lanes with the same cell key form a
-//     "segment" that shares one candidate list;
-//   * the candidates of the segment's 27 cells are staged ONCE in shared memory as float4
-//     (x, y, z, index), and while staging they are culled against the segment's bounding box:
-//     a candidate farther than h from the box cannot be inside any member's support, exactly
-//     (the box test uses the same fused distance formula on component-wise smaller offsets).
-//     This keeps about 30 % of the 27-cell candidates;
-//   * the support test then runs with lanes across candidates (one coalesced LDS.128 each,
-//     every lane busy whatever the cell occupancy), per particle of the segment;
-//   * density: survivors accumulate (h^2 - s)^3 and one shuffle reduction per particle;
-//   * forces: survivors are compacted (ballot + popc) into a per-particle neighbour list in
-//     shared memory; the expensive pair terms then run one thread per particle over its own
-//     list with register accumulators, so no cross-lane reduction of the ten force sums.
+//   * candidates are staged in shared memory as float4 (x, y, z, index) and culled while staging
+//     against the bounding box of the particles that will use them: a candidate farther than h
+//     from the box cannot be inside any member's support, exactly (the box test uses the same
+//     fused distance formula on component-wise smaller offsets, and fp32 ops are monotone);
+//   * the support test runs with lanes across candidates (one coalesced LDS.128 each, every
+//     lane busy whatever the cell occupancy), one particle at a time;
+//   * the expensive per-pair force terms run one thread per particle over a compacted neighbour
+//     list, with register accumulators, so the ten force sums need no cross-lane reduction.
 //
-// Both kernels are FP32-issue / shared-memory bound, not HBM bound (SURVEY hard part 1); their
-// HBM traffic is the 16-32 B/particle of coalesced reads plus L2-resident candidate gathers.
+// Two organisations of the pair work are built (clsph_context picks one, default = lists):
+//   lists   k_density_lists does the search ONCE per whole grid cell, with a second, octant-level
+//           cull in shared memory, accumulates the density and writes every particle's neighbour
+//           indices to HBM; k_forces_lists then runs one thread per particle over its own list.
+//           Particles whose list would exceed the row budget are flagged and redone by the
+//           searching force kernel.
+//   twice   k_density + k_forces each stage and test on their own (no list memory).
+//
+// Between the passes the density kernel leaves, per particle j, p_j/rho_j^2 in pos[j].w and
+// m/rho_j in vel[j].w (the w lanes are otherwise unused), so a pair costs two 16-byte gathers.
+//
+// All of these are FP32-issue / shared-memory bound, not HBM bound (SURVEY hard part 1); their
+// HBM traffic is the 16-32 B/particle of coalesced reads, L2-resident candidate gathers and, in
+// list mode, about 2 x 4 B x (neighbours per particle) of list traffic.
 #include "kernels.cuh"
 
 namespace clsph {
 
 namespace {
 
-constexpr int kNbWarps = 8;                  // warps per CTA
+// ---- two-pass ("twice") kernels and the list-mode fallback: 8 warps per CTA
+constexpr int kNbWarps = 8;
 constexpr int kNbThreads = kNbWarps * 32;
 constexpr int kCandCap = 384;                // staged candidates per warp (float4 each)
 constexpr int kListLen = 48;                 // neighbour-list entries per particle before a flush
 constexpr int kListStride = kListLen + 1;    // odd word stride: lanes hit distinct banks
-
 constexpr size_t kDensitySmem = (size_t)kNbWarps * kCandCap * sizeof(float4);
 constexpr size_t kForceSmem = kDensitySmem + (size_t)kNbWarps * 32 * kListStride * sizeof(uint32_t);
+
+// ---- list mode
+constexpr int kDlWarps = 4;                  // warps per CTA of k_density_lists (small CTAs: units vary in size)
+constexpr int kDlThreads = kDlWarps * 32;
+constexpr int kCap1 = 352;                   // level-1 staged candidates per warp (unit box), + 32 padding
+constexpr int kCap2 = 160;                   // level-2 staged candidates per warp (octant group box), + 32 padding
+constexpr int kOwnedCellMax = 64;            // cells up to this size are processed whole by one warp
+constexpr int kSplitMin = 12;                // targets needed before a unit is cut into octant groups
+constexpr size_t kDensityListSmem = (size_t)kDlWarps * (kCap1 + 32 + kCap2 + 32) * sizeof(float4);
+constexpr int kFlWarps = 8;                  // warps per CTA of k_forces_lists
+constexpr int kTileStride = 33;              // 32 entries per particle + 1: lanes hit distinct banks
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -57,8 +75,13 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
   return v;
 }
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(kFullMask, v, o));
+  return v;
+}
 
-// Bounding box of the segment's particles, identical in every lane.
+// Axis-aligned box, identical in every lane.
 struct Box {
   float lx, ly, lz, hx, hy, hz;
 };
@@ -85,7 +108,8 @@ __device__ __forceinline__ float box_dist2(const Box& b, float cx, float cy, flo
 }
 
 // Ranges of the 27 neighbour cells of `key`, one per lane 0..26, in the reference's visiting
-// order (z outermost, x innermost: forces.cl:25-27). Other lanes get an empty range.
+// order (z outermost, x innermost: forces.cl:25-27); lane 13 is the cell itself. Other lanes get
+// an empty range.
 __device__ __forceinline__ uint2 neighbour_cell_range(uint32_t key, const GridState& g,
                                                       const uint32_t* __restrict__ cell_start,
                                                       const uint32_t* __restrict__ cell_end,
@@ -100,14 +124,84 @@ __device__ __forceinline__ uint2 neighbour_cell_range(uint32_t key, const GridSt
   return cell_range(morton3(x, y, z), g, cell_start, cell_end, skey);
 }
 
+// Sums of one particle's force pass (forces.cl:50-55).
+struct ForceSums {
+  float px = 0.f, py = 0.f, pz = 0.f;   // pressure term          forces.cl:70-77
+  float wx = 0.f, wy = 0.f, wz = 0.f;   // viscosity term         forces.cl:79-85
+  float nx = 0.f, ny = 0.f, nz = 0.f;   // colour-field normal    forces.cl:88-91
+  float lap = 0.f;                      // colour-field laplacian forces.cl:93-97
+};
+
+// Contribution of neighbour j (known to be inside the support, window == 1) to particle i.
+// pj = (x, y, z, p_j/rho_j^2), vj = (vx, vy, vz, m/rho_j); a_i = p_i/rho_i^2.
+__device__ __forceinline__ void add_pair(ForceSums& f, const SphConst& c, bool is_self, const float4& pi, const float4& vi,
+                                         float a_i, const float4& pj, const float4& vj) {
+  const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+  const float s = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const float r = sqrtf(s);
+  const float mass_over_rho = vj.w;
+  if (!is_self) {
+    float gx, gy, gz;
+    if (r < 0.0000001f) {  // smoothing.cl:23-25 (erratum E3): a scalar broadcast to x, y, z
+      gx = gy = gz = c.spiky_degenerate;
+    } else {               // smoothing.cl:26-28
+      const float hr = c.h - r;
+      const float k = c.c_spiky * hr * hr / r;
+      gx = k * dx; gy = k * dy; gz = k * dz;
+    }
+    const float pc = (pj.w + a_i) * c.mass;
+    f.px = fmaf(pc, gx, f.px); f.py = fmaf(pc, gy, f.py); f.pz = fmaf(pc, gz, f.pz);
+    const float vc = mass_over_rho * (c.c_visc * (c.h - r));  // smoothing.cl:31-34
+    f.wx = fmaf(vj.x - vi.x, vc, f.wx); f.wy = fmaf(vj.y - vi.y, vc, f.wy); f.wz = fmaf(vj.z - vi.z, vc, f.wz);
+  }
+  const float t = c.h2 - r * r;
+  const float gc = mass_over_rho * (c.c_poly6_grad * t * t);  // smoothing.cl:6-10
+  f.nx = fmaf(gc, dx, f.nx); f.ny = fmaf(gc, dy, f.ny); f.nz = fmaf(gc, dz, f.nz);
+  f.lap = fmaf(mass_over_rho, c.c_poly6_lap * t * (3.f * c.h2 - 7.f * r * r), f.lap);  // smoothing.cl:12-17
+}
+
+// forces.cl:103-109 and sph.cl:53-58: F = -rho P + mu V (+ surface tension), a = F / rho + g.
+__device__ __forceinline__ float4 finish_force(const ForceSums& f, const SphConst& c, float rho) {
+  float fx = -rho * f.px + f.wx * c.mu, fy = -rho * f.py + f.wy * c.mu, fz = -rho * f.pz + f.wz * c.mu;
+  const float nlen = sqrtf(fmaf(f.nz, f.nz, fmaf(f.ny, f.ny, f.nx * f.nx)));
+  if (nlen > c.tension_threshold) {
+    const float k = -c.sigma * f.lap / nlen;
+    fx = fmaf(k, f.nx, fx); fy = fmaf(k, f.ny, fy); fz = fmaf(k, f.nz, fz);
+  }
+  return make_float4(fx / rho + c.gx, fy / rho + c.gy, fz / rho + c.gz, 0.f);
+}
+
+// forces.cl:33-36 / smoothing.cl:1-4: rho = sum m C6 (h^2 - r^2)^3; sph.cl:37-39: Tait pressure.
+// Writes (rho, p) to aux[i] and the two per-neighbour factors the force pass gathers.
+__device__ __forceinline__ void finish_density(const SphConst& c, float sum_cubed, uint32_t i, float4* __restrict__ aux,
+                                               float4* pos, float4* vel) {
+  const float rho = c.mass * c.c_poly6 * sum_cubed;
+  const float q = rho / c.rho0;
+  const float q2 = q * q, q4 = q2 * q2;
+  const float prs = c.K * (q4 * q2 * q - 1.f);
+  aux[i] = make_float4(rho, prs, 0.f, 0.f);
+  reinterpret_cast<float*>(pos + i)[3] = prs / (rho * rho);  // only the w lane: other warps may be reading x, y, z
+  reinterpret_cast<float*>(vel + i)[3] = c.mass / rho;
+}
+
+// Rounds a staged list up to a multiple of 32 with candidates at +infinity (never inside a
+// support), so the support-test loops need no bounds check. The lists have 32 spare slots.
+__device__ __forceinline__ uint32_t pad_list(float4* list, uint32_t count) {
+  const uint32_t padded = (count + 31u) & ~31u;
+  const float inf = __int_as_float(0x7f800000);
+  if (count + lane_id() < padded) list[count + lane_id()] = make_float4(inf, inf, inf, 0.f);
+  return padded;
+}
+
 }  // namespace
 
 // =============================================================================================
-// Density + Tait pressure
+// Two-pass mode: density + Tait pressure. One warp = 32 consecutive sorted particles; lanes with
+// the same cell key form a segment that shares one staged candidate list.
 // =============================================================================================
 template <bool kTaps>
 __global__ void __launch_bounds__(kNbThreads, 4)
-k_density(const float4* __restrict__ pos, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ cell_start,
+k_density(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ cell_start,
           const uint32_t* __restrict__ cell_end, const GridState* __restrict__ grid, const SphConst c,
           float4* __restrict__ aux, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ supp_count) {
   extern __shared__ float4 s_dyn[];
@@ -193,12 +287,7 @@ k_density(const float4* __restrict__ pos, const uint32_t* __restrict__ skey, con
   }
 
   if (valid) {
-    // forces.cl:33-36 / smoothing.cl:1-4: rho = sum m * C6 * (h^2 - r^2)^3 ; sph.cl:37-39 Tait.
-    const float rho = c.mass * c.c_poly6 * acc;
-    const float q = rho / c.rho0;
-    const float q2 = q * q, q4 = q2 * q2;
-    const float prs = c.K * (q4 * q2 * q - 1.f);
-    aux[i] = make_float4(rho, prs, prs / (rho * rho), c.mass / rho);
+    finish_density(c, acc, i, aux, pos, vel);
     if (kTaps) {
       cand_count[i] = n_cand;
       supp_count[i] = n_supp;
@@ -207,12 +296,16 @@ k_density(const float4* __restrict__ pos, const uint32_t* __restrict__ skey, con
 }
 
 // =============================================================================================
-// Forces: pressure (spiky), viscosity, surface tension (poly6 colour field); a = F / rho + g
+// Two-pass mode: forces (pressure, viscosity, surface tension); a = F / rho + g.
+// kOnlyOverflow: list-mode fallback; only windows holding a particle whose neighbour list
+// overflowed (ncount > list_rows) do any work, and they redo all of their particles.
 // =============================================================================================
+template <bool kOnlyOverflow>
 __global__ void __launch_bounds__(kNbThreads, 2)
 k_forces(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
          const uint32_t* __restrict__ skey, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
-         const GridState* __restrict__ grid, const SphConst c, float4* __restrict__ accel) {
+         const GridState* __restrict__ grid, const SphConst c, float4* __restrict__ accel,
+         const uint32_t* __restrict__ ncount, uint32_t list_rows) {
   extern __shared__ float4 s_dyn[];
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   float4* s_cand = s_dyn + warp * kCandCap;
@@ -223,17 +316,17 @@ k_forces(const float4* __restrict__ pos, const float4* __restrict__ vel, const f
   if (base >= g.n) return;
   const uint32_t i = base + lane;
   const bool valid = i < g.n;
+  if (kOnlyOverflow) {
+    const bool overflowed = valid && ncount[i] > list_rows;
+    if (!__any_sync(kFullMask, overflowed)) return;
+  }
   const float4 pi = valid ? pos[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 vi = valid ? vel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 ai = valid ? aux[i] : make_float4(1.f, 0.f, 0.f, 0.f);  // rho, p, p/rho^2, m/rho
+  const float rho_i = valid ? aux[i].x : 1.f;
   const uint32_t key_i = valid ? skey[i] : 0xFFFFFFFFu;
 
-  // register accumulators of this lane's own particle
-  float px = 0.f, py = 0.f, pz = 0.f;   // pressure term        forces.cl:70-77
-  float wx = 0.f, wy = 0.f, wz = 0.f;   // viscosity term       forces.cl:79-85
-  float nx = 0.f, ny = 0.f, nz = 0.f;   // colour-field normal  forces.cl:88-91
-  float lap = 0.f;                      // colour-field laplacian forces.cl:93-97
-  uint32_t my_count = 0;                // entries waiting in this lane's neighbour list
+  ForceSums sums;         // register accumulators of this lane's own particle
+  uint32_t my_count = 0;  // entries waiting in this lane's neighbour list
 
   // One thread per particle: consume the lane's own neighbour list (global indices).
   auto flush = [&]() {
@@ -241,31 +334,7 @@ k_forces(const float4* __restrict__ pos, const float4* __restrict__ vel, const f
     const uint32_t* mine = s_list + lane * kListStride;
     for (uint32_t e = 0; e < my_count; ++e) {
       const uint32_t j = mine[e];
-      const float4 pj = pos[j];
-      const float4 vj = vel[j];
-      const float4 aj = aux[j];
-      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      const float s = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      const float r = sqrtf(s);
-      const float mass_over_rho = aj.w;
-      if (j != i) {
-        float gx, gy, gz;
-        if (r < 0.0000001f) {  // smoothing.cl:23-25 (erratum E3): a scalar broadcast to x, y, z
-          gx = gy = gz = c.spiky_degenerate;
-        } else {               // smoothing.cl:26-28 with the window == 1
-          const float hr = c.h - r;
-          const float k = c.c_spiky * hr * hr / r;
-          gx = k * dx; gy = k * dy; gz = k * dz;
-        }
-        const float pc = (aj.z + ai.z) * c.mass;
-        px = fmaf(pc, gx, px); py = fmaf(pc, gy, py); pz = fmaf(pc, gz, pz);
-        const float vc = mass_over_rho * (c.c_visc * (c.h - r));  // smoothing.cl:31-34
-        wx = fmaf(vj.x - vi.x, vc, wx); wy = fmaf(vj.y - vi.y, vc, wy); wz = fmaf(vj.z - vi.z, vc, wz);
-      }
-      const float t = c.h2 - r * r;
-      const float gc = mass_over_rho * (c.c_poly6_grad * t * t);  // smoothing.cl:6-10
-      nx = fmaf(gc, dx, nx); ny = fmaf(gc, dy, ny); nz = fmaf(gc, dz, nz);
-      lap = fmaf(mass_over_rho, c.c_poly6_lap * t * (3.f * c.h2 - 7.f * r * r), lap);  // smoothing.cl:12-17
+      add_pair(sums, c, j == i, pi, vi, pi.w, pos[j], vel[j]);
     }
     my_count = 0;
     __syncwarp();
@@ -340,46 +409,286 @@ k_forces(const float4* __restrict__ pos, const float4* __restrict__ vel, const f
   }
   flush();
 
-  if (valid) {
-    const float rho = ai.x;
-    // forces.cl:103-109
-    float fx = -rho * px + wx * c.mu, fy = -rho * py + wy * c.mu, fz = -rho * pz + wz * c.mu;
-    const float nlen = sqrtf(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
-    if (nlen > c.tension_threshold) {
-      const float k = -c.sigma * lap / nlen;
-      fx = fmaf(k, nx, fx); fy = fmaf(k, ny, fy); fz = fmaf(k, nz, fz);
+  if (valid) accel[i] = finish_force(sums, c, rho_i);
+}
+
+// =============================================================================================
+// List mode, pass 1: density + pressure + per-particle neighbour lists
+// =============================================================================================
+// nlist is particle-major: nlist[i * list_rows + e] = e-th neighbour (sorted index) of particle
+// i, so the survivors of one support-test iteration (all for the same particle) land in one
+// 128-byte line. ncount[i] = neighbours found; more than list_rows means the list is incomplete.
+//
+// Work unit = one grid cell. A cell of up to kOwnedCellMax particles is processed whole (two
+// particles per lane) by the warp whose 32-particle window holds the cell's first particle; larger
+// cells are processed window by window. Per unit:
+//   1. candidates of the 27 cells are culled against the unit's bounding box into shared memory
+//      (level 1, ~30 % survive);
+//   2. with kSplitMin or more particles the unit is cut at the box centre into 8 octant groups,
+//      and level 1 is culled again against each group's box (level 2, ~1/3 survive) -- both culls
+//      are exact lower bounds of the true distance, so no neighbour can be lost;
+//   3. each particle tests its group's list with lanes across candidates; survivors add to the
+//      density and go straight to the particle's list in HBM.
+template <bool kTaps>
+__global__ void __launch_bounds__(kDlThreads, 6)
+k_density_lists(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ cell_start,
+                const uint32_t* __restrict__ cell_end, const GridState* __restrict__ grid, const SphConst c,
+                float4* __restrict__ aux, uint32_t* __restrict__ nlist, uint32_t* __restrict__ ncount,
+                uint32_t list_rows, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ supp_count) {
+  extern __shared__ float4 s_dyn[];
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  float4* s_l1 = s_dyn + warp * (kCap1 + 32);                              // level 1: culled against the unit's box
+  float4* s_l2 = s_dyn + kDlWarps * (kCap1 + 32) + warp * (kCap2 + 32);    // level 2: one octant group's box
+
+  const GridState g = *grid;
+  const uint32_t base = (blockIdx.x * kDlWarps + warp) * 32u;
+  if (base >= g.n) return;
+  const uint32_t i = base + lane;
+  const bool valid = i < g.n;
+  const uint32_t key_i = valid ? skey[i] : 0xFFFFFFFFu;
+
+  for (unsigned remaining = __ballot_sync(kFullMask, valid); remaining;) {
+    const int leader = __ffs(remaining) - 1;
+    const uint32_t seg_key = __shfl_sync(kFullMask, key_i, leader);
+    const bool in_seg = valid && key_i == seg_key;
+    remaining &= ~__ballot_sync(kFullMask, in_seg);
+
+    const uint2 rng = neighbour_cell_range(seg_key, g, cell_start, cell_end, skey);
+    const uint32_t cs = __shfl_sync(kFullMask, rng.x, 13), ce = __shfl_sync(kFullMask, rng.y, 13);
+    const bool owned = ce - cs <= (uint32_t)kOwnedCellMax;
+    if (owned && cs < base) continue;  // an earlier window owns this cell
+
+    // Targets of this unit: two per lane for an owned cell, the lane's own particle otherwise.
+    const uint32_t ti0 = owned ? cs + lane : i, ti1 = cs + 32u + lane;
+    const bool tv0 = owned ? ti0 < ce : in_seg, tv1 = owned && ti1 < ce;
+    const float4 tp0 = tv0 ? pos[ti0] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 tp1 = tv1 ? pos[ti1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned tm0 = __ballot_sync(kFullMask, tv0), tm1 = __ballot_sync(kFullMask, tv1);
+    float acc0 = 0.f, acc1 = 0.f;   // sum of (h^2 - s)^3
+    uint32_t cnt0 = 0, cnt1 = 0;    // neighbours found so far
+
+    const float inf = __int_as_float(0x7f800000);
+    Box box;
+    box.lx = warp_min(fminf(tv0 ? tp0.x : inf, tv1 ? tp1.x : inf));
+    box.ly = warp_min(fminf(tv0 ? tp0.y : inf, tv1 ? tp1.y : inf));
+    box.lz = warp_min(fminf(tv0 ? tp0.z : inf, tv1 ? tp1.z : inf));
+    box.hx = warp_max(fmaxf(tv0 ? tp0.x : -inf, tv1 ? tp1.x : -inf));
+    box.hy = warp_max(fmaxf(tv0 ? tp0.y : -inf, tv1 ? tp1.y : -inf));
+    box.hz = warp_max(fmaxf(tv0 ? tp0.z : -inf, tv1 ? tp1.z : -inf));
+    uint32_t n_cand = 0;
+    if (kTaps) n_cand = warp_sum_u32(rng.y - rng.x);
+
+    // Support test of a padded staged list for every target in `mask` of one register slot.
+    auto cull_slot = [&](unsigned mask, const float4* list, uint32_t padded, const float4& tp, uint32_t ti, float& acc,
+                         uint32_t& cnt) {
+      for (unsigned todo = mask; todo; todo &= todo - 1u) {
+        const int p = __ffs(todo) - 1;
+        const float xi = __shfl_sync(kFullMask, tp.x, p), yi = __shfl_sync(kFullMask, tp.y, p),
+                    zi = __shfl_sync(kFullMask, tp.z, p);
+        uint32_t* row = nlist + (size_t)__shfl_sync(kFullMask, ti, p) * list_rows;
+        uint32_t cnt_p = __shfl_sync(kFullMask, cnt, p);
+        float part = 0.f;
+        for (uint32_t q = lane; q < padded; q += 32u) {  // padded is a multiple of 32: uniform trip count
+          const float4 cj = list[q];
+          const float s = dist2_contract(xi, yi, zi, cj.x, cj.y, cj.z);
+          const bool hit = s < c.support_s;
+          if (hit) {
+            const float t = c.h2 - s;
+            part = fmaf(t * t, t, part);
+          }
+          const unsigned m = __ballot_sync(kFullMask, hit);
+          if (m != 0u) {
+            const uint32_t at = cnt_p + __popc(m & lanemask_lt());
+            if (hit && at < list_rows) row[at] = __float_as_uint(cj.w);
+            cnt_p += __popc(m);
+          }
+        }
+        part = warp_sum(part);
+        if ((int)lane == p) {
+          acc += part;
+          cnt = cnt_p;
+        }
+      }
+    };
+    auto cull = [&](unsigned m0, unsigned m1, const float4* list, uint32_t padded) {
+      cull_slot(m0, list, padded, tp0, ti0, acc0, cnt0);
+      cull_slot(m1, list, padded, tp1, ti1, acc1, cnt1);
+    };
+
+    // Level 2: one pass per occupied octant of the unit's box. `padded1` = level-1 entries, padded.
+    auto process_level1 = [&](uint32_t padded1) {
+      if (__popc(tm0) + __popc(tm1) < kSplitMin) {
+        cull(tm0, tm1, s_l1, padded1);
+        return;
+      }
+      const float mx = 0.5f * (box.lx + box.hx), my = 0.5f * (box.ly + box.hy), mz = 0.5f * (box.lz + box.hz);
+      const int oct0 = (tp0.x > mx ? 1 : 0) | (tp0.y > my ? 2 : 0) | (tp0.z > mz ? 4 : 0);
+      const int oct1 = (tp1.x > mx ? 1 : 0) | (tp1.y > my ? 2 : 0) | (tp1.z > mz ? 4 : 0);
+      for (int o = 0; o < 8; ++o) {
+        const unsigned m0 = __ballot_sync(kFullMask, tv0 && oct0 == o), m1 = __ballot_sync(kFullMask, tv1 && oct1 == o);
+        if ((m0 | m1) == 0u) continue;
+        // coordinates <= the centre are in [lo, centre], the others in [centre, hi]
+        Box gb;
+        gb.lx = (o & 1) ? mx : box.lx; gb.hx = (o & 1) ? box.hx : mx;
+        gb.ly = (o & 2) ? my : box.ly; gb.hy = (o & 2) ? box.hy : my;
+        gb.lz = (o & 4) ? mz : box.lz; gb.hz = (o & 4) ? box.hz : mz;
+        uint32_t staged2 = 0;
+        for (uint32_t q = lane; q < padded1; q += 32u) {
+          const float4 cj = s_l1[q];
+          const bool keep = box_dist2(gb, cj.x, cj.y, cj.z) < c.support_s;  // padding is at +inf: never kept
+          const unsigned m = __ballot_sync(kFullMask, keep);
+          if (staged2 + (uint32_t)__popc(m) > (uint32_t)kCap2) {
+            const uint32_t full2 = pad_list(s_l2, staged2);
+            __syncwarp();
+            cull(m0, m1, s_l2, full2);
+            __syncwarp();
+            staged2 = 0;
+          }
+          if (keep) s_l2[staged2 + __popc(m & lanemask_lt())] = cj;
+          staged2 += __popc(m);
+        }
+        const uint32_t padded2 = pad_list(s_l2, staged2);
+        __syncwarp();
+        cull(m0, m1, s_l2, padded2);
+        __syncwarp();
+      }
+    };
+
+    // Level 1: the 27 cells in the reference's visiting order, culled against the unit's box.
+    uint32_t staged1 = 0;
+    for (int cell = 0; cell < 27; ++cell) {
+      const uint32_t first = __shfl_sync(kFullMask, rng.x, cell), end = __shfl_sync(kFullMask, rng.y, cell);
+      for (uint32_t j0 = first; j0 < end; j0 += 32u) {
+        const uint32_t j = j0 + lane;
+        bool keep = j < end;
+        float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (keep) {
+          pj = pos[j];
+          keep = box_dist2(box, pj.x, pj.y, pj.z) < c.support_s;
+        }
+        const unsigned m = __ballot_sync(kFullMask, keep);
+        if (staged1 + (uint32_t)__popc(m) > (uint32_t)kCap1) {
+          const uint32_t padded1 = pad_list(s_l1, staged1);
+          __syncwarp();
+          process_level1(padded1);
+          __syncwarp();
+          staged1 = 0;
+        }
+        if (keep) s_l1[staged1 + __popc(m & lanemask_lt())] = make_float4(pj.x, pj.y, pj.z, __uint_as_float(j));
+        staged1 += __popc(m);
+      }
     }
-    // sph.cl:53-58
-    accel[i] = make_float4(fx / rho + c.gx, fy / rho + c.gy, fz / rho + c.gz, 0.f);
+    const uint32_t padded1 = pad_list(s_l1, staged1);
+    __syncwarp();
+    process_level1(padded1);
+    __syncwarp();
+
+    if (tv0) {
+      finish_density(c, acc0, ti0, aux, pos, vel);
+      ncount[ti0] = cnt0;
+      if (kTaps) { cand_count[ti0] = n_cand; supp_count[ti0] = cnt0; }
+    }
+    if (tv1) {
+      finish_density(c, acc1, ti1, aux, pos, vel);
+      ncount[ti1] = cnt1;
+      if (kTaps) { cand_count[ti1] = n_cand; supp_count[ti1] = cnt1; }
+    }
   }
+}
+
+// =============================================================================================
+// List mode, pass 2: forces from the stored neighbour lists, one thread per particle.
+// The warp first copies its 32 rows, 32 entries at a time, into a shared-memory tile with
+// coalesced 128-byte reads; each lane then walks its own row.
+// =============================================================================================
+__global__ void __launch_bounds__(kFlWarps * 32, 3)
+k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
+               const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
+               const GridState* __restrict__ grid, const SphConst c, float4* __restrict__ accel) {
+  __shared__ uint32_t s_tile[kFlWarps][32 * kTileStride];
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t n = grid->n;
+  const uint32_t base = (blockIdx.x * kFlWarps + warp) * 32u;
+  if (base >= n) return;
+  const uint32_t i = base + lane;
+  const bool valid = i < n;
+  uint32_t count = valid ? ncount[i] : 0u;
+  const bool listed = count <= list_rows;  // otherwise redone by k_forces<true>
+  if (!listed) count = 0u;
+  const float4 pi = valid ? pos[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 vi = valid ? vel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  ForceSums sums;
+  uint32_t* tile = s_tile[warp];
+  const uint32_t max_count = warp_max_u32(count);
+  for (uint32_t e0 = 0; e0 < max_count; e0 += 32u) {
+    for (int p = 0; p < 32; ++p) {  // row p of the tile <- entries e0 .. e0+31 of particle base+p
+      const uint32_t count_p = __shfl_sync(kFullMask, count, p);
+      if (e0 + lane < count_p) tile[p * kTileStride + lane] = nlist[(size_t)(base + p) * list_rows + e0 + lane];
+    }
+    __syncwarp();
+    const uint32_t mine = count > e0 ? min(count - e0, 32u) : 0u;
+    const uint32_t* row = tile + lane * kTileStride;
+#pragma unroll 2
+    for (uint32_t e = 0; e < mine; ++e) {
+      const uint32_t j = row[e];
+      add_pair(sums, c, j == i, pi, vi, pi.w, pos[j], vel[j]);
+    }
+    __syncwarp();
+  }
+  if (valid && listed) accel[i] = finish_force(sums, c, aux[i].x);
 }
 
 // ---------------------------------------------------------------------------------------------
 void neighbors_init() {
   cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDensitySmem);
   cudaFuncSetAttribute(k_density<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDensitySmem);
-  cudaFuncSetAttribute(k_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kForceSmem);
+  cudaFuncSetAttribute(k_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kForceSmem);
+  cudaFuncSetAttribute(k_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kForceSmem);
+  cudaFuncSetAttribute(k_density_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDensityListSmem);
+  cudaFuncSetAttribute(k_density_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDensityListSmem);
 }
 
-void launch_density(const float4* pos, const uint32_t* skey, const uint32_t* cell_start, const uint32_t* cell_end,
-                    const GridState* grid, const SphConst& c, float4* aux, const DebugTaps& taps, bool debug,
-                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
-  const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
-  if (debug)
-    k_density<true><<<blocks, kNbThreads, kDensitySmem, stream>>>(pos, skey, cell_start, cell_end, grid, c, aux,
-                                                                  taps.candidate_count, taps.support_count);
-  else
-    k_density<false><<<blocks, kNbThreads, kDensitySmem, stream>>>(pos, skey, cell_start, cell_end, grid, c, aux,
-                                                                   nullptr, nullptr);
+void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* cell_start, const uint32_t* cell_end,
+                    const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
+                    const DebugTaps& taps, bool debug, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+  uint32_t* cand = debug ? taps.candidate_count : nullptr;
+  uint32_t* supp = debug ? taps.support_count : nullptr;
+  if (lists.rows) {
+    const unsigned blocks = (n_launch + kDlThreads - 1) / kDlThreads;
+    if (debug)
+      k_density_lists<true><<<blocks, kDlThreads, kDensityListSmem, stream>>>(pos, vel, skey, cell_start, cell_end, grid, c,
+                                                                              aux, lists.entries, lists.count, lists.rows,
+                                                                              cand, supp);
+    else
+      k_density_lists<false><<<blocks, kDlThreads, kDensityListSmem, stream>>>(pos, vel, skey, cell_start, cell_end, grid, c,
+                                                                               aux, lists.entries, lists.count, lists.rows,
+                                                                               cand, supp);
+  } else {
+    const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
+    if (debug)
+      k_density<true><<<blocks, kNbThreads, kDensitySmem, stream>>>(pos, vel, skey, cell_start, cell_end, grid, c, aux, cand, supp);
+    else
+      k_density<false><<<blocks, kNbThreads, kDensitySmem, stream>>>(pos, vel, skey, cell_start, cell_end, grid, c, aux, cand, supp);
+  }
   if (launches) ++*launches;
 }
 
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
-                   float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+                   const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
-  k_forces<<<blocks, kNbThreads, kForceSmem, stream>>>(pos, vel, aux, skey, cell_start, cell_end, grid, c, accel);
-  if (launches) ++*launches;
+  if (lists.rows) {
+    k_forces_lists<<<(n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32), kFlWarps * 32, 0, stream>>>(
+        pos, vel, aux, lists.entries, lists.count, lists.rows, grid, c, accel);
+    // particles with more neighbours than list rows: redone with the searching kernel (exits at once elsewhere)
+    k_forces<true><<<blocks, kNbThreads, kForceSmem, stream>>>(pos, vel, aux, skey, cell_start, cell_end, grid, c, accel,
+                                                               lists.count, lists.rows);
+    if (launches) *launches += 2;
+  } else {
+    k_forces<false><<<blocks, kNbThreads, kForceSmem, stream>>>(pos, vel, aux, skey, cell_start, cell_end, grid, c, accel,
+                                                                nullptr, 0u);
+    if (launches) ++*launches;
+  }
 }
 
 }  // namespace clsph

@@ -6,6 +6,7 @@
 # What gets compiled, straight from $REFERENCE with no edits:
 #   libclsph/sph_simulation.cpp  libclsph/scene.cpp  util/cl_boilerplate.cpp
 #   util/tinyobj/tiny_obj_loader.cc            (+ vendored picojson / cereal headers)
+#   libclsph/file_save_delegates/houdini_file_saver.cpp  util/houdini_geo/HoudiniFileDumpHelper.cpp
 # against oracle/ref_shim/CL/cl.hpp (an in-process OpenCL stand-in), and the kernel program
 #   libclsph/kernels/*.cl + libclsph/common/{structures,util}.h
 # compiled as C++ behind oracle/ref_shim/cl_device.h. The kernel files need three one-line
@@ -51,6 +52,8 @@ $CXX $FLAGS $INC -c "$REFERENCE/libclsph/sph_simulation.cpp"     -o "$OUT/obj/sp
 $CXX $FLAGS $INC -c "$REFERENCE/libclsph/scene.cpp"              -o "$OUT/obj/scene.o"
 $CXX $FLAGS $INC -c "$REFERENCE/util/cl_boilerplate.cpp"         -o "$OUT/obj/cl_boilerplate.o"
 $CXX $FLAGS $INC -c "$REFERENCE/util/tinyobj/tiny_obj_loader.cc" -o "$OUT/obj/tiny_obj_loader.o"
+$CXX $FLAGS $INC -c "$REFERENCE/libclsph/file_save_delegates/houdini_file_saver.cpp" -o "$OUT/obj/houdini_file_saver.o"
+$CXX $FLAGS $INC -c "$REFERENCE/util/houdini_geo/HoudiniFileDumpHelper.cpp" -o "$OUT/obj/HoudiniFileDumpHelper.o"
 $CXX $FLAGS $INC -DREF_KERNEL_PROGRAM="\"$GEN/kernels/sph.cl\"" \
                  -c "$HERE/ref_shim/cl_runtime.cpp"              -o "$OUT/obj/cl_runtime.o"
 $CXX $FLAGS $INC -c "$HERE/ref_shim/ref_api.cpp"                 -o "$OUT/obj/ref_api.o"

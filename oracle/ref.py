@@ -58,6 +58,8 @@ def lib():
         L.clsph_ref_kernel_forces.argtypes = [vp, vp, vp, vp, vp]
         L.clsph_ref_kernel_advection_collision.restype = ctypes.c_int
         L.clsph_ref_kernel_advection_collision.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp, ctypes.c_uint32]
+        L.clsph_ref_write_frames.restype = ctypes.c_int
+        L.clsph_ref_write_frames.argtypes = [ctypes.c_char_p, vp, vp, ctypes.c_int]
         L.clsph_ref_num_threads.restype = ctypes.c_int
         L.clsph_ref_set_num_threads.argtypes = [ctypes.c_int]
         _lib = L
@@ -143,6 +145,12 @@ def kernel_advection_collision(particles, params, terms, scene):
                                                     scene.vertices.size, _vp(scene.indices), scene.face_count)
     assert rc == 0, rc
     return out
+
+
+def write_frames(prefix, particles, params, frames=1):
+    """The reference's houdini_file_saver: writes <prefix>frames/frame000000K.geo, K = 1..frames."""
+    rc = lib().clsph_ref_write_frames(prefix.encode(), particle_ptr(particles), ctypes.byref(params), frames)
+    assert rc == 0, rc
 
 
 def num_threads():

@@ -17,6 +17,7 @@
 #include <stdexcept>
 
 #include "sph_simulation.h" /* the reference's, via -I<reference>/libclsph */
+#include "file_save_delegates/houdini_file_saver.h" /* the reference's */
 
 namespace {
 
@@ -161,6 +162,14 @@ int clsph_ref_simulate(const char* work_dir, const simulation_parameters* p,
   }
   std::remove("last_frame.bin");
   return rc;
+}
+
+/* houdini_file_saver::writeFrameToFile (libclsph/file_save_delegates/houdini_file_saver.cpp:25-92),
+ * `frames` times in a row: writes <prefix>frames/frame000000K.geo. */
+int clsph_ref_write_frames(const char* prefix, particle* particles, const simulation_parameters* p, int frames) {
+  houdini_file_saver saver = houdini_file_saver(std::string(prefix));
+  for (int k = 0; k < frames; ++k) saver.writeFrameToFile(particles, *p);
+  return 0;
 }
 
 /* ---- single reference kernels through the shim's cl:: objects ---------------------------- */

@@ -18,8 +18,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4  # fp32 relative tolerance stated by the north star
 
 
-def make_ctx(n, scene, params, terms, debug=True, cell_table_capacity=0):
+def make_ctx(n, scene, params, terms, debug=True, cell_table_capacity=0, options=None):
     ctx = capi.Context(n, cell_table_capacity=cell_table_capacity)
+    for k, v in (options or {}).items():
+        ctx.set_option(k, v)
     ctx.set_scene(scene.face_normals, scene.vertices, scene.indices)
     ctx.set_parameters(params, terms)
     ctx.set_debug(debug)
@@ -127,6 +129,18 @@ def test_binary_search_fallback_matches_dense_table(box_scene):
     for k in taps_d:
         assert np.array_equal(taps_d[k], taps_s[k]), k
     assert dense.tobytes() == sparse.tobytes()
+
+
+@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8),
+                                     dict(neighbour_lists=1, list_rows=24)])
+def test_neighbour_organisations_agree_with_the_oracle(options, box_scene, plane_scene):
+    """Two-pass search, stored neighbour lists, and lists too short for most particles (which
+    sends them through the fallback kernel) all meet the same bar."""
+    p, terms, vol = H.config("water", 20000)
+    check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
+    p, terms, vol = H.config("mucus", 6000)
+    check_against_oracle(H.drop_state(p, vol, scene_floor_y=-1.0), p, terms, plane_scene, "crowded %r" % (options,),
+                         options=options)
 
 
 def test_simulate_single_frame_host_in_host_out(box_scene):

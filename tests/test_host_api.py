@@ -1,0 +1,130 @@
+"""The C++ drop-in host classes (libclsph_b200/host): settings, scene, frame writer on the CPU;
+sph_simulation::simulate on the GPU."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from libclsph_b200 import abi, hostapi, workloads
+from oracle import oracle as O
+from tests import helpers as H
+
+GOLDEN = os.path.join(H.ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    hostapi.build()
+
+
+@pytest.mark.parametrize("fluid", ["water", "mucus"])
+def test_load_settings_matches_the_reference(fluid):
+    z = np.load(os.path.join(GOLDEN, "load_settings.npz"))
+    p, t, vol, flags = hostapi.load_settings(os.path.join(H.ROOT, "fluid_properties", fluid + ".json"),
+                                             os.path.join(H.ROOT, "simulation_properties", "default.json"))
+    assert H.struct_bytes(p) == z[fluid + "_params"].tobytes()
+    assert H.struct_bytes(t) == z[fluid + "_terms"].tobytes()
+    assert np.float32(vol) == z[fluid + "_volume"]
+    assert flags == dict(write_all_frames=False, serialize=False)
+
+
+def test_load_settings_errors(tmp_path):
+    sim = os.path.join(H.ROOT, "simulation_properties", "default.json")
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"fluid_density": 1000, "dynamic_viscosity": 1, "restitution": 1.5, "k": 1,'
+                   ' "surface_tension_threshold": 1, "surface_tension": 1, "particles_inside_influence_radius": 20}')
+    with pytest.raises(RuntimeError, match="Restitution has an invalid value"):
+        hostapi.load_settings(str(bad), sim)
+    missing = tmp_path / "missing.json"
+    missing.write_text('{"fluid_density": 1000};')
+    with pytest.raises(RuntimeError, match="missing key"):
+        hostapi.load_settings(str(missing), sim)
+    with pytest.raises(RuntimeError, match="Cannot open"):
+        hostapi.load_settings(str(tmp_path / "nope.json"), sim)
+
+
+@pytest.mark.parametrize("scene_name", ["box.obj", "cone.obj", "cube.obj", "labyrinth.obj", "monkey.obj", "plane.obj",
+                                        "river.obj", "shower.obj"])
+def test_scene_load_matches_the_reference(scene_name):
+    """Same three arrays as the reference's scene::load (tinyobj re-indexing included)."""
+    z = np.load(os.path.join(GOLDEN, "scenes.npz"))
+    normals, vertices, indices = hostapi.scene_load(scene_name, cwd=H.ROOT)
+    assert np.array_equal(indices, z[scene_name + ":indices"])
+    assert vertices.tobytes() == z[scene_name + ":vertices"].tobytes()
+    assert normals.tobytes() == z[scene_name + ":normals"].tobytes()
+
+
+def test_scene_load_failure(tmp_path):
+    with pytest.raises(RuntimeError):
+        hostapi.scene_load("does_not_exist.obj", cwd=H.ROOT)
+
+
+def test_geo_frame_is_byte_identical_to_the_reference_writer(tmp_path):
+    z = np.load(os.path.join(GOLDEN, "frame_water_n256_input.npz"))
+    p = abi.SimulationParameters()
+    ctypes.memmove(ctypes.addressof(p), z["params"].tobytes(), ctypes.sizeof(p))
+    os.makedirs(tmp_path / "frames")
+    hostapi.write_frames(str(tmp_path) + "/", z["particles"].copy(), p, frames=2)
+    assert sorted(os.listdir(tmp_path / "frames")) == ["frame0000001.geo", "frame0000002.geo"]
+    got = open(tmp_path / "frames" / "frame0000002.geo", "rb").read()
+    want = open(os.path.join(GOLDEN, "frame_water_n256.geo"), "rb").read()
+    assert got == want
+
+
+# ------------------------------------------------------------------------------------------------
+def _workdir(tmp_path):
+    for d in ("scenes", "fluid_properties", "simulation_properties"):
+        shutil.copytree(os.path.join(H.ROOT, d), tmp_path / d)
+    os.makedirs(tmp_path / "frames")
+    return str(tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("policy,callbacks", [(0, True), (1, True), (0, False)])
+def test_simulate_matches_oracle_steps(tmp_path, policy, callbacks):
+    """sph_simulation::simulate for one frame (10 sub-steps) from the lattice: same result whatever
+    the host-sync policy, and within tolerance of ten oracle steps."""
+    p, terms, vol, _ = workloads.make_config(fluid="water", particles_count=4096)
+    normals, vertices, indices = hostapi.scene_load("box.obj", cwd=H.ROOT)
+    got, p_after, calls = hostapi.simulate(p, terms, vol, normals, vertices, indices, frames=1, policy=policy,
+                                           callbacks=callbacks, cwd=_workdir(tmp_path))
+    assert calls == (2 * (1 + 10) if callbacks else 0)  # pre+post around the frame and around each sub-step
+    scene = O.Scene(vertices, indices, normals)
+    cur = O.init_particles(p, vol)
+    po = p.copy()
+    for _ in range(10):
+        cur = O.step(cur, po, terms, scene, taps=False).particles
+    assert np.array_equal(got["grid_index"], cur["grid_index"])
+    H.assert_close_fields(got, cur, tol=1e-3, what="10 sub-steps")
+    assert H.struct_bytes(p_after) == H.struct_bytes(po)
+
+
+@pytest.mark.gpu
+def test_clsphparticles_cli_writes_frames_and_checkpoint(tmp_path):
+    """The command-line driver end to end: JSON in, .geo frames and last_frame.bin out, resume."""
+    wd = _workdir(tmp_path)
+    sim = open(os.path.join(wd, "simulation_properties", "default.json")).read()
+    sim = sim.replace('"particles_count" : 32000', '"particles_count" : 2048').replace('"serialize" : false', '"serialize" : true')
+    open(os.path.join(wd, "simulation_properties", "small.json"), "w").write(sim)
+    run = lambda: subprocess.run([hostapi.CLI_PATH, "water", "small", "box.obj", "", "--yes", "--frames", "2"], cwd=wd,
+                                 capture_output=True, text=True, timeout=300)
+    r = run()
+    assert r.returncode == 0, r.stderr
+    assert "Kernel support radius (h):" in r.stdout
+    frames = sorted(os.listdir(os.path.join(wd, "frames")))
+    assert frames == ["frame0000001.geo", "frame0000002.geo"]
+    head = open(os.path.join(wd, "frames", frames[0])).read().splitlines()
+    assert head[0] == "PGEOMETRY V5" and head[1] == "NPoints 2048 NPrims 1"
+    ckpt = os.path.join(wd, "last_frame.bin")
+    assert os.path.getsize(ckpt) == 2048 * 80
+    first = np.fromfile(ckpt, dtype=abi.PARTICLE)
+    r = run()  # resumes from the checkpoint
+    assert "Serialized frame found" in r.stdout
+    second = np.fromfile(ckpt, dtype=abi.PARTICLE)
+    assert first["position"][:, 1].mean() > second["position"][:, 1].mean()  # kept falling
+    open(ckpt, "ab").write(b"x")  # wrong size -> refuses to run
+    r = run()
+    assert "incorrect size" in r.stdout
