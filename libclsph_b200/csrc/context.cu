@@ -230,6 +230,7 @@ int ensure_lists(clsph_context* ctx) {
     ctx->list_words = words;
   }
   if (!ctx->lists.count) {
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->lists.window_counter, 1));
     CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->lists.count, ctx->capacity));
     CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->lists.count, 0, sizeof(uint32_t) * ctx->capacity, ctx->stream));
   }
@@ -266,7 +267,7 @@ int enqueue_substep(clsph_context* ctx) {
   if (prof) next_event(ctx);
 
   launch_density(dst.pos, dst.vel, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                 ctx->taps, ctx->debug, n, st, lc);
+                 ctx->taps, ctx->debug, n, ctx->sm_count, st, lc);
   if (prof) next_event(ctx);
   launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst,
                 ctx->lists, ctx->accel, n, st, lc);
@@ -392,6 +393,7 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->ref_table);
   cudaFree(ctx->lists.entries);
   cudaFree(ctx->lists.count);
+  cudaFree(ctx->lists.window_counter);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();

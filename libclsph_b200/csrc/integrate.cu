@@ -96,16 +96,22 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
       float hit_depth = 0.f, hit_dist = 0.f;
       for (uint32_t f = 0; f < face_count; ++f) {
         const float4* fr = reinterpret_cast<const float4*>(faces + f);
-        const float4 f0 = __ldg(fr + 0);
+        const float4 f0 = __ldg(fr + 0), f1 = __ldg(fr + 1);
         const V3 n0 = mk(f0.x, f0.y, f0.z);
+        const V3 a = mk(f1.x, f1.y, f1.z);
         const float nd = dot(n0, travel);
+        if (nd == 0.f) continue;  // :54-56 (the oriented denominator is +-nd)
+        const float na = dot(n0, sub(a, x));
+        // The plane parameter is r = (+-na) / (+-nd) = na / nd whatever the orientation, and a hit
+        // needs 0 <= r <= 1 (:58-60). Two division-free rejections that can never drop such a face:
+        // opposite signs with a quotient that cannot underflow to -0, and |na| beyond |nd| by more
+        // than the half ulp that could still round the quotient down to 1. Nearly every face of a
+        // scene leaves here: a sub-step moves a particle by millimetres.
+        if ((na < 0.f) != (nd < 0.f) && fabsf(na) > 1e-30f * fabsf(nd)) continue;
+        if (fabsf(na) > fabsf(nd) * 1.0000002f) continue;
         // :27-29 orient the normal along the travel direction
         const bool flip = __fdiv_rn(nd, __fmul_rn(f0.w, travel_len)) <= 0.f;
         const float denom = flip ? -nd : nd;  // dot(-n, d) == -dot(n, d) exactly
-        if (denom == 0.f) continue;           // :54-56
-        const float4 f1 = __ldg(fr + 1);
-        const V3 a = mk(f1.x, f1.y, f1.z);
-        const float na = dot(n0, sub(a, x));
         const float r = __fdiv_rn(flip ? -na : na, denom);  // :58
         if (!(0.f <= r && r <= 1.f)) continue;
         const float4 f2 = __ldg(fr + 2), f3 = __ldg(fr + 3), f4 = __ldg(fr + 4);

@@ -77,6 +77,7 @@ struct NeighbourLists {
   uint32_t* entries = nullptr;  // [capacity][rows]: entries[i * rows + e] = e-th neighbour of particle i
   uint32_t* count = nullptr;    // [capacity]: entries of particle i, 0xFFFFFFFF = more than `rows`
   uint32_t rows = 0;
+  uint32_t* window_counter = nullptr;  // work counter of the persistent list-building kernel
 };
 
 // ---- neighbors.cu
@@ -84,7 +85,8 @@ void neighbors_init();  // opts the kernels into their dynamic shared memory siz
 // Also leaves p/rho^2 in pos[].w and m/rho in vel[].w for the force pass.
 void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* cell_start, const uint32_t* cell_end,
                     const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                    const DebugTaps& taps, bool debug, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+                    const DebugTaps& taps, bool debug, uint32_t n_launch, int sm_count, cudaStream_t stream,
+                    uint64_t* launches);
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
                    const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);

@@ -51,7 +51,10 @@ constexpr int kCap1 = 352;                   // level-1 staged candidates per wa
 constexpr int kCap2 = 160;                   // level-2 staged candidates per warp (octant group box), + 32 padding
 constexpr int kOwnedCellMax = 64;            // cells up to this size are processed whole by one warp
 constexpr int kSplitMin = 12;                // targets needed before a unit is cut into octant groups
-constexpr size_t kDensityListSmem = (size_t)kDlWarps * (kCap1 + 32 + kCap2 + 32) * sizeof(float4);
+constexpr int kRing = 3;                     // candidate chunks in flight per warp (cp.async ring, 32 x float4 each)
+constexpr int kDlWarpSmem = kCap1 + 32 + kCap2 + 32 + kRing * 32;  // float4 per warp
+constexpr size_t kDensityListSmem = (size_t)kDlWarps * kDlWarpSmem * sizeof(float4);
+constexpr int kDlCtasPerSm = 5;
 constexpr int kFlWarps = 8;                  // warps per CTA of k_forces_lists
 constexpr int kTileStride = 33;              // 32 entries per particle + 1: lanes hit distinct banks
 
@@ -183,6 +186,16 @@ __device__ __forceinline__ void finish_density(const SphConst& c, float sum_cube
   reinterpret_cast<float*>(pos + i)[3] = prs / (rho * rho);  // only the w lane: other warps may be reading x, y, z
   reinterpret_cast<float*>(vel + i)[3] = c.mass / rho;
 }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS); each lane later reads only what it copied
+// itself, so cp.async.wait_group alone orders it.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 // Rounds a staged list up to a multiple of 32 with candidates at +infinity (never inside a
 // support), so the support-test loops need no bounds check. The lists have 32 spare slots.
@@ -430,19 +443,27 @@ k_forces(const float4* __restrict__ pos, const float4* __restrict__ vel, const f
 //   3. each particle tests its group's list with lanes across candidates; survivors add to the
 //      density and go straight to the particle's list in HBM.
 template <bool kTaps>
-__global__ void __launch_bounds__(kDlThreads, 6)
+__global__ void __launch_bounds__(kDlThreads, kDlCtasPerSm)
 k_density_lists(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ cell_start,
                 const uint32_t* __restrict__ cell_end, const GridState* __restrict__ grid, const SphConst c,
                 float4* __restrict__ aux, uint32_t* __restrict__ nlist, uint32_t* __restrict__ ncount,
-                uint32_t list_rows, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ supp_count) {
+                uint32_t list_rows, uint32_t* __restrict__ window_counter, uint32_t* __restrict__ cand_count,
+                uint32_t* __restrict__ supp_count) {
   extern __shared__ float4 s_dyn[];
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-  float4* s_l1 = s_dyn + warp * (kCap1 + 32);                              // level 1: culled against the unit's box
-  float4* s_l2 = s_dyn + kDlWarps * (kCap1 + 32) + warp * (kCap2 + 32);    // level 2: one octant group's box
+  float4* s_l1 = s_dyn + warp * kDlWarpSmem;    // level 1: culled against the unit's box
+  float4* s_l2 = s_l1 + kCap1 + 32;             // level 2: culled against one octant group's box
+  float4* s_ring = s_l2 + kCap2 + 32;           // raw candidate chunks in flight
 
   const GridState g = *grid;
-  const uint32_t base = (blockIdx.x * kDlWarps + warp) * 32u;
-  if (base >= g.n) return;
+  // Persistent warps: every warp keeps taking the next 32-particle window until none is left, so
+  // uneven units (empty windows, crowded cells) do not leave warp slots idle.
+  for (;;) {
+  uint32_t window = 0;
+  if (lane == 0) window = atomicAdd(window_counter, 1u);
+  window = __shfl_sync(kFullMask, window, 0);
+  if ((uint64_t)window * 32u >= g.n) break;
+  const uint32_t base = window * 32u;
   const uint32_t i = base + lane;
   const bool valid = i < g.n;
   const uint32_t key_i = valid ? skey[i] : 0xFFFFFFFFu;
@@ -555,29 +576,62 @@ k_density_lists(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     };
 
     // Level 1: the 27 cells in the reference's visiting order, culled against the unit's box.
+    // Raw chunks of 32 candidates travel global -> shared through a ring of kRing cp.async
+    // groups, so each lane has kRing loads in flight while it tests an older chunk.
+    int cur_cell = -1;
+    uint32_t cur_j0 = 0, cur_end = 0;
+    auto next_chunk = [&]() -> bool {  // advances (cur_cell, cur_j0) to the next non-empty chunk; uniform
+      cur_j0 += 32u;
+      while (cur_j0 >= cur_end) {
+        if (++cur_cell >= 27) return false;
+        cur_j0 = __shfl_sync(kFullMask, rng.x, cur_cell);
+        cur_end = __shfl_sync(kFullMask, rng.y, cur_cell);
+      }
+      return true;
+    };
+    bool live[kRing];
+    bool mine_valid[kRing];
+    uint32_t mine_j[kRing];
+    bool exhausted = false;
+    auto issue = [&](int slot) {
+      live[slot] = !exhausted && next_chunk();
+      if (!live[slot]) exhausted = true;
+      mine_j[slot] = cur_j0 + lane;
+      mine_valid[slot] = live[slot] && mine_j[slot] < cur_end;
+      if (mine_valid[slot]) cp_async16(s_ring + slot * 32 + lane, pos + mine_j[slot]);
+      cp_async_commit();  // always, so the group count stays in step with the slots
+    };
     uint32_t staged1 = 0;
-    for (int cell = 0; cell < 27; ++cell) {
-      const uint32_t first = __shfl_sync(kFullMask, rng.x, cell), end = __shfl_sync(kFullMask, rng.y, cell);
-      for (uint32_t j0 = first; j0 < end; j0 += 32u) {
-        const uint32_t j = j0 + lane;
-        bool keep = j < end;
-        float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (keep) {
-          pj = pos[j];
-          keep = box_dist2(box, pj.x, pj.y, pj.z) < c.support_s;
-        }
-        const unsigned m = __ballot_sync(kFullMask, keep);
-        if (staged1 + (uint32_t)__popc(m) > (uint32_t)kCap1) {
-          const uint32_t padded1 = pad_list(s_l1, staged1);
-          __syncwarp();
-          process_level1(padded1);
-          __syncwarp();
-          staged1 = 0;
-        }
-        if (keep) s_l1[staged1 + __popc(m & lanemask_lt())] = make_float4(pj.x, pj.y, pj.z, __uint_as_float(j));
-        staged1 += __popc(m);
+    auto consume = [&](int slot) {
+      cp_async_wait<kRing - 1>();  // all but the kRing-1 newest groups have landed: this slot's did
+      bool keep = mine_valid[slot];
+      float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (keep) {
+        pj = s_ring[slot * 32 + lane];
+        keep = box_dist2(box, pj.x, pj.y, pj.z) < c.support_s;
+      }
+      const unsigned m = __ballot_sync(kFullMask, keep);
+      if (staged1 + (uint32_t)__popc(m) > (uint32_t)kCap1) {
+        const uint32_t full1 = pad_list(s_l1, staged1);
+        __syncwarp();
+        process_level1(full1);
+        __syncwarp();
+        staged1 = 0;
+      }
+      if (keep) s_l1[staged1 + __popc(m & lanemask_lt())] = make_float4(pj.x, pj.y, pj.z, __uint_as_float(mine_j[slot]));
+      staged1 += __popc(m);
+    };
+#pragma unroll
+    for (int slot = 0; slot < kRing; ++slot) issue(slot);
+    for (bool more = true; more;) {
+#pragma unroll
+      for (int slot = 0; slot < kRing; ++slot) {
+        if (!live[slot]) { more = false; break; }
+        consume(slot);
+        issue(slot);
       }
     }
+    cp_async_wait<0>();
     const uint32_t padded1 = pad_list(s_l1, staged1);
     __syncwarp();
     process_level1(padded1);
@@ -594,6 +648,7 @@ k_density_lists(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
       if (kTaps) { cand_count[ti1] = n_cand; supp_count[ti1] = cnt1; }
     }
   }
+  }  // persistent window loop
 }
 
 // =============================================================================================
@@ -621,15 +676,30 @@ k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, c
   uint32_t* tile = s_tile[warp];
   const uint32_t max_count = warp_max_u32(count);
   for (uint32_t e0 = 0; e0 < max_count; e0 += 32u) {
-    for (int p = 0; p < 32; ++p) {  // row p of the tile <- entries e0 .. e0+31 of particle base+p
-      const uint32_t count_p = __shfl_sync(kFullMask, count, p);
-      if (e0 + lane < count_p) tile[p * kTileStride + lane] = nlist[(size_t)(base + p) * list_rows + e0 + lane];
+#pragma unroll
+    for (int p0 = 0; p0 < 32; p0 += 8) {  // rows p of the tile <- entries e0 .. e0+31 of particle base+p, 8 loads in flight
+      uint32_t v[8];
+      bool ok[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        ok[k] = e0 + lane < __shfl_sync(kFullMask, count, p0 + k);
+        v[k] = ok[k] ? nlist[(size_t)(base + p0 + k) * list_rows + e0 + lane] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (ok[k]) tile[(p0 + k) * kTileStride + lane] = v[k];
     }
     __syncwarp();
     const uint32_t mine = count > e0 ? min(count - e0, 32u) : 0u;
     const uint32_t* row = tile + lane * kTileStride;
-#pragma unroll 2
-    for (uint32_t e = 0; e < mine; ++e) {
+    uint32_t e = 0;
+    for (; e + 2 <= mine; e += 2) {  // two neighbours per trip: four independent gathers in flight
+      const uint32_t ja = row[e], jb = row[e + 1];
+      const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb];
+      add_pair(sums, c, ja == i, pi, vi, pi.w, pa, va);
+      add_pair(sums, c, jb == i, pi, vi, pi.w, pb, vb);
+    }
+    if (e < mine) {
       const uint32_t j = row[e];
       add_pair(sums, c, j == i, pi, vi, pi.w, pos[j], vel[j]);
     }
@@ -650,19 +720,23 @@ void neighbors_init() {
 
 void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* cell_start, const uint32_t* cell_end,
                     const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                    const DebugTaps& taps, bool debug, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+                    const DebugTaps& taps, bool debug, uint32_t n_launch, int sm_count, cudaStream_t stream,
+                    uint64_t* launches) {
   uint32_t* cand = debug ? taps.candidate_count : nullptr;
   uint32_t* supp = debug ? taps.support_count : nullptr;
   if (lists.rows) {
-    const unsigned blocks = (n_launch + kDlThreads - 1) / kDlThreads;
+    // persistent: one resident set of CTAs, warps pull 32-particle windows from a counter
+    const unsigned needed = (n_launch + kDlThreads - 1) / kDlThreads;
+    const unsigned blocks = std::max(1u, std::min(needed, (unsigned)sm_count * kDlCtasPerSm));
+    cudaMemsetAsync(lists.window_counter, 0, sizeof(uint32_t), stream);
     if (debug)
       k_density_lists<true><<<blocks, kDlThreads, kDensityListSmem, stream>>>(pos, vel, skey, cell_start, cell_end, grid, c,
                                                                               aux, lists.entries, lists.count, lists.rows,
-                                                                              cand, supp);
+                                                                              lists.window_counter, cand, supp);
     else
       k_density_lists<false><<<blocks, kDlThreads, kDensityListSmem, stream>>>(pos, vel, skey, cell_start, cell_end, grid, c,
                                                                                aux, lists.entries, lists.count, lists.rows,
-                                                                               cand, supp);
+                                                                               lists.window_counter, cand, supp);
   } else {
     const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
     if (debug)

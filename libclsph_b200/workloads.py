@@ -29,6 +29,11 @@ CONFIGS = {
     "config2_dambreak_1m": ("water", 1048576, 0.005, "box.obj"),
     "config3_mucus_labyrinth_4m": ("mucus", 4194304, 0.05 * 32000 / 4194304, "labyrinth.obj"),
     "config4_river_16m": ("water", 16777216, 0.05, "river.obj"),
+    # config 5: uniform-block scaling sweep (water, plane.obj, state S1), N = 2^20 .. 2^26
+    "sweep_1m": ("water", 1 << 20, 0.05, "plane.obj"),
+    "sweep_4m": ("water", 1 << 22, 0.05, "plane.obj"),
+    "sweep_16m": ("water", 1 << 24, 0.05, "plane.obj"),
+    "sweep_64m": ("water", 1 << 26, 0.05, "plane.obj"),
 }
 
 
