@@ -146,6 +146,31 @@ int clsph_download_particles(clsph_context* ctx, particle* aos_out);
 int clsph_simulate_single_frame(clsph_context* ctx, const particle* in, particle* out,
                                 simulation_parameters* params, const precomputed_kernel_values* terms);
 
+/* ---- multi-GPU: slab decomposition, one process per GPU ------------------------------------
+ * The reference is single-device; this is new functionality with the same per-particle results.
+ * The fluid is cut along x by fixed planes; every sub-step all-reduces the AABB (so all ranks
+ * derive the same grid and keys), migrates particles whose cell changed owner and refreshes two
+ * ghost cell layers per side, in one NCCL group on the context's stream. */
+
+/* NCCL unique id (128 bytes) to hand to every rank, e.g. through torch.distributed. */
+int clsph_comm_unique_id(void* out, size_t bytes);
+
+/* Joins the communicator. plane_lo / plane_hi = world-space x bounds of this rank's slab
+ * (-INFINITY for rank 0, +INFINITY for the last rank); neighbouring ranks must pass the same
+ * plane. Slabs must stay at least four grid cells (8 h) thick. Capacities are records per
+ * message per sub-step (0 = capacity/16 + 1024 emigrants, capacity/4 + 1024 ghosts); exceeding
+ * them, or max_particles (owned + ghost copies), is reported as CLSPH_ECOMM by the next
+ * synchronising call. */
+int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_id, float plane_lo, float plane_hi,
+                    uint32_t emigrant_capacity, uint32_t ghost_capacity);
+
+/* This rank's particles with their global ids (any unique 32-bit labels below 2^32-1). */
+int clsph_dist_upload(clsph_context* ctx, const particle* aos, const uint32_t* ids, uint32_t n);
+
+/* Owned particles (no ghost copies) in local cell-sorted order with their ids. Pass NULL arrays
+ * to query the count only. Synchronises. */
+int clsph_dist_download(clsph_context* ctx, particle* aos_out, uint32_t* ids_out, uint32_t capacity, uint32_t* n_out);
+
 /* ---- observation ----------------------------------------------------------------------- */
 
 /* The reference's `advection_collision` kernel on its own (kernels/sph.cl:64-112, argument

@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libclsph_cuda.so")
-SOURCES = ["context.cu", "sort.cu", "grid.cu", "neighbors.cu", "integrate.cu"]
-HEADERS = ["common.cuh", "kernels.cuh"]
+SOURCES = ["context.cu", "sort.cu", "grid.cu", "neighbors.cu", "integrate.cu", "dist.cu"]
+HEADERS = ["common.cuh", "kernels.cuh", "dist.cuh"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -59,7 +59,7 @@ def build(force=False, verbose=False, extra_flags=()):
     if failed:
         raise RuntimeError("nvcc failed")
     subprocess.run([nvcc, *ARCH_FLAGS, "-shared", "-ccbin", shutil.which("g++") or "g++", "-o", LIB_PATH, *objs,
-                    "-lcudart"], check=True)
+                    "-lcudart", "-ldl"], check=True)
     return LIB_PATH
 
 

@@ -16,7 +16,8 @@ SYMBOLS = [
     "clsph_device_count", "clsph_create", "clsph_destroy", "clsph_last_error", "clsph_set_scene",
     "clsph_set_parameters", "clsph_set_option", "clsph_upload_particles", "clsph_step", "clsph_synchronize",
     "clsph_get_parameters", "clsph_download_particles", "clsph_simulate_single_frame", "clsph_set_debug",
-    "clsph_debug_fetch", "clsph_kernel_advection_collision", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_stream",
+    "clsph_debug_fetch", "clsph_kernel_advection_collision", "clsph_comm_unique_id", "clsph_dist_init",
+    "clsph_dist_upload", "clsph_dist_download", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_stream",
 ]
 
 TAP_SORTED_KEYS, TAP_PERMUTATION, TAP_CELL_TABLE, TAP_KEYS_INPUT, TAP_CANDIDATE_COUNT = 0, 1, 2, 3, 4
@@ -69,6 +70,10 @@ def load_library(path=None):
     L.clsph_download_particles.argtypes = [vp, vp]
     L.clsph_simulate_single_frame.argtypes = [vp, vp, vp, vp, vp]
     L.clsph_kernel_advection_collision.argtypes = [vp, vp, vp, u32]
+    L.clsph_comm_unique_id.argtypes = [vp, sz]
+    L.clsph_dist_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_float, ctypes.c_float, u32, u32]
+    L.clsph_dist_upload.argtypes = [vp, vp, vp, u32]
+    L.clsph_dist_download.argtypes = [vp, vp, vp, u32, ctypes.POINTER(u32)]
     L.clsph_set_debug.argtypes = [vp, ctypes.c_int]
     L.clsph_debug_fetch.argtypes = [vp, ctypes.c_int, vp, sz]
     L.clsph_profile_enable.argtypes = [vp, ctypes.c_int]
@@ -86,6 +91,16 @@ def load_library(path=None):
 
 def _vp(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (bytes) for clsph_dist_init; create on one rank, broadcast to all."""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(128)
+    rc = lib.clsph_comm_unique_id(buf, 128)
+    if rc:
+        raise ClsphError(rc, (lib.clsph_last_error(None) or b"").decode())
+    return buf.raw
 
 
 class Context:
@@ -174,6 +189,30 @@ class Context:
         self._check(self._lib.clsph_kernel_advection_collision(self._h, particle_ptr(particles_in), particle_ptr(out),
                                                                particles_in.size))
         return out
+
+    def dist_init(self, rank, world, unique_id, plane_lo, plane_hi, emigrant_capacity=0, ghost_capacity=0):
+        """Join the slab decomposition: this rank owns plane_lo <= x < plane_hi (snapped to cells)."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.clsph_dist_init(self._h, rank, world, buf, plane_lo, plane_hi, emigrant_capacity,
+                                              ghost_capacity))
+
+    def dist_upload(self, particles, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._check(self._lib.clsph_dist_upload(self._h, particle_ptr(particles), _vp(ids), particles.size))
+
+    def dist_count(self):
+        n = ctypes.c_uint32()
+        self._check(self._lib.clsph_dist_download(self._h, None, None, 0, ctypes.byref(n)))
+        return n.value
+
+    def dist_download(self):
+        """(owned particles in local sorted order, their ids)."""
+        n = self.dist_count()
+        out = np.empty(n, dtype=PARTICLE)
+        ids = np.empty(n, dtype=np.uint32)
+        got = ctypes.c_uint32()
+        self._check(self._lib.clsph_dist_download(self._h, particle_ptr(out), _vp(ids), n, ctypes.byref(got)))
+        return out[: got.value], ids[: got.value]
 
     def set_debug(self, enable=True):
         self._check(self._lib.clsph_set_debug(self._h, 1 if enable else 0))

@@ -26,7 +26,13 @@ struct GridState {
   uint32_t n;                        // particles on this device
   uint32_t sort_passes;              // ceil(bits(cell_count - 1) / 8), 1..4
   uint32_t dense;                    // 1: cell_count fits the dense table; 0: binary-search fallback
-  uint32_t error;                    // bit 0: a grid axis reached 1024 cells
+  uint32_t error;                    // bit 0: a grid axis reached 1024 cells; bit 1: a multi-GPU buffer overflowed
+  // Slab decomposition (multi-GPU): this rank owns the cells with own_lo <= cx < own_hi. One GPU:
+  // [0, INT_MAX). Particles of other cells held locally are ghost copies of a neighbour's.
+  int own_lo, own_hi;
+  int prev_lo, prev_hi;              // the range of the previous sub-step (whose keys the arrays still carry)
+  uint32_t fresh;                    // 1 after an upload: every local particle counts as owned
+  uint32_t pad1[3];
 };
 
 // AABB accumulators: floats mapped to order-preserving unsigned so atomicMin/Max apply.
@@ -83,6 +89,17 @@ __host__ __device__ inline uint32_t compact10(uint32_t v) {
   v = (v | (v >> 8)) & 0x030000FFu;
   v = (v | (v >> 16)) & 0x000003FFu;
   return v;
+}
+
+// Role of a cell in the slab decomposition, from the x coordinate of its Morton key.
+__device__ __forceinline__ bool cell_is_owned(uint32_t key, const GridState& g) {
+  const int cx = (int)compact10(key);
+  return cx >= g.own_lo && cx < g.own_hi;
+}
+// Owned, or in the first ghost layer on either side (whose density the force pass needs).
+__device__ __forceinline__ bool cell_needs_density(uint32_t key, const GridState& g) {
+  const int cx = (int)compact10(key);
+  return cx >= g.own_lo - 1 && cx <= g.own_hi;
 }
 
 // Cell coordinate of a position along one axis, grid.cl:56-61: (uint)((p - min) / (2h)) with a

@@ -11,10 +11,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
 #include "clsph_cuda.h"
+#include "dist.cuh"
 #include "kernels.cuh"
 
 using namespace clsph;
@@ -23,7 +25,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum Stage { kStBounds = 0, kStKeys, kStSort, kStReorder, kStDensity, kStForces, kStIntegrate, kStEnd, kStages = kStEnd };
+enum Stage { kStBounds = 0, kStExchange, kStKeys, kStSort, kStReorder, kStDensity, kStForces, kStIntegrate, kStEnd, kStages = kStEnd };
 
 }  // namespace
 
@@ -61,6 +63,11 @@ struct clsph_context {
   uint32_t list_rows_override = 0;  // 0 = derive from the rest density
   NeighbourLists lists{};
   size_t list_words = 0;            // allocated words of lists.entries
+
+  // multi-GPU slab decomposition (dist.cu); pid = persistent particle ids, ping-pong like the state
+  DistState dist{};
+  uint32_t* pid[2] = {nullptr, nullptr};
+  uint32_t* export_ids = nullptr;
 
   DebugTaps taps{};
   uint32_t* ref_table = nullptr;
@@ -170,6 +177,7 @@ void drain_events(clsph_context* ctx) {
       ms[s] = f;
     }
     ctx->times.ms_bounds_grid += ms[kStBounds];
+    ctx->times.ms_exchange += ms[kStExchange];
     ctx->times.ms_keys += ms[kStKeys];
     ctx->times.ms_sort += ms[kStSort];
     ctx->times.ms_reorder += ms[kStReorder];
@@ -185,6 +193,12 @@ int check_device_flags(clsph_context* ctx) {
   GridState g;
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&g, ctx->grid, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
   CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (g.error & 2u) {
+    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(&ctx->grid->error, 0, sizeof(uint32_t), ctx->stream));
+    return fail(ctx, CLSPH_ECOMM, "multi-GPU buffer overflow: more local, migrating or ghost particles than the capacities given "
+                "to clsph_create / clsph_dist_init (local %u, emigrants %u, ghosts %u per message)", ctx->capacity,
+                ctx->dist.emax, ctx->dist.gmax);
+  }
   if (g.error & 1u) {
     CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(&ctx->grid->error, 0, sizeof(uint32_t), ctx->stream));
     return fail(ctx, CLSPH_EGRID, "grid overflow: %d x %d x %d cells, each axis must stay below 1024 "
@@ -238,22 +252,37 @@ int ensure_lists(clsph_context* ctx) {
   return CLSPH_OK;
 }
 
-// One sub-step, enqueued on ctx->stream.
+// One sub-step, enqueued on ctx->stream. Multi-GPU differences: the AABB is all-reduced, the
+// particle count lives on the device (launches are sized by the capacity), and a migration +
+// ghost exchange (dist.cu) assembles the unsorted local array in the other ping-pong side before
+// the sort brings it back, so `cur` does not flip.
 int enqueue_substep(clsph_context* ctx) {
   cudaStream_t st = ctx->stream;
   uint64_t* lc = &ctx->launches;
-  const uint32_t n = ctx->n;
+  const bool multi = ctx->dist.active;
+  const uint32_t n = multi ? ctx->capacity : ctx->n;  // upper bound used to size launches
   const bool prof = ctx->profiling;
-  StateArrays& src = ctx->state[ctx->cur];
-  StateArrays& dst = ctx->state[ctx->cur ^ 1];
+  const float inf = std::numeric_limits<float>::infinity();
 
   if (prof) next_event(ctx);
   if (!ctx->bounds_valid) {  // first step after an upload; later steps get the AABB from the integrator
     launch_bounds_reset(ctx->bounds, st, lc);
-    launch_bounds(src.pos, n, ctx->bounds, ctx->sm_count, st, lc);
+    launch_bounds(ctx->state[ctx->cur].pos, ctx->n, ctx->bounds, ctx->sm_count, st, lc);
     ctx->bounds_valid = true;
   }
-  launch_grid_setup(ctx->bounds, ctx->grid, ctx->params.h, n, ctx->cell_capacity, st, lc);
+  if (multi && dist_allreduce_bounds(&ctx->dist, ctx->bounds, st)) return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
+  launch_grid_setup(ctx->bounds, ctx->grid, ctx->params.h, ctx->n, ctx->cell_capacity, multi ? ctx->dist.plane_lo : -inf,
+                    multi ? ctx->dist.plane_hi : inf, multi, st, lc);
+  if (prof) next_event(ctx);
+
+  if (multi) {
+    if (dist_exchange(&ctx->dist, ctx->state[ctx->cur], ctx->pid[ctx->cur], ctx->skey, ctx->grid, ctx->state[ctx->cur ^ 1],
+                      ctx->pid[ctx->cur ^ 1], ctx->capacity, st, lc))
+      return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
+    ctx->cur ^= 1;  // the unsorted local array is the source of this step's sort
+  }
+  StateArrays& src = ctx->state[ctx->cur];
+  StateArrays& dst = ctx->state[ctx->cur ^ 1];
   if (prof) next_event(ctx);
 
   launch_sort_keys(ctx->sort, src.pos, ctx->grid, n, ctx->sm_count, ctx->debug ? ctx->taps.keys_input : nullptr, st, lc);
@@ -262,7 +291,8 @@ int enqueue_substep(clsph_context* ctx) {
   if (prof) next_event(ctx);
 
   launch_clear_cells(ctx->cell_start, ctx->cell_end, ctx->grid, ctx->cell_capacity, ctx->sm_count, st, lc);
-  launch_reorder(src, dst, ctx->sort, ctx->skey, ctx->perm, ctx->cell_start, ctx->cell_end, ctx->grid, n, st, lc);
+  launch_reorder(src, dst, ctx->sort, ctx->skey, ctx->perm, ctx->cell_start, ctx->cell_end, ctx->grid,
+                 multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr, n, st, lc);
   ctx->cur ^= 1;
   if (prof) next_event(ctx);
 
@@ -275,7 +305,7 @@ int enqueue_substep(clsph_context* ctx) {
   if (ctx->debug)  // the integrator consumes the acceleration; keep a copy for the tap
     CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->taps.acceleration, ctx->accel, sizeof(float4) * n,
                                         cudaMemcpyDeviceToDevice, st));
-  launch_integrate(dst, ctx->accel, ctx->faces, ctx->face_count, ctx->grid, ctx->konst, ctx->bounds,
+  launch_integrate(dst, ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->grid, ctx->konst, ctx->bounds,
                    ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, lc);
   if (prof) next_event(ctx);
   CLSPH_CUDA_TRY(ctx, cudaGetLastError());
@@ -351,7 +381,12 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
   CREATE_TRY(dev_alloc(&ctx->grid, 1));
   CREATE_TRY(dev_alloc(&ctx->bounds, 1));
   CREATE_TRY(cudaMalloc(&ctx->aos_stage, cap * sizeof(particle)));
-  CREATE_TRY(cudaMemset(ctx->grid, 0, sizeof(GridState)));
+  {
+    GridState g0;
+    std::memset(&g0, 0, sizeof(g0));
+    g0.own_hi = g0.prev_hi = 0x7fffffff;  // one GPU: every cell is owned
+    CREATE_TRY(cudaMemcpy(ctx->grid, &g0, sizeof(g0), cudaMemcpyHostToDevice));
+  }
   CREATE_TRY(cudaMemset(ctx->cell_start, 0, sizeof(uint32_t) * ctx->cell_capacity));
   CREATE_TRY(cudaMemset(ctx->cell_end, 0, sizeof(uint32_t) * ctx->cell_capacity));
   neighbors_init();
@@ -391,6 +426,10 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->taps.acceleration);
   cudaFree(ctx->taps.collision_iters);
   cudaFree(ctx->ref_table);
+  dist_destroy(&ctx->dist);
+  cudaFree(ctx->pid[0]);
+  cudaFree(ctx->pid[1]);
+  cudaFree(ctx->export_ids);
   cudaFree(ctx->lists.entries);
   cudaFree(ctx->lists.count);
   cudaFree(ctx->lists.window_counter);
@@ -468,11 +507,78 @@ int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) 
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, aos, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, n, ctx->stream, &ctx->launches);
+  const uint32_t count_and_fresh[2] = {n, 1u};
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->n, &count_and_fresh[0], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->fresh, &count_and_fresh[1], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->dist.active) launch_fill_ids(ctx->pid[ctx->cur], nullptr, 0u, n, ctx->stream, &ctx->launches);
   CLSPH_CUDA_TRY(ctx, cudaGetLastError());
   ctx->n = n;
   ctx->have_particles = true;
   ctx->bounds_valid = false;
   return CLSPH_OK;
+}
+
+/* ---- multi-GPU ---------------------------------------------------------------------------- */
+
+int clsph_comm_unique_id(void* out, size_t bytes) {
+  if (!out) return CLSPH_EINVAL;
+  if (dist_unique_id(out, bytes)) return fail(nullptr, CLSPH_ECOMM, "clsph_comm_unique_id: %s", dist_last_error());
+  return CLSPH_OK;
+}
+
+int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_id, float plane_lo, float plane_hi,
+                    uint32_t emigrant_capacity, uint32_t ghost_capacity) {
+  if (!ctx || !unique_id) return CLSPH_EINVAL;
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, CLSPH_EINVAL, "clsph_dist_init: rank %d of %d", rank, world);
+  if (ctx->dist.active) return fail(ctx, CLSPH_ESTATE, "clsph_dist_init: already initialised");
+  if (!(plane_lo < plane_hi)) return fail(ctx, CLSPH_EINVAL, "clsph_dist_init: plane_lo must be below plane_hi");
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (dist_init(&ctx->dist, rank, world, unique_id, plane_lo, plane_hi, emigrant_capacity ? emigrant_capacity : ctx->capacity / 16 + 1024,
+                ghost_capacity ? ghost_capacity : ctx->capacity / 4 + 1024))
+    return fail(ctx, CLSPH_ECOMM, "clsph_dist_init: %s", dist_last_error());
+  for (int s = 0; s < 2; ++s) CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pid[s], ctx->capacity));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->export_ids, ctx->capacity));
+  return CLSPH_OK;
+}
+
+int clsph_dist_upload(clsph_context* ctx, const particle* aos, const uint32_t* ids, uint32_t n) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (!ctx->dist.active) return fail(ctx, CLSPH_ESTATE, "clsph_dist_upload: call clsph_dist_init first");
+  if (!aos || !ids || n == 0 || n > ctx->capacity) return fail(ctx, CLSPH_EINVAL, "clsph_dist_upload: bad arguments (n = %u, capacity %u)", n, ctx->capacity);
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, aos, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, st));
+  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, n, st, &ctx->launches);
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->export_ids, ids, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+  launch_fill_ids(ctx->pid[ctx->cur], ctx->export_ids, 0u, n, st, &ctx->launches);
+  const uint32_t count_and_fresh[2] = {n, 1u};
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->n, &count_and_fresh[0], sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->fresh, &count_and_fresh[1], sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  ctx->n = n;
+  ctx->have_particles = true;
+  ctx->bounds_valid = false;
+  return CLSPH_OK;
+}
+
+int clsph_dist_download(clsph_context* ctx, particle* aos_out, uint32_t* ids_out, uint32_t capacity, uint32_t* n_out) {
+  if (!ctx || !n_out) return CLSPH_EINVAL;
+  if (!ctx->dist.active || !ctx->have_particles) return fail(ctx, CLSPH_ESTATE, "clsph_dist_download: nothing to download");
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  uint32_t* count = ctx->dist.counters + 1;
+  launch_dist_export(ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->pid[ctx->cur], ctx->grid, ctx->aos_stage, ctx->export_ids,
+                     count, ctx->capacity, st, &ctx->launches);
+  uint32_t n = 0;
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&n, count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  *n_out = n;
+  if (aos_out && ids_out) {
+    if (n > capacity) return fail(ctx, CLSPH_EINVAL, "clsph_dist_download: %u owned particles, room for %u", n, capacity);
+    CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(aos_out, ctx->aos_stage, sizeof(particle) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ids_out, ctx->export_ids, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  return clsph_synchronize(ctx);
 }
 
 int clsph_step(clsph_context* ctx, uint32_t n_substeps) {
@@ -557,7 +663,7 @@ int clsph_kernel_advection_collision(clsph_context* ctx, const particle* in, par
     int rc = ensure_debug_buffers(ctx);
     if (rc) return rc;
   }
-  launch_integrate(ctx->state[ctx->cur], ctx->accel, ctx->faces, ctx->face_count, ctx->grid, ctx->konst, ctx->bounds,
+  launch_integrate(ctx->state[ctx->cur], ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->grid, ctx->konst, ctx->bounds,
                    ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, &ctx->launches);
   ctx->n = n;
   ctx->have_particles = true;

@@ -62,7 +62,12 @@ __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ pos, 
 // sph_simulation.cpp:221-252, operation for operation in fp32:
 //   cell = h*2;  min -= cell*2;  max += cell*2;  grid_size = (uint)((max - min) / cell);
 //   grid_cell_count = morton(grid_size).  Also re-arms the AABB accumulator for the next step.
-__global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity) {
+// Multi-GPU: plane_lo / plane_hi are the fixed world-space x planes bounding this rank's slab
+// (-inf / +inf at the ends); they are snapped to the nearest cell boundary of the current grid, the
+// same on every rank because the AABB was all-reduced. keep_n: the particle count lives on the
+// device (it changes with migration) and must not be overwritten.
+__global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity,
+                             float plane_lo, float plane_hi, int keep_n) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float cell = __fmul_rn(h, 2.f);
   const float pad = __fmul_rn(cell, 2.f);
@@ -83,7 +88,13 @@ __global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t 
   grid->max_x = mx[0]; grid->max_y = mx[1]; grid->max_z = mx[2]; grid->pad0 = 0.f;
   grid->gx = gs[0]; grid->gy = gs[1]; grid->gz = gs[2];
   grid->cell_count = count;
-  grid->n = n;
+  if (!keep_n) grid->n = n;
+  grid->prev_lo = grid->own_lo;
+  grid->prev_hi = grid->own_hi;
+  const float inf = __int_as_float(0x7f800000);
+  // nearest cell boundary: floor((plane - min) / cell + 0.5), clamped to the grid
+  grid->own_lo = (plane_lo == -inf) ? 0 : max(0, min(gs[0], (int)floorf((plane_lo - mn[0]) / cell + 0.5f)));
+  grid->own_hi = (plane_hi == inf) ? 0x7fffffff : max(0, min(gs[0], (int)floorf((plane_hi - mn[0]) / cell + 0.5f)));
   const uint32_t top = count > 1u ? count - 1u : 1u;
   const uint32_t bits = 32u - (uint32_t)__clz((int)top);
   grid->sort_passes = err ? 4u : max(1u, (bits + 7u) / 8u);
@@ -108,7 +119,8 @@ k_reorder(const float4* __restrict__ src_pos, const float4* __restrict__ src_vel
           float4* __restrict__ dst_pos, float4* __restrict__ dst_vel, float4* __restrict__ dst_ivel,
           const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const uint32_t* __restrict__ vals_a,
           const uint32_t* __restrict__ vals_b, uint32_t* __restrict__ skey, uint32_t* __restrict__ perm_out,
-          uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end, const GridState* __restrict__ grid) {
+          uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end, const GridState* __restrict__ grid,
+          const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid) {
   const uint32_t n = grid->n;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -123,6 +135,7 @@ k_reorder(const float4* __restrict__ src_pos, const float4* __restrict__ src_vel
   dst_ivel[r] = src_ivel[from];
   skey[r] = key;
   perm_out[r] = from;
+  if (src_pid) dst_pid[r] = src_pid[from];
   // keys are < cell_count whenever the grid fits (Morton is monotone in each coordinate); the
   // bound check only matters after a grid overflow, which is reported as CLSPH_EGRID
   const uint32_t count = grid->cell_count;
@@ -210,9 +223,9 @@ void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, 
   if (launches) ++*launches;
 }
 
-void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity,
-                       cudaStream_t stream, uint64_t* launches) {
-  k_grid_setup<<<1, 32, 0, stream>>>(acc, grid, h, n, cell_capacity);
+void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
+                       float plane_hi, bool keep_n, cudaStream_t stream, uint64_t* launches) {
+  k_grid_setup<<<1, 32, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0);
   if (launches) ++*launches;
 }
 
@@ -225,10 +238,11 @@ void launch_clear_cells(uint32_t* cell_start, uint32_t* cell_end, const GridStat
 
 void launch_reorder(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                     uint32_t* perm_out, uint32_t* cell_start, uint32_t* cell_end, const GridState* grid,
-                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+                    const uint32_t* src_pid, uint32_t* dst_pid, uint32_t n_launch, cudaStream_t stream,
+                    uint64_t* launches) {
   k_reorder<<<blocks_for(n_launch, 256), 256, 0, stream>>>(src.pos, src.vel, src.ivel, dst.pos, dst.vel, dst.ivel,
                                                            sort.keys_a, sort.keys_b, sort.vals_a, sort.vals_b, skey,
-                                                           perm_out, cell_start, cell_end, grid);
+                                                           perm_out, cell_start, cell_end, grid, src_pid, dst_pid);
   if (launches) ++*launches;
 }
 

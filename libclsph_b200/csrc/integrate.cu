@@ -65,14 +65,17 @@ __global__ void k_prepare_faces(const float* __restrict__ normals, const float* 
 
 __global__ void __launch_bounds__(256)
 k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ ivel,
-            const float4* __restrict__ accel, const Face* __restrict__ faces, uint32_t face_count,
-            const GridState* __restrict__ grid, const SphConst c, BoundsAcc* next_bounds,
+            const float4* __restrict__ accel, const uint32_t* __restrict__ skey, const Face* __restrict__ faces,
+            uint32_t face_count, const GridState* __restrict__ grid, const SphConst c, BoundsAcc* next_bounds,
             uint32_t* __restrict__ iters_tap) {
-  const uint32_t n = grid->n;
+  const GridState g = *grid;
+  const uint32_t n = g.n;
+  const bool sliced = g.own_lo > 0 || g.own_hi != 0x7fffffff;  // multi-GPU: ghosts are not advanced
   float lo[3] = {2147483648.f, 2147483648.f, 2147483648.f};
   float hi[3] = {-2147483648.f, -2147483648.f, -2147483648.f};
 
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (sliced && !cell_is_owned(skey[i], g)) continue;
     const float4 p4 = pos[i], iv4 = ivel[i], a4 = accel[i];
     V3 x = mk(p4.x, p4.y, p4.z);
     V3 v = mk(iv4.x, iv4.y, iv4.z);
@@ -185,11 +188,11 @@ void launch_prepare_faces(const float* normals, const float* vertices, const uin
   if (launches) ++*launches;
 }
 
-void launch_integrate(const StateArrays& s, const float4* accel, const Face* faces, uint32_t face_count,
-                      const GridState* grid, const SphConst& c, BoundsAcc* next_bounds, uint32_t* iters_tap,
-                      uint32_t n_launch, int sm_count, cudaStream_t stream, uint64_t* launches) {
+void launch_integrate(const StateArrays& s, const float4* accel, const uint32_t* skey, const Face* faces,
+                      uint32_t face_count, const GridState* grid, const SphConst& c, BoundsAcc* next_bounds,
+                      uint32_t* iters_tap, uint32_t n_launch, int sm_count, cudaStream_t stream, uint64_t* launches) {
   const unsigned blocks = std::min<unsigned>((n_launch + 255) / 256, (unsigned)sm_count * 8u);
-  k_integrate<<<std::max(1u, blocks), 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, faces, face_count, grid, c,
+  k_integrate<<<std::max(1u, blocks), 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, grid, c,
                                                         next_bounds, iters_tap);
   if (launches) ++*launches;
 }

@@ -56,14 +56,15 @@ void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_
 // ---- grid.cu
 void launch_bounds_reset(BoundsAcc* acc, cudaStream_t stream, uint64_t* launches);
 void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, cudaStream_t stream, uint64_t* launches);
-void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity,
-                       cudaStream_t stream, uint64_t* launches);
+void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
+                       float plane_hi, bool keep_n, cudaStream_t stream, uint64_t* launches);
 void launch_clear_cells(uint32_t* cell_start, uint32_t* cell_end, const GridState* grid, uint32_t cell_capacity,
                         int sm_count, cudaStream_t stream, uint64_t* launches);
 // Gathers `src` into `dst` through the sort permutation, writes sorted keys and the cell table.
 void launch_reorder(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                     uint32_t* perm_out, uint32_t* cell_start, uint32_t* cell_end, const GridState* grid,
-                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+                    const uint32_t* src_pid, uint32_t* dst_pid, uint32_t n_launch, cudaStream_t stream,
+                    uint64_t* launches);
 void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uint32_t* skey, float4* accel, uint32_t n,
                        cudaStream_t stream, uint64_t* launches);
 void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, void* aos, uint32_t n,
@@ -87,6 +88,7 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
                     const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
                     const DebugTaps& taps, bool debug, uint32_t n_launch, int sm_count, cudaStream_t stream,
                     uint64_t* launches);
+// Only particles of owned cells get an acceleration (multi-GPU: ghosts are skipped).
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
                    const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
@@ -94,8 +96,8 @@ void launch_forces(const float4* pos, const float4* vel, const float4* aux, cons
 // ---- integrate.cu
 void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,
                           Face* faces, cudaStream_t stream, uint64_t* launches);
-void launch_integrate(const StateArrays& s, const float4* accel, const Face* faces, uint32_t face_count,
-                      const GridState* grid, const SphConst& c, BoundsAcc* next_bounds, uint32_t* iters_tap,
-                      uint32_t n_launch, int sm_count, cudaStream_t stream, uint64_t* launches);
+void launch_integrate(const StateArrays& s, const float4* accel, const uint32_t* skey, const Face* faces,
+                      uint32_t face_count, const GridState* grid, const SphConst& c, BoundsAcc* next_bounds,
+                      uint32_t* iters_tap, uint32_t n_launch, int sm_count, cudaStream_t stream, uint64_t* launches);
 
 }  // namespace clsph

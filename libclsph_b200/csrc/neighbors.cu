@@ -264,6 +264,7 @@ k_density(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uin
     const bool in_seg = valid && key_i == seg_key;
     const unsigned seg_mask = __ballot_sync(kFullMask, in_seg);
     remaining &= ~seg_mask;
+    if (!cell_needs_density(seg_key, g)) continue;  // multi-GPU: outer ghost layer, candidates only
 
     const Box box = segment_box(in_seg, pi);
     const uint2 rng = neighbour_cell_range(seg_key, g, cell_start, cell_end, skey);
@@ -390,6 +391,7 @@ k_forces(const float4* __restrict__ pos, const float4* __restrict__ vel, const f
     const bool in_seg = valid && key_i == seg_key;
     const unsigned seg_mask = __ballot_sync(kFullMask, in_seg);
     remaining &= ~seg_mask;
+    if (!cell_is_owned(seg_key, g)) continue;  // multi-GPU: ghosts get no force
 
     const Box box = segment_box(in_seg, pi);
     const uint2 rng = neighbour_cell_range(seg_key, g, cell_start, cell_end, skey);
@@ -422,7 +424,7 @@ k_forces(const float4* __restrict__ pos, const float4* __restrict__ vel, const f
   }
   flush();
 
-  if (valid) accel[i] = finish_force(sums, c, rho_i);
+  if (valid && cell_is_owned(key_i, g)) accel[i] = finish_force(sums, c, rho_i);
 }
 
 // =============================================================================================
@@ -473,6 +475,7 @@ k_density_lists(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     const uint32_t seg_key = __shfl_sync(kFullMask, key_i, leader);
     const bool in_seg = valid && key_i == seg_key;
     remaining &= ~__ballot_sync(kFullMask, in_seg);
+    if (!cell_needs_density(seg_key, g)) continue;  // multi-GPU: outer ghost layer, candidates only
 
     const uint2 rng = neighbour_cell_range(seg_key, g, cell_start, cell_end, skey);
     const uint32_t cs = __shfl_sync(kFullMask, rng.x, 13), ce = __shfl_sync(kFullMask, rng.y, 13);
@@ -659,14 +662,16 @@ k_density_lists(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
 __global__ void __launch_bounds__(kFlWarps * 32, 3)
 k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
                const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
-               const GridState* __restrict__ grid, const SphConst c, float4* __restrict__ accel) {
+               const uint32_t* __restrict__ skey, const GridState* __restrict__ grid, const SphConst c,
+               float4* __restrict__ accel) {
   __shared__ uint32_t s_tile[kFlWarps][32 * kTileStride];
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-  const uint32_t n = grid->n;
+  const GridState g = *grid;
+  const uint32_t n = g.n;
   const uint32_t base = (blockIdx.x * kFlWarps + warp) * 32u;
   if (base >= n) return;
   const uint32_t i = base + lane;
-  const bool valid = i < n;
+  const bool valid = i < n && cell_is_owned(skey[min(i, n - 1u)], g);  // multi-GPU: ghosts get no force
   uint32_t count = valid ? ncount[i] : 0u;
   const bool listed = count <= list_rows;  // otherwise redone by k_forces<true>
   if (!listed) count = 0u;
@@ -753,7 +758,7 @@ void launch_forces(const float4* pos, const float4* vel, const float4* aux, cons
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
   if (lists.rows) {
     k_forces_lists<<<(n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32), kFlWarps * 32, 0, stream>>>(
-        pos, vel, aux, lists.entries, lists.count, lists.rows, grid, c, accel);
+        pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     // particles with more neighbours than list rows: redone with the searching kernel (exits at once elsewhere)
     k_forces<true><<<blocks, kNbThreads, kForceSmem, stream>>>(pos, vel, aux, skey, cell_start, cell_end, grid, c, accel,
                                                                lists.count, lists.rows);

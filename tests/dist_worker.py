@@ -1,0 +1,140 @@
+"""Multi-GPU worker, launched by tests/test_multi_gpu.py (or by hand) under torchrun:
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_worker.py [n] [steps]
+
+Every rank runs one slab of the same fluid block through the CUDA library (clsph_dist_*); rank 0
+also runs the whole block on its own GPU without decomposition and, for the first sub-step, on the
+CPU oracle. Particles are matched by the persistent ids the library carries. Prints DIST_OK."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from libclsph_b200 import abi, capi, slabs, workloads  # noqa: E402
+
+
+def gather_owned(ctx, rank, world, device):
+    """All ranks' owned particles and ids on rank 0 (padded all_gather over NCCL)."""
+    parts, ids = ctx.dist_download()
+    n = torch.tensor([parts.size], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    cap = max(counts)
+    buf = torch.zeros(cap * 84, dtype=torch.uint8, device=device)
+    raw = np.concatenate([parts.view(np.uint8).reshape(-1), ids.view(np.uint8).reshape(-1)])
+    buf[: raw.size] = torch.from_numpy(raw).to(device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    if rank != 0:
+        return None, None, counts
+    all_p, all_i = [], []
+    for r in range(world):
+        b = bufs[r].cpu().numpy()
+        all_p.append(b[: counts[r] * 80].view(abi.PARTICLE).copy())
+        all_i.append(b[counts[r] * 80: counts[r] * 84].view(np.uint32).copy())
+    return np.concatenate(all_p), np.concatenate(all_i), counts
+
+
+def rel(a, b):
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / np.abs(b).max())
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+
+    p, terms, vol, scene_file = workloads.make_config(fluid="water", particles_count=n, particle_mass=0.05)
+    state = workloads.jittered_state(p, vol)
+    state["intermediate_velocity"][:, 0] += np.float32(1.5)  # a drift along x so that particles do migrate
+    state["velocity"][:, 0] += np.float32(1.5)
+    normals, vertices, indices = workloads.scene_arrays(scene_file)
+    planes = slabs.equal_count_planes(state["position"][:, 0], world)
+    owner = slabs.slab_of(state["position"][:, 0], planes)
+    mine = np.nonzero(owner == rank)[0].astype(np.uint32)
+
+    # one NCCL id for the library's own communicator
+    if rank == 0:
+        uid = torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device=device)
+    else:
+        uid = torch.zeros(128, dtype=torch.uint8, device=device)
+    dist.broadcast(uid, 0)
+    uid = bytes(uid.cpu().numpy().tolist())
+
+    cap = int(n * (1.0 / world + 0.5)) + 4096  # owned + two ghost layers per side with slack
+    ctx = capi.Context(cap, device=local)
+    ctx.set_scene(normals, vertices, indices)
+    ctx.set_parameters(p, terms)
+    ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
+    ctx.dist_upload(np.ascontiguousarray(state[mine]), mine)
+
+    single = None
+    if rank == 0:
+        single = capi.Context(n, device=local)
+        single.set_scene(normals, vertices, indices)
+        single.set_parameters(p, terms)
+        single.upload(state)
+
+    ok = True
+    ref_state = state  # state in the single run's order at the start of the current step
+    ref_ids = np.arange(n, dtype=np.uint32)
+    for k in range(steps):
+        ctx.step(1)
+        ctx.synchronize()
+        got, ids, counts = gather_owned(ctx, rank, world, device)
+        if rank == 0:
+            single.step(1)
+            want = single.download()
+            perm = single.fetch(capi.TAP_PERMUTATION)
+            ref_ids = ref_ids[perm]  # id of the particle at each sorted position of the single run
+            assert sum(counts) == n, "particles lost or duplicated: %r" % (counts,)
+            assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32)), "ids are not a permutation"
+            by_id_got = np.empty(n, dtype=abi.PARTICLE)
+            by_id_got[ids] = got
+            by_id_want = np.empty(n, dtype=abi.PARTICLE)
+            by_id_want[ref_ids] = want
+            same_keys = np.array_equal(by_id_got["grid_index"], by_id_want["grid_index"])
+            errs = {f: rel(by_id_got[f][:, :3] if by_id_got[f].ndim == 2 else by_id_got[f],
+                           by_id_want[f][:, :3] if by_id_want[f].ndim == 2 else by_id_want[f])
+                    for f in ("position", "velocity", "intermediate_velocity", "density", "pressure")}
+            moved = int((slabs.slab_of(by_id_got["position"][:, 0], planes) != owner).sum())
+            print("step %d: counts %r keys equal %s, rel err vs single GPU %s, particles outside their first slab %d"
+                  % (k, counts, same_keys, {a: "%.2e" % b for a, b in errs.items()}, moved), flush=True)
+            tol = 1e-4 if k == 0 else 2e-3
+            ok = ok and all(v <= tol for v in errs.values()) and (same_keys or k > 0)
+            if k == 0:
+                from oracle import oracle as O
+                scene = O.Scene(vertices, indices, normals)
+                r = O.step(state, p.copy(), terms, scene)
+                by_id_or = np.empty(n, dtype=abi.PARTICLE)
+                by_id_or[r.permutation] = r.particles
+                oerrs = {f: rel(by_id_got[f][:, :3] if by_id_got[f].ndim == 2 else by_id_got[f],
+                                by_id_or[f][:, :3] if by_id_or[f].ndim == 2 else by_id_or[f])
+                         for f in ("position", "velocity", "density", "pressure")}
+                okeys = np.array_equal(by_id_got["grid_index"], by_id_or["grid_index"])
+                print("step 0 vs oracle: keys equal %s, rel err %s" % (okeys, {a: "%.2e" % b for a, b in oerrs.items()}), flush=True)
+                ok = ok and okeys and all(v <= 1e-4 for v in oerrs.values())
+    flag = torch.tensor([1 if ok else 0], device=device)
+    dist.broadcast(flag, 0)
+    ctx.close()
+    if single is not None:
+        single.close()
+    dist.barrier()
+    if rank == 0:
+        print("DIST_OK" if ok else "DIST_FAILED", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
