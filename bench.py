@@ -193,6 +193,11 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
+def ctx_capacity(ctx, n):
+    """Room for a rank's download: its own particles plus what may have migrated in."""
+    return int(n * 1.25) + 4096
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -224,19 +229,46 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     torch.cuda.set_device(local_rank)
-    p, terms, vol, scene_file, state = sample_workload(args)
-    n = state.size
+    device = torch.device("cuda", local_rank)
+    fluid, n_cfg, mass, scene_file = workloads.CONFIGS[args.config]
+    n_cfg = args.particles or n_cfg
     normals, vertices, indices = workloads.scene_arrays(scene_file)
-    ctx = capi.Context(n, device=local_rank)
+    if world == 1:
+        p, terms, vol, _, state = sample_workload(args)
+        ids = None
+        n = state.size
+        ctx = capi.Context(n, device=local_rank)
+    else:
+        # weak scaling: world x the configured count as ONE fluid block (same particle mass, hence same h
+        # and spacing), cut into x slabs; each rank generates only its own slab
+        p, terms, vol, _ = workloads.make_config(fluid=fluid, particles_count=n_cfg * world, particle_mass=mass)
+        index, planes = workloads.slab_indices(p, vol, rank, world)
+        state = workloads.jittered_state(p, vol, index=index)
+        ids = index
+        n = state.size
+        ctx = capi.Context(int(n * 1.5) + 65536, device=local_rank)
     for opt in args.option:
         k, v = opt.split("=")
         ctx.set_option(k, int(v))
     ctx.set_scene(normals, vertices, indices)
     ctx.set_parameters(p, terms)
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    if world > 1:
+        if rank == 0:
+            uid = torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device=device)
+        else:
+            uid = torch.zeros(128, dtype=torch.uint8, device=device)
+        dist.broadcast(uid, 0)
+        ctx.dist_init(rank, world, bytes(uid.cpu().numpy().tolist()), float(planes[rank]), float(planes[rank + 1]))
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+
+    def upload_state():
+        if world == 1:
+            ctx.upload(state)
+        else:
+            ctx.dist_upload(state, ids)
 
     # ---- device-resident throughput ("value")
-    ctx.upload(state)
+    upload_state()
     ctx.step(args.warmup)
     ctx.synchronize()
     sampler = ClockSampler(local_rank)
@@ -280,23 +312,32 @@ def run_ours(args, rank, world, local_rank):
                 "stage_ms": per,
                 "note": "density/force passes are FP32-issue / shared-memory bound at the reference's 2h cell geometry (SURVEY 8d)"}
 
-    # ---- end to end through the reference-shaped call, pinned host buffers
+    # ---- end to end through the host-buffer calls, pinned host memory: every step uploads the 80-byte AoS
+    # array, runs one sub-step and downloads the result (the reference's call shape when a callback is installed)
+    import ctypes
+    lib = capi.load_library()
     if args.e2e_steps > 0:
         host_in = torch.empty(n * 80, dtype=torch.uint8).pin_memory()
-        host_out = torch.empty(n * 80, dtype=torch.uint8).pin_memory()
+        host_out = torch.empty(ctx_capacity(ctx, n) * 80, dtype=torch.uint8).pin_memory()
         host_in.numpy()[:] = state.view(np.uint8).reshape(-1)
-    import ctypes
-    from libclsph_b200.abi import particle_ptr
-    lib = capi.load_library()
-    p_io = p.copy()
+        p_io = p.copy()
+        if world > 1:
+            ids_in = torch.from_numpy(ids.astype(np.uint32)).pin_memory()
+            ids_out = torch.empty(ctx_capacity(ctx, n), dtype=torch.int32).pin_memory()
+            got = ctypes.c_uint32()
 
-    def e2e_step():
-        rc = lib.clsph_simulate_single_frame(ctx._h, ctypes.c_void_p(host_in.data_ptr()),
-                                             ctypes.c_void_p(host_out.data_ptr()), ctypes.byref(p_io), ctypes.byref(terms))
-        if rc:
-            raise RuntimeError(lib.clsph_last_error(ctx._h).decode())
+        def e2e_step():
+            if world == 1:
+                rc = lib.clsph_simulate_single_frame(ctx._h, ctypes.c_void_p(host_in.data_ptr()),
+                                                     ctypes.c_void_p(host_out.data_ptr()), ctypes.byref(p_io), ctypes.byref(terms))
+            else:
+                rc = lib.clsph_dist_upload(ctx._h, ctypes.c_void_p(host_in.data_ptr()), ctypes.c_void_p(ids_in.data_ptr()), n)
+                rc = rc or lib.clsph_step(ctx._h, 1)
+                rc = rc or lib.clsph_dist_download(ctx._h, ctypes.c_void_p(host_out.data_ptr()), ctypes.c_void_p(ids_out.data_ptr()),
+                                                   ctx_capacity(ctx, n), ctypes.byref(got))
+            if rc:
+                raise RuntimeError(lib.clsph_last_error(ctx._h).decode())
 
-    if args.e2e_steps > 0:
         for _ in range(3):
             e2e_step()
         barrier()
@@ -304,9 +345,10 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(args.e2e_steps):
             e2e_step()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 80, "d2h_bytes_per_step": n * 80,
-               "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "path": "clsph_simulate_single_frame(host AoS in, host AoS out), pinned buffers"}
+        e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * (80 if world == 1 else 84),
+               "d2h_bytes_per_step": n * (80 if world == 1 else 84), "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "path": ("clsph_simulate_single_frame(host AoS in, host AoS out)" if world == 1 else
+                        "clsph_dist_upload + clsph_step + clsph_dist_download per rank") + ", pinned buffers"}
     else:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "steps": 0,
                "path": "skipped (--e2e-steps 0)"}
@@ -316,9 +358,11 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config, "particles_per_gpu": n, "fluid": workloads.CONFIGS[args.config][0],
+        "config": {"workload": args.config, "particles_per_gpu": n, "particles_total": int(n_total), "fluid": fluid,
                    "scene": scene_file, "state": "S1 jittered lattice, seed 20261017",
-                   "parallelism": "single GPU" if world == 1 else "replicas: one independent fluid block per GPU, no exchange",
+                   "parallelism": "single GPU" if world == 1 else
+                   "one fluid block of %d x the configured count, slab-decomposed along x over %d GPUs; per sub-step: AABB "
+                   "all-reduce, migration + two ghost cell layers per side in one NCCL send/recv group" % (world, world),
                    "l2": "per-step working set ~%d MB vs 126 MB L2, no flush: sub-steps form a dependent chain" % (n * 200 // (1 << 20)),
                    "grid": [grid.grid_size_x, grid.grid_size_y, grid.grid_size_z], "grid_cell_count": grid.grid_cell_count,
                    "options": args.option},
@@ -336,6 +380,9 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    # NCCL prints its version banner on stdout at some debug levels; stdout must carry the JSON line only
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

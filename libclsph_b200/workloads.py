@@ -65,17 +65,23 @@ def lattice_geometry(params, initial_volume):
     return per_side, side, spacing
 
 
-def lattice_state(params, initial_volume):
-    """State S0: the reference's cubic lattice, everything else zero."""
-    n = params.particles_count
+def lattice_positions(params, initial_volume, index):
+    """Lattice positions (reference init_particles, sph_simulation.cpp:71-92) of the given global indices."""
     per_side, side, spacing = lattice_geometry(params, initial_volume)
-    i = np.arange(n, dtype=np.uint32)
+    i = np.asarray(index, dtype=np.uint32)
     ups = np.uint32(per_side)
     half = side / f32(2.0)
-    buf = np.zeros(n, dtype=PARTICLE)
-    buf["position"][:, 0] = (i % ups).astype(f32) * spacing - half
-    buf["position"][:, 1] = ((i // ups) % ups).astype(f32) * spacing
-    buf["position"][:, 2] = (i // (ups * ups)).astype(f32) * spacing - half
+    pos = np.zeros((i.size, 4), dtype=f32)
+    pos[:, 0] = (i % ups).astype(f32) * spacing - half
+    pos[:, 1] = ((i // ups) % ups).astype(f32) * spacing
+    pos[:, 2] = (i // (ups * ups)).astype(f32) * spacing - half
+    return pos
+
+
+def lattice_state(params, initial_volume):
+    """State S0: the reference's cubic lattice, everything else zero."""
+    buf = np.zeros(params.particles_count, dtype=PARTICLE)
+    buf["position"] = lattice_positions(params, initial_volume, np.arange(params.particles_count, dtype=np.uint32))
     return buf
 
 
@@ -94,12 +100,18 @@ def uniform01(seed, counters):
     return (z >> np.uint64(40)).astype(np.float64) / float(1 << 24)
 
 
-def jittered_state(params, initial_volume, seed=20261017, position_jitter=0.25, velocity_jitter=0.5):
-    """State S1: S0 plus uniform offsets of +-position_jitter*spacing and +-velocity_jitter m/s."""
-    buf = lattice_state(params, initial_volume)
-    n = params.particles_count
+def jittered_state(params, initial_volume, seed=20261017, position_jitter=0.25, velocity_jitter=0.5, index=None):
+    """State S1: S0 plus uniform offsets of +-position_jitter*spacing and +-velocity_jitter m/s.
+
+    `index` (global particle indices) restricts the result to a subset; the jitter of a particle
+    depends only on its global index, so subsets generated on different ranks agree."""
+    if index is None:
+        index = np.arange(params.particles_count, dtype=np.uint32)
+    index = np.asarray(index, dtype=np.uint32)
+    buf = np.zeros(index.size, dtype=PARTICLE)
+    buf["position"] = lattice_positions(params, initial_volume, index)
     _, _, spacing = lattice_geometry(params, initial_volume)
-    i = np.arange(n, dtype=np.uint64)
+    i = index.astype(np.uint64)
     for c in range(3):
         u = uniform01(seed, np.uint64(6) * i + np.uint64(c))
         buf["position"][:, c] += ((u - 0.5) * 2.0 * position_jitter * float(spacing)).astype(f32)
@@ -108,6 +120,23 @@ def jittered_state(params, initial_volume, seed=20261017, position_jitter=0.25, 
         buf["velocity"][:, c] = vel
         buf["intermediate_velocity"][:, c] = vel
     return buf
+
+
+def slab_indices(params, initial_volume, rank, world):
+    """Global indices of the lattice columns that slab `rank` of `world` starts with, and the x
+    planes (world+1 values, -inf/+inf at the ends) halfway between neighbouring slabs' columns."""
+    per_side, side, spacing = lattice_geometry(params, initial_volume)
+    n = params.particles_count
+    cols = [(per_side * r) // world for r in range(world + 1)]
+    planes = np.full(world + 1, np.inf, dtype=f32)
+    planes[0] = -np.inf
+    for r in range(1, world):
+        planes[r] = f32(cols[r]) * spacing - side / f32(2.0) - spacing / f32(2.0)
+    x = np.arange(cols[rank], cols[rank + 1], dtype=np.uint64)
+    rows = np.arange((n + per_side - 1) // per_side, dtype=np.uint64)  # (y, z) pairs, row-major
+    idx = (rows[:, None] * np.uint64(per_side) + x[None, :]).reshape(-1)
+    idx = idx[idx < n]
+    return idx.astype(np.uint32), planes
 
 
 def make_config(name=None, fluid="water", particles_count=32000, particle_mass=0.05, **overrides):
