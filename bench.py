@@ -199,6 +199,11 @@ def ctx_capacity(ctx, n):
 
 
 def run_ours(args, rank, world, local_rank):
+    # stdout must carry exactly one JSON line: native libraries (NCCL's version banner) write to fd 1 too,
+    # so everything goes to stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     from libclsph_b200 import capi, workloads
@@ -373,6 +378,8 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu_baseline(args)
         except Exception as exc:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
