@@ -61,6 +61,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(config, world, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, when this run matches the capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            t = json.load(fh)
+        if world != 1 or t["config"] != config or kernel not in t["kernels"]:
+            return None, None
+        k = t["kernels"][kernel]
+        return (k["read_mb"] + k["write_mb"]) * 1e6, "ncu --set full, %s (profiles/r01_traffic.json)" % k["capture"]
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -168,7 +181,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     fluid, n_full, mass, scene = __import__("libclsph_b200.workloads", fromlist=["CONFIGS"]).CONFIGS[args.config]
-    n_full = args.particles or n_full
+    n_full = (args.particles or n_full) * max(1, args.gpus)  # the GPU arm runs gpus x the configured count as one block
     # bounded sample: calibrate, then size N so that K+W sub-steps take about two minutes
     n_cal = min(16384, n_full)
     rate, kind, cores, _ = cpu_run(args, n_cal, 2, 1)
@@ -195,7 +208,7 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 def ctx_capacity(ctx, n):
     """Room for a rank's download: its own particles plus what may have migrated in."""
-    return int(n * 1.25) + 4096
+    return int(n * 1.5) + 65536
 
 
 def run_ours(args, rank, world, local_rank):
@@ -251,7 +264,12 @@ def run_ours(args, rank, world, local_rank):
         state = workloads.jittered_state(p, vol, index=index)
         ids = index
         n = state.size
-        ctx = capi.Context(int(n * 1.5) + 65536, device=local_rank)
+        # one grid-cell layer of the block's cross-section: the unit of ghost traffic (two layers per side)
+        # and of bursty migration (a snapped slab boundary jumps by one cell now and then)
+        per_side, side, spacing = workloads.lattice_geometry(p, vol)
+        layer = int(p.particles_count / per_side * (2.0 * p.h / float(spacing))) + 1
+        emigrant_cap, ghost_cap = int(2.0 * layer) + 8192, int(4.0 * layer) + 8192
+        ctx = capi.Context(int(1.2 * n) + 2 * layer + 2 * ghost_cap + 65536, device=local_rank)
     for opt in args.option:
         k, v = opt.split("=")
         ctx.set_option(k, int(v))
@@ -263,7 +281,8 @@ def run_ours(args, rank, world, local_rank):
         else:
             uid = torch.zeros(128, dtype=torch.uint8, device=device)
         dist.broadcast(uid, 0)
-        ctx.dist_init(rank, world, bytes(uid.cpu().numpy().tolist()), float(planes[rank]), float(planes[rank + 1]))
+        ctx.dist_init(rank, world, bytes(uid.cpu().numpy().tolist()), float(planes[rank]), float(planes[rank + 1]),
+                      emigrant_capacity=emigrant_cap, ghost_capacity=ghost_cap)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
 
     def upload_state():
@@ -301,14 +320,17 @@ def run_ours(args, rank, world, local_rank):
     ctx.step(args.steps)
     stage = ctx.profile_read()
     ctx.profile_enable(False)
+    ctx.synchronize()  # surfaces device-side errors (grid or buffer overflow) of the profiled steps here
     per = {k[3:]: stage[k] / max(1, stage["substeps"]) for k in stage if k.startswith("ms_")}
     kb = dict(KERNEL_BYTES)
     kb["sort"] = 4.0 + 16.0 * passes
     dominant = max((k for k in kb), key=lambda k: per.get(k, 0.0))
     peak, peak_src = measured_peak()
     achieved = n * kb[dominant] / (per[dominant] * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(args.config if not args.particles else None, world, "k_" + dominant)
     roofline = {"bound": "hbm", "kernel": "k_" + dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": n * kb[dominant], "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": kb[dominant], "ms_per_launch": per[dominant],
                 "whole_step": {"bytes_per_particle_step": step_bytes(passes), "radix_passes": passes,
                                "achieved": value / world * step_bytes(passes) / 1e9,
@@ -403,7 +425,15 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_ours(args, rank, world, local_rank)
+    try:
+        run_ours(args, rank, world, local_rank)
+    except BaseException:
+        # A failed rank must not linger: its peers would wait in NCCL forever. Report and leave at once,
+        # without destructors that synchronise streams with unmatched receives on them.
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

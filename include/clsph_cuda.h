@@ -158,9 +158,12 @@ int clsph_comm_unique_id(void* out, size_t bytes);
 /* Joins the communicator. plane_lo / plane_hi = world-space x bounds of this rank's slab
  * (-INFINITY for rank 0, +INFINITY for the last rank); neighbouring ranks must pass the same
  * plane. Slabs must stay at least four grid cells (8 h) thick. Capacities are records per
- * message per sub-step (0 = capacity/16 + 1024 emigrants, capacity/4 + 1024 ghosts); exceeding
- * them, or max_particles (owned + ghost copies), is reported as CLSPH_ECOMM by the next
- * synchronising call. */
+ * message per sub-step. The planes are snapped to the cell boundaries of a grid whose origin
+ * follows the fluid, so occasionally a boundary jumps by one cell and a whole cell layer
+ * migrates at once: emigrant_capacity must hold one cell layer of the slab's cross-section and
+ * ghost_capacity two (0 = max_particles/6 + 1024 and max_particles/3 + 1024). Exceeding them, or
+ * max_particles (owned + ghost copies), is reported as CLSPH_ECOMM by the next synchronising
+ * call. */
 int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_id, float plane_lo, float plane_hi,
                     uint32_t emigrant_capacity, uint32_t ghost_capacity);
 

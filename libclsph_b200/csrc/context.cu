@@ -533,8 +533,11 @@ int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_
   if (ctx->dist.active) return fail(ctx, CLSPH_ESTATE, "clsph_dist_init: already initialised");
   if (!(plane_lo < plane_hi)) return fail(ctx, CLSPH_EINVAL, "clsph_dist_init: plane_lo must be below plane_hi");
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  if (dist_init(&ctx->dist, rank, world, unique_id, plane_lo, plane_hi, emigrant_capacity ? emigrant_capacity : ctx->capacity / 16 + 1024,
-                ghost_capacity ? ghost_capacity : ctx->capacity / 4 + 1024))
+  // A slab boundary is a fixed plane snapped to the nearest cell boundary of a grid whose origin follows
+  // the fluid, so now and then it jumps by one cell and a whole cell layer changes owner in one
+  // sub-step: the emigrant capacity must hold a layer, the ghost capacity two.
+  if (dist_init(&ctx->dist, rank, world, unique_id, plane_lo, plane_hi, emigrant_capacity ? emigrant_capacity : ctx->capacity / 6 + 1024,
+                ghost_capacity ? ghost_capacity : ctx->capacity / 3 + 1024))
     return fail(ctx, CLSPH_ECOMM, "clsph_dist_init: %s", dist_last_error());
   for (int s = 0; s < 2; ++s) CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pid[s], ctx->capacity));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->export_ids, ctx->capacity));
