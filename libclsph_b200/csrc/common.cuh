@@ -116,9 +116,13 @@ __device__ __forceinline__ float dist2_contract(float ax, float ay, float az, fl
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
+#ifdef CLSPH_EMU  // tests/emu: CPU build of the kernels for logic tests, no PTX
+  return (1u << lane_id()) - 1u;
+#else
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+#endif
 }
 
 // Cell range lookup. Dense: two loads. Fallback (grid larger than the table): lower_bound over

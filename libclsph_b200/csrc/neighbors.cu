@@ -189,6 +189,12 @@ __device__ __forceinline__ void finish_density(const SphConst& c, float sum_cube
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); each lane later reads only what it copied
 // itself, so cp.async.wait_group alone orders it.
+#ifdef CLSPH_EMU  // tests/emu: CPU build of the kernels for logic tests, the copy completes at once
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
@@ -196,6 +202,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+#endif
 
 // Rounds a staged list up to a multiple of 32 with candidates at +infinity (never inside a
 // support), so the support-test loops need no bounds check. The lists have 32 spare slots.

@@ -1,0 +1,120 @@
+"""Kernel LOGIC tests on the CPU: the CUDA sources compiled against the test-only emulator
+(tests/emu/) and driven through the same C ABI and the same checks as the GPU parity tests, at
+small sizes. Not a product path, not a fallback -- capi.Context keeps loading libclsph_cuda.so and
+fails without a GPU; this module swaps in tests/emu/_build/libclsph_emu.so for its own duration
+only. It catches indexing, collective, barrier and bookkeeping errors before GPU time is spent;
+the -m gpu suite stays the parity gate (the emulator knows nothing about races or performance).
+"""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from libclsph_b200 import capi, workloads
+from oracle import oracle as O
+from tests import helpers as H
+from tests import test_gpu_parity as G
+from tests.emu import build_emu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulator_library():
+    saved = capi._lib
+    capi._lib = capi.load_library(build_emu.build())
+    yield capi._lib
+    capi._lib = saved
+
+
+def test_every_abi_symbol_is_exported_by_the_emulator_build(emulator_library):
+    for name in capi.SYMBOLS:
+        assert hasattr(emulator_library, name), name
+
+
+@pytest.mark.parametrize("n", [128, 1000, 4096])
+def test_lattice_state_s0(n, box_scene):
+    G.test_lattice_state_s0(n, box_scene)
+
+
+@pytest.mark.parametrize("fluid,n", [("water", 4096), ("mucus", 3000)])
+def test_jittered_state_s1(fluid, n, box_scene):
+    G.test_jittered_state_s1(fluid, n, box_scene)
+
+
+def test_ragged_count(box_scene):
+    p, terms, vol = H.config("water", 2345)
+    G.check_against_oracle(H.state_s1(p, vol, seed=3), p, terms, box_scene, "ragged n=2345")
+
+
+def test_collision_heavy_step(plane_scene):
+    p, terms, vol = H.config("mucus", 2048)
+    s = H.drop_state(p, vol, scene_floor_y=-1.0)
+    got, taps, want = G.check_against_oracle(s, p, terms, plane_scene, "drop onto plane")
+    assert (want.collision_iters > 1).mean() > 0.2
+
+
+def test_labyrinth_scene_many_faces():
+    scene = O.load_obj(os.path.join(H.ROOT, "scenes", "labyrinth.obj"))
+    p, terms, vol = H.config("mucus", 4096, mass=0.05 * 32000 / 4194304 * 256)
+    G.check_against_oracle(H.state_s1(p, vol), p, terms, scene, "labyrinth")
+
+
+def test_advection_collision_kernel_bit_exact(box_scene):
+    p, terms, vol = H.config("water", 4000)
+    s = H.drop_state(p, vol, scene_floor_y=-2.0, speed=2.9, slab=0.02)
+    rng = np.random.default_rng(11)
+    s["acceleration"][:, :3] = rng.normal(0, 30, size=(s.size, 3)).astype(np.float32)
+    s["intermediate_velocity"][:, 0] = rng.uniform(-2, 2, s.size).astype(np.float32)
+    want, iters = O.advection_collision(s, p, box_scene)
+    ctx = G.make_ctx(s.size, box_scene, p, terms)
+    got = ctx.kernel_advection_collision(s)
+    got_iters = ctx.fetch(capi.TAP_COLLISION_ITERS)
+    ctx.close()
+    assert (iters > 1).sum() > 20
+    assert np.array_equal(got_iters, iters)
+    for f in H.FIELDS_XYZ:
+        assert np.array_equal(got[f][:, :3], want[f][:, :3]), f
+
+
+def test_binary_search_fallback_matches_dense_table(box_scene):
+    p, terms, vol = H.config("water", 2048)
+    s = H.state_s1(p, vol)
+    dense, taps_d, _ = G.gpu_step_with_taps(s, p, terms, box_scene)
+    sparse, taps_s, _ = G.gpu_step_with_taps(s, p, terms, box_scene, cell_table_capacity=8)
+    for k in taps_d:
+        assert np.array_equal(taps_d[k], taps_s[k]), k
+    assert dense.tobytes() == sparse.tobytes()
+
+
+@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8)])
+def test_neighbour_organisations(options, box_scene, plane_scene):
+    p, terms, vol = H.config("water", 3000)
+    G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
+    p, terms, vol = H.config("mucus", 1500)
+    G.check_against_oracle(H.drop_state(p, vol, scene_floor_y=-1.0), p, terms, plane_scene, "crowded %r" % (options,),
+                           options=options)
+
+
+def test_host_in_host_out_and_resident_steps(box_scene):
+    G.test_simulate_single_frame_host_in_host_out(box_scene)
+    p, terms, vol = H.config("water", 2048)
+    s = H.state_s1(p, vol)
+    ctx = G.make_ctx(s.size, box_scene, p, terms, debug=False)
+    ctx.upload(s)
+    ctx.step(3)
+    resident = ctx.download()
+    cur = s
+    for _ in range(3):
+        ctx.upload(cur)
+        ctx.step(1)
+        cur = ctx.download()
+    ctx.close()
+    assert resident.tobytes() == cur.tobytes()
+
+
+def test_error_paths(box_scene):
+    G.test_error_paths(box_scene)
+
+
+def test_empty_scene_no_faces():
+    G.test_empty_scene_no_faces()
