@@ -26,13 +26,18 @@ struct GridState {
   uint32_t n;                        // particles on this device
   uint32_t sort_passes;              // ceil(bits(cell_count - 1) / 8), 1..4
   uint32_t dense;                    // 1: cell_count fits the dense table; 0: binary-search fallback
-  uint32_t error;                    // bit 0: a grid axis reached 1024 cells; bit 1: a multi-GPU buffer overflowed
+  uint32_t error;                    // bit 0: a grid axis reached 1024 cells; bit 1: a multi-GPU buffer overflowed;
+                                     // bit 2: sub-cell keys need more than 32 bits (an axis beyond 512 cells)
   // Slab decomposition (multi-GPU): this rank owns the cells with own_lo <= cx < own_hi. One GPU:
   // [0, INT_MAX). Particles of other cells held locally are ghost copies of a neighbour's.
   int own_lo, own_hi;
   int prev_lo, prev_hi;              // the range of the previous sub-step (whose keys the arrays still carry)
   uint32_t fresh;                    // 1 after an upload: every local particle counts as owned
-  uint32_t pad1[3];
+  // Sub-cell order (subgrid.cu): the arrays are sorted by (cell key << 3 | octant of the cell), so the
+  // particles of a cell are grouped by the h-sized sub-cell they are in.
+  uint32_t sub;                      // 1: this sub-step sorts by sub-cell keys
+  uint32_t sub_dense;                // 1: cell_count fits the dense sub-cell table; 0: binary search
+  uint32_t pad1;
 };
 
 // AABB accumulators: floats mapped to order-preserving unsigned so atomicMin/Max apply.
@@ -44,6 +49,7 @@ struct BoundsAcc {
 // Per-run constants, passed to kernels by value.
 struct SphConst {
   float h, h2, support_s;      // support_s: smallest s = |d|^2 with sqrt(s)/h >= 1 (exact window test)
+  float h_margin;              // h (1 + 2^-10): search half-width of the sub-cell traversal (subgrid.cu)
   float mass, rho0, K;
   float c_poly6, c_spiky, c_visc, c_poly6_grad, c_poly6_lap;
   float mu, sigma, tension_threshold;
@@ -106,6 +112,13 @@ __device__ __forceinline__ bool cell_needs_density(uint32_t key, const GridState
 // correctly rounded subtract and divide (no reciprocal, no contraction).
 __device__ __forceinline__ uint32_t cell_coord(float p, float mn, float cell) {
   return __float2uint_rz(__fdiv_rn(__fsub_rn(p, mn), cell));
+}
+
+// Sub-cell coordinate (cells of side h): floor(2q) for the same q = (p - min) / (2h); the doubling is
+// exact, so sub_coord >> 1 == cell_coord always.
+__device__ __forceinline__ uint32_t sub_coord(float p, float mn, float cell) {
+  const float q = __fdiv_rn(__fsub_rn(p, mn), cell);
+  return __float2uint_rz(__fadd_rn(q, q));
 }
 
 // Squared distance exactly as the oracle's distance(): d = a - b, s = fma(dz,dz,fma(dy,dy,dx*dx)).

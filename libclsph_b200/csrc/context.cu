@@ -58,6 +58,14 @@ struct clsph_context {
   Face* faces = nullptr;
   uint32_t face_count = 0;
 
+  // sub-cell order (subgrid.cu): arrays sorted by (cell key << 3 | octant); rrank = index of each
+  // particle in the reference's array, rr_tmp = the gathered ranks of the previous sub-step
+  bool sub_order = false;
+  uint32_t sub_capacity = 0;   // cells the dense sub-cell table holds (9 words each)
+  uint32_t* sub_lb = nullptr;
+  uint32_t* rrank = nullptr;
+  uint32_t* rr_tmp = nullptr;
+
   // list mode (default): the density pass stores neighbour lists, the force pass reads them
   bool use_lists = true;
   uint32_t list_rows_override = 0;  // 0 = derive from the rest density
@@ -132,6 +140,8 @@ void derive_constants(clsph_context* ctx) {
   volatile float h2 = p.h * p.h;
   c.h2 = h2;
   c.support_s = support_threshold(p.h);
+  volatile float hm = p.h * 1.0009765625f;  // h (1 + 2^-10), see sub_bounds in subgrid.cu
+  c.h_margin = hm;
   c.mass = p.particle_mass;
   c.rho0 = p.fluid_density;
   c.K = p.K;
@@ -228,8 +238,18 @@ uint32_t list_rows_for(const clsph_context* ctx) {
   return ((uint32_t)rows + 7u) & ~7u;
 }
 
+// Arrays of the sub-cell order, allocated the first time it is selected.
+int ensure_sub(clsph_context* ctx) {
+  if (!ctx->sub_order || ctx->sub_lb) return CLSPH_OK;
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->sub_lb, (size_t)ctx->sub_capacity * 9u));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->rrank, ctx->capacity));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->rr_tmp, ctx->capacity));
+  CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sub_lb, 0, sizeof(uint32_t) * 9u * (size_t)ctx->sub_capacity, ctx->stream));
+  return CLSPH_OK;
+}
+
 int ensure_lists(clsph_context* ctx) {
-  if (!ctx->use_lists) {
+  if (!ctx->use_lists && !ctx->sub_order) {
     ctx->lists.rows = 0;
     return CLSPH_OK;
   }
@@ -271,8 +291,9 @@ int enqueue_substep(clsph_context* ctx) {
     ctx->bounds_valid = true;
   }
   if (multi && dist_allreduce_bounds(&ctx->dist, ctx->bounds, st)) return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
+  const bool sub = ctx->sub_order;
   launch_grid_setup(ctx->bounds, ctx->grid, ctx->params.h, ctx->n, ctx->cell_capacity, multi ? ctx->dist.plane_lo : -inf,
-                    multi ? ctx->dist.plane_hi : inf, multi, st, lc);
+                    multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, st, lc);
   if (prof) next_event(ctx);
 
   if (multi) {
@@ -285,23 +306,44 @@ int enqueue_substep(clsph_context* ctx) {
   StateArrays& dst = ctx->state[ctx->cur ^ 1];
   if (prof) next_event(ctx);
 
-  launch_sort_keys(ctx->sort, src.pos, ctx->grid, n, ctx->sm_count, ctx->debug ? ctx->taps.keys_input : nullptr, st, lc);
+  // sub-cell order: the pre-step keys tap is written by k_rank, in the reference's order
+  launch_sort_keys(ctx->sort, src.pos, ctx->grid, n, ctx->sm_count, (ctx->debug && !sub) ? ctx->taps.keys_input : nullptr, sub,
+                   st, lc);
   if (prof) next_event(ctx);
   launch_sort_passes(ctx->sort, ctx->grid, n, st, lc);
   if (prof) next_event(ctx);
 
-  launch_clear_cells(ctx->cell_start, ctx->cell_end, ctx->grid, ctx->cell_capacity, ctx->sm_count, st, lc);
-  launch_reorder(src, dst, ctx->sort, ctx->skey, ctx->perm, ctx->cell_start, ctx->cell_end, ctx->grid,
-                 multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr, n, st, lc);
-  ctx->cur ^= 1;
-  if (prof) next_event(ctx);
+  if (sub) {
+    launch_clear_sub(ctx->sub_lb, ctx->grid, ctx->sub_capacity, ctx->sm_count, st, lc);
+    launch_reorder_sub(src, dst, ctx->sort, ctx->skey, multi ? nullptr : ctx->rrank, ctx->rr_tmp, ctx->sub_lb, ctx->grid,
+                       multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr, n, st, lc);
+    ctx->cur ^= 1;
+    if (!multi)  // across ranks the reference's global order is not tracked (multi-GPU)
+      launch_rank(ctx->skey, ctx->rr_tmp, ctx->rrank, ctx->sub_lb, ctx->sort, ctx->grid, ctx->perm,
+                  ctx->debug ? ctx->taps.keys_input : nullptr, n, st, lc);
+    if (prof) next_event(ctx);
+    launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
+                       ctx->taps, ctx->debug, n, st, lc);
+    if (prof) next_event(ctx);
+    launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
+                  false, ctx->accel, n, st, lc);
+    launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
+                               ctx->lists, ctx->accel, n, st, lc);
+    if (prof) next_event(ctx);
+  } else {
+    launch_clear_cells(ctx->cell_start, ctx->cell_end, ctx->grid, ctx->cell_capacity, ctx->sm_count, st, lc);
+    launch_reorder(src, dst, ctx->sort, ctx->skey, ctx->perm, ctx->cell_start, ctx->cell_end, ctx->grid,
+                   multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr, n, st, lc);
+    ctx->cur ^= 1;
+    if (prof) next_event(ctx);
 
-  launch_density(dst.pos, dst.vel, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                 ctx->taps, ctx->debug, n, ctx->sm_count, st, lc);
-  if (prof) next_event(ctx);
-  launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst,
-                ctx->lists, ctx->accel, n, st, lc);
-  if (prof) next_event(ctx);
+    launch_density(dst.pos, dst.vel, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
+                   ctx->taps, ctx->debug, n, ctx->sm_count, st, lc);
+    if (prof) next_event(ctx);
+    launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst,
+                  ctx->lists, true, ctx->accel, n, st, lc);
+    if (prof) next_event(ctx);
+  }
   if (ctx->debug)  // the integrator consumes the acceleration; keep a copy for the tap
     CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->taps.acceleration, ctx->accel, sizeof(float4) * n,
                                         cudaMemcpyDeviceToDevice, st));
@@ -343,6 +385,11 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
   // Morton-indexed tables are 1.1x-6.4x the cell count for compact fluids; 8 entries
   // per particle with a 4 Mi floor covers every BASELINE config; larger grids use the fallback.
   if (const char* env = std::getenv("CLSPH_NEIGHBOUR_LISTS")) ctx->use_lists = std::atoi(env) != 0;
+  if (const char* env = std::getenv("CLSPH_SUB_CELL_ORDER")) ctx->sub_order = std::atoi(env) != 0;
+  // dense sub-cell table: 9 words per cell; two cells per particle covers every BASELINE config
+  // (a spread-out 16 Mi river fills ~0.7 cells per particle), larger grids use binary search
+  ctx->sub_capacity = cell_table_capacity ? cell_table_capacity
+                                          : (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_particles * 2u, 1u << 20), 1u << 28);
   ctx->cell_capacity = cell_table_capacity ? cell_table_capacity
                                            : (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)max_particles * 8u, 1u << 22), 1u << 28);
 #define CREATE_TRY(expr)                                                                                          \
@@ -391,6 +438,11 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
   CREATE_TRY(cudaMemset(ctx->cell_end, 0, sizeof(uint32_t) * ctx->cell_capacity));
   neighbors_init();
   CREATE_TRY(cudaGetLastError());
+  if (ctx->sub_order && ensure_sub(ctx) != CLSPH_OK) {
+    g_create_error = ctx->error;
+    clsph_destroy(ctx);
+    return CLSPH_ENOMEM;
+  }
 #undef CREATE_TRY
   *out = ctx;
   return CLSPH_OK;
@@ -433,6 +485,9 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->lists.entries);
   cudaFree(ctx->lists.count);
   cudaFree(ctx->lists.window_counter);
+  cudaFree(ctx->sub_lb);
+  cudaFree(ctx->rrank);
+  cudaFree(ctx->rr_tmp);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
@@ -490,6 +545,13 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (!std::strcmp(name, "neighbour_lists")) {
     ctx->use_lists = value != 0;
+  } else if (!std::strcmp(name, "sub_cell_order")) {
+    // the two organisations keep the arrays in different orders: switch only while no particles are held
+    if (ctx->have_particles && ctx->sub_order != (value != 0))
+      return fail(ctx, CLSPH_ESTATE, "clsph_set_option: sub_cell_order must be set before particles are uploaded");
+    ctx->sub_order = value != 0;
+    int rc = ensure_sub(ctx);
+    if (rc) return rc;
   } else if (!std::strcmp(name, "list_rows")) {
     if (value < 0 || value > 1024) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: list_rows must be in [0, 1024]");
     ctx->list_rows_override = (uint32_t)value;
@@ -506,7 +568,8 @@ int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) 
   if (n > ctx->capacity) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: %u particles exceed the capacity %u", n, ctx->capacity);
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, aos, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, n, ctx->stream, &ctx->launches);
+  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, ctx->sub_order ? ctx->rrank : nullptr, n,
+                    ctx->stream, &ctx->launches);
   const uint32_t count_and_fresh[2] = {n, 1u};
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->n, &count_and_fresh[0], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->fresh, &count_and_fresh[1], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -551,7 +614,7 @@ int clsph_dist_upload(clsph_context* ctx, const particle* aos, const uint32_t* i
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, aos, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, st));
-  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, n, st, &ctx->launches);
+  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, nullptr, n, st, &ctx->launches);
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->export_ids, ids, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
   launch_fill_ids(ctx->pid[ctx->cur], ctx->export_ids, 0u, n, st, &ctx->launches);
   const uint32_t count_and_fresh[2] = {n, 1u};
@@ -634,7 +697,8 @@ int clsph_download_particles(clsph_context* ctx, particle* aos_out) {
   if (!aos_out) return fail(ctx, CLSPH_EINVAL, "clsph_download_particles: aos_out is null");
   if (!ctx->have_particles) return fail(ctx, CLSPH_ESTATE, "clsph_download_particles: no particles uploaded");
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  launch_soa_to_aos(ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->aos_stage, ctx->n, ctx->stream, &ctx->launches);
+  launch_soa_to_aos(ctx->state[ctx->cur], ctx->aux, ctx->skey, (ctx->sub_order && !ctx->dist.active) ? ctx->rrank : nullptr,
+                    ctx->aos_stage, ctx->n, ctx->stream, &ctx->launches);
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(aos_out, ctx->aos_stage, sizeof(particle) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   return clsph_synchronize(ctx);
 }
@@ -659,7 +723,8 @@ int clsph_kernel_advection_collision(clsph_context* ctx, const particle* in, par
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, in, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, st));
-  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->accel, n, st, &ctx->launches);
+  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->accel, ctx->sub_order ? ctx->rrank : nullptr, n,
+                    st, &ctx->launches);
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->n, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   launch_bounds_reset(ctx->bounds, st, &ctx->launches);
   if (ctx->debug) {
@@ -692,7 +757,7 @@ int clsph_debug_fetch(clsph_context* ctx, int what, void* dst, size_t bytes) {
   const void* src = nullptr;
   size_t need = 0;
   bool needs_debug = false;
-  std::vector<float> packed;
+  const bool scatter = ctx->sub_order && !ctx->dist.active;  // per-particle taps go through the reference rank
   switch (what) {
     case CLSPH_TAP_SORTED_KEYS: src = ctx->skey; need = 4 * n; break;
     case CLSPH_TAP_PERMUTATION: src = ctx->perm; need = 4 * n; break;
@@ -725,7 +790,12 @@ int clsph_debug_fetch(clsph_context* ctx, int what, void* dst, size_t bytes) {
       need = acc ? 12 * n : 4 * n;
       if (bytes != need) return fail(ctx, CLSPH_EINVAL, "clsph_debug_fetch: tap %d is %zu bytes, got %zu", what, need, bytes);
       std::vector<float> host(4 * n);
-      CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), acc ? ctx->taps.acceleration : ctx->aux, 16 * n, cudaMemcpyDeviceToHost, ctx->stream));
+      const void* from = acc ? ctx->taps.acceleration : ctx->aux;
+      if (scatter) {  // sub-cell order: bring the records into the reference's order first
+        launch_scatter_words(from, ctx->rrank, ctx->aos_stage, (uint32_t)n, 4u, ctx->stream, &ctx->launches);
+        from = ctx->aos_stage;
+      }
+      CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), from, 16 * n, cudaMemcpyDeviceToHost, ctx->stream));
       CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       float* o = static_cast<float*>(dst);
       for (size_t i = 0; i < n; ++i) {
@@ -739,6 +809,11 @@ int clsph_debug_fetch(clsph_context* ctx, int what, void* dst, size_t bytes) {
   }
   if (needs_debug && (!ctx->debug || !src)) return fail(ctx, CLSPH_ESTATE, "clsph_debug_fetch: enable clsph_set_debug before the step");
   if (bytes != need) return fail(ctx, CLSPH_EINVAL, "clsph_debug_fetch: tap %d is %zu bytes, got %zu", what, need, bytes);
+  if (scatter && (what == CLSPH_TAP_CANDIDATE_COUNT || what == CLSPH_TAP_SUPPORT_COUNT || what == CLSPH_TAP_COLLISION_ITERS)) {
+    // recorded in the internal (sub-cell) order; the other integer taps are already in the reference's
+    launch_scatter_words(src, ctx->rrank, ctx->aos_stage, (uint32_t)n, 1u, ctx->stream, &ctx->launches);
+    src = ctx->aos_stage;
+  }
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
   CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   CLSPH_CUDA_TRY(ctx, cudaGetLastError());

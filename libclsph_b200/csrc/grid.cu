@@ -66,8 +66,10 @@ __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ pos, 
 // (-inf / +inf at the ends); they are snapped to the nearest cell boundary of the current grid, the
 // same on every rank because the AABB was all-reduced. keep_n: the particle count lives on the
 // device (it changes with migration) and must not be overwritten.
+// sub_mode: sort by sub-cell keys (cell key << 3 | octant), which need 3 more key bits; sub_capacity =
+// cells the dense sub-cell table can hold.
 __global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity,
-                             float plane_lo, float plane_hi, int keep_n) {
+                             float plane_lo, float plane_hi, int keep_n, uint32_t sub_mode, uint32_t sub_capacity) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float cell = __fmul_rn(h, 2.f);
   const float pad = __fmul_rn(cell, 2.f);
@@ -95,10 +97,14 @@ __global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t 
   // nearest cell boundary: floor((plane - min) / cell + 0.5), clamped to the grid
   grid->own_lo = (plane_lo == -inf) ? 0 : max(0, min(gs[0], (int)floorf((plane_lo - mn[0]) / cell + 0.5f)));
   grid->own_hi = (plane_hi == inf) ? 0x7fffffff : max(0, min(gs[0], (int)floorf((plane_hi - mn[0]) / cell + 0.5f)));
-  const uint32_t top = count > 1u ? count - 1u : 1u;
+  if (sub_mode && count > (1u << 29)) err |= 4u;  // (key << 3 | octant) would not fit 32 bits
+  // largest sort key: count - 1, or 8 * count - 1 with the octant bits appended
+  const uint32_t top = sub_mode ? (count >= (1u << 29) ? 0xFFFFFFFFu : max(count * 8u, 2u) - 1u) : (count > 1u ? count - 1u : 1u);
   const uint32_t bits = 32u - (uint32_t)__clz((int)top);
   grid->sort_passes = err ? 4u : max(1u, (bits + 7u) / 8u);
   grid->dense = (count <= cell_capacity) ? 1u : 0u;
+  grid->sub = sub_mode ? 1u : 0u;
+  grid->sub_dense = (sub_mode && count <= sub_capacity) ? 1u : 0u;
   grid->error |= err;  // sticky until the host reads and clears it
 }
 
@@ -158,7 +164,7 @@ k_reorder(const float4* __restrict__ src_pos, const float4* __restrict__ src_vel
 __global__ void __launch_bounds__(256) k_aos_to_soa(const float4* __restrict__ aos, float4* __restrict__ pos,
                                                     float4* __restrict__ vel, float4* __restrict__ ivel,
                                                     float4* __restrict__ aux, uint32_t* __restrict__ skey,
-                                                    float4* __restrict__ accel, uint32_t n) {
+                                                    float4* __restrict__ accel, uint32_t* __restrict__ rrank, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4* rec = aos + (size_t)i * 5;
@@ -169,14 +175,16 @@ __global__ void __launch_bounds__(256) k_aos_to_soa(const float4* __restrict__ a
   const float4 tail = rec[4];
   aux[i] = make_float4(tail.x, tail.y, 0.f, 0.f);
   skey[i] = __float_as_uint(tail.z);
+  if (rrank) rrank[i] = i;  // the uploaded order is the reference's order
 }
 
 __global__ void __launch_bounds__(256) k_soa_to_aos(const float4* __restrict__ pos, const float4* __restrict__ vel,
                                                     const float4* __restrict__ ivel, const float4* __restrict__ aux,
-                                                    const uint32_t* __restrict__ skey, float4* __restrict__ aos, uint32_t n) {
+                                                    const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rrank,
+                                                    float4* __restrict__ aos, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float4* rec = aos + (size_t)i * 5;
+  float4* rec = aos + (size_t)(rrank ? rrank[i] : i) * 5;  // sub-cell order: slot in the reference's array
   float4 p = pos[i], v = vel[i], iv = ivel[i];
   p.w = 0.f; v.w = 0.f; iv.w = 0.f;
   const float4 a = aux[i];
@@ -224,8 +232,10 @@ void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, 
 }
 
 void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
-                       float plane_hi, bool keep_n, cudaStream_t stream, uint64_t* launches) {
-  k_grid_setup<<<1, 32, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0);
+                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, cudaStream_t stream,
+                       uint64_t* launches) {
+  k_grid_setup<<<1, 32, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0, sub_mode,
+                                     sub_capacity);
   if (launches) ++*launches;
 }
 
@@ -246,15 +256,15 @@ void launch_reorder(const StateArrays& src, const StateArrays& dst, const SortBu
   if (launches) ++*launches;
 }
 
-void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uint32_t* skey, float4* accel, uint32_t n,
-                       cudaStream_t stream, uint64_t* launches) {
-  k_aos_to_soa<<<blocks_for(n, 256), 256, 0, stream>>>((const float4*)aos, dst.pos, dst.vel, dst.ivel, aux, skey, accel, n);
+void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uint32_t* skey, float4* accel,
+                       uint32_t* rrank, uint32_t n, cudaStream_t stream, uint64_t* launches) {
+  k_aos_to_soa<<<blocks_for(n, 256), 256, 0, stream>>>((const float4*)aos, dst.pos, dst.vel, dst.ivel, aux, skey, accel, rrank, n);
   if (launches) ++*launches;
 }
 
-void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, void* aos, uint32_t n,
-                       cudaStream_t stream, uint64_t* launches) {
-  k_soa_to_aos<<<blocks_for(n, 256), 256, 0, stream>>>(src.pos, src.vel, src.ivel, aux, skey, (float4*)aos, n);
+void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, const uint32_t* rrank, void* aos,
+                       uint32_t n, cudaStream_t stream, uint64_t* launches) {
+  k_soa_to_aos<<<blocks_for(n, 256), 256, 0, stream>>>(src.pos, src.vel, src.ivel, aux, skey, rrank, (float4*)aos, n);
   if (launches) ++*launches;
 }
 

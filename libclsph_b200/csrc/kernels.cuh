@@ -48,8 +48,9 @@ struct DebugTaps {           // all nullable; sorted order unless stated
 // ---- sort.cu
 uint32_t sort_tiles_for(uint32_t n);
 size_t sort_scratch_words(uint32_t max_particles);
+// sub_keys: keys are (cell key << 3 | octant) instead of the cell key (subgrid.cu).
 void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* grid, uint32_t n_launch, int sm_count,
-                      uint32_t* keys_tap, cudaStream_t stream, uint64_t* launches);
+                      uint32_t* keys_tap, bool sub_keys, cudaStream_t stream, uint64_t* launches);
 void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_launch, cudaStream_t stream,
                         uint64_t* launches);
 
@@ -57,7 +58,8 @@ void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_
 void launch_bounds_reset(BoundsAcc* acc, cudaStream_t stream, uint64_t* launches);
 void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, cudaStream_t stream, uint64_t* launches);
 void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
-                       float plane_hi, bool keep_n, cudaStream_t stream, uint64_t* launches);
+                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, cudaStream_t stream,
+                       uint64_t* launches);
 void launch_clear_cells(uint32_t* cell_start, uint32_t* cell_end, const GridState* grid, uint32_t cell_capacity,
                         int sm_count, cudaStream_t stream, uint64_t* launches);
 // Gathers `src` into `dst` through the sort permutation, writes sorted keys and the cell table.
@@ -65,10 +67,12 @@ void launch_reorder(const StateArrays& src, const StateArrays& dst, const SortBu
                     uint32_t* perm_out, uint32_t* cell_start, uint32_t* cell_end, const GridState* grid,
                     const uint32_t* src_pid, uint32_t* dst_pid, uint32_t n_launch, cudaStream_t stream,
                     uint64_t* launches);
-void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uint32_t* skey, float4* accel, uint32_t n,
-                       cudaStream_t stream, uint64_t* launches);
-void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, void* aos, uint32_t n,
-                       cudaStream_t stream, uint64_t* launches);
+// rrank (nullable): reference rank per particle (subgrid.cu); set to the identity on upload, and
+// record i goes to slot rrank[i] of the AoS array on download.
+void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uint32_t* skey, float4* accel,
+                       uint32_t* rrank, uint32_t n, cudaStream_t stream, uint64_t* launches);
+void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, const uint32_t* rrank, void* aos,
+                       uint32_t n, cudaStream_t stream, uint64_t* launches);
 void launch_reference_cell_table(const uint32_t* skey, const GridState* grid, uint32_t* table, uint32_t n_launch,
                                  cudaStream_t stream, uint64_t* launches);
 void launch_copy_u32(const uint32_t* src, uint32_t* dst, uint32_t n, cudaStream_t stream, uint64_t* launches);
@@ -89,9 +93,32 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
                     const DebugTaps& taps, bool debug, uint32_t n_launch, int sm_count, cudaStream_t stream,
                     uint64_t* launches);
 // Only particles of owned cells get an acceleration (multi-GPU: ghosts are skipped).
+// search_fallback: in list mode, also run the searching kernel for particles whose list overflowed
+// (sub-cell order has its own, launch_forces_sub_overflow).
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
-                   const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+                   const NeighbourLists& lists, bool search_fallback, float4* accel, uint32_t n_launch,
+                   cudaStream_t stream, uint64_t* launches);
+
+// ---- subgrid.cu: sub-cell order (arrays sorted by cell key << 3 | octant)
+void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capacity, int sm_count, cudaStream_t stream,
+                      uint64_t* launches);
+void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
+                        const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
+                        const uint32_t* src_pid, uint32_t* dst_pid, uint32_t n_launch, cudaStream_t stream,
+                        uint64_t* launches);
+void launch_rank(const uint32_t* skey, const uint32_t* rr_old, uint32_t* rr_new, const uint32_t* sub_lb,
+                 const SortBuffers& sort, const GridState* grid, uint32_t* perm_out, uint32_t* keys_input_tap,
+                 uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+void launch_density_sub(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
+                        const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
+                        const DebugTaps& taps, bool debug, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+void launch_forces_sub_overflow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
+                                const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, const SphConst& c,
+                                const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream,
+                                uint64_t* launches);
+void launch_scatter_words(const void* src, const uint32_t* rrank, void* dst, uint32_t n, uint32_t words,
+                          cudaStream_t stream, uint64_t* launches);
 
 // ---- integrate.cu
 void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,

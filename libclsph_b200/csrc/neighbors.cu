@@ -30,6 +30,7 @@
 // HBM traffic is the 16-32 B/particle of coalesced reads, L2-resident candidate gathers and, in
 // list mode, about 2 x 4 B x (neighbours per particle) of list traffic.
 #include "kernels.cuh"
+#include "pair_terms.cuh"
 
 namespace clsph {
 
@@ -125,66 +126,6 @@ __device__ __forceinline__ uint2 neighbour_cell_range(uint32_t key, const GridSt
   if (cx == 0u || cy == 0u || cz == 0u) return make_uint2(0u, 0u);
   const uint32_t x = cx + (lane % 3u) - 1u, y = cy + ((lane / 3u) % 3u) - 1u, z = cz + (lane / 9u) - 1u;
   return cell_range(morton3(x, y, z), g, cell_start, cell_end, skey);
-}
-
-// Sums of one particle's force pass (forces.cl:50-55).
-struct ForceSums {
-  float px = 0.f, py = 0.f, pz = 0.f;   // pressure term          forces.cl:70-77
-  float wx = 0.f, wy = 0.f, wz = 0.f;   // viscosity term         forces.cl:79-85
-  float nx = 0.f, ny = 0.f, nz = 0.f;   // colour-field normal    forces.cl:88-91
-  float lap = 0.f;                      // colour-field laplacian forces.cl:93-97
-};
-
-// Contribution of neighbour j (known to be inside the support, window == 1) to particle i.
-// pj = (x, y, z, p_j/rho_j^2), vj = (vx, vy, vz, m/rho_j); a_i = p_i/rho_i^2.
-__device__ __forceinline__ void add_pair(ForceSums& f, const SphConst& c, bool is_self, const float4& pi, const float4& vi,
-                                         float a_i, const float4& pj, const float4& vj) {
-  const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-  const float s = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-  const float r = sqrtf(s);
-  const float mass_over_rho = vj.w;
-  if (!is_self) {
-    float gx, gy, gz;
-    if (r < 0.0000001f) {  // smoothing.cl:23-25 (erratum E3): a scalar broadcast to x, y, z
-      gx = gy = gz = c.spiky_degenerate;
-    } else {               // smoothing.cl:26-28
-      const float hr = c.h - r;
-      const float k = c.c_spiky * hr * hr / r;
-      gx = k * dx; gy = k * dy; gz = k * dz;
-    }
-    const float pc = (pj.w + a_i) * c.mass;
-    f.px = fmaf(pc, gx, f.px); f.py = fmaf(pc, gy, f.py); f.pz = fmaf(pc, gz, f.pz);
-    const float vc = mass_over_rho * (c.c_visc * (c.h - r));  // smoothing.cl:31-34
-    f.wx = fmaf(vj.x - vi.x, vc, f.wx); f.wy = fmaf(vj.y - vi.y, vc, f.wy); f.wz = fmaf(vj.z - vi.z, vc, f.wz);
-  }
-  const float t = c.h2 - r * r;
-  const float gc = mass_over_rho * (c.c_poly6_grad * t * t);  // smoothing.cl:6-10
-  f.nx = fmaf(gc, dx, f.nx); f.ny = fmaf(gc, dy, f.ny); f.nz = fmaf(gc, dz, f.nz);
-  f.lap = fmaf(mass_over_rho, c.c_poly6_lap * t * (3.f * c.h2 - 7.f * r * r), f.lap);  // smoothing.cl:12-17
-}
-
-// forces.cl:103-109 and sph.cl:53-58: F = -rho P + mu V (+ surface tension), a = F / rho + g.
-__device__ __forceinline__ float4 finish_force(const ForceSums& f, const SphConst& c, float rho) {
-  float fx = -rho * f.px + f.wx * c.mu, fy = -rho * f.py + f.wy * c.mu, fz = -rho * f.pz + f.wz * c.mu;
-  const float nlen = sqrtf(fmaf(f.nz, f.nz, fmaf(f.ny, f.ny, f.nx * f.nx)));
-  if (nlen > c.tension_threshold) {
-    const float k = -c.sigma * f.lap / nlen;
-    fx = fmaf(k, f.nx, fx); fy = fmaf(k, f.ny, fy); fz = fmaf(k, f.nz, fz);
-  }
-  return make_float4(fx / rho + c.gx, fy / rho + c.gy, fz / rho + c.gz, 0.f);
-}
-
-// forces.cl:33-36 / smoothing.cl:1-4: rho = sum m C6 (h^2 - r^2)^3; sph.cl:37-39: Tait pressure.
-// Writes (rho, p) to aux[i] and the two per-neighbour factors the force pass gathers.
-__device__ __forceinline__ void finish_density(const SphConst& c, float sum_cubed, uint32_t i, float4* __restrict__ aux,
-                                               float4* pos, float4* vel) {
-  const float rho = c.mass * c.c_poly6 * sum_cubed;
-  const float q = rho / c.rho0;
-  const float q2 = q * q, q4 = q2 * q2;
-  const float prs = c.K * (q4 * q2 * q - 1.f);
-  aux[i] = make_float4(rho, prs, 0.f, 0.f);
-  reinterpret_cast<float*>(pos + i)[3] = prs / (rho * rho);  // only the w lane: other warps may be reading x, y, z
-  reinterpret_cast<float*>(vel + i)[3] = c.mass / rho;
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); each lane later reads only what it copied
@@ -761,15 +702,19 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
-                   const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+                   const NeighbourLists& lists, bool search_fallback, float4* accel, uint32_t n_launch,
+                   cudaStream_t stream, uint64_t* launches) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
   if (lists.rows) {
     k_forces_lists<<<(n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32), kFlWarps * 32, 0, stream>>>(
         pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
-    // particles with more neighbours than list rows: redone with the searching kernel (exits at once elsewhere)
-    k_forces<true><<<blocks, kNbThreads, kForceSmem, stream>>>(pos, vel, aux, skey, cell_start, cell_end, grid, c, accel,
-                                                               lists.count, lists.rows);
-    if (launches) *launches += 2;
+    if (launches) ++*launches;
+    if (search_fallback) {
+      // particles with more neighbours than list rows: redone with the searching kernel (exits at once elsewhere)
+      k_forces<true><<<blocks, kNbThreads, kForceSmem, stream>>>(pos, vel, aux, skey, cell_start, cell_end, grid, c, accel,
+                                                                 lists.count, lists.rows);
+      if (launches) ++*launches;
+    }
   } else {
     k_forces<false><<<blocks, kNbThreads, kForceSmem, stream>>>(pos, vel, aux, skey, cell_start, cell_end, grid, c, accel,
                                                                 nullptr, 0u);

@@ -53,6 +53,11 @@ __device__ __forceinline__ uint32_t block256_exclusive_scan(uint32_t v, uint32_t
 // ---------------------------------------------------------------------------------------------
 // Keys + histograms.  grid.cl:56-64: key = morton((uint)((p - min) / (2h)) per axis).
 // ---------------------------------------------------------------------------------------------
+// kSub: the key gets three more bits, the octant of the cell the particle is in (which half along
+// x, y, z): floor(2q) & 1 with q = (p - min) / (2h) as above; 2q is exact, and floor(2q) >> 1 ==
+// floor(q), so the cell part is unchanged and a stable sort by the longer key is a stable sort by
+// cell refined by octant.
+template <bool kSub>
 __global__ void __launch_bounds__(256) k_keys_hist(const float4* __restrict__ pos, uint32_t* __restrict__ keys,
                                                    const GridState* __restrict__ grid, uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_hist[kMaxSortPasses * kRadix];
@@ -70,7 +75,13 @@ __global__ void __launch_bounds__(256) k_keys_hist(const float4* __restrict__ po
     const unsigned vmask = __ballot_sync(kFullMask, valid);
     if (!valid) continue;
     const float4 p = pos[i];
-    const uint32_t key = morton3(cell_coord(p.x, mnx, cell), cell_coord(p.y, mny, cell), cell_coord(p.z, mnz, cell));
+    uint32_t key;
+    if (kSub) {
+      const uint32_t fx = sub_coord(p.x, mnx, cell), fy = sub_coord(p.y, mny, cell), fz = sub_coord(p.z, mnz, cell);
+      key = (morton3(fx >> 1, fy >> 1, fz >> 1) << 3) | (fx & 1u) | ((fy & 1u) << 1) | ((fz & 1u) << 2);
+    } else {
+      key = morton3(cell_coord(p.x, mnx, cell), cell_coord(p.y, mny, cell), cell_coord(p.z, mnz, cell));
+    }
     keys[i] = key;
     for (int pass = 0; pass < passes; ++pass) {
       const uint32_t d = (key >> (8 * pass)) & 0xFFu;
@@ -233,14 +244,15 @@ ScratchLayout layout_of(const SortBuffers& b) {
 
 // Zeroes the scratch, computes keys into keys_a and all digit histograms.
 void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* grid, uint32_t n_launch, int sm_count,
-                      uint32_t* keys_tap, cudaStream_t stream, uint64_t* launches) {
+                      uint32_t* keys_tap, bool sub_keys, cudaStream_t stream, uint64_t* launches) {
   const ScratchLayout l = layout_of(b);
   const uint32_t tiles = sort_tiles_for(n_launch);
   // histograms, tile counters and the look-back status words of the tiles in use start at zero
   const size_t zero_words = (size_t)2 * kMaxSortPasses * kRadix + 64 + (size_t)kMaxSortPasses * tiles * kRadix;
   cudaMemsetAsync(b.scratch, 0, zero_words * sizeof(uint32_t), stream);
   const unsigned hist_blocks = (unsigned)std::min<uint64_t>(((uint64_t)n_launch + 255) / 256, (uint64_t)sm_count * 8);
-  k_keys_hist<<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist);
+  if (sub_keys) k_keys_hist<true><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist);
+  else k_keys_hist<false><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist);
   if (launches) ++*launches;
   if (keys_tap) launch_copy_u32(b.keys_a, keys_tap, n_launch, stream, launches);
 }

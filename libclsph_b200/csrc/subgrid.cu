@@ -1,0 +1,341 @@
+// subgrid.cu -- "sub-cell order": the neighbour search on cells of side h inside the reference's
+// grid of side 2h.
+//
+// The reference scans the 27 cells (side 2h) around a particle: ~1000 candidates for ~20 real
+// neighbours (SURVEY hard part 1). Its observable contract -- cell keys, the stable sort
+// permutation, the cell table, candidate counts, the support test -- is defined on that grid, but
+// nothing forces the ARRAYS IN HBM to be kept in the reference's order. Here they are sorted by
+//     sub-cell key = (Morton cell key << 3) | octant of the cell (which half along x, y, z),
+// i.e. by the Morton code of a grid of side h. Consequences:
+//   * the particles of a reference cell are still contiguous, in the same segment [start, end) as
+//     in the reference's order -- only permuted inside it -- so cell table, sorted keys and
+//     candidate counts are unchanged;
+//   * the particles of each sub-cell are contiguous too, so a particle only visits the 3 x 3 x 3
+//     (occasionally 4 along an axis, see sub_bounds) sub-cells around it: ~130 candidates instead
+//     of ~1000, with no culling work at all, one thread per particle, no shared memory needed;
+//   * the reference's array order is carried as one uint32 per particle, `rrank` = the index the
+//     particle has in the reference's array. The reference's next order is the stable sort of its
+//     current order by cell key, so  rrank' = cell_start + #{j in the same cell : rrank_j < rrank_i},
+//     a count over the ~40 particles of the cell (k_rank). Downloads and taps scatter through it,
+//     so everything observable is in the reference's order, bit for bit.
+//
+// Replaces, like neighbors.cu, kernels/sph.cl:9-62 with forces.cl:15-112; the force pass proper is
+// k_forces_lists of neighbors.cu (it only consumes the lists written here).
+#include "kernels.cuh"
+#include "pair_terms.cuh"
+
+namespace clsph {
+
+namespace {
+
+constexpr int kSubThreads = 128;
+
+// What a kernel needs to turn (cell, octant range) into an index range of the sorted arrays.
+struct SubView {
+  const uint32_t* lb;     // dense table: lb[cell * 9 + o] = first index of the cell's octant >= o; [8] = end
+  const uint32_t* fkeys;  // sorted sub-cell keys (binary-search fallback)
+  uint32_t n, cell_count;
+  bool dense;
+};
+
+__device__ __forceinline__ SubView make_view(const GridState& g, const uint32_t* sub_lb, const uint32_t* keys_a,
+                                             const uint32_t* keys_b) {
+  SubView v;
+  v.lb = sub_lb;
+  v.fkeys = (g.sort_passes & 1u) ? keys_b : keys_a;  // an odd number of passes ends in the "b" buffers
+  v.n = g.n;
+  v.cell_count = g.cell_count;
+  v.dense = g.sub_dense != 0u;
+  return v;
+}
+
+// Particles of cell `key` whose octant is in [o_lo, o_hi]: one contiguous range.
+__device__ __forceinline__ uint2 sub_range(const SubView& v, uint32_t key, uint32_t o_lo, uint32_t o_hi) {
+  if (key >= v.cell_count) return make_uint2(0u, 0u);
+  if (v.dense) {
+    const uint32_t* row = v.lb + (size_t)key * 9u;
+    return make_uint2(__ldg(row + o_lo), __ldg(row + o_hi + 1u));
+  }
+  const uint32_t base = key << 3;  // key < 2^29 in sub-cell mode
+  const uint32_t a = lower_bound_key(v.fkeys, v.n, base + o_lo);
+  const uint32_t b = (base + o_hi == 0xFFFFFFFFu) ? v.n : lower_bound_key(v.fkeys, v.n, base + o_hi + 1u);
+  return make_uint2(a, b);
+}
+
+// Sub-cell coordinates [lo, hi] along one axis that can hold a particle within the support of a
+// particle at offset u = p - min. A pair inside the support has |dx| < h (1 + 2^-21); u itself
+// carries up to 2^-13 h of rounding (u < 2048 h). Both are covered by searching
+// [u - hm, u + hm] with hm = h (1 + 2^-10), mapped to sub-cells by the SAME monotone rounding
+// sequence as sub_coord: every neighbour's sub-cell lies in [lo, hi]. Usually hi - lo = 2; 3 when
+// the particle is within 2^-10 h of a sub-cell boundary.
+__device__ __forceinline__ void sub_bounds(float p, float mn, float cell, float hm, uint32_t& lo, uint32_t& hi) {
+  const float u = __fsub_rn(p, mn);
+  const float ql = __fdiv_rn(__fsub_rn(u, hm), cell), qh = __fdiv_rn(__fadd_rn(u, hm), cell);
+  lo = __float2uint_rz(__fadd_rn(ql, ql));  // negative -> 0
+  hi = __float2uint_rz(__fadd_rn(qh, qh));
+}
+
+// *addr = v when ok, as ONE predicated store: the compiler would otherwise branch around the store
+// and its address arithmetic, and in a warp that branch is nearly always taken by some lane.
+__device__ __forceinline__ void store_if(bool ok, uint32_t* addr, uint32_t v) {
+#ifdef CLSPH_EMU  // tests/emu: CPU build of the kernels for logic tests, no PTX
+  if (ok) *addr = v;
+#else
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)ok), "l"(addr), "r"(v)
+               : "memory");
+#endif
+}
+
+// Calls visit(j, pos[j], s, inside) for every candidate j of the sub-cells around pi, z outermost /
+// x innermost; inside = (s = |pi - pj|^2) < support_s is the reference's window test (self included).
+// The visitor gets every candidate so that it can stay branch-free: about one candidate in seven is
+// inside, so in a warp some lane nearly always is, and a divergent "inside" branch would run for all.
+template <class Visit>
+__device__ __forceinline__ void for_each_neighbour(const SubView& v, const GridState& g, const SphConst& c,
+                                                   const float4* pos, const float4& pi, Visit&& visit) {
+  uint32_t xlo, xhi, ylo, yhi, zlo, zhi;
+  sub_bounds(pi.x, g.min_x, g.cell, c.h_margin, xlo, xhi);
+  sub_bounds(pi.y, g.min_y, g.cell, c.h_margin, ylo, yhi);
+  sub_bounds(pi.z, g.min_z, g.cell, c.h_margin, zlo, zhi);
+  const uint32_t cx_lo = xlo >> 1, cx_hi = xhi >> 1;
+  for (uint32_t fz = zlo; fz <= zhi; ++fz) {
+    const uint32_t kz = spread10(fz >> 1) << 2, oz = (fz & 1u) << 2;
+    for (uint32_t fy = ylo; fy <= yhi; ++fy) {
+      const uint32_t kzy = kz | (spread10(fy >> 1) << 1), ozy = oz | ((fy & 1u) << 1);
+      // the x extent of the row covers two (rarely three) cells; inside a cell the octants with
+      // x bit 0 and 1 are adjacent, so each cell contributes one range
+      for (uint32_t cx = cx_lo; cx <= cx_hi; ++cx) {
+        const uint32_t o_lo = ozy | (cx == cx_lo ? (xlo & 1u) : 0u);
+        const uint32_t o_hi = ozy | (cx == cx_hi ? (xhi & 1u) : 1u);
+        const uint2 r = sub_range(v, kzy | spread10(cx), o_lo, o_hi);
+        for (uint32_t j = r.x; j < r.y; ++j) {
+          const float4 pj = pos[j];
+          const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+          visit(j, pj, s, s < c.support_s);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// =============================================================================================
+// Sub-cell table: cleared, then written by the gather kernel from the sorted keys.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_clear_sub(uint32_t* __restrict__ sub_lb, const GridState* __restrict__ grid) {
+  if (!grid->sub_dense) return;
+  const size_t words = (size_t)grid->cell_count * 9u;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x)
+    sub_lb[w] = 0u;
+}
+
+// Sorted slot r takes the particle that sat at vals[r]. skey gets the CELL key (what every other
+// kernel and the exported grid_index expect); rr_dst the particle's reference rank of the previous
+// sub-step. Slots where the sub-cell key changes fill the octant boundaries of the dense table:
+// lb[cell][o] = first index whose octant is >= o, lb[cell][8] = end of the cell; untouched (empty)
+// cells stay [0, 0).
+__global__ void __launch_bounds__(256)
+k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src_vel, const float4* __restrict__ src_ivel,
+              float4* __restrict__ dst_pos, float4* __restrict__ dst_vel, float4* __restrict__ dst_ivel,
+              const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const uint32_t* __restrict__ vals_a,
+              const uint32_t* __restrict__ vals_b, uint32_t* __restrict__ skey, const uint32_t* __restrict__ rr_src,
+              uint32_t* __restrict__ rr_dst, uint32_t* __restrict__ sub_lb, const GridState* __restrict__ grid,
+              const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid) {
+  const uint32_t n = grid->n;
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const bool in_b = (grid->sort_passes & 1u) != 0u;
+  const uint32_t* __restrict__ keys = in_b ? keys_b : keys_a;
+  const uint32_t* __restrict__ vals = in_b ? vals_b : vals_a;
+  const uint32_t fkey = keys[r];
+  const uint32_t from = vals[r];
+  dst_pos[r] = src_pos[from];
+  dst_vel[r] = src_vel[from];
+  dst_ivel[r] = src_ivel[from];
+  const uint32_t key = fkey >> 3, oct = fkey & 7u;
+  skey[r] = key;
+  if (rr_src) rr_dst[r] = rr_src[from];
+  if (src_pid) dst_pid[r] = src_pid[from];
+  if (!grid->sub_dense) return;
+  const uint32_t count = grid->cell_count;  // keys are < count whenever the grid fits (see k_reorder)
+  uint32_t* row = sub_lb + (size_t)key * 9u;
+  if (r == 0) {
+    if (key < count)
+      for (uint32_t o = 0; o <= oct; ++o) row[o] = 0u;
+  } else {
+    const uint32_t pf = keys[r - 1];
+    const uint32_t pkey = pf >> 3, poct = pf & 7u;
+    if (pkey != key) {
+      if (key < count)
+        for (uint32_t o = 0; o <= oct; ++o) row[o] = r;
+      if (pkey < count) {
+        uint32_t* prow = sub_lb + (size_t)pkey * 9u;
+        for (uint32_t o = poct + 1u; o <= 8u; ++o) prow[o] = r;
+      }
+    } else if (poct != oct && key < count) {
+      for (uint32_t o = poct + 1u; o <= oct; ++o) row[o] = r;
+    }
+  }
+  if (r == n - 1 && key < count)
+    for (uint32_t o = oct + 1u; o <= 8u; ++o) row[o] = n;
+}
+
+// Reference rank after this sub-step's sort (see the header comment). Also writes the permutation
+// tap in the reference's terms (sorted slot -> pre-step index) and, when asked, the pre-step keys.
+__global__ void __launch_bounds__(kSubThreads)
+k_rank(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rr_old, uint32_t* __restrict__ rr_new,
+       const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b,
+       const GridState* __restrict__ grid, uint32_t* __restrict__ perm_out, uint32_t* __restrict__ keys_input_tap) {
+  const GridState g = *grid;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const uint32_t key = skey[i];
+  const uint2 cell = sub_range(v, key, 0u, 7u);
+  const uint32_t mine = rr_old[i];
+  uint32_t before = 0;
+  for (uint32_t j = cell.x; j < cell.y; ++j) before += (__ldg(rr_old + j) < mine) ? 1u : 0u;
+  const uint32_t rank = cell.x + before;
+  rr_new[i] = rank;
+  perm_out[rank] = mine;
+  if (keys_input_tap) keys_input_tap[mine] = key;
+}
+
+// =============================================================================================
+// Density + Tait pressure + neighbour lists, one thread per particle.
+// nlist[i * list_rows + e] = e-th neighbour of particle i (indices into the sorted arrays);
+// ncount[i] = neighbours found, more than list_rows = list incomplete (k_forces_sub redoes it).
+// =============================================================================================
+template <bool kTaps>
+__global__ void __launch_bounds__(kSubThreads)
+k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
+              const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
+              const SphConst c, float4* __restrict__ aux, uint32_t* __restrict__ nlist, uint32_t* __restrict__ ncount,
+              uint32_t list_rows, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ supp_count) {
+  const GridState g = *grid;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const uint32_t key = skey[i];
+  if (!cell_needs_density(key, g)) return;  // multi-GPU: outer ghost layer, candidates only
+  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const float4 pi = pos[i];
+  uint32_t* row = nlist + (size_t)i * list_rows;
+#ifndef CLSPH_EMU
+  // keep the row address in registers: rebuilt from nlist + i * list_rows + cnt it costs four
+  // integer instructions per candidate instead of one
+  asm volatile("" : "+l"(row));
+#endif
+  float acc = 0.f;   // sum of (h^2 - s)^3 over the support
+  uint32_t cnt = 0;
+  for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4&, float s, bool inside) {
+    const float t = inside ? c.h2 - s : 0.f;
+    acc = fmaf(t * t, t, acc);
+    store_if(inside && cnt < list_rows, row + cnt, j);
+    cnt += inside ? 1u : 0u;
+  });
+  finish_density(c, acc, i, aux, pos, vel);
+  ncount[i] = cnt;
+  if (kTaps) {
+    // the reference's candidate count: every particle of the 27 cells around this one (forces.cl:25-40)
+    const uint32_t cx = compact10(key), cy = compact10(key >> 1), cz = compact10(key >> 2);
+    uint32_t total = 0;
+    if (cx != 0u && cy != 0u && cz != 0u) {  // with a 0 coordinate the reference's unsigned loop does not run
+      for (uint32_t z = cz - 1u; z <= cz + 1u; ++z)
+        for (uint32_t y = cy - 1u; y <= cy + 1u; ++y)
+          for (uint32_t x = cx - 1u; x <= cx + 1u; ++x) {
+            const uint2 r = sub_range(v, morton3(x, y, z), 0u, 7u);
+            total += r.y - r.x;
+          }
+    }
+    cand_count[i] = total;
+    supp_count[i] = cnt;
+  }
+}
+
+// Forces for the particles whose list overflowed: same traversal, pair terms evaluated in place.
+__global__ void __launch_bounds__(kSubThreads)
+k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
+             const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
+             const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const SphConst c,
+             const uint32_t* __restrict__ ncount, uint32_t list_rows, float4* __restrict__ accel) {
+  const GridState g = *grid;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  if (!(ncount[i] > list_rows)) return;
+  if (!cell_is_owned(skey[i], g)) return;  // multi-GPU: ghosts get no force
+  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const float4 pi = pos[i], vi = vel[i];
+  ForceSums sums;
+  for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4& pj, float, bool inside) {
+    if (inside) add_pair(sums, c, j == i, pi, vi, pi.w, pj, vel[j]);
+  });
+  accel[i] = finish_force(sums, c, aux[i].x);
+}
+
+// dst[rrank[i]] = src[i], `words` 32-bit words per item: internal order -> the reference's order.
+__global__ void __launch_bounds__(256) k_scatter_words(const uint32_t* __restrict__ src, const uint32_t* __restrict__ rrank,
+                                                       uint32_t* __restrict__ dst, uint32_t n, uint32_t words) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t at = rrank[i];
+  for (uint32_t w = 0; w < words; ++w) dst[(size_t)at * words + w] = src[(size_t)i * words + w];
+}
+
+// ---------------------------------------------------------------------------------------------
+void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capacity, int sm_count, cudaStream_t stream,
+                      uint64_t* launches) {
+  const uint64_t words = (uint64_t)sub_capacity * 9u;
+  const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1u, (words + 255) / 256), (uint64_t)sm_count * 8u);
+  k_clear_sub<<<blocks, 256, 0, stream>>>(sub_lb, grid);
+  if (launches) ++*launches;
+}
+
+void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
+                        const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
+                        const uint32_t* src_pid, uint32_t* dst_pid, uint32_t n_launch, cudaStream_t stream,
+                        uint64_t* launches) {
+  k_reorder_sub<<<(n_launch + 255) / 256, 256, 0, stream>>>(src.pos, src.vel, src.ivel, dst.pos, dst.vel, dst.ivel, sort.keys_a,
+                                                            sort.keys_b, sort.vals_a, sort.vals_b, skey, rr_src, rr_dst, sub_lb,
+                                                            grid, src_pid, dst_pid);
+  if (launches) ++*launches;
+}
+
+void launch_rank(const uint32_t* skey, const uint32_t* rr_old, uint32_t* rr_new, const uint32_t* sub_lb,
+                 const SortBuffers& sort, const GridState* grid, uint32_t* perm_out, uint32_t* keys_input_tap,
+                 uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+  k_rank<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(skey, rr_old, rr_new, sub_lb, sort.keys_a,
+                                                                                 sort.keys_b, grid, perm_out, keys_input_tap);
+  if (launches) ++*launches;
+}
+
+void launch_density_sub(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
+                        const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
+                        const DebugTaps& taps, bool debug, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+  const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
+  if (debug)
+    k_density_sub<true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                            lists.entries, lists.count, lists.rows, taps.candidate_count,
+                                                            taps.support_count);
+  else
+    k_density_sub<false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                             lists.entries, lists.count, lists.rows, nullptr, nullptr);
+  if (launches) ++*launches;
+}
+
+void launch_forces_sub_overflow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
+                                const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, const SphConst& c,
+                                const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream,
+                                uint64_t* launches) {
+  k_forces_sub<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(
+      pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, lists.count, lists.rows, accel);
+  if (launches) ++*launches;
+}
+
+void launch_scatter_words(const void* src, const uint32_t* rrank, void* dst, uint32_t n, uint32_t words,
+                          cudaStream_t stream, uint64_t* launches) {
+  k_scatter_words<<<(n + 255) / 256, 256, 0, stream>>>((const uint32_t*)src, rrank, (uint32_t*)dst, n, words);
+  if (launches) ++*launches;
+}
+
+}  // namespace clsph

@@ -86,7 +86,11 @@ def test_binary_search_fallback_matches_dense_table(box_scene):
     assert dense.tobytes() == sparse.tobytes()
 
 
-@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8)])
+SUB = dict(sub_cell_order=1)
+
+
+@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8),
+                                     SUB, dict(sub_cell_order=1, list_rows=8)])
 def test_neighbour_organisations(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
@@ -118,3 +122,55 @@ def test_error_paths(box_scene):
 
 def test_empty_scene_no_faces():
     G.test_empty_scene_no_faces()
+
+
+# ---- sub-cell order (subgrid.cu): arrays sorted by (cell key << 3 | octant), reference order carried as a rank
+
+@pytest.mark.parametrize("n", [128, 1000, 4096])
+def test_sub_cell_order_lattice(n, box_scene):
+    p, terms, vol = H.config("water", n)
+    G.check_against_oracle(H.state_s0(p, vol), p, terms, box_scene, "sub S0 n=%d" % n, options=SUB)
+
+
+def test_sub_cell_order_mucus_labyrinth():
+    scene = O.load_obj(os.path.join(H.ROOT, "scenes", "labyrinth.obj"))
+    p, terms, vol = H.config("mucus", 4096, mass=0.05 * 32000 / 4194304 * 256)
+    G.check_against_oracle(H.state_s1(p, vol), p, terms, scene, "sub labyrinth", options=SUB)
+
+
+def test_sub_cell_order_binary_search_fallback(box_scene):
+    p, terms, vol = H.config("water", 2048)
+    s = H.state_s1(p, vol)
+    dense, taps_d, _ = G.gpu_step_with_taps(s, p, terms, box_scene, options=SUB)
+    sparse, taps_s, _ = G.gpu_step_with_taps(s, p, terms, box_scene, cell_table_capacity=8, options=SUB)
+    for k in taps_d:
+        assert np.array_equal(taps_d[k], taps_s[k]), k
+    assert dense.tobytes() == sparse.tobytes()
+    G.check_against_oracle(s, p, terms, box_scene, "sub, binary search", cell_table_capacity=8, options=SUB)
+
+
+@pytest.mark.parametrize("options", [dict(neighbour_lists=1), SUB])
+def test_resident_steps_keep_the_reference_order(options, box_scene, plane_scene):
+    p, terms, vol = H.config("water", 3000)
+    s = H.state_s1(p, vol)
+    s["intermediate_velocity"][:, 0] += (2.5 * np.sign(s["position"][:, 2])).astype(np.float32)  # shear: cells change
+    G.check_resident_steps_against_oracle(s, p, terms, box_scene, 5, "water %r" % (options,), options=options)
+    p, terms, vol = H.config("mucus", 1500)
+    G.check_resident_steps_against_oracle(H.drop_state(p, vol, scene_floor_y=-1.0), p, terms, plane_scene, 3,
+                                          "crowded %r" % (options,), options=options)
+
+
+def test_sub_cell_order_host_round_trip_and_option_rules(box_scene):
+    p, terms, vol = H.config("water", 2048)
+    s = H.state_s1(p, vol)
+    ctx = G.make_ctx(s.size, box_scene, p, terms, debug=False, options=SUB)
+    ctx.upload(s)
+    ctx.step(1)
+    want = ctx.download()
+    with pytest.raises(capi.ClsphError) as e:
+        ctx.set_option("sub_cell_order", 0)  # the arrays are in another order: not while particles are held
+    assert e.value.code == capi.E_STATE
+    buf = s.copy()
+    ctx.simulate_single_frame(buf, p.copy(), terms, out=buf)
+    ctx.close()
+    assert buf.tobytes() == want.tobytes()

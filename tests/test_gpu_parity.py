@@ -69,6 +69,31 @@ def check_against_oracle(state, params, terms, scene, what, **kw):
     return got, taps, want
 
 
+def check_resident_steps_against_oracle(state, params, terms, scene, steps, what, options=None):
+    """Device-resident sub-steps (no re-upload), each checked against the oracle stepped from the
+    PREVIOUS downloaded state: the permutation tap and the output order must be exactly the
+    reference's at every step, which is what exercises the carried reference rank of the sub-cell
+    order (the arrays in HBM are in another order there)."""
+    ctx = make_ctx(state.size, scene, params, terms, options=options)
+    ctx.upload(state)
+    prev = state
+    for k in range(steps):
+        ctx.step(1)
+        got = ctx.download()
+        perm = ctx.fetch(capi.TAP_PERMUTATION)
+        keys_in = ctx.fetch(capi.TAP_KEYS_INPUT)
+        supp = ctx.fetch(capi.TAP_SUPPORT_COUNT)
+        want = O.step(prev, params.copy(), terms, scene)
+        tag = "%s, sub-step %d" % (what, k)
+        assert np.array_equal(keys_in, want.keys), tag + ": cell keys in pre-step order"
+        assert np.array_equal(perm, want.permutation), tag + ": sort permutation"
+        assert np.array_equal(got["grid_index"], want.particles["grid_index"]), tag + ": grid_index"
+        assert np.array_equal(supp, want.support_count), tag + ": support counts"
+        H.assert_close_fields(got, want.particles, tol=TOL, what=tag)
+        prev = got
+    ctx.close()
+
+
 @pytest.mark.parametrize("n", [128, 1000, 4096, 32000])
 def test_lattice_state_s0(n, box_scene):
     p, terms, vol = H.config("water", n)
