@@ -50,8 +50,8 @@ def by_id(parts, ids, n):
     return out
 
 
-@pytest.mark.parametrize("world,copies", [(2, 2), (4, 4)])
-def test_slab_decomposition_matches_single_rank_and_oracle(world, copies):
+@pytest.mark.parametrize("world,copies,sub", [(2, 2, 0), (4, 4, 0), (3, 3, 1)])
+def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
     steps = 3
     p, terms, state, scene_file = elongated_state(copies)
     n = state.size
@@ -68,6 +68,7 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies):
         try:
             mine = np.nonzero(owner == rank)[0].astype(np.uint32)
             ctx = capi.Context(int(n * (1.0 / world + 0.5)) + 4096)
+            ctx.set_option("sub_cell_order", sub)
             ctx.set_scene(normals, vertices, indices)
             ctx.set_parameters(p, terms)
             ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
@@ -88,6 +89,7 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies):
 
     # meanwhile: the whole block on one emulated device, and the oracle for the first sub-step
     single = capi.Context(n)
+    single.set_option("sub_cell_order", sub)
     single.set_scene(normals, vertices, indices)
     single.set_parameters(p, terms)
     single.upload(state)
