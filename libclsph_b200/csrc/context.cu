@@ -57,6 +57,14 @@ struct clsph_context {
 
   Face* faces = nullptr;
   uint32_t face_count = 0;
+  // face grid (option "face_grid"): cell lists of the scene's triangles for the collision pass
+  bool use_face_grid = false;
+  FaceGrid face_grid{};
+  uint32_t* fg_cell_start = nullptr;
+  uint32_t* fg_ids = nullptr;
+  uint32_t* fg_global = nullptr;
+  std::vector<float> scene_vertices;     // host copies, to (re)build the grid when the option changes
+  std::vector<uint32_t> scene_indices;
 
   // sub-cell order (subgrid.cu): arrays sorted by (cell key << 3 | octant); rrank = index of each
   // particle in the reference's array, rr_tmp = the gathered ranks of the previous sub-step
@@ -238,6 +246,34 @@ uint32_t list_rows_for(const clsph_context* ctx) {
   return ((uint32_t)rows + 7u) & ~7u;
 }
 
+// (Re)builds the face grid of the current scene, or drops it when the option is off.
+int refresh_face_grid(clsph_context* ctx) {
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->fg_cell_start);
+  cudaFree(ctx->fg_ids);
+  cudaFree(ctx->fg_global);
+  ctx->fg_cell_start = ctx->fg_ids = ctx->fg_global = nullptr;
+  ctx->face_grid = FaceGrid{};
+  if (!ctx->use_face_grid || ctx->face_count == 0) return CLSPH_OK;
+  std::vector<uint32_t> cell_start, ids, global_ids;
+  FaceGrid g;
+  build_face_grid(ctx->scene_vertices.data(), ctx->scene_indices.data(), ctx->face_count, &g, &cell_start, &ids, &global_ids);
+  if (g.nx == 0) return CLSPH_OK;
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->fg_cell_start, cell_start.size()));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->fg_ids, ids.size()));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->fg_global, global_ids.size()));
+  CLSPH_CUDA_TRY(ctx, cudaMemcpy(ctx->fg_cell_start, cell_start.data(), sizeof(uint32_t) * cell_start.size(), cudaMemcpyHostToDevice));
+  if (!ids.empty())
+    CLSPH_CUDA_TRY(ctx, cudaMemcpy(ctx->fg_ids, ids.data(), sizeof(uint32_t) * ids.size(), cudaMemcpyHostToDevice));
+  if (!global_ids.empty())
+    CLSPH_CUDA_TRY(ctx, cudaMemcpy(ctx->fg_global, global_ids.data(), sizeof(uint32_t) * global_ids.size(), cudaMemcpyHostToDevice));
+  g.cell_start = ctx->fg_cell_start;
+  g.ids = ctx->fg_ids;
+  g.global_ids = ctx->fg_global;
+  ctx->face_grid = g;
+  return CLSPH_OK;
+}
+
 // Arrays of the sub-cell order, allocated the first time it is selected.
 int ensure_sub(clsph_context* ctx) {
   if (!ctx->sub_order || ctx->sub_lb) return CLSPH_OK;
@@ -347,7 +383,7 @@ int enqueue_substep(clsph_context* ctx) {
   if (ctx->debug)  // the integrator consumes the acceleration; keep a copy for the tap
     CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->taps.acceleration, ctx->accel, sizeof(float4) * n,
                                         cudaMemcpyDeviceToDevice, st));
-  launch_integrate(dst, ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->grid, ctx->konst, ctx->bounds,
+  launch_integrate(dst, ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->face_grid, ctx->grid, ctx->konst, ctx->bounds,
                    ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, lc);
   if (prof) next_event(ctx);
   CLSPH_CUDA_TRY(ctx, cudaGetLastError());
@@ -386,6 +422,7 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
   // per particle with a 4 Mi floor covers every BASELINE config; larger grids use the fallback.
   if (const char* env = std::getenv("CLSPH_NEIGHBOUR_LISTS")) ctx->use_lists = std::atoi(env) != 0;
   if (const char* env = std::getenv("CLSPH_SUB_CELL_ORDER")) ctx->sub_order = std::atoi(env) != 0;
+  if (const char* env = std::getenv("CLSPH_FACE_GRID")) ctx->use_face_grid = std::atoi(env) != 0;
   // dense sub-cell table: 9 words per cell; two cells per particle covers every BASELINE config
   // (a spread-out 16 Mi river fills ~0.7 cells per particle), larger grids use binary search
   ctx->sub_capacity = cell_table_capacity ? cell_table_capacity
@@ -485,6 +522,9 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->lists.entries);
   cudaFree(ctx->lists.count);
   cudaFree(ctx->lists.window_counter);
+  cudaFree(ctx->fg_cell_start);
+  cudaFree(ctx->fg_ids);
+  cudaFree(ctx->fg_global);
   cudaFree(ctx->sub_lb);
   cudaFree(ctx->rrank);
   cudaFree(ctx->rr_tmp);
@@ -508,6 +548,9 @@ int clsph_set_scene(clsph_context* ctx, const float* face_normals, const float* 
   ctx->faces = nullptr;
   ctx->face_count = face_count;
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->faces, face_count));
+  ctx->scene_vertices.assign(vertices, vertices + (face_count ? n_vertex_floats : 0));
+  ctx->scene_indices.assign(indices, indices + (size_t)face_count * 3);
+  if (int rc = refresh_face_grid(ctx)) return rc;
   if (face_count == 0) return CLSPH_OK;
   float *d_n = nullptr, *d_v = nullptr;
   uint32_t* d_i = nullptr;
@@ -552,6 +595,9 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     ctx->sub_order = value != 0;
     int rc = ensure_sub(ctx);
     if (rc) return rc;
+  } else if (!std::strcmp(name, "face_grid")) {
+    ctx->use_face_grid = value != 0;
+    if (int rc = refresh_face_grid(ctx)) return rc;
   } else if (!std::strcmp(name, "list_rows")) {
     if (value < 0 || value > 1024) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: list_rows must be in [0, 1024]");
     ctx->list_rows_override = (uint32_t)value;
@@ -731,7 +777,7 @@ int clsph_kernel_advection_collision(clsph_context* ctx, const particle* in, par
     int rc = ensure_debug_buffers(ctx);
     if (rc) return rc;
   }
-  launch_integrate(ctx->state[ctx->cur], ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->grid, ctx->konst, ctx->bounds,
+  launch_integrate(ctx->state[ctx->cur], ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->face_grid, ctx->grid, ctx->konst, ctx->bounds,
                    ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, &ctx->launches);
   ctx->n = n;
   ctx->have_particles = true;

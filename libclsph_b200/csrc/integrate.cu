@@ -10,6 +10,8 @@
 // Per-triangle quantities that do not depend on the particle (edges, their dot products, the
 // barycentric determinant, |n|) are evaluated once in k_prepare_faces with the same operations,
 // which is where the reference's per-particle-per-face redundancy goes.
+#include <cmath>
+
 #include "kernels.cuh"
 
 namespace clsph {
@@ -63,11 +65,19 @@ __global__ void k_prepare_faces(const float* __restrict__ normals, const float* 
   faces[f] = o;
 }
 
+// kGrid: only the faces registered in the face-grid cells touched by the segment are tested (plus
+// the grid's "global" faces). A face that passes the hit test has its intersection point inside the
+// segment's box and inside the triangle, both up to rounding that is orders of magnitude below the
+// padding used at registration (build_face_grid), so it is registered in the cell holding that
+// point: no hit is lost. A face may be met twice (two cells) and out of index order, so "ties go to
+// the later face" (collisions.cl:77-80, where faces come in ascending order) is applied as
+// "nearer wins; at equal distance the higher face index wins", which is the same thing.
+template <bool kGrid>
 __global__ void __launch_bounds__(256)
 k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ ivel,
             const float4* __restrict__ accel, const uint32_t* __restrict__ skey, const Face* __restrict__ faces,
-            uint32_t face_count, const GridState* __restrict__ grid, const SphConst c, BoundsAcc* next_bounds,
-            uint32_t* __restrict__ iters_tap) {
+            uint32_t face_count, const FaceGrid fg, const GridState* __restrict__ grid, const SphConst c,
+            BoundsAcc* next_bounds, uint32_t* __restrict__ iters_tap) {
   const GridState g = *grid;
   const uint32_t n = g.n;
   const bool sliced = g.own_lo > 0 || g.own_hi != 0x7fffffff;  // multi-GPU: ghosts are not advanced
@@ -97,26 +107,27 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
       collided = false;
       V3 hit_n = mk(0.f, 0.f, 0.f), hit_p = mk(0.f, 0.f, 0.f);
       float hit_depth = 0.f, hit_dist = 0.f;
-      for (uint32_t f = 0; f < face_count; ++f) {
+      uint32_t hit_face = 0;
+      auto test_face = [&](uint32_t f) {
         const float4* fr = reinterpret_cast<const float4*>(faces + f);
         const float4 f0 = __ldg(fr + 0), f1 = __ldg(fr + 1);
         const V3 n0 = mk(f0.x, f0.y, f0.z);
         const V3 a = mk(f1.x, f1.y, f1.z);
         const float nd = dot(n0, travel);
-        if (nd == 0.f) continue;  // :54-56 (the oriented denominator is +-nd)
+        if (nd == 0.f) return;  // :54-56 (the oriented denominator is +-nd)
         const float na = dot(n0, sub(a, x));
         // The plane parameter is r = (+-na) / (+-nd) = na / nd whatever the orientation, and a hit
         // needs 0 <= r <= 1 (:58-60). Two division-free rejections that can never drop such a face:
         // opposite signs with a quotient that cannot underflow to -0, and |na| beyond |nd| by more
         // than the half ulp that could still round the quotient down to 1. Nearly every face of a
         // scene leaves here: a sub-step moves a particle by millimetres.
-        if ((na < 0.f) != (nd < 0.f) && fabsf(na) > 1e-30f * fabsf(nd)) continue;
-        if (fabsf(na) > fabsf(nd) * 1.0000002f) continue;
+        if ((na < 0.f) != (nd < 0.f) && fabsf(na) > 1e-30f * fabsf(nd)) return;
+        if (fabsf(na) > fabsf(nd) * 1.0000002f) return;
         // :27-29 orient the normal along the travel direction
         const bool flip = __fdiv_rn(nd, __fmul_rn(f0.w, travel_len)) <= 0.f;
         const float denom = flip ? -nd : nd;  // dot(-n, d) == -dot(n, d) exactly
         const float r = __fdiv_rn(flip ? -na : na, denom);  // :58
-        if (!(0.f <= r && r <= 1.f)) continue;
+        if (!(0.f <= r && r <= 1.f)) return;
         const float4 f2 = __ldg(fr + 2), f3 = __ldg(fr + 3), f4 = __ldg(fr + 4);
         const V3 u = mk(f2.x, f2.y, f2.z), vv3 = mk(f3.x, f3.y, f3.z);
         const float uu = f2.w, vv = f3.w, uv = f1.w, det = f4.x;
@@ -127,13 +138,56 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
         const float t = __fdiv_rn(__fsub_rn(__fmul_rn(uv, wu), __fmul_rn(uu, wv)), det);  // :73
         if (s >= 0.f && t >= 0.f && __fadd_rn(s, t) <= 1.f) {
           const float dist = length(sub(x, hit));
-          if (collided && dist > hit_dist) continue;  // :77-80
+          if (collided && (dist > hit_dist || (dist == hit_dist && f < hit_face))) return;  // :77-80
           hit_n = flip ? neg(n0) : n0;
           hit_p = hit;
           hit_depth = length(sub(np, hit));
           hit_dist = dist;
+          hit_face = f;
           collided = true;
         }
+      };
+      // Face lists to visit: every face (one list, ids = 0 .. face_count-1), or the grid's global
+      // list followed by the list of each cell the segment's box overlaps.
+      int cx0 = 0, cy0 = 0, cz0 = 0, wx = 0, wy = 0;
+      int lists = -1;  // -1: every face
+      if (kGrid) {
+        // cells overlapped by the segment's box, widened by 1 % of a cell (the registration is widened too)
+        const float x0 = (fminf(x.x, np.x) - fg.ox) * fg.inv - 0.01f, x1 = (fmaxf(x.x, np.x) - fg.ox) * fg.inv + 0.01f;
+        const float y0 = (fminf(x.y, np.y) - fg.oy) * fg.inv - 0.01f, y1 = (fmaxf(x.y, np.y) - fg.oy) * fg.inv + 0.01f;
+        const float z0 = (fminf(x.z, np.z) - fg.oz) * fg.inv - 0.01f, z1 = (fmaxf(x.z, np.z) - fg.oz) * fg.inv + 0.01f;
+        // anything odd (NaN, a huge span) keeps the full scan
+        const bool finite = x0 <= x1 && y0 <= y1 && z0 <= z1 && fabsf(x0) < 1e9f && fabsf(x1) < 1e9f && fabsf(y0) < 1e9f &&
+                            fabsf(y1) < 1e9f && fabsf(z0) < 1e9f && fabsf(z1) < 1e9f;
+        if (finite) {
+          cx0 = max(0, (int)floorf(x0));
+          cy0 = max(0, (int)floorf(y0));
+          cz0 = max(0, (int)floorf(z0));
+          wx = min(fg.nx - 1, (int)floorf(x1)) - cx0 + 1;
+          wy = min(fg.ny - 1, (int)floorf(y1)) - cy0 + 1;
+          const int wz = min(fg.nz - 1, (int)floorf(z1)) - cz0 + 1;
+          // a box entirely outside the grid meets no registered face: only the global list remains
+          const long long cells = (wx <= 0 || wy <= 0 || wz <= 0) ? 0 : (long long)wx * wy * wz;
+          if (cells <= 64) lists = 1 + (int)cells;
+        }
+      }
+      for (int li = 0; li < (lists < 0 ? 1 : lists); ++li) {
+        const uint32_t* ids = nullptr;
+        uint32_t e = 0, e1 = face_count;
+        if (kGrid && lists >= 0) {
+          if (li == 0) {
+            ids = fg.global_ids;
+            e1 = fg.n_global;
+          } else {
+            const int k = li - 1;
+            const int cx = cx0 + k % wx, cy = cy0 + (k / wx) % wy, cz = cz0 + k / (wx * wy);
+            const uint32_t cell = ((uint32_t)cz * (uint32_t)fg.ny + (uint32_t)cy) * (uint32_t)fg.nx + (uint32_t)cx;
+            ids = fg.ids;
+            e = __ldg(fg.cell_start + cell);
+            e1 = __ldg(fg.cell_start + cell + 1);
+          }
+        }
+        for (; e < e1; ++e) test_face(ids ? __ldg(ids + e) : e);
       }
 
       // collisions.cl:91-128
@@ -189,12 +243,125 @@ void launch_prepare_faces(const float* normals, const float* vertices, const uin
 }
 
 void launch_integrate(const StateArrays& s, const float4* accel, const uint32_t* skey, const Face* faces,
-                      uint32_t face_count, const GridState* grid, const SphConst& c, BoundsAcc* next_bounds,
-                      uint32_t* iters_tap, uint32_t n_launch, int sm_count, cudaStream_t stream, uint64_t* launches) {
-  const unsigned blocks = std::min<unsigned>((n_launch + 255) / 256, (unsigned)sm_count * 8u);
-  k_integrate<<<std::max(1u, blocks), 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, grid, c,
-                                                        next_bounds, iters_tap);
+                      uint32_t face_count, const FaceGrid& face_grid, const GridState* grid, const SphConst& c,
+                      BoundsAcc* next_bounds, uint32_t* iters_tap, uint32_t n_launch, int sm_count, cudaStream_t stream,
+                      uint64_t* launches) {
+  const unsigned blocks = std::max(1u, std::min<unsigned>((n_launch + 255) / 256, (unsigned)sm_count * 8u));
+  if (face_grid.nx > 0 && face_count > 0)
+    k_integrate<true><<<blocks, 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, face_grid, grid, c,
+                                                  next_bounds, iters_tap);
+  else
+    k_integrate<false><<<blocks, 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, face_grid, grid, c,
+                                                   next_bounds, iters_tap);
   if (launches) ++*launches;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host: face grid construction (double precision, conservative).
+// ---------------------------------------------------------------------------------------------
+void build_face_grid(const float* vertices, const uint32_t* indices, uint32_t face_count, FaceGrid* out,
+                     std::vector<uint32_t>* cell_start, std::vector<uint32_t>* ids, std::vector<uint32_t>* global_ids) {
+  FaceGrid g{};
+  cell_start->clear();
+  ids->clear();
+  global_ids->clear();
+  struct Tri {
+    double lo[3], hi[3], v0[3], n[3], pad;
+  };
+  std::vector<Tri> tris;
+  std::vector<uint32_t> tri_face;
+  std::vector<double> extents;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (uint32_t f = 0; f < face_count; ++f) {
+    double v[3][3];
+    bool finite = true;
+    for (int k = 0; k < 3; ++k)
+      for (int a = 0; a < 3; ++a) {
+        v[k][a] = (double)vertices[3 * (size_t)indices[3 * f + k] + a];
+        finite = finite && std::isfinite(v[k][a]) && std::fabs(v[k][a]) < 1e9;
+      }
+    double u[3], w[3];
+    for (int a = 0; a < 3; ++a) { u[a] = v[1][a] - v[0][a]; w[a] = v[2][a] - v[0][a]; }
+    const double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], ww = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    const double uw = u[0] * w[0] + u[1] * w[1] + u[2] * w[2];
+    // conditioning of the barycentric solve (collisions.cl:71-73): sin^2 of the angle between the edges.
+    // Below 1e-3 the fp32 inside test could accept points visibly outside the triangle: such faces
+    // (and non-finite ones) are tested for every particle, exactly like the reference does.
+    const bool regular = finite && uu > 0.0 && ww > 0.0 && (uu * ww - uw * uw) >= 1e-3 * uu * ww;
+    if (!regular) {
+      global_ids->push_back(f);
+      continue;
+    }
+    Tri t;
+    double extent = 0.0;
+    for (int a = 0; a < 3; ++a) {
+      t.lo[a] = std::min(v[0][a], std::min(v[1][a], v[2][a]));
+      t.hi[a] = std::max(v[0][a], std::max(v[1][a], v[2][a]));
+      extent = std::max(extent, t.hi[a] - t.lo[a]);
+      t.v0[a] = v[0][a];
+    }
+    t.n[0] = u[1] * w[2] - u[2] * w[1];
+    t.n[1] = u[2] * w[0] - u[0] * w[2];
+    t.n[2] = u[0] * w[1] - u[1] * w[0];
+    // 2 % of the triangle's size + 0.1 mm: >= 100x the distance by which a point accepted by the
+    // fp32 inside test can lie outside a triangle this well conditioned
+    t.pad = 0.02 * extent + 1e-4;
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = std::min(lo[a], t.lo[a] - t.pad);
+      hi[a] = std::max(hi[a], t.hi[a] + t.pad);
+    }
+    tris.push_back(t);
+    tri_face.push_back(f);
+    extents.push_back(extent);
+  }
+  if (tris.empty()) {  // nothing to grid: nx = 0 selects the full scan
+    *out = g;
+    return;
+  }
+  std::vector<double> sorted = extents;
+  std::sort(sorted.begin(), sorted.end());
+  const double median = sorted[sorted.size() / 2];
+  const double span = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+  // cell side: about half a typical triangle, at most 64 and at least 4 cells along the longest axis
+  double cell = std::min(std::max(0.5 * median, span / 64.0), span / 4.0);
+  if (!(cell > 0.0)) cell = 1.0;
+  int dims[3];
+  for (int a = 0; a < 3; ++a) dims[a] = std::max(1, std::min(64, (int)std::ceil((hi[a] - lo[a]) / cell)));
+  const double inv = 1.0 / cell;
+  const size_t cells = (size_t)dims[0] * dims[1] * dims[2];
+  std::vector<std::vector<uint32_t>> lists(cells);
+  const double slack = 0.02;  // in cells: covers the device's fp32 cell arithmetic (it widens by 0.01 itself)
+  for (size_t k = 0; k < tris.size(); ++k) {
+    const Tri& t = tris[k];
+    int c0[3], c1[3];
+    for (int a = 0; a < 3; ++a) {
+      c0[a] = std::max(0, (int)std::floor((t.lo[a] - t.pad - lo[a]) * inv - slack));
+      c1[a] = std::min(dims[a] - 1, (int)std::floor((t.hi[a] + t.pad - lo[a]) * inv + slack));
+    }
+    const double nabs[3] = {std::fabs(t.n[0]), std::fabs(t.n[1]), std::fabs(t.n[2])};
+    const double half = 0.5 * cell + t.pad + slack * cell;
+    for (int cz = c0[2]; cz <= c1[2]; ++cz)
+      for (int cy = c0[1]; cy <= c1[1]; ++cy)
+        for (int cx = c0[0]; cx <= c1[0]; ++cx) {
+          // skip cells whose (widened) box lies entirely on one side of the triangle's plane
+          const double ctr[3] = {lo[0] + (cx + 0.5) * cell, lo[1] + (cy + 0.5) * cell, lo[2] + (cz + 0.5) * cell};
+          const double d = t.n[0] * (ctr[0] - t.v0[0]) + t.n[1] * (ctr[1] - t.v0[1]) + t.n[2] * (ctr[2] - t.v0[2]);
+          const double r = (nabs[0] + nabs[1] + nabs[2]) * half;
+          if (std::fabs(d) > r) continue;
+          lists[((size_t)cz * dims[1] + cy) * dims[0] + cx].push_back(tri_face[k]);  // k ascending => ids ascending
+        }
+  }
+  cell_start->resize(cells + 1);
+  for (size_t c = 0; c < cells; ++c) {
+    (*cell_start)[c] = (uint32_t)ids->size();
+    ids->insert(ids->end(), lists[c].begin(), lists[c].end());
+  }
+  (*cell_start)[cells] = (uint32_t)ids->size();
+  g.ox = (float)lo[0]; g.oy = (float)lo[1]; g.oz = (float)lo[2];
+  g.inv = (float)inv;
+  g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+  g.n_global = (uint32_t)global_ids->size();
+  *out = g;
 }
 
 }  // namespace clsph

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -35,6 +36,20 @@ struct Face {
   float ux, uy, uz, uu;     // edge v1 - v0, dot(u, u)
   float vx, vy, vz, vv;     // edge v2 - v0, dot(v, v)
   float det, pad0, pad1, pad2;  // uv*uv - uu*vv
+};
+
+// Uniform grid over the scene's triangles (integrate.cu, built on the host by build_face_grid):
+// a particle only tests the faces registered in the cells its sub-step segment touches. The
+// registration is conservative (padded boxes), so the faces that can pass the reference's hit test
+// are always among them and the result is bit-identical to testing every face.
+struct FaceGrid {
+  float ox, oy, oz;   // origin
+  float inv;          // cells per unit length
+  int nx, ny, nz;     // 0 cells: no grid, every face is tested
+  uint32_t n_global;  // faces tested for every particle (ill-conditioned or non-finite triangles)
+  const uint32_t* cell_start;  // [nx * ny * nz + 1] offsets into ids
+  const uint32_t* ids;         // face indices per cell, ascending
+  const uint32_t* global_ids;  // ascending
 };
 
 struct DebugTaps {           // all nullable; sorted order unless stated
@@ -124,7 +139,12 @@ void launch_scatter_words(const void* src, const uint32_t* rrank, void* dst, uin
 void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,
                           Face* faces, cudaStream_t stream, uint64_t* launches);
 void launch_integrate(const StateArrays& s, const float4* accel, const uint32_t* skey, const Face* faces,
-                      uint32_t face_count, const GridState* grid, const SphConst& c, BoundsAcc* next_bounds,
-                      uint32_t* iters_tap, uint32_t n_launch, int sm_count, cudaStream_t stream, uint64_t* launches);
+                      uint32_t face_count, const FaceGrid& face_grid, const GridState* grid, const SphConst& c,
+                      BoundsAcc* next_bounds, uint32_t* iters_tap, uint32_t n_launch, int sm_count, cudaStream_t stream,
+                      uint64_t* launches);
+// Host side: cell lists for the triangles (vertices 3V floats, indices 3F). Fills the three vectors
+// and the geometry of `out`; the caller uploads them and sets the pointers.
+void build_face_grid(const float* vertices, const uint32_t* indices, uint32_t face_count, FaceGrid* out,
+                     std::vector<uint32_t>* cell_start, std::vector<uint32_t>* ids, std::vector<uint32_t>* global_ids);
 
 }  // namespace clsph

@@ -174,3 +174,68 @@ def test_sub_cell_order_host_round_trip_and_option_rules(box_scene):
     ctx.simulate_single_frame(buf, p.copy(), terms, out=buf)
     ctx.close()
     assert buf.tobytes() == want.tobytes()
+
+
+# ---- face grid (integrate.cu): only the faces of the cells a segment touches are tested; bit-identical results
+
+def surface_state(scene, n, reach, speed, seed):
+    """Particles scattered within `reach` of random points on the scene's triangles, moving in random
+    directions at up to `speed`: many of them hit a face (or several) during one sub-step."""
+    rng = np.random.default_rng(seed)
+    v = scene.vertices.reshape(-1, 3)
+    t = scene.indices.reshape(-1, 3)
+    ok = np.isfinite(scene.face_normals.reshape(-1, 3)).all(axis=1)
+    f = rng.choice(np.nonzero(ok)[0], size=n)
+    a, b = rng.random(n), rng.random(n)
+    flip = a + b > 1
+    a[flip], b[flip] = 1 - a[flip], 1 - b[flip]
+    on = v[t[f, 0]] + a[:, None] * (v[t[f, 1]] - v[t[f, 0]]) + b[:, None] * (v[t[f, 2]] - v[t[f, 0]])
+    s = np.zeros(n, dtype=abi_particle())
+    s["position"][:, :3] = (on + rng.normal(0, reach, size=(n, 3))).astype(np.float32)
+    d = rng.normal(0, 1, size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    s["intermediate_velocity"][:, :3] = (d * rng.uniform(0, speed, size=(n, 1))).astype(np.float32)
+    s["velocity"] = s["intermediate_velocity"]
+    s["acceleration"][:, :3] = rng.normal(0, 10, size=(n, 3)).astype(np.float32)
+    return s
+
+
+def abi_particle():
+    from libclsph_b200 import abi
+    return abi.PARTICLE
+
+
+@pytest.mark.parametrize("scene_file", ["labyrinth.obj", "river.obj", "box.obj", "cone.obj", "shower.obj", "monkey.obj"])
+def test_face_grid_is_bit_identical_to_testing_every_face(scene_file):
+    scene = O.load_obj(os.path.join(H.ROOT, "scenes", scene_file))
+    p, terms, vol = H.config("water", 4096)
+    total_hits = 0
+    # short segments (a sub-step's millimetres), segments crossing a few grid cells, and segments so
+    # long that the kernel falls back to the full scan
+    for reach, speed, vmax, seed in [(0.002, 3.0, None, 1), (0.05, 80.0, 80.0, 2), (0.5, 3000.0, 3000.0, 3)]:
+        q = p.copy()
+        q.particles_count = 1500  # the oracle takes the count from the parameters
+        if vmax is not None:
+            q.max_velocity = vmax
+        s = surface_state(scene, q.particles_count, reach, speed, seed)
+        want, iters = O.advection_collision(s, q, scene)
+        for grid_on in (0, 1):
+            ctx = G.make_ctx(s.size, scene, q, terms, options=dict(face_grid=grid_on))
+            got = ctx.kernel_advection_collision(s)
+            got_iters = ctx.fetch(capi.TAP_COLLISION_ITERS)
+            ctx.close()
+            what = "%s reach %g grid %d" % (scene_file, reach, grid_on)
+            assert np.array_equal(got_iters, iters), what
+            for f in H.FIELDS_XYZ:
+                assert got[f].tobytes() == want[f].tobytes() or np.array_equal(got[f][:, :3], want[f][:, :3]), what + " " + f
+        total_hits += int((iters > 1).sum())
+    assert total_hits > 100, total_hits
+
+
+def test_face_grid_in_the_full_step(plane_scene):
+    scene = O.load_obj(os.path.join(H.ROOT, "scenes", "labyrinth.obj"))
+    p, terms, vol = H.config("mucus", 4096, mass=0.05 * 32000 / 4194304 * 256)
+    G.check_against_oracle(H.state_s1(p, vol), p, terms, scene, "labyrinth, face grid", options=dict(face_grid=1, sub_cell_order=1))
+    p, terms, vol = H.config("mucus", 1500)
+    G.check_resident_steps_against_oracle(H.drop_state(p, vol, scene_floor_y=-1.0), p, terms, plane_scene, 3,
+                                          "crowded, face grid", options=dict(face_grid=1))

@@ -1,0 +1,126 @@
+"""GPU parity tests of the paths added after the last GPU session of round 1 and so far exercised
+only on the CPU emulator (tests/emu/): the sub-cell order of the neighbour passes (subgrid.cu) and
+the face grid of the collision pass (integrate.cu). Same bar as tests/test_gpu_parity.py. The file
+sorts last on purpose: with `pytest -x` a failure here cannot hide the results of the established
+paths."""
+import os
+
+import numpy as np
+import pytest
+
+from libclsph_b200 import capi, workloads
+from oracle import oracle as O
+from tests import helpers as H
+from tests import test_gpu_parity as G
+
+pytestmark = pytest.mark.gpu
+
+SUB = dict(sub_cell_order=1)
+GRID = dict(face_grid=1)
+BOTH = dict(sub_cell_order=1, face_grid=1)
+
+
+@pytest.mark.parametrize("n", [128, 1000, 4096, 32000])
+def test_sub_cell_order_lattice(n, box_scene):
+    p, terms, vol = H.config("water", n)
+    G.check_against_oracle(H.state_s0(p, vol), p, terms, box_scene, "sub S0 n=%d" % n, options=SUB)
+
+
+@pytest.mark.parametrize("fluid,n", [("water", 4096), ("water", 102400), ("mucus", 20000), ("water", 12345)])
+def test_sub_cell_order_jittered(fluid, n, box_scene):
+    p, terms, vol = H.config(fluid, n)
+    G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "sub S1 %s n=%d" % (fluid, n), options=SUB)
+
+
+@pytest.mark.parametrize("options", [SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, list_rows=24), BOTH])
+def test_sub_cell_order_crowded_and_overflowing_lists(options, box_scene, plane_scene):
+    p, terms, vol = H.config("water", 20000)
+    G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
+    p, terms, vol = H.config("mucus", 6000)
+    G.check_against_oracle(H.drop_state(p, vol, scene_floor_y=-1.0), p, terms, plane_scene, "crowded %r" % (options,),
+                           options=options)
+
+
+def test_sub_cell_order_binary_search_fallback(box_scene):
+    p, terms, vol = H.config("water", 8192)
+    s = H.state_s1(p, vol)
+    dense, taps_d, _ = G.gpu_step_with_taps(s, p, terms, box_scene, options=SUB)
+    sparse, taps_s, _ = G.gpu_step_with_taps(s, p, terms, box_scene, cell_table_capacity=8, options=SUB)
+    for k in taps_d:
+        assert np.array_equal(taps_d[k], taps_s[k]), k
+    assert dense.tobytes() == sparse.tobytes()
+
+
+@pytest.mark.parametrize("options", [SUB, BOTH])
+def test_resident_steps_keep_the_reference_order(options, box_scene, plane_scene):
+    p, terms, vol = H.config("water", 20000)
+    s = H.state_s1(p, vol)
+    s["intermediate_velocity"][:, 0] += (2.5 * np.sign(s["position"][:, 2])).astype(np.float32)
+    G.check_resident_steps_against_oracle(s, p, terms, box_scene, 6, "water %r" % (options,), options=options)
+    p, terms, vol = H.config("mucus", 6000)
+    G.check_resident_steps_against_oracle(H.drop_state(p, vol, scene_floor_y=-1.0), p, terms, plane_scene, 4,
+                                          "crowded %r" % (options,), options=options)
+
+
+@pytest.mark.parametrize("scene_file", ["labyrinth.obj", "river.obj", "box.obj", "cone.obj", "shower.obj", "monkey.obj"])
+def test_face_grid_is_bit_identical_to_testing_every_face(scene_file):
+    from tests.test_emu_kernel_logic import surface_state
+    scene = O.load_obj(os.path.join(H.ROOT, "scenes", scene_file))
+    p, terms, vol = H.config("water", 4096)
+    for reach, speed, vmax, seed in [(0.002, 3.0, None, 1), (0.05, 80.0, 80.0, 2), (0.5, 3000.0, 3000.0, 3)]:
+        q = p.copy()
+        q.particles_count = 20000
+        if vmax is not None:
+            q.max_velocity = vmax
+        s = surface_state(scene, q.particles_count, reach, speed, seed)
+        want, iters = O.advection_collision(s, q, scene)
+        ctx = G.make_ctx(s.size, scene, q, terms, options=GRID)
+        got = ctx.kernel_advection_collision(s)
+        got_iters = ctx.fetch(capi.TAP_COLLISION_ITERS)
+        ctx.close()
+        assert np.array_equal(got_iters, iters), (scene_file, reach)
+        for f in H.FIELDS_XYZ:
+            assert np.array_equal(got[f][:, :3], want[f][:, :3]), (scene_file, reach, f)
+
+
+def test_labyrinth_full_step_with_both():
+    scene = O.load_obj(os.path.join(H.ROOT, "scenes", "labyrinth.obj"))
+    p, terms, vol = H.config("mucus", 16384, mass=0.05 * 32000 / 4194304 * 256)
+    G.check_against_oracle(H.state_s1(p, vol), p, terms, scene, "labyrinth, sub-cell order + face grid", options=BOTH)
+
+
+def test_one_million_particles_config2_sub_cell_order(box_scene):
+    p, terms, vol, _ = workloads.make_config("config2_dambreak_1m")
+    s = workloads.jittered_state(p, vol)
+    got, taps, want = G.check_against_oracle(s, p, terms, box_scene, "config 2, 1 Mi, sub-cell order + face grid", options=BOTH)
+    assert np.array_equal(np.sort(taps["permutation"]), np.arange(s.size, dtype=np.uint32))
+
+
+def test_organisations_agree_on_the_device_at_four_million():
+    """Config 3 size (4 Mi, mucus, labyrinth): the new paths against the established one, bit for bit
+    on every integer observable and the exported order, to rounding on the rest."""
+    p, terms, vol, scene_file = workloads.make_config("config3_mucus_labyrinth_4m")
+    normals, vertices, indices = workloads.scene_arrays(scene_file)
+    s = workloads.jittered_state(p, vol)
+    outs = []
+    for options in (dict(), BOTH):
+        ctx = capi.Context(s.size)
+        for k, v in options.items():
+            ctx.set_option(k, v)
+        ctx.set_scene(normals, vertices, indices)
+        ctx.set_parameters(p, terms)
+        ctx.set_debug(True)
+        ctx.upload(s)
+        ctx.step(1)
+        ctx.synchronize()
+        taps = {k: ctx.fetch(v) for k, v in dict(keys=capi.TAP_KEYS_INPUT, perm=capi.TAP_PERMUTATION, skeys=capi.TAP_SORTED_KEYS,
+                                                 table=capi.TAP_CELL_TABLE, cand=capi.TAP_CANDIDATE_COUNT,
+                                                 supp=capi.TAP_SUPPORT_COUNT, iters=capi.TAP_COLLISION_ITERS).items()}
+        outs.append((ctx.download(), taps, ctx.fetch(capi.TAP_ACCELERATION)))
+        ctx.close()
+    (a, ta, acc_a), (b, tb, acc_b) = outs
+    for k in ta:
+        assert np.array_equal(ta[k], tb[k]), k
+    assert np.array_equal(a["grid_index"], b["grid_index"])
+    assert H.rel_err(acc_b, acc_a) <= 1e-4
+    H.assert_close_fields(b, a, tol=1e-4, what="4 Mi, new paths vs established")
