@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=102400)
     ap.add_argument("--option", action="append", default=[], help="name=value passed to clsph_set_option (tuning)")
+    ap.add_argument("--organisation", default="auto", choices=["auto", "default", "candidate"],
+                    help="auto: adopt the candidate kernel organisation (sub-cell order + face grid) only if a subprocess "
+                         "self-check on this GPU finds it identical to the default one and faster; default / candidate: no check")
     return ap.parse_args()
 
 
@@ -206,6 +209,31 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
+CANDIDATE_OPTIONS = ["sub_cell_order=1", "face_grid=1"]
+
+
+def choose_organisation(args, local_rank, n_particles):
+    """(options, report). The candidate options select kernels that were written after the last GPU
+    session of round 1; they are adopted only when libclsph_b200.selfcheck, run in a SUBPROCESS on
+    this GPU, finds every integer observable identical to the default organisation's (which passed
+    the GPU parity suite against the oracle), the rest equal to rounding, and the step faster."""
+    if args.option or args.organisation == "default":
+        return list(args.option), {"mode": "as given" if args.option else "default"}
+    if args.organisation == "candidate":
+        return list(CANDIDATE_OPTIONS), {"mode": "candidate, unchecked"}
+    import subprocess
+    cmd = [sys.executable, "-m", "libclsph_b200.selfcheck", "--config", args.config, "--device", str(local_rank),
+           "--particles", str(min(n_particles, 1 << 22))] + [x for o in CANDIDATE_OPTIONS for x in ("--candidate", o)]
+    report = {"mode": "auto", "candidate": CANDIDATE_OPTIONS}
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        report.update(json.loads(lines[-1]) if lines else {"agree": False, "error": "no output, exit code %d: %s" % (r.returncode, r.stderr[-300:])})
+    except Exception as exc:  # a hang or crash of the candidate kernels must not take the benchmark down
+        report.update({"agree": False, "error": repr(exc)})
+    adopt = bool(report.get("agree")) and report.get("ms_per_step_candidate", 1e30) < report.get("ms_per_step_default", 0.0)
+    report["adopted"] = adopt
+    return (list(CANDIDATE_OPTIONS) if adopt else []), report
 def ctx_capacity(ctx, n):
     """Room for a rank's download: its own particles plus what may have migrated in."""
     return int(n * 1.5) + 65536
@@ -250,6 +278,16 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     fluid, n_cfg, mass, scene_file = workloads.CONFIGS[args.config]
     n_cfg = args.particles or n_cfg
+    # kernel organisation: decided once (rank 0), the same on every rank
+    if rank == 0:
+        options, organisation = choose_organisation(args, local_rank, n_cfg)
+    else:
+        options, organisation = [], {}
+    if dist is not None:
+        flag = torch.tensor([1 if options == CANDIDATE_OPTIONS else 0], dtype=torch.int32, device=device)
+        dist.broadcast(flag, 0)
+        if rank != 0:
+            options = list(CANDIDATE_OPTIONS) if int(flag.item()) else list(args.option)
     normals, vertices, indices = workloads.scene_arrays(scene_file)
     if world == 1:
         p, terms, vol, _, state = sample_workload(args)
@@ -270,7 +308,7 @@ def run_ours(args, rank, world, local_rank):
         layer = int(p.particles_count / per_side * (2.0 * p.h / float(spacing))) + 1
         emigrant_cap, ghost_cap = int(2.0 * layer) + 8192, int(4.0 * layer) + 8192
         ctx = capi.Context(int(1.2 * n) + 2 * layer + 2 * ghost_cap + 65536, device=local_rank)
-    for opt in args.option:
+    for opt in options:
         k, v = opt.split("=")
         ctx.set_option(k, int(v))
     ctx.set_scene(normals, vertices, indices)
@@ -392,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
                    "all-reduce, migration + two ghost cell layers per side in one NCCL send/recv group" % (world, world),
                    "l2": "per-step working set ~%d MB vs 126 MB L2, no flush: sub-steps form a dependent chain" % (n * 200 // (1 << 20)),
                    "grid": [grid.grid_size_x, grid.grid_size_y, grid.grid_size_z], "grid_cell_count": grid.grid_cell_count,
-                   "options": args.option},
+                   "options": options, "organisation": organisation},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

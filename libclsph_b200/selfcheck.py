@@ -1,0 +1,114 @@
+"""On-device cross-check and timing of two option sets of the CUDA library.
+
+    python -m libclsph_b200.selfcheck --config config2_dambreak_1m [--particles N] [--device D]
+                                      [--candidate sub_cell_order=1 --candidate face_grid=1]
+
+Runs the same state through the library twice -- once with the default options (the organisation
+that has passed the GPU parity suite against the oracle) and once with the candidate options --
+and compares everything observable: cell keys, sort permutation, sorted keys, cell table, candidate
+and support counts, collision loop trips and the exported array order must be IDENTICAL; densities,
+pressures, accelerations, positions and velocities must agree within 1e-5 relative (the two
+organisations add the same terms in a different order). Then it times both, device resident.
+Prints one JSON line; exit code 0 = the candidate agrees. bench.py runs this in a subprocess before
+it adopts the candidate options, so a fault in a new kernel can neither poison the benchmark
+process nor produce a number from wrong results. No CPU code takes part in the comparison.
+"""
+import argparse
+import json
+import sys
+import time
+
+import numpy as np
+
+from . import capi, workloads
+
+INT_TAPS = dict(keys=capi.TAP_KEYS_INPUT, permutation=capi.TAP_PERMUTATION, sorted_keys=capi.TAP_SORTED_KEYS,
+                cell_table=capi.TAP_CELL_TABLE, candidate_count=capi.TAP_CANDIDATE_COUNT,
+                support_count=capi.TAP_SUPPORT_COUNT, collision_iters=capi.TAP_COLLISION_ITERS)
+FLOAT_TOL = 1e-5
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = float(np.abs(b).max())
+    return float(np.abs(a - b).max() / (scale if scale > 0 else 1.0))
+
+
+def run(options, device, params, terms, scene, state, steps, timed_steps):
+    ctx = capi.Context(state.size, device=device)
+    for k, v in options.items():
+        ctx.set_option(k, v)
+    ctx.set_scene(*scene)
+    ctx.set_parameters(params, terms)
+    ctx.set_debug(True)
+    ctx.upload(state)
+    snaps = []
+    for _ in range(steps):
+        ctx.step(1)
+        ctx.synchronize()
+        taps = {k: ctx.fetch(v) for k, v in INT_TAPS.items()}
+        floats = dict(density=ctx.fetch(capi.TAP_DENSITY), pressure=ctx.fetch(capi.TAP_PRESSURE),
+                      acceleration=ctx.fetch(capi.TAP_ACCELERATION))
+        snaps.append((ctx.download(), taps, floats))
+    ms = None
+    if timed_steps > 0:
+        ctx.set_debug(False)
+        ctx.upload(state)
+        ctx.step(3)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        ctx.step(timed_steps)
+        ctx.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0) / timed_steps
+    ctx.close()
+    return snaps, ms
+
+
+def compare(base, cand):
+    """Worst relative difference of the float observables; raises AssertionError on any integer mismatch."""
+    worst = 0.0
+    for k, ((out_a, taps_a, fl_a), (out_b, taps_b, fl_b)) in enumerate(zip(base, cand)):
+        for name in INT_TAPS:
+            assert np.array_equal(taps_a[name], taps_b[name]), "sub-step %d: %s differs" % (k, name)
+        assert np.array_equal(out_a["grid_index"], out_b["grid_index"]), "sub-step %d: exported grid_index differs" % k
+        for name in fl_a:
+            worst = max(worst, rel(fl_b[name], fl_a[name]))
+        for name in ("position", "velocity", "intermediate_velocity"):
+            worst = max(worst, rel(out_b[name][:, :3], out_a[name][:, :3]))
+        if k == 0:
+            assert worst <= FLOAT_TOL, "sub-step 0: float observables differ by %.3e relative" % worst
+    return worst
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="config2_dambreak_1m")
+    ap.add_argument("--particles", type=int, default=0)
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--timed-steps", type=int, default=20)
+    ap.add_argument("--candidate", action="append", default=[], help="name=value option of the candidate set")
+    args = ap.parse_args(argv)
+    fluid, n, mass, scene_file = workloads.CONFIGS[args.config]
+    n = args.particles or n
+    params, terms, vol, _ = workloads.make_config(fluid=fluid, particles_count=n, particle_mass=mass)
+    state = workloads.jittered_state(params, vol)
+    scene = workloads.scene_arrays(scene_file)
+    cand_opts = dict((k, int(v)) for k, v in (o.split("=") for o in args.candidate)) or dict(sub_cell_order=1, face_grid=1)
+    result = {"config": args.config, "particles": n, "candidate": cand_opts, "agree": False}
+    try:
+        # One sub-step from identical inputs: integer observables must match exactly, the rest to
+        # rounding. (Later sub-steps start from states that already differ in the last bits, where a
+        # key may legitimately flip for a particle on a cell boundary.)
+        base, ms_base = run({}, args.device, params, terms, scene, state, 1, args.timed_steps)
+        cand, ms_cand = run(cand_opts, args.device, params, terms, scene, state, 1, args.timed_steps)
+        worst = compare(base, cand)
+        result.update(agree=True, max_rel_diff=worst, ms_per_step_default=ms_base, ms_per_step_candidate=ms_cand)
+    except BaseException as exc:  # noqa: BLE001 - reported to the caller as "does not agree"
+        result["error"] = "%s: %s" % (type(exc).__name__, exc)
+    print(json.dumps(result), flush=True)
+    return 0 if result["agree"] else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -55,3 +55,25 @@ def assert_close_fields(got, want, tol=1e-4, fields=FIELDS_XYZ + ("density", "pr
         w = want[f][:, :3] if want[f].ndim == 2 else want[f]
         e = rel_err(g, w)
         assert e <= tol, "%s %s: relative error %.3e > %.1e" % (what, f, e, tol)
+
+
+def surface_state(scene, n, reach, speed, seed):
+    """Particles scattered within `reach` of random points on the scene's triangles, moving in random
+    directions at up to `speed`: many of them hit a face (or several) during one sub-step."""
+    rng = np.random.default_rng(seed)
+    v = scene.vertices.reshape(-1, 3)
+    t = scene.indices.reshape(-1, 3)
+    ok = np.isfinite(scene.face_normals.reshape(-1, 3)).all(axis=1)
+    f = rng.choice(np.nonzero(ok)[0], size=n)
+    a, b = rng.random(n), rng.random(n)
+    flip = a + b > 1
+    a[flip], b[flip] = 1 - a[flip], 1 - b[flip]
+    on = v[t[f, 0]] + a[:, None] * (v[t[f, 1]] - v[t[f, 0]]) + b[:, None] * (v[t[f, 2]] - v[t[f, 0]])
+    s = np.zeros(n, dtype=abi.PARTICLE)
+    s["position"][:, :3] = (on + rng.normal(0, reach, size=(n, 3))).astype(np.float32)
+    d = rng.normal(0, 1, size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    s["intermediate_velocity"][:, :3] = (d * rng.uniform(0, speed, size=(n, 1))).astype(np.float32)
+    s["velocity"] = s["intermediate_velocity"]
+    s["acceleration"][:, :3] = rng.normal(0, 10, size=(n, 3)).astype(np.float32)
+    return s

@@ -54,3 +54,40 @@ def test_kernel_byte_table_matches_the_survey_total():
         # = 304 + 16 P; SURVEY 8(d) fuses force+integrate (104) and counts the cell table read (4): 256 + 16 P
         assert sum(kb.values()) == 304 + 16 * passes
         assert bench.step_bytes(passes) == 256 + 16 * passes
+
+
+def test_organisation_choice_adopts_the_candidate_only_after_a_clean_selfcheck(monkeypatch):
+    sys.path.insert(0, H.ROOT)
+    import subprocess as sp
+    import types
+    import bench
+
+    def fake(stdout, returncode=0, raises=None):
+        def run_(cmd, **kw):
+            assert "libclsph_b200.selfcheck" in cmd and "--candidate" in cmd
+            if raises:
+                raise raises
+            return types.SimpleNamespace(stdout=stdout, stderr="boom", returncode=returncode)
+        return run_
+
+    args = types.SimpleNamespace(option=[], organisation="auto", config="config2_dambreak_1m")
+    ok = json.dumps({"agree": True, "max_rel_diff": 1e-7, "ms_per_step_default": 0.9, "ms_per_step_candidate": 0.5})
+    monkeypatch.setattr(sp, "run", fake("NCCL noise\n" + ok + "\n"))
+    opts, rep = bench.choose_organisation(args, 0, 1 << 20)
+    assert opts == bench.CANDIDATE_OPTIONS and rep["adopted"] and rep["agree"]
+    slower = json.dumps({"agree": True, "max_rel_diff": 1e-7, "ms_per_step_default": 0.5, "ms_per_step_candidate": 0.9})
+    monkeypatch.setattr(sp, "run", fake(slower))
+    assert bench.choose_organisation(args, 0, 1 << 20)[0] == []
+    monkeypatch.setattr(sp, "run", fake(json.dumps({"agree": False, "error": "AssertionError: permutation differs"}), returncode=1))
+    opts, rep = bench.choose_organisation(args, 0, 1 << 20)
+    assert opts == [] and not rep["adopted"] and "permutation" in rep["error"]
+    monkeypatch.setattr(sp, "run", fake("", returncode=-11))   # the subprocess crashed
+    opts, rep = bench.choose_organisation(args, 0, 1 << 20)
+    assert opts == [] and not rep["adopted"] and "exit code -11" in rep["error"]
+    monkeypatch.setattr(sp, "run", fake("", raises=sp.TimeoutExpired("selfcheck", 600)))   # ... or hung
+    assert bench.choose_organisation(args, 0, 1 << 20)[0] == []
+    # explicit choices bypass the check
+    args.organisation = "default"
+    assert bench.choose_organisation(args, 0, 1 << 20)[0] == []
+    args.organisation, args.option = "auto", ["list_rows=48"]
+    assert bench.choose_organisation(args, 0, 1 << 20)[0] == ["list_rows=48"]

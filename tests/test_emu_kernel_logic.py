@@ -178,33 +178,6 @@ def test_sub_cell_order_host_round_trip_and_option_rules(box_scene):
 
 # ---- face grid (integrate.cu): only the faces of the cells a segment touches are tested; bit-identical results
 
-def surface_state(scene, n, reach, speed, seed):
-    """Particles scattered within `reach` of random points on the scene's triangles, moving in random
-    directions at up to `speed`: many of them hit a face (or several) during one sub-step."""
-    rng = np.random.default_rng(seed)
-    v = scene.vertices.reshape(-1, 3)
-    t = scene.indices.reshape(-1, 3)
-    ok = np.isfinite(scene.face_normals.reshape(-1, 3)).all(axis=1)
-    f = rng.choice(np.nonzero(ok)[0], size=n)
-    a, b = rng.random(n), rng.random(n)
-    flip = a + b > 1
-    a[flip], b[flip] = 1 - a[flip], 1 - b[flip]
-    on = v[t[f, 0]] + a[:, None] * (v[t[f, 1]] - v[t[f, 0]]) + b[:, None] * (v[t[f, 2]] - v[t[f, 0]])
-    s = np.zeros(n, dtype=abi_particle())
-    s["position"][:, :3] = (on + rng.normal(0, reach, size=(n, 3))).astype(np.float32)
-    d = rng.normal(0, 1, size=(n, 3))
-    d /= np.linalg.norm(d, axis=1)[:, None]
-    s["intermediate_velocity"][:, :3] = (d * rng.uniform(0, speed, size=(n, 1))).astype(np.float32)
-    s["velocity"] = s["intermediate_velocity"]
-    s["acceleration"][:, :3] = rng.normal(0, 10, size=(n, 3)).astype(np.float32)
-    return s
-
-
-def abi_particle():
-    from libclsph_b200 import abi
-    return abi.PARTICLE
-
-
 @pytest.mark.parametrize("scene_file", ["labyrinth.obj", "river.obj", "box.obj", "cone.obj", "shower.obj", "monkey.obj"])
 def test_face_grid_is_bit_identical_to_testing_every_face(scene_file):
     scene = O.load_obj(os.path.join(H.ROOT, "scenes", scene_file))
@@ -217,7 +190,7 @@ def test_face_grid_is_bit_identical_to_testing_every_face(scene_file):
         q.particles_count = 1500  # the oracle takes the count from the parameters
         if vmax is not None:
             q.max_velocity = vmax
-        s = surface_state(scene, q.particles_count, reach, speed, seed)
+        s = H.surface_state(scene, q.particles_count, reach, speed, seed)
         want, iters = O.advection_collision(s, q, scene)
         for grid_on in (0, 1):
             ctx = G.make_ctx(s.size, scene, q, terms, options=dict(face_grid=grid_on))
@@ -239,3 +212,15 @@ def test_face_grid_in_the_full_step(plane_scene):
     p, terms, vol = H.config("mucus", 1500)
     G.check_resident_steps_against_oracle(H.drop_state(p, vol, scene_floor_y=-1.0), p, terms, plane_scene, 3,
                                           "crowded, face grid", options=dict(face_grid=1))
+
+
+def test_selfcheck_module_finds_the_candidate_options_equivalent(capsys):
+    """libclsph_b200.selfcheck is what bench.py runs (in a subprocess, on the GPU) before adopting the
+    candidate options; here in-process against the emulator build."""
+    import json
+    from libclsph_b200 import selfcheck
+    for cfg, n in (("config1_box_100k", 3000), ("config3_mucus_labyrinth_4m", 4096)):
+        rc = selfcheck.main(["--config", cfg, "--particles", str(n), "--timed-steps", "2"])
+        line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+        assert rc == 0 and line["agree"] and line["max_rel_diff"] <= 1e-5, line
+        assert line["ms_per_step_default"] > 0 and line["ms_per_step_candidate"] > 0

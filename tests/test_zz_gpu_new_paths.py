@@ -64,7 +64,6 @@ def test_resident_steps_keep_the_reference_order(options, box_scene, plane_scene
 
 @pytest.mark.parametrize("scene_file", ["labyrinth.obj", "river.obj", "box.obj", "cone.obj", "shower.obj", "monkey.obj"])
 def test_face_grid_is_bit_identical_to_testing_every_face(scene_file):
-    from tests.test_emu_kernel_logic import surface_state
     scene = O.load_obj(os.path.join(H.ROOT, "scenes", scene_file))
     p, terms, vol = H.config("water", 4096)
     for reach, speed, vmax, seed in [(0.002, 3.0, None, 1), (0.05, 80.0, 80.0, 2), (0.5, 3000.0, 3000.0, 3)]:
@@ -72,7 +71,7 @@ def test_face_grid_is_bit_identical_to_testing_every_face(scene_file):
         q.particles_count = 20000
         if vmax is not None:
             q.max_velocity = vmax
-        s = surface_state(scene, q.particles_count, reach, speed, seed)
+        s = H.surface_state(scene, q.particles_count, reach, speed, seed)
         want, iters = O.advection_collision(s, q, scene)
         ctx = G.make_ctx(s.size, scene, q, terms, options=GRID)
         got = ctx.kernel_advection_collision(s)
