@@ -112,7 +112,18 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
  *                      and the force pass reads them; 0: both passes search on their own.
  *                      (Environment override at creation: CLSPH_NEIGHBOUR_LISTS=0/1.)
  *   "list_rows"        list entries kept per particle (0 = derive from the rest density);
- *                      particles with more neighbours fall back to the searching force kernel. */
+ *                      particles with more neighbours fall back to the searching force kernel.
+ *   "sub_cell_order"   1: keep the arrays in HBM sorted by (cell key << 3 | octant of the cell), so
+ *                      that each particle searches the ~27 sub-cells of side h around it (~130
+ *                      candidates) instead of the 27 cells of side 2h (~1000). The reference's array
+ *                      order is carried as a per-particle rank; downloads and taps are in the
+ *                      reference's order exactly as with 0 (default this round: 0).
+ *                      Needs a grid whose Morton cell count stays below 2^29 (z axis < 512 cells);
+ *                      set it before particles are uploaded. (Environment: CLSPH_SUB_CELL_ORDER.)
+ *   "face_grid"        1: the collision pass tests only the scene triangles registered in the grid
+ *                      cells a particle's sub-step segment touches (conservative registration:
+ *                      results are bit-identical to testing every triangle). Default 0 this round.
+ *                      (Environment: CLSPH_FACE_GRID.) */
 int clsph_set_option(clsph_context* ctx, const char* name, long long value);
 
 /* Host AoS (80-byte records) -> device SoA. n must be >= 128 (sort.cl:9-20, erratum E8) and

@@ -27,7 +27,7 @@ struct GridState {
   uint32_t sort_passes;              // ceil(bits(cell_count - 1) / 8), 1..4
   uint32_t dense;                    // 1: cell_count fits the dense table; 0: binary-search fallback
   uint32_t error;                    // bit 0: a grid axis reached 1024 cells; bit 1: a multi-GPU buffer overflowed;
-                                     // bit 2: sub-cell keys need more than 32 bits (an axis beyond 512 cells)
+                                     // bit 2: sub-cell keys need more than 32 bits (Morton cell count beyond 2^29: z axis of 512+ cells)
   // Slab decomposition (multi-GPU): this rank owns the cells with own_lo <= cx < own_hi. One GPU:
   // [0, INT_MAX). Particles of other cells held locally are ghost copies of a neighbour's.
   int own_lo, own_hi;

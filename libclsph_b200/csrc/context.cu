@@ -222,6 +222,12 @@ int check_device_flags(clsph_context* ctx) {
     return fail(ctx, CLSPH_EGRID, "grid overflow: %d x %d x %d cells, each axis must stay below 1024 "
                 "(10-bit Morton code; the reference asserts at sph_simulation.cpp:247-249)", g.gx, g.gy, g.gz);
   }
+  if (g.error & 4u) {
+    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(&ctx->grid->error, 0, sizeof(uint32_t), ctx->stream));
+    return fail(ctx, CLSPH_EGRID, "grid of %d x %d x %d cells is too large for the sub-cell order (its keys are the Morton cell key "
+                "plus three bits, in 32: the z axis must stay below 512 cells); set the option sub_cell_order to 0 for this domain",
+                g.gx, g.gy, g.gz);
+  }
   return CLSPH_OK;
 }
 

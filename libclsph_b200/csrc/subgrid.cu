@@ -81,7 +81,8 @@ __device__ __forceinline__ void store_if(bool ok, uint32_t* addr, uint32_t v) {
 #ifdef CLSPH_EMU  // tests/emu: CPU build of the kernels for logic tests, no PTX
   if (ok) *addr = v;
 #else
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)ok), "l"(addr), "r"(v)
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)ok),
+               "l"(__cvta_generic_to_global(addr)), "r"(v)
                : "memory");
 #endif
 }

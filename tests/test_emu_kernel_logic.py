@@ -224,3 +224,26 @@ def test_selfcheck_module_finds_the_candidate_options_equivalent(capsys):
         line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
         assert rc == 0 and line["agree"] and line["max_rel_diff"] <= 1e-5, line
         assert line["ms_per_step_default"] > 0 and line["ms_per_step_candidate"] > 0
+
+
+def test_sub_cell_order_reports_a_grid_too_large_for_its_keys(box_scene):
+    """With 512 to 1023 cells along z the reference still works but (Morton cell key << 3 | octant)
+    no longer fits 32 bits: CLSPH_EGRID with advice, and the context stays usable."""
+    p, terms, vol = H.config("water", 4096)
+    s = H.state_s0(p, vol)
+    far = s.copy()
+    far["position"][: s.size // 2, 2] += np.float32(700 * 2 * p.h)
+    for sub, expect_error in ((1, True), (0, False)):
+        ctx = G.make_ctx(s.size, box_scene, p, terms, debug=False, options=dict(sub_cell_order=sub))
+        ctx.upload(far)
+        ctx.step(1)
+        if expect_error:
+            with pytest.raises(capi.ClsphError) as e:
+                ctx.synchronize()
+            assert e.value.code == capi.E_GRID and "sub_cell_order" in str(e.value)
+        else:
+            ctx.synchronize()
+        ctx.upload(s)
+        ctx.step(1)
+        ctx.synchronize()
+        ctx.close()

@@ -50,7 +50,7 @@ def by_id(parts, ids, n):
     return out
 
 
-@pytest.mark.parametrize("world,copies,sub", [(2, 2, 0), (4, 4, 0), (3, 3, 1)])
+@pytest.mark.parametrize("world,copies,sub", [(2, 2, 0), (3, 3, 1)])
 def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
     steps = 3
     p, terms, state, scene_file = elongated_state(copies)
