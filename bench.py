@@ -239,6 +239,25 @@ def ctx_capacity(ctx, n):
     return int(n * 1.5) + 65536
 
 
+def multi_gpu_workload(config, n_per_gpu, rank, world):
+    """This rank's share of the weak-scaling workload: `world` x the configured count as ONE fluid block
+    (same particle mass, hence same h and spacing), cut into x slabs. Returns a dict with the parameters,
+    the rank's particles and ids, its slab planes and the capacities to create the context with."""
+    from libclsph_b200 import workloads
+    fluid, _, mass, _ = workloads.CONFIGS[config]
+    p, terms, vol, _ = workloads.make_config(fluid=fluid, particles_count=n_per_gpu * world, particle_mass=mass)
+    index, planes = workloads.slab_indices(p, vol, rank, world)
+    state = workloads.jittered_state(p, vol, index=index)
+    n = state.size
+    # one grid-cell layer of the block's cross-section: the unit of ghost traffic (two layers per side)
+    # and of bursty migration (a snapped slab boundary jumps by one cell now and then)
+    per_side, side, spacing = workloads.lattice_geometry(p, vol)
+    layer = int(p.particles_count / per_side * (2.0 * p.h / float(spacing))) + 1
+    emigrant_cap, ghost_cap = int(2.0 * layer) + 8192, int(4.0 * layer) + 8192
+    return dict(params=p, terms=terms, volume=vol, state=state, ids=index, planes=planes, emigrant_capacity=emigrant_cap,
+                ghost_capacity=ghost_cap, capacity=int(1.2 * n) + 2 * layer + 2 * ghost_cap + 65536)
+
+
 def run_ours(args, rank, world, local_rank):
     # stdout must carry exactly one JSON line: native libraries (NCCL's version banner) write to fd 1 too,
     # so everything goes to stderr until the line is ready
@@ -295,19 +314,12 @@ def run_ours(args, rank, world, local_rank):
         n = state.size
         ctx = capi.Context(n, device=local_rank)
     else:
-        # weak scaling: world x the configured count as ONE fluid block (same particle mass, hence same h
-        # and spacing), cut into x slabs; each rank generates only its own slab
-        p, terms, vol, _ = workloads.make_config(fluid=fluid, particles_count=n_cfg * world, particle_mass=mass)
-        index, planes = workloads.slab_indices(p, vol, rank, world)
-        state = workloads.jittered_state(p, vol, index=index)
-        ids = index
+        # weak scaling: each rank generates only its own slab of the common block
+        w = multi_gpu_workload(args.config, n_cfg, rank, world)
+        p, terms, vol, state, ids, planes = w["params"], w["terms"], w["volume"], w["state"], w["ids"], w["planes"]
+        emigrant_cap, ghost_cap = w["emigrant_capacity"], w["ghost_capacity"]
         n = state.size
-        # one grid-cell layer of the block's cross-section: the unit of ghost traffic (two layers per side)
-        # and of bursty migration (a snapped slab boundary jumps by one cell now and then)
-        per_side, side, spacing = workloads.lattice_geometry(p, vol)
-        layer = int(p.particles_count / per_side * (2.0 * p.h / float(spacing))) + 1
-        emigrant_cap, ghost_cap = int(2.0 * layer) + 8192, int(4.0 * layer) + 8192
-        ctx = capi.Context(int(1.2 * n) + 2 * layer + 2 * ghost_cap + 65536, device=local_rank)
+        ctx = capi.Context(w["capacity"], device=local_rank)
     for opt in options:
         k, v = opt.split("=")
         ctx.set_option(k, int(v))

@@ -129,3 +129,53 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
             w = wants[k][f][:, :3] if wants[k][f].ndim == 2 else wants[k][f]
             assert rel(g, w) <= (1e-4 if k == 0 else 2e-3), (k, f, rel(g, w))
     assert moved_total > 0, "the shear should have moved particles across a slab plane"
+
+
+def test_bench_multi_gpu_flow_with_its_own_capacities():
+    """bench.py's N>1 path, rank for rank (threads as ranks, emulator): the workload split, the
+    capacities it derives, resident stepping, then its end-to-end loop (upload + step + download per
+    sub-step). The first 8-GPU run of round 1 died on a buffer overflow; this keeps the formulas honest
+    at a scale the emulator can run. Total particle count must be conserved throughout."""
+    import sys
+    sys.path.insert(0, H.ROOT)
+    import bench
+    world, n_per_gpu = 2, 40000  # 80 k block: slabs ~6 cells thick (the protocol needs >= 4)
+    uid = capi.comm_unique_id()
+    normals, vertices, indices = workloads.scene_arrays("box.obj")
+    counts = [[None, None] for _ in range(world)]
+    errors = []
+    barrier = threading.Barrier(world)
+
+    def run_rank(rank):
+        try:
+            w = bench.multi_gpu_workload("config2_dambreak_1m", n_per_gpu, rank, world)
+            ctx = capi.Context(w["capacity"])
+            ctx.set_option("sub_cell_order", 1)
+            ctx.set_option("face_grid", 1)
+            ctx.set_scene(normals, vertices, indices)
+            ctx.set_parameters(w["params"], w["terms"])
+            ctx.dist_init(rank, world, uid, float(w["planes"][rank]), float(w["planes"][rank + 1]),
+                          emigrant_capacity=w["emigrant_capacity"], ghost_capacity=w["ghost_capacity"])
+            ctx.dist_upload(w["state"], w["ids"])
+            ctx.step(6)
+            ctx.synchronize()
+            counts[rank][0] = ctx.dist_count()
+            for _ in range(2):  # the e2e loop of bench.py
+                ctx.dist_upload(w["state"], w["ids"])
+                ctx.step(1)
+                parts, ids = ctx.dist_download()
+            counts[rank][1] = parts.size
+            barrier.wait(timeout=600)
+            ctx.close()
+        except BaseException as exc:  # noqa: BLE001
+            errors.append((rank, exc))
+            barrier.abort()
+
+    threads = [threading.Thread(target=run_rank, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=1200)
+    assert not errors, errors
+    assert sum(c[0] for c in counts) == world * n_per_gpu, counts
+    assert sum(c[1] for c in counts) == world * n_per_gpu, counts
