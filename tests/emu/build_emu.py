@@ -119,8 +119,14 @@ def _inputs():
 
 
 def build(force=False, verbose=False):
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(f) for f in _inputs()):
-        return LIB_PATH
+    """EMU_ASAN=1 in the environment builds libclsph_emu_asan.so instead: AddressSanitizer with plain
+    malloc'ed device memory, i.e. red zones around every device allocation (a memcheck of the kernels). Run as
+      EMU_ASAN=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 \
+          python -m pytest tests/test_emu_kernel_logic.py tests/test_emu_multi_rank.py"""
+    asan = os.environ.get("EMU_ASAN") == "1"
+    lib_path = LIB_PATH.replace(".so", "_asan.so") if asan else LIB_PATH
+    if not force and os.path.exists(lib_path) and os.path.getmtime(lib_path) >= max(os.path.getmtime(f) for f in _inputs()):
+        return lib_path
     gen = os.path.join(OUT, "gen")
     os.makedirs(gen, exist_ok=True)
     sources = []
@@ -138,6 +144,8 @@ def build(force=False, verbose=False):
     flags = ["-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-pthread",
              "-Wall", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unknown-pragmas", "-Wno-sign-compare",
              "-I" + HERE, "-I" + gen, "-I" + os.path.join(ROOT, "include")]
+    if asan:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer", "-DEMU_ASAN=1", "-O1"]
     try:
         with open("/proc/cpuinfo") as fh:
             if " fma " in fh.read():
@@ -146,7 +154,7 @@ def build(force=False, verbose=False):
         pass
     objs, procs = [], []
     for s in sources:
-        o = os.path.join(OUT, os.path.basename(s) + ".o")
+        o = os.path.join(OUT, os.path.basename(s) + (".asan.o" if asan else ".o"))
         objs.append(o)
         procs.append((s, subprocess.Popen(["g++", *flags, "-c", s, "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
@@ -157,8 +165,8 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("emulator build failed")
-    subprocess.run(["g++", "-shared", "-pthread", "-o", LIB_PATH, *objs, "-ldl"], check=True)
-    return LIB_PATH
+    subprocess.run(["g++", "-shared", "-pthread", *(["-fsanitize=address"] if asan else []), "-o", lib_path, *objs, "-ldl"], check=True)
+    return lib_path
 
 
 if __name__ == "__main__":

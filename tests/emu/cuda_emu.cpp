@@ -287,6 +287,19 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "error"); }
 
+#ifdef EMU_ASAN  // AddressSanitizer build: its red zones replace the guard page (both sides, and use after free)
+cudaError_t cudaMalloc(void** p, size_t bytes) {
+  void* m = nullptr;
+  if (posix_memalign(&m, 256, bytes ? bytes : 1) != 0) return cudaErrorMemoryAllocation;
+  std::memset(m, 0xA5, bytes);
+  *p = m;
+  return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+  free(p);
+  return cudaSuccess;
+}
+#else
 cudaError_t cudaMalloc(void** p, size_t bytes) {
   const size_t page = (size_t)sysconf(_SC_PAGESIZE);
   const size_t need = (bytes + 15) & ~(size_t)15;
@@ -320,6 +333,7 @@ cudaError_t cudaFree(void* p) {
   std::fprintf(stderr, "cuda_emu: cudaFree of a pointer cudaMalloc did not return\n");
   std::abort();
 }
+#endif
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) {
   std::memmove(dst, src, bytes);
   return cudaSuccess;
