@@ -212,9 +212,23 @@ void launch_raw(dim3 grid, dim3 block, size_t smem_bytes, void (*fn)(void*), voi
       t.uc.uc_link = &b.sched;
       makecontext(&t.uc, trampoline, 0);
     }
+    // EMU_SCHEDULE=reverse | random[:seed] runs the threads of a block in another order; results that
+    // depend on it point at a missing barrier (the default is ascending thread index)
+    static const char* schedule = std::getenv("EMU_SCHEDULE");
+    static thread_local uint64_t rng = 0;
+    if (rng == 0) rng = (schedule && std::strchr(schedule, ':')) ? std::strtoull(std::strchr(schedule, ':') + 1, nullptr, 10) * 2654435761u + 88172645463325252ull : 88172645463325252ull;
+    const bool reverse = schedule && !std::strncmp(schedule, "reverse", 7), shuffle = schedule && !std::strncmp(schedule, "random", 6);
+    std::vector<unsigned> order(nthreads);
+    for (unsigned i = 0; i < nthreads; ++i) order[i] = reverse ? nthreads - 1 - i : i;
     while (b.live > 0) {
       const uint64_t before = b.progress;
-      for (unsigned i = 0; i < nthreads; ++i) {
+      if (shuffle)
+        for (unsigned i = nthreads - 1; i > 0; --i) {
+          rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+          std::swap(order[i], order[rng % (i + 1)]);
+        }
+      for (unsigned k = 0; k < nthreads; ++k) {
+        const unsigned i = order[k];
         Thread& t = b.threads[i];
         if (t.done) continue;
         b.running = &t;
