@@ -182,7 +182,12 @@ int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_
 int clsph_dist_upload(clsph_context* ctx, const particle* aos, const uint32_t* ids, uint32_t n);
 
 /* Owned particles (no ghost copies) in local cell-sorted order with their ids. Pass NULL arrays
- * to query the count only. Synchronises. */
+ * to query the count only. Synchronises.
+ * With the option sub_cell_order the padding word of each record (byte offset 76) holds the
+ * particle's rank inside its cell in the REFERENCE's order: concatenating all ranks' downloads and
+ * sorting by (grid_index, that word) gives exactly the array a single device -- and the reference --
+ * would hold (ids passed to clsph_dist_upload must then be the indices of the initial global
+ * array). Without the option the word is 0 and only per-particle values can be compared. */
 int clsph_dist_download(clsph_context* ctx, particle* aos_out, uint32_t* ids_out, uint32_t capacity, uint32_t* n_out);
 
 /* ---- observation ----------------------------------------------------------------------- */

@@ -84,6 +84,11 @@ struct clsph_context {
   DistState dist{};
   uint32_t* pid[2] = {nullptr, nullptr};
   uint32_t* export_ids = nullptr;
+  // order keys across ranks (sub-cell order only): (cell key, rank in cell) of the previous sub-step,
+  // ping-pong like pid, and the rank in the cell after the current one
+  uint32_t* ordk[2] = {nullptr, nullptr};
+  uint32_t* ordr[2] = {nullptr, nullptr};
+  uint32_t* wrank = nullptr;
 
   DebugTaps taps{};
   uint32_t* ref_table = nullptr;
@@ -339,8 +344,9 @@ int enqueue_substep(clsph_context* ctx) {
   if (prof) next_event(ctx);
 
   if (multi) {
-    if (dist_exchange(&ctx->dist, ctx->state[ctx->cur], ctx->pid[ctx->cur], ctx->skey, ctx->grid, ctx->state[ctx->cur ^ 1],
-                      ctx->pid[ctx->cur ^ 1], ctx->capacity, st, lc))
+    if (dist_exchange(&ctx->dist, ctx->state[ctx->cur], ctx->pid[ctx->cur], ctx->skey, sub ? ctx->wrank : nullptr, ctx->grid,
+                      ctx->state[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], sub ? ctx->ordk[ctx->cur ^ 1] : nullptr,
+                      sub ? ctx->ordr[ctx->cur ^ 1] : nullptr, ctx->capacity, st, lc))
       return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
     ctx->cur ^= 1;  // the unsorted local array is the source of this step's sort
   }
@@ -358,11 +364,15 @@ int enqueue_substep(clsph_context* ctx) {
   if (sub) {
     launch_clear_sub(ctx->sub_lb, ctx->grid, ctx->sub_capacity, ctx->sm_count, st, lc);
     launch_reorder_sub(src, dst, ctx->sort, ctx->skey, multi ? nullptr : ctx->rrank, ctx->rr_tmp, ctx->sub_lb, ctx->grid,
-                       multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr, n, st, lc);
+                       multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr,
+                       multi ? ctx->ordk[ctx->cur] : nullptr, multi ? ctx->ordr[ctx->cur] : nullptr,
+                       multi ? ctx->ordk[ctx->cur ^ 1] : nullptr, multi ? ctx->ordr[ctx->cur ^ 1] : nullptr, n, st, lc);
     ctx->cur ^= 1;
-    if (!multi)  // across ranks the reference's global order is not tracked (multi-GPU)
+    if (!multi)  // one GPU: absolute index in the reference's array
       launch_rank(ctx->skey, ctx->rr_tmp, ctx->rrank, ctx->sub_lb, ctx->sort, ctx->grid, ctx->perm,
                   ctx->debug ? ctx->taps.keys_input : nullptr, n, st, lc);
+    else         // across ranks: (cell key, rank in cell), merged at export
+      launch_rank_pair(ctx->skey, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->wrank, ctx->sub_lb, ctx->sort, ctx->grid, n, st, lc);
     if (prof) next_event(ctx);
     launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
                        ctx->taps, ctx->debug, n, st, lc);
@@ -522,8 +532,12 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->taps.collision_iters);
   cudaFree(ctx->ref_table);
   dist_destroy(&ctx->dist);
-  cudaFree(ctx->pid[0]);
-  cudaFree(ctx->pid[1]);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(ctx->pid[s]);
+    cudaFree(ctx->ordk[s]);
+    cudaFree(ctx->ordr[s]);
+  }
+  cudaFree(ctx->wrank);
   cudaFree(ctx->export_ids);
   cudaFree(ctx->lists.entries);
   cudaFree(ctx->lists.count);
@@ -654,7 +668,12 @@ int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_
   if (dist_init(&ctx->dist, rank, world, unique_id, plane_lo, plane_hi, emigrant_capacity ? emigrant_capacity : ctx->capacity / 6 + 1024,
                 ghost_capacity ? ghost_capacity : ctx->capacity / 3 + 1024))
     return fail(ctx, CLSPH_ECOMM, "clsph_dist_init: %s", dist_last_error());
-  for (int s = 0; s < 2; ++s) CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pid[s], ctx->capacity));
+  for (int s = 0; s < 2; ++s) {
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pid[s], ctx->capacity));
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->ordk[s], ctx->capacity));
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->ordr[s], ctx->capacity));
+  }
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->wrank, ctx->capacity));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->export_ids, ctx->capacity));
   return CLSPH_OK;
 }
@@ -685,7 +704,8 @@ int clsph_dist_download(clsph_context* ctx, particle* aos_out, uint32_t* ids_out
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   uint32_t* count = ctx->dist.counters + 1;
-  launch_dist_export(ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->pid[ctx->cur], ctx->grid, ctx->aos_stage, ctx->export_ids,
+  launch_dist_export(ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->pid[ctx->cur], ctx->sub_order ? ctx->wrank : nullptr, ctx->grid,
+                     ctx->aos_stage, ctx->export_ids,
                      count, ctx->capacity, st, &ctx->launches);
   uint32_t n = 0;
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&n, count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -110,10 +110,11 @@ const char* dist_last_error() { return g_nccl_error; }
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ ivel,
-                const uint32_t* __restrict__ pid, const uint32_t* __restrict__ skey, GridState* grid,
-                float4* __restrict__ u_pos, float4* __restrict__ u_vel, float4* __restrict__ u_ivel,
-                uint32_t* __restrict__ u_pid, uint32_t* __restrict__ u_count, uint32_t capacity, void* send_left,
-                void* send_right, uint32_t emax, uint32_t gmax) {
+                const uint32_t* __restrict__ pid, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ wrank,
+                GridState* grid, float4* __restrict__ u_pos, float4* __restrict__ u_vel, float4* __restrict__ u_ivel,
+                uint32_t* __restrict__ u_pid, uint32_t* __restrict__ u_ordk, uint32_t* __restrict__ u_ordr,
+                uint32_t* __restrict__ u_count, uint32_t capacity, void* send_left, void* send_right, uint32_t emax,
+                uint32_t gmax) {
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if ((i & ~31u) >= g.n) return;  // whole warp out of range
@@ -124,10 +125,18 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   }
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, iv = p;
   uint32_t id = 0;
+  // Order key (sub-cell order only, wrank != null): where the particle stands in the reference's GLOBAL
+  // array = (its cell key, its rank inside that cell) of the previous sub-step, compared
+  // lexicographically; right after an upload (0, id): ids are the indices of the uploaded global array.
+  uint32_t ok_k = 0, ok_r = 0;
   int cx = 0;
   if (owned) {
     p = pos[i]; v = vel[i]; iv = ivel[i]; id = pid[i];
     cx = (int)cell_coord(p.x, g.min_x, g.cell);
+    if (wrank) {
+      ok_k = g.fresh ? 0u : skey[i];
+      ok_r = g.fresh ? id : wrank[i];
+    }
   }
   const bool has_left = g.own_lo > 0, has_right = g.own_hi != 0x7fffffff;
   const bool go_left = owned && has_left && cx < g.own_lo;
@@ -139,20 +148,22 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   // local array: stayers as owned, emigrants as ghost copies (their new key marks them as such)
   const uint32_t at = warp_append(owned, u_count);
   if (owned) {
-    if (at < capacity) { u_pos[at] = p; u_vel[at] = v; u_ivel[at] = iv; u_pid[at] = id; }
-    else atomicOr(&grid->error, 2u);
+    if (at < capacity) {
+      u_pos[at] = p; u_vel[at] = v; u_ivel[at] = iv; u_pid[at] = id;
+      if (u_ordk) { u_ordk[at] = ok_k; u_ordr[at] = ok_r; }
+    } else atomicOr(&grid->error, 2u);
   }
   MsgHeader* hl = static_cast<MsgHeader*>(send_left);
   MsgHeader* hr = static_cast<MsgHeader*>(send_right);
   uint32_t e;
   e = warp_append(go_left, &hl->n_emigrants);
   if (go_left) {
-    if (e < emax) { float4* r = msg_emigrants(send_left) + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), 0.f, 0.f, 0.f); }
+    if (e < emax) { float4* r = msg_emigrants(send_left) + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f); }
     else atomicOr(&grid->error, 2u);
   }
   e = warp_append(go_right, &hr->n_emigrants);
   if (go_right) {
-    if (e < emax) { float4* r = msg_emigrants(send_right) + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), 0.f, 0.f, 0.f); }
+    if (e < emax) { float4* r = msg_emigrants(send_right) + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f); }
     else atomicOr(&grid->error, 2u);
   }
   e = warp_append(ghost_left, &hl->n_ghosts);
@@ -172,7 +183,8 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
 __global__ void __launch_bounds__(256)
 k_dist_unpack(void* msg, uint32_t emax, uint32_t gmax, GridState* grid, float4* __restrict__ u_pos,
               float4* __restrict__ u_vel, float4* __restrict__ u_ivel, uint32_t* __restrict__ u_pid,
-              uint32_t* __restrict__ u_count, uint32_t capacity) {
+              uint32_t* __restrict__ u_ordk, uint32_t* __restrict__ u_ordr, uint32_t* __restrict__ u_count,
+              uint32_t capacity) {
   const MsgHeader h = *static_cast<const MsgHeader*>(msg);
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t ne = min(h.n_emigrants, emax), ng = min(h.n_ghosts, gmax);
@@ -180,17 +192,21 @@ k_dist_unpack(void* msg, uint32_t emax, uint32_t gmax, GridState* grid, float4* 
   const bool is_g = t >= emax && t - emax < ng;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, iv = p;
   uint32_t id = 0xFFFFFFFFu;  // ghosts carry no identity here
+  uint32_t ok_k = 0xFFFFFFFFu, ok_r = 0u;  // ... and no place in the reference's order
   if (is_e) {
     const float4* r = msg_emigrants(msg) + (size_t)t * 4;
     p = r[0]; v = r[1]; iv = r[2]; id = __float_as_uint(r[3].x);
+    ok_k = __float_as_uint(r[3].y); ok_r = __float_as_uint(r[3].z);
   } else if (is_g) {
     const float4* r = msg_ghosts(msg, emax) + (size_t)(t - emax) * 2;
     p = r[0]; v = r[1];
   }
   const uint32_t at = warp_append(is_e || is_g, u_count);
   if (is_e || is_g) {
-    if (at < capacity) { u_pos[at] = p; u_vel[at] = v; u_ivel[at] = iv; u_pid[at] = id; }
-    else atomicOr(&grid->error, 2u);
+    if (at < capacity) {
+      u_pos[at] = p; u_vel[at] = v; u_ivel[at] = iv; u_pid[at] = id;
+      if (u_ordk) { u_ordk[at] = ok_k; u_ordr[at] = ok_r; }
+    } else atomicOr(&grid->error, 2u);
   }
 }
 
@@ -205,8 +221,8 @@ __global__ void k_dist_finish(GridState* grid, const uint32_t* u_count, uint32_t
 __global__ void __launch_bounds__(256)
 k_dist_export(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ ivel,
               const float4* __restrict__ aux, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ pid,
-              const GridState* __restrict__ grid, float4* __restrict__ aos, uint32_t* __restrict__ ids,
-              uint32_t* __restrict__ out_count) {
+              const uint32_t* __restrict__ wrank, const GridState* __restrict__ grid, float4* __restrict__ aos,
+              uint32_t* __restrict__ ids, uint32_t* __restrict__ out_count) {
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if ((i & ~31u) >= g.n) return;
@@ -219,7 +235,8 @@ k_dist_export(const float4* __restrict__ pos, const float4* __restrict__ vel, co
   float4* rec = aos + (size_t)at * 5;
   rec[0] = p; rec[1] = v; rec[2] = iv;
   rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-  rec[4] = make_float4(a.x, a.y, __uint_as_float(skey[i]), 0.f);
+  // padding word: rank inside the cell in the reference's order (0 when not tracked), see clsph_dist_download
+  rec[4] = make_float4(a.x, a.y, __uint_as_float(skey[i]), __uint_as_float((wrank && !g.fresh) ? wrank[i] : 0u));
   ids[at] = pid[i];
 }
 
@@ -289,16 +306,18 @@ int dist_allreduce_bounds(DistState* d, BoundsAcc* acc, cudaStream_t stream) {
   return ok ? 0 : 1;
 }
 
-int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pid, const uint32_t* skey, GridState* grid,
-                  const StateArrays& u, uint32_t* u_pid, uint32_t capacity, cudaStream_t stream, uint64_t* launches) {
+int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pid, const uint32_t* skey,
+                  const uint32_t* wrank, GridState* grid, const StateArrays& u, uint32_t* u_pid, uint32_t* u_ordk,
+                  uint32_t* u_ordr, uint32_t capacity, cudaStream_t stream, uint64_t* launches) {
   ncclComm_t comm = static_cast<ncclComm_t>(d->comm);
   uint32_t* u_count = d->counters;
   cudaMemsetAsync(u_count, 0, sizeof(uint32_t), stream);
   cudaMemsetAsync(d->send[0], 0, 16, stream);
   cudaMemsetAsync(d->send[1], 0, 16, stream);
   const unsigned blocks = (capacity + 255) / 256;
-  k_dist_classify<<<blocks, 256, 0, stream>>>(prev.pos, prev.vel, prev.ivel, prev_pid, skey, grid, u.pos, u.vel, u.ivel,
-                                              u_pid, u_count, capacity, d->send[0], d->send[1], d->emax, d->gmax);
+  k_dist_classify<<<blocks, 256, 0, stream>>>(prev.pos, prev.vel, prev.ivel, prev_pid, skey, wrank, grid, u.pos, u.vel, u.ivel,
+                                              u_pid, u_ordk, u_ordr, u_count, capacity, d->send[0], d->send[1], d->emax,
+                                              d->gmax);
   const bool has_left = d->rank > 0, has_right = d->rank + 1 < d->world;
   if (!nccl_check(nccl().GroupStart(), "ncclGroupStart")) return 1;
   bool ok = true;
@@ -313,20 +332,22 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
   if (!nccl_check(nccl().GroupEnd(), "ncclGroupEnd") || !ok) return 1;
   const unsigned ublocks = (d->emax + d->gmax + 255) / 256;
   if (has_left)
-    k_dist_unpack<<<ublocks, 256, 0, stream>>>(d->recv[0], d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_count, capacity);
+    k_dist_unpack<<<ublocks, 256, 0, stream>>>(d->recv[0], d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk, u_ordr,
+                                               u_count, capacity);
   if (has_right)
-    k_dist_unpack<<<ublocks, 256, 0, stream>>>(d->recv[1], d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_count, capacity);
+    k_dist_unpack<<<ublocks, 256, 0, stream>>>(d->recv[1], d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk, u_ordr,
+                                               u_count, capacity);
   k_dist_finish<<<1, 32, 0, stream>>>(grid, u_count, capacity);
   if (launches) *launches += 2 + (has_left ? 1 : 0) + (has_right ? 1 : 0);
   return 0;
 }
 
 void launch_dist_export(const StateArrays& s, const float4* aux, const uint32_t* skey, const uint32_t* pid,
-                        const GridState* grid, void* aos, uint32_t* ids, uint32_t* out_count, uint32_t capacity,
-                        cudaStream_t stream, uint64_t* launches) {
+                        const uint32_t* wrank, const GridState* grid, void* aos, uint32_t* ids, uint32_t* out_count,
+                        uint32_t capacity, cudaStream_t stream, uint64_t* launches) {
   cudaMemsetAsync(out_count, 0, sizeof(uint32_t), stream);
-  k_dist_export<<<(capacity + 255) / 256, 256, 0, stream>>>(s.pos, s.vel, s.ivel, aux, skey, pid, grid, (float4*)aos, ids,
-                                                            out_count);
+  k_dist_export<<<(capacity + 255) / 256, 256, 0, stream>>>(s.pos, s.vel, s.ivel, aux, skey, pid, wrank, grid, (float4*)aos,
+                                                            ids, out_count);
   if (launches) ++*launches;
 }
 

@@ -26,11 +26,13 @@ int dist_init(DistState* d, int rank, int world, const void* id_bytes, float pla
 void dist_destroy(DistState* d);
 int dist_allreduce_bounds(DistState* d, BoundsAcc* acc, cudaStream_t stream);
 // prev (sorted by last step's keys, owned + ghosts) -> u (unsorted: owned + new ghosts); sets grid->n.
-int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pid, const uint32_t* skey, GridState* grid,
-                  const StateArrays& u, uint32_t* u_pid, uint32_t capacity, cudaStream_t stream, uint64_t* launches);
+// wrank / u_ordk / u_ordr (all null or all set): order keys of the sub-cell order, see k_dist_classify.
+int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pid, const uint32_t* skey,
+                  const uint32_t* wrank, GridState* grid, const StateArrays& u, uint32_t* u_pid, uint32_t* u_ordk,
+                  uint32_t* u_ordr, uint32_t capacity, cudaStream_t stream, uint64_t* launches);
 void launch_dist_export(const StateArrays& s, const float4* aux, const uint32_t* skey, const uint32_t* pid,
-                        const GridState* grid, void* aos, uint32_t* ids, uint32_t* out_count, uint32_t capacity,
-                        cudaStream_t stream, uint64_t* launches);
+                        const uint32_t* wrank, const GridState* grid, void* aos, uint32_t* ids, uint32_t* out_count,
+                        uint32_t capacity, cudaStream_t stream, uint64_t* launches);
 void launch_fill_ids(uint32_t* pid, const uint32_t* src, uint32_t first, uint32_t n, cudaStream_t stream,
                      uint64_t* launches);
 

@@ -142,7 +142,8 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
               const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const uint32_t* __restrict__ vals_a,
               const uint32_t* __restrict__ vals_b, uint32_t* __restrict__ skey, const uint32_t* __restrict__ rr_src,
               uint32_t* __restrict__ rr_dst, uint32_t* __restrict__ sub_lb, const GridState* __restrict__ grid,
-              const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid) {
+              const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid, const uint32_t* __restrict__ src_ordk,
+              const uint32_t* __restrict__ src_ordr, uint32_t* __restrict__ dst_ordk, uint32_t* __restrict__ dst_ordr) {
   const uint32_t n = grid->n;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -158,6 +159,10 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
   skey[r] = key;
   if (rr_src) rr_dst[r] = rr_src[from];
   if (src_pid) dst_pid[r] = src_pid[from];
+  if (src_ordk) {  // multi-GPU: order keys (cell key and rank inside the cell of the previous sub-step)
+    dst_ordk[r] = src_ordk[from];
+    dst_ordr[r] = src_ordr[from];
+  }
   if (!grid->sub_dense) return;
   const uint32_t count = grid->cell_count;  // keys are < count whenever the grid fits (see k_reorder)
   uint32_t* row = sub_lb + (size_t)key * 9u;
@@ -201,6 +206,35 @@ k_rank(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rr_old, u
   rr_new[i] = rank;
   perm_out[rank] = mine;
   if (keys_input_tap) keys_input_tap[mine] = key;
+}
+
+// Multi-GPU form of k_rank. Across ranks an absolute index in the reference's global array would need
+// a global scan every sub-step; the position is kept instead as the pair (cell key, rank inside the
+// cell), which orders particles exactly like the global index does (cell starts grow with the key). A
+// cell is owned by one rank and all its particles are there, so the rank inside the cell is a local
+// count over the previous pairs, compared lexicographically. The global array, when wanted, is the
+// merge of the ranks' downloads by (grid_index, rank in cell): clsph_dist_download.
+__global__ void __launch_bounds__(kSubThreads)
+k_rank_pair(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ordk, const uint32_t* __restrict__ ordr,
+            uint32_t* __restrict__ wrank, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
+            const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid) {
+  const GridState g = *grid;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const uint32_t key = skey[i];
+  if (!cell_is_owned(key, g)) {  // ghost copies have no place in this rank's part of the order
+    wrank[i] = 0u;
+    return;
+  }
+  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const uint2 cell = sub_range(v, key, 0u, 7u);
+  const uint32_t mk = ordk[i], mr = ordr[i];
+  uint32_t before = 0;
+  for (uint32_t j = cell.x; j < cell.y; ++j) {
+    const uint32_t jk = __ldg(ordk + j), jr = __ldg(ordr + j);
+    before += (jk < mk || (jk == mk && jr < mr)) ? 1u : 0u;
+  }
+  wrank[i] = before;
 }
 
 // =============================================================================================
@@ -294,11 +328,12 @@ void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capa
 
 void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                         const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
-                        const uint32_t* src_pid, uint32_t* dst_pid, uint32_t n_launch, cudaStream_t stream,
+                        const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,
+                        uint32_t* dst_ordk, uint32_t* dst_ordr, uint32_t n_launch, cudaStream_t stream,
                         uint64_t* launches) {
   k_reorder_sub<<<(n_launch + 255) / 256, 256, 0, stream>>>(src.pos, src.vel, src.ivel, dst.pos, dst.vel, dst.ivel, sort.keys_a,
                                                             sort.keys_b, sort.vals_a, sort.vals_b, skey, rr_src, rr_dst, sub_lb,
-                                                            grid, src_pid, dst_pid);
+                                                            grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr);
   if (launches) ++*launches;
 }
 
@@ -307,6 +342,14 @@ void launch_rank(const uint32_t* skey, const uint32_t* rr_old, uint32_t* rr_new,
                  uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
   k_rank<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(skey, rr_old, rr_new, sub_lb, sort.keys_a,
                                                                                  sort.keys_b, grid, perm_out, keys_input_tap);
+  if (launches) ++*launches;
+}
+
+void launch_rank_pair(const uint32_t* skey, const uint32_t* ordk, const uint32_t* ordr, uint32_t* wrank,
+                      const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, uint32_t n_launch,
+                      cudaStream_t stream, uint64_t* launches) {
+  k_rank_pair<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(skey, ordk, ordr, wrank, sub_lb,
+                                                                                      sort.keys_a, sort.keys_b, grid);
   if (launches) ++*launches;
 }
 

@@ -1,6 +1,9 @@
 """Multi-GPU worker, launched by tests/test_multi_gpu.py (or by hand) under torchrun:
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_worker.py [n] [steps]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_worker.py [n] [steps] [--sub]
+
+--sub selects the sub-cell order (+ face grid) and additionally checks that the ranks' downloads, merged by
+(grid_index, padding word), reproduce the single-GPU run's array ORDER exactly.
 
 Every rank runs one slab of the same fluid block through the CUDA library (clsph_dist_*); rank 0
 also runs the whole block on its own GPU without decomposition and, for the first sub-step, on the
@@ -46,8 +49,10 @@ def rel(a, b):
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    sub = "--sub" in sys.argv
+    n = int(argv[0]) if len(argv) > 0 else 60000
+    steps = int(argv[1]) if len(argv) > 1 else 3
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -74,6 +79,9 @@ def main():
 
     cap = int(n * (1.0 / world + 0.5)) + 4096  # owned + two ghost layers per side with slack
     ctx = capi.Context(cap, device=local)
+    if sub:
+        ctx.set_option("sub_cell_order", 1)
+        ctx.set_option("face_grid", 1)
     ctx.set_scene(normals, vertices, indices)
     ctx.set_parameters(p, terms)
     ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
@@ -82,6 +90,9 @@ def main():
     single = None
     if rank == 0:
         single = capi.Context(n, device=local)
+        if sub:
+            single.set_option("sub_cell_order", 1)
+            single.set_option("face_grid", 1)
         single.set_scene(normals, vertices, indices)
         single.set_parameters(p, terms)
         single.upload(state)
@@ -105,6 +116,11 @@ def main():
             by_id_want = np.empty(n, dtype=abi.PARTICLE)
             by_id_want[ref_ids] = want
             same_keys = np.array_equal(by_id_got["grid_index"], by_id_want["grid_index"])
+            if sub and (same_keys or k == 0):
+                merged = np.lexsort((got["_pad"], got["grid_index"]))
+                same_order = np.array_equal(ids[merged], ref_ids)
+                print("step %d: merged global order equals the single-GPU array order: %s" % (k, same_order), flush=True)
+                ok = ok and same_order
             errs = {f: rel(by_id_got[f][:, :3] if by_id_got[f].ndim == 2 else by_id_got[f],
                            by_id_want[f][:, :3] if by_id_want[f].ndim == 2 else by_id_want[f])
                     for f in ("position", "velocity", "intermediate_velocity", "density", "pressure")}

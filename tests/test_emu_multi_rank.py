@@ -93,12 +93,13 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
     single.set_scene(normals, vertices, indices)
     single.set_parameters(p, terms)
     single.upload(state)
-    wants, ref_ids = [], np.arange(n, dtype=np.uint32)
+    wants, orders, ref_ids = [], [], np.arange(n, dtype=np.uint32)
     for k in range(steps):
         single.step(1)
         want = single.download()
         ref_ids = ref_ids[single.fetch(capi.TAP_PERMUTATION)]
         wants.append(by_id(want, ref_ids, n))
+        orders.append(ref_ids.copy())  # id of the particle at each position of the reference's array
     single.close()
     scene = O.Scene(vertices, indices, normals)
     r0 = O.step(state, p.copy(), terms, scene)
@@ -117,6 +118,11 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
         holder = np.empty(n, dtype=np.int64)
         holder[ids] = np.concatenate([np.full(results[r][k][1].size, r) for r in range(world)])
         moved_total = int((holder != owner).sum())
+        if sub:
+            # the reference's GLOBAL array order: merge the ranks' downloads by (grid_index, rank in cell),
+            # the latter carried in the records' padding word (clsph_dist_download)
+            order = np.lexsort((parts["_pad"], parts["grid_index"]))
+            assert np.array_equal(ids[order], orders[k]), "step %d: merged order differs from the single-rank array order" % k
         if k == 0:
             assert np.array_equal(got["grid_index"], wants[0]["grid_index"]), "keys differ from the single-rank run"
             assert np.array_equal(got["grid_index"], oracle_by_id["grid_index"]), "keys differ from the oracle"

@@ -123,3 +123,18 @@ def test_organisations_agree_on_the_device_at_four_million():
     assert np.array_equal(a["grid_index"], b["grid_index"])
     assert H.rel_err(acc_b, acc_a) <= 1e-4
     H.assert_close_fields(b, a, tol=1e-4, what="4 Mi, new paths vs established")
+
+
+@pytest.mark.parametrize("world,n", [(2, 60000), (4, 120000)])
+def test_slab_decomposition_in_sub_cell_order_reproduces_the_global_array_order(world, n):
+    import subprocess
+    import sys
+    if capi.load_library().clsph_device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), os.path.join(H.ROOT, "tests", "dist_worker.py"),
+           str(n), "4", "--sub"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=H.ROOT)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    assert r.returncode == 0 and "DIST_OK" in r.stdout
