@@ -1,5 +1,6 @@
 /* houdini_file_saver.h -- per-frame ASCII Houdini .geo writer (same public surface as the
- * reference's libclsph/file_save_delegates/houdini_file_saver.h:8-20). */
+ * reference's libclsph/file_save_delegates/houdini_file_saver.h:8-20, plus `asynchronous` and
+ * wait()). */
 #ifndef CLSPH_HOUDINI_FILE_SAVER_H_
 #define CLSPH_HOUDINI_FILE_SAVER_H_
 
@@ -9,17 +10,28 @@
 
 class houdini_file_saver {
  public:
-  houdini_file_saver(std::string frames_folder_prefix)
-      : frames_folder_prefix(frames_folder_prefix), frame_count(0) {}
+  houdini_file_saver(std::string frames_folder_prefix);
+  houdini_file_saver(const houdini_file_saver& other);            /* copies settings, not pending frames */
+  houdini_file_saver& operator=(const houdini_file_saver& other);
+  ~houdini_file_saver();                                          /* waits for pending frames */
 
   /* Writes <prefix>frames/frameNNNNNNN.geo ("PGEOMETRY V5": position, v, colour ramp from the
-   * density, mass) and returns 0; prints to stderr if the file cannot be opened. */
+   * density, mass), byte for byte what the reference writes, and returns 0; prints to stderr if
+   * the file cannot be opened. With `asynchronous` (default) the call only copies what the frame
+   * needs and returns; formatting (all host cores) and the write happen on a background thread,
+   * at most two frames in flight. */
   int writeFrameToFile(particle* particles, const simulation_parameters& parameters);
 
+  /* Blocks until every frame handed to writeFrameToFile is on disk. */
+  void wait();
+
   std::string frames_folder_prefix;
+  bool asynchronous;
 
  private:
+  struct writer;
   int frame_count;
+  writer* writer_;
 };
 
 #endif

@@ -128,3 +128,38 @@ def test_clsphparticles_cli_writes_frames_and_checkpoint(tmp_path):
     open(ckpt, "ab").write(b"x")  # wrong size -> refuses to run
     r = run()
     assert "incorrect size" in r.stdout
+
+
+def test_geo_numbers_match_printf_g_on_adversarial_values(tmp_path):
+    """The frame writer formats with std::to_chars on worker threads; every number must still read
+    exactly like the reference's iostream output (printf %g): checked against Python's %g over
+    magnitudes from denormal to huge, signed zeros and non-finite values, on enough particles to
+    use several formatting threads."""
+    rng = np.random.default_rng(5)
+    n = 40000
+    s = np.zeros(n, dtype=abi.PARTICLE)
+    mag = (10.0 ** rng.uniform(-44, 38, size=(n, 6))) * rng.choice([-1.0, 1.0], size=(n, 6))
+    with np.errstate(over="ignore"):
+        vals = mag.astype(np.float32)
+    vals[0] = [0.0, -0.0, np.inf, -np.inf, 1e-45, 3.4028235e38]
+    vals[1] = [100000.0, 1000000.0, 999999.5, 0.0001, 0.00001, 123456.5]
+    vals[2, 0] = np.nan
+    s["position"][:, :3] = vals[:, :3]
+    s["velocity"][:, :3] = vals[:, 3:]
+    s["density"] = rng.uniform(-100, 2500, n).astype(np.float32)
+    p, terms, vol = H.config("water", n)
+    os.makedirs(tmp_path / "frames")
+    hostapi.write_frames(str(tmp_path) + "/", s, p, frames=1)
+    lines = open(tmp_path / "frames" / "frame0000001.geo").read().split("\n")
+    first = lines.index("mass 1 float 1") + 1
+    g = lambda x: "%g" % float(x)
+    for i in list(range(64)) + list(rng.integers(0, n, 3000)):
+        rho = np.float32(s["density"][i])
+        one, k, half = np.float32(1), np.float32(1000), np.float32(500)
+        r = (rho - k) / k if k < rho <= 2 * k else np.float32(0)
+        gr = one - rho / k if 0 <= rho < k else np.float32(0)
+        b = (rho - half) / half if half <= rho <= k else (one - (rho - k) / half if k <= rho <= k + half else np.float32(0))
+        want = "%s %s %s 0 (%s %s %s\t%s %s %s\t%s)" % (g(vals[i, 0]), g(vals[i, 1]), g(vals[i, 2]), g(vals[i, 3]), g(vals[i, 4]),
+                                                      g(vals[i, 5]), g(r), g(gr), g(b), g(np.float32(p.particle_mass)))
+        assert lines[first + i] == want, (i, lines[first + i], want)
+    assert lines[first + n + 3].startswith("Part %d 0 1 2 3" % n) and lines[first + n + 3].endswith(" %d [0\t0]" % (n - 1))
