@@ -7,7 +7,7 @@ Runs the same state through the library twice -- once with the default options (
 that has passed the GPU parity suite against the oracle) and once with the candidate options --
 and compares everything observable: cell keys, sort permutation, sorted keys, cell table, candidate
 and support counts, collision loop trips and the exported array order must be IDENTICAL; densities,
-pressures, accelerations, positions and velocities must agree within 1e-5 relative (the two
+pressures, accelerations, positions and velocities must agree within 5e-5 relative (the two
 organisations add the same terms in a different order). Then it times both, device resident.
 Prints one JSON line; exit code 0 = the candidate agrees. bench.py runs this in a subprocess before
 it adopts the candidate options, so a fault in a new kernel can neither poison the benchmark
@@ -25,7 +25,7 @@ from . import capi, workloads
 INT_TAPS = dict(keys=capi.TAP_KEYS_INPUT, permutation=capi.TAP_PERMUTATION, sorted_keys=capi.TAP_SORTED_KEYS,
                 cell_table=capi.TAP_CELL_TABLE, candidate_count=capi.TAP_CANDIDATE_COUNT,
                 support_count=capi.TAP_SUPPORT_COUNT, collision_iters=capi.TAP_COLLISION_ITERS)
-FLOAT_TOL = 1e-5
+FLOAT_TOL = 5e-5  # half the 1e-4 parity bar; a wrong kernel is off by orders of magnitude, summation order by ~1e-6
 
 
 def rel(a, b):
