@@ -77,3 +77,59 @@ def surface_state(scene, n, reach, speed, seed):
     s["velocity"] = s["intermediate_velocity"]
     s["acceleration"][:, :3] = rng.normal(0, 10, size=(n, 3)).astype(np.float32)
     return s
+
+
+def edge_state(kind, p, vol, seed=3):
+    """Small states built to sit on the decisions of the path rather than around them.
+
+    coincident   a quarter of the particles share their position exactly with another one:
+                 spiky_gradient's |r| < 1e-7 branch (erratum E3), r = 0 in every kernel
+    on_support   pairs placed at distance h (1 +- a few ulp) along an axis and along a diagonal:
+                 the window test floor(r/h) < 1 at its threshold
+    on_cells     positions snapped to multiples of the cell side and of h: cell / sub-cell coordinates
+                 exactly at their boundaries, right after the AABB padding
+    one_cell     the whole fluid inside a single grid cell (a ball of radius 0.6 h): one huge cell, every
+                 list overflows
+    sparse       spacing of 3 h: every particle alone in its support
+    """
+    rng = np.random.default_rng(seed)
+    s = workloads.jittered_state(p, vol, seed=seed)
+    n = s.size
+    h = np.float32(p.h)
+    if kind == "coincident":
+        src = rng.integers(0, n, n // 4)
+        dst = rng.permutation(n)[: n // 4]
+        s["position"][dst] = s["position"][src]
+    elif kind == "on_support":
+        half = n // 2
+        base = s["position"][:half, :3].copy()
+        ulps = rng.integers(-3, 4, half)
+        d = np.nextafter(h, np.float32(np.inf)) if False else h
+        dist = (d * (np.float32(1) + ulps.astype(np.float32) * np.float32(2.0 ** -23))).astype(np.float32)
+        direction = np.zeros((half, 3), dtype=np.float32)
+        axis = rng.integers(0, 4, half)
+        for a in range(3):
+            direction[axis == a, a] = 1
+        direction[axis == 3] = np.float32(1 / np.sqrt(3))
+        s["position"][half:2 * half, :3] = base + direction * dist[:, None]
+    elif kind == "on_cells":
+        cell = np.float32(2) * h
+        q = np.round(s["position"][:, :3] / h).astype(np.float32)
+        s["position"][:, :3] = np.where(rng.random((n, 3)) < 0.5, q * h, np.round(q / 2) * cell)
+    elif kind == "one_cell":
+        d = rng.normal(0, 1, (n, 3))
+        d /= np.linalg.norm(d, axis=1)[:, None]
+        s["position"][:, :3] = (d * (rng.random((n, 1)) ** (1 / 3)) * 0.6 * float(h)).astype(np.float32)
+        s["position"][:, 1] += np.float32(0.5)
+    elif kind == "sparse":
+        per_side = int(np.ceil(n ** (1 / 3)))
+        i = np.arange(n)
+        s["position"][:, 0] = (i % per_side) * 3 * h
+        s["position"][:, 1] = ((i // per_side) % per_side) * 3 * h
+        s["position"][:, 2] = (i // (per_side * per_side)) * 3 * h
+    else:
+        raise ValueError(kind)
+    return s
+
+
+EDGE_KINDS = ("coincident", "on_support", "on_cells", "one_cell", "sparse")

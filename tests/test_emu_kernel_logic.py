@@ -247,3 +247,13 @@ def test_sub_cell_order_reports_a_grid_too_large_for_its_keys(box_scene):
         ctx.step(1)
         ctx.synchronize()
         ctx.close()
+
+
+@pytest.mark.parametrize("kind", H.EDGE_KINDS)
+@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1)])
+def test_edge_states(kind, options, box_scene):
+    """States sitting ON the path's decisions (tests/helpers.edge_state; the oracle is pinned against the
+    reference's own kernels on the same states in test_oracle_vs_ref.py), in every organisation."""
+    p, terms, vol = H.config("water", 1024)
+    s = H.edge_state(kind, p, vol)
+    G.check_against_oracle(s, p, terms, box_scene, "%s %r" % (kind, options), options=options)

@@ -35,6 +35,25 @@ def test_simulate_matches_oracle_bit_for_bit(fluid, n, scene_name, steps):
     assert H.struct_bytes(po) == H.struct_bytes(p_after)
 
 
+@pytest.mark.parametrize("kind", H.EDGE_KINDS)
+def test_edge_states_match_bit_for_bit(kind):
+    """States that sit ON the decisions of the path (coincident particles and erratum E3, pairs at
+    distance h, positions on cell boundaries, one crowded cell, isolated particles): the oracle must
+    follow the reference's own kernels there too."""
+    p, terms, vol, _ = workloads.make_config(fluid="water", particles_count=1024, particle_mass=0.05)
+    nrm, v, i = R.scene_load(H.ROOT, "box.obj")
+    scene = O.Scene(v, i, nrm)
+    s = H.edge_state(kind, p, vol)
+    states, p_after, _ = R.simulate(p, terms, vol, scene, initial=s, substeps=2, record_all=True)
+    po = p.copy()
+    cur = s
+    for k in range(2):
+        cur = O.step(cur, po, terms, scene, taps=False).particles
+        for f in EXACT_FIELDS:
+            assert np.array_equal(cur[f], states[k][f], equal_nan=True), (kind, k, f)
+    assert H.struct_bytes(po) == H.struct_bytes(p_after)
+
+
 def test_default_lattice_of_init_particles_matches():
     """Without last_frame.bin the reference places its own lattice (sph_simulation.cpp:71-92)."""
     p, terms, vol, _ = workloads.make_config(fluid="water", particles_count=1000)

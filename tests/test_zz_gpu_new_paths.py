@@ -138,3 +138,15 @@ def test_slab_decomposition_in_sub_cell_order_reproduces_the_global_array_order(
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0 and "DIST_OK" in r.stdout
+
+
+@pytest.mark.parametrize("kind", H.EDGE_KINDS)
+@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), BOTH])
+def test_edge_states(kind, options, box_scene):
+    """States sitting ON the path's decisions (coincident particles / erratum E3, pairs at distance h,
+    positions on cell and sub-cell boundaries, the whole fluid in one cell, isolated particles), in every
+    organisation. The oracle is pinned against the reference's own kernels on the same kind of states
+    (tests/test_oracle_vs_ref.py)."""
+    p, terms, vol = H.config("water", 4096)
+    s = H.edge_state(kind, p, vol)
+    G.check_against_oracle(s, p, terms, box_scene, "%s %r" % (kind, options), options=options)
