@@ -57,6 +57,7 @@ struct SphConst {
   float dt;                    // time_delta * simulation_scale
   float vmax, restitution;
   float spiky_degenerate;      // -45 / (pi h^6) as smoothing.cl:24 evaluates it (erratum E3)
+  float degenerate_s;          // smallest s = |d|^2 with sqrt(s) >= 1e-7: smoothing.cl:23's test on s (add_pair_fast)
 };
 
 __host__ __device__ inline uint32_t float_to_ordered(float f) {

@@ -145,6 +145,21 @@ float support_threshold(float h) {
   return s;
 }
 
+// Smallest s with sqrtf(s) >= 1e-7f: smoothing.cl:23's `length(r) < 0.0000001f` as a test on s.
+float degenerate_threshold() {
+  uint32_t lo = 0u, hi = 0x7f800000u;
+  while (hi - lo > 1u) {
+    const uint32_t mid = lo + (hi - lo) / 2u;
+    float s;
+    std::memcpy(&s, &mid, 4);
+    volatile float r = sqrtf(s);
+    if (r >= 0.0000001f) hi = mid; else lo = mid;
+  }
+  float s;
+  std::memcpy(&s, &hi, 4);
+  return s;
+}
+
 void derive_constants(clsph_context* ctx) {
   const simulation_parameters& p = ctx->params;
   const precomputed_kernel_values& t = ctx->terms;
@@ -176,6 +191,7 @@ void derive_constants(clsph_context* ctx) {
   volatile float h6 = p.h;  // pown(h, 6) by sequential fp32 multiplies, smoothing.cl:24
   for (int k = 1; k < 6; ++k) h6 = h6 * p.h;
   c.spiky_degenerate = -45.f / (float)(3.14159265358979323846 * (double)h6);
+  c.degenerate_s = degenerate_threshold();
 }
 
 cudaEvent_t next_event(clsph_context* ctx) {

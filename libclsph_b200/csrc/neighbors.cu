@@ -607,6 +607,8 @@ k_density_lists(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
 // The warp first copies its 32 rows, 32 entries at a time, into a shared-memory tile with
 // coalesced 128-byte reads; each lane then walks its own row.
 // =============================================================================================
+// kFast: pair terms through add_pair_fast (sub-cell organisation).
+template <bool kFast>
 __global__ void __launch_bounds__(kFlWarps * 32, 3)
 k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
                const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
@@ -649,12 +651,12 @@ k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, c
     for (; e + 2 <= mine; e += 2) {  // two neighbours per trip: four independent gathers in flight
       const uint32_t ja = row[e], jb = row[e + 1];
       const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb];
-      add_pair(sums, c, ja == i, pi, vi, pi.w, pa, va);
-      add_pair(sums, c, jb == i, pi, vi, pi.w, pb, vb);
+      add_pair_sel<kFast>(sums, c, ja == i, pi, vi, pi.w, pa, va);
+      add_pair_sel<kFast>(sums, c, jb == i, pi, vi, pi.w, pb, vb);
     }
     if (e < mine) {
       const uint32_t j = row[e];
-      add_pair(sums, c, j == i, pi, vi, pi.w, pos[j], vel[j]);
+      add_pair_sel<kFast>(sums, c, j == i, pi, vi, pi.w, pos[j], vel[j]);
     }
     __syncwarp();
   }
@@ -706,8 +708,13 @@ void launch_forces(const float4* pos, const float4* vel, const float4* aux, cons
                    cudaStream_t stream, uint64_t* launches) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
   if (lists.rows) {
-    k_forces_lists<<<(n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32), kFlWarps * 32, 0, stream>>>(
-        pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
+    if (search_fallback)
+      k_forces_lists<false><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
+                                                                  grid, c, accel);
+    else  // sub-cell organisation
+      k_forces_lists<true><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
+                                                                 grid, c, accel);
     if (launches) ++*launches;
     if (search_fallback) {
       // particles with more neighbours than list rows: redone with the searching kernel (exits at once elsewhere)

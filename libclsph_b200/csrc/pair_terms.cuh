@@ -43,6 +43,45 @@ __device__ __forceinline__ void add_pair(ForceSums& f, const SphConst& c, bool i
   f.lap = fmaf(mass_over_rho, c.c_poly6_lap * t * (3.f * c.h2 - 7.f * r * r), f.lap);  // smoothing.cl:12-17
 }
 
+// The same contribution with one MUFU.RSQ in place of the IEEE square root and the IEEE divide
+// (about 20 of add_pair's ~80 instructions): r = s rsqrt(s) and 1/r = rsqrt(s) are good to ~2 ulp and
+// h^2 - r^2 is taken as h^2 - s, all far inside the 1e-4 bar these sums are held to. The one discrete
+// decision, smoothing.cl:23's |r| < 1e-7, is kept exact as s < degenerate_s (smallest s whose rounded
+// square root reaches 1e-7; sqrt is monotone). Used by the sub-cell organisation only; the established
+// kernels keep add_pair.
+__device__ __forceinline__ void add_pair_fast(ForceSums& f, const SphConst& c, bool is_self, const float4& pi,
+                                              const float4& vi, float a_i, const float4& pj, const float4& vj) {
+  const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+  const float s = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const float inv_r = rsqrtf(s);             // +inf at s = 0 (self, coincident particles): not used there
+  const float r = s > 0.f ? s * inv_r : 0.f;
+  const float mass_over_rho = vj.w;
+  if (!is_self) {
+    float gx, gy, gz;
+    if (s < c.degenerate_s) {
+      gx = gy = gz = c.spiky_degenerate;
+    } else {
+      const float hr = c.h - r;
+      const float k = c.c_spiky * hr * hr * inv_r;
+      gx = k * dx; gy = k * dy; gz = k * dz;
+    }
+    const float pc = (pj.w + a_i) * c.mass;
+    f.px = fmaf(pc, gx, f.px); f.py = fmaf(pc, gy, f.py); f.pz = fmaf(pc, gz, f.pz);
+    const float vc = mass_over_rho * (c.c_visc * (c.h - r));
+    f.wx = fmaf(vj.x - vi.x, vc, f.wx); f.wy = fmaf(vj.y - vi.y, vc, f.wy); f.wz = fmaf(vj.z - vi.z, vc, f.wz);
+  }
+  const float t = c.h2 - s;
+  const float gc = mass_over_rho * (c.c_poly6_grad * t * t);
+  f.nx = fmaf(gc, dx, f.nx); f.ny = fmaf(gc, dy, f.ny); f.nz = fmaf(gc, dz, f.nz);
+  f.lap = fmaf(mass_over_rho, c.c_poly6_lap * t * (3.f * c.h2 - 7.f * s), f.lap);
+}
+template <bool kFast>
+__device__ __forceinline__ void add_pair_sel(ForceSums& f, const SphConst& c, bool is_self, const float4& pi,
+                                             const float4& vi, float a_i, const float4& pj, const float4& vj) {
+  if (kFast) add_pair_fast(f, c, is_self, pi, vi, a_i, pj, vj);
+  else add_pair(f, c, is_self, pi, vi, a_i, pj, vj);
+}
+
 // forces.cl:103-109 and sph.cl:53-58: F = -rho P + mu V (+ surface tension), a = F / rho + g.
 __device__ __forceinline__ float4 finish_force(const ForceSums& f, const SphConst& c, float rho) {
   float fx = -rho * f.px + f.wx * c.mu, fy = -rho * f.py + f.wy * c.mu, fz = -rho * f.pz + f.wz * c.mu;

@@ -129,6 +129,7 @@ inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }  // MUFU.RSQ on the GPU (2 ulp)
 inline unsigned __float2uint_rz(float f) {  // cvt.rzi.u32.f32 saturates; NaN -> 0
   if (!(f > 0.f)) return 0u;
   if (f >= 4294967296.f) return 0xffffffffu;
