@@ -129,10 +129,11 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   // array = (its cell key, its rank inside that cell) of the previous sub-step, compared
   // lexicographically; right after an upload (0, id): ids are the indices of the uploaded global array.
   uint32_t ok_k = 0, ok_r = 0;
-  int cx = 0;
+  int cx = 0, fx = 0;
   if (owned) {
     p = pos[i]; v = vel[i]; iv = ivel[i]; id = pid[i];
     cx = (int)cell_coord(p.x, g.min_x, g.cell);
+    fx = (int)sub_coord(p.x, g.min_x, g.cell);
     if (wrank) {
       ok_k = g.fresh ? 0u : skey[i];
       ok_r = g.fresh ? id : wrank[i];
@@ -142,8 +143,12 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   const bool go_left = owned && has_left && cx < g.own_lo;
   const bool go_right = owned && has_right && cx >= g.own_hi;
   const bool stay = owned && !go_left && !go_right;
-  const bool ghost_left = stay && has_left && cx < g.own_lo + 2;
-  const bool ghost_right = stay && has_right && cx >= g.own_hi - 2;
+  // Ghost depth. The neighbour needs, beyond its boundary, the particles within h (candidates of its own
+  // particles) whose densities it recomputes, hence those within 2h. The established kernels work on whole
+  // cells of side 2h, which makes that two cell layers; the sub-cell order searches by sub-cells of side
+  // h, so two SUB-cell layers (one cell layer) are enough: half the ghost volume.
+  const bool ghost_left = stay && has_left && (g.sub ? fx < 2 * g.own_lo + 2 : cx < g.own_lo + 2);
+  const bool ghost_right = stay && has_right && (g.sub ? fx >= 2 * g.own_hi - 2 : cx >= g.own_hi - 2);
 
   // local array: stayers as owned, emigrants as ghost copies (their new key marks them as such)
   const uint32_t at = warp_append(owned, u_count);

@@ -251,9 +251,14 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
-  const uint32_t key = skey[i];
-  if (!cell_needs_density(key, g)) return;  // multi-GPU: outer ghost layer, candidates only
   const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const uint32_t key = skey[i];
+  if (g.own_lo > 0 || g.own_hi != 0x7fffffff) {
+    // multi-GPU: owned sub-cells and ONE ghost sub-cell layer (side h) on either side get a density; the
+    // outer ghost sub-layer only supplies candidates (see the ghost depth in k_dist_classify)
+    const long long fx = 2ll * (long long)compact10(key) + (long long)(__ldg(v.fkeys + i) & 1u);
+    if (fx < 2ll * g.own_lo - 1 || fx > 2ll * g.own_hi) return;
+  }
   const float4 pi = pos[i];
   uint32_t* row = nlist + (size_t)i * list_rows;
 #ifndef CLSPH_EMU
