@@ -53,8 +53,9 @@ __device__ __forceinline__ void add_pair_fast(ForceSums& f, const SphConst& c, b
                                               const float4& vi, float a_i, const float4& pj, const float4& vj) {
   const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
   const float s = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-  const float inv_r = rsqrtf(s);             // +inf at s = 0 (self, coincident particles): not used there
-  const float r = s > 0.f ? s * inv_r : 0.f;
+  const float inv_r = rsqrtf(s);             // +inf at s = 0 or denormal (self, coincident particles): not used there
+  float r = s * inv_r;
+  if (s < c.degenerate_s) r = sqrtf(s);      // rare: keep r finite and exact where rsqrt is not usable
   const float mass_over_rho = vj.w;
   if (!is_self) {
     float gx, gy, gz;
