@@ -210,6 +210,7 @@ def run_reference(args, rank):
 # GPU side
 # ------------------------------------------------------------------------------------------------
 CANDIDATE_OPTIONS = ["sub_cell_order=1", "face_grid=1"]
+_SAVED_STDOUT = None  # the real stdout while run_ours has fd 1 pointed at stderr
 
 
 def choose_organisation(args, local_rank, n_particles):
@@ -262,7 +263,8 @@ def run_ours(args, rank, world, local_rank):
     # stdout must carry exactly one JSON line: native libraries (NCCL's version banner) write to fd 1 too,
     # so everything goes to stderr until the line is ready
     sys.stdout.flush()
-    saved_stdout = os.dup(1)
+    global _SAVED_STDOUT
+    saved_stdout = _SAVED_STDOUT = os.dup(1)
     os.dup2(2, 1)
     import numpy as np
     import torch
@@ -488,6 +490,17 @@ def main():
         import traceback
         traceback.print_exc()
         sys.stderr.flush()
+        if world == 1 and args.organisation == "auto" and not args.option:
+            # The candidate organisation passed its self-check but the run failed later (the CUDA context of
+            # this process may be unusable now): measure the established organisation in a fresh process.
+            import subprocess
+            sys.stderr.write("bench: re-running with --organisation default in a fresh process\n")
+            sys.stderr.flush()
+            sys.stdout.flush()
+            if _SAVED_STDOUT is not None:
+                os.dup2(_SAVED_STDOUT, 1)  # the child must inherit the real stdout for its JSON line
+            rc = subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--organisation", "default"])
+            os._exit(rc)
         os._exit(1)
 
 
