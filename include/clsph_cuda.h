@@ -120,6 +120,9 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
  *                      reference's order exactly as with 0 (default this round: 0).
  *                      Needs a grid whose Morton cell count stays below 2^29 (z axis < 512 cells);
  *                      set it before particles are uploaded. (Environment: CLSPH_SUB_CELL_ORDER.)
+ *   "deferred_lists"   (with sub_cell_order) 1: the density pass collects the hits of up to 32 consecutive
+ *                      candidates in a bit mask and writes the list entries in a short loop afterwards,
+ *                      instead of one predicated store per candidate. Same lists, same order. Default 0.
  *   "face_grid"        1: the collision pass tests only the scene triangles registered in the grid
  *                      cells a particle's sub-step segment touches (conservative registration:
  *                      results are bit-identical to testing every triangle). Default 0 this round.

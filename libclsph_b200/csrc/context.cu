@@ -69,6 +69,7 @@ struct clsph_context {
   // sub-cell order (subgrid.cu): arrays sorted by (cell key << 3 | octant); rrank = index of each
   // particle in the reference's array, rr_tmp = the gathered ranks of the previous sub-step
   bool sub_order = false;
+  bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
   uint32_t sub_capacity = 0;   // cells the dense sub-cell table holds (9 words each)
   uint32_t* sub_lb = nullptr;
   uint32_t* rrank = nullptr;
@@ -391,7 +392,7 @@ int enqueue_substep(clsph_context* ctx) {
       launch_rank_pair(ctx->skey, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->wrank, ctx->sub_lb, ctx->sort, ctx->grid, n, st, lc);
     if (prof) next_event(ctx);
     launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                       ctx->taps, ctx->debug, n, st, lc);
+                       ctx->taps, ctx->debug, ctx->deferred_lists, n, st, lc);
     if (prof) next_event(ctx);
     launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
                   false, ctx->accel, n, st, lc);
@@ -631,6 +632,8 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     ctx->sub_order = value != 0;
     int rc = ensure_sub(ctx);
     if (rc) return rc;
+  } else if (!std::strcmp(name, "deferred_lists")) {
+    ctx->deferred_lists = value != 0;
   } else if (!std::strcmp(name, "face_grid")) {
     ctx->use_face_grid = value != 0;
     if (int rc = refresh_face_grid(ctx)) return rc;

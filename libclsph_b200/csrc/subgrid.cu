@@ -87,13 +87,15 @@ __device__ __forceinline__ void store_if(bool ok, uint32_t* addr, uint32_t v) {
 #endif
 }
 
+// for_each_range: calls range(begin, end) for every index range of candidates of the sub-cells around pi.
+// for_each_neighbour, on top of it:
 // Calls visit(j, pos[j], s, inside) for every candidate j of the sub-cells around pi, z outermost /
 // x innermost; inside = (s = |pi - pj|^2) < support_s is the reference's window test (self included).
 // The visitor gets every candidate so that it can stay branch-free: about one candidate in seven is
 // inside, so in a warp some lane nearly always is, and a divergent "inside" branch would run for all.
-template <class Visit>
-__device__ __forceinline__ void for_each_neighbour(const SubView& v, const GridState& g, const SphConst& c,
-                                                   const float4* pos, const float4& pi, Visit&& visit) {
+template <class Range>
+__device__ __forceinline__ void for_each_range(const SubView& v, const GridState& g, const SphConst& c, const float4& pi,
+                                               Range&& range) {
   uint32_t xlo, xhi, ylo, yhi, zlo, zhi;
   sub_bounds(pi.x, g.min_x, g.cell, c.h_margin, xlo, xhi);
   sub_bounds(pi.y, g.min_y, g.cell, c.h_margin, ylo, yhi);
@@ -109,14 +111,22 @@ __device__ __forceinline__ void for_each_neighbour(const SubView& v, const GridS
         const uint32_t o_lo = ozy | (cx == cx_lo ? (xlo & 1u) : 0u);
         const uint32_t o_hi = ozy | (cx == cx_hi ? (xhi & 1u) : 1u);
         const uint2 r = sub_range(v, kzy | spread10(cx), o_lo, o_hi);
-        for (uint32_t j = r.x; j < r.y; ++j) {
-          const float4 pj = pos[j];
-          const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
-          visit(j, pj, s, s < c.support_s);
-        }
+        range(r.x, r.y);
       }
     }
   }
+}
+
+template <class Visit>
+__device__ __forceinline__ void for_each_neighbour(const SubView& v, const GridState& g, const SphConst& c,
+                                                   const float4* pos, const float4& pi, Visit&& visit) {
+  for_each_range(v, g, c, pi, [&](uint32_t begin, uint32_t end) {
+    for (uint32_t j = begin; j < end; ++j) {
+      const float4 pj = pos[j];
+      const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+      visit(j, pj, s, s < c.support_s);
+    }
+  });
 }
 
 }  // namespace
@@ -242,7 +252,10 @@ k_rank_pair(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ordk
 // nlist[i * list_rows + e] = e-th neighbour of particle i (indices into the sorted arrays);
 // ncount[i] = neighbours found, more than list_rows = list incomplete (k_forces_sub redoes it).
 // =============================================================================================
-template <bool kTaps>
+// kDeferred: list entries are not stored candidate by candidate; the hits of up to 32 consecutive
+// candidates are collected in a bit mask (two instructions per candidate instead of six for the predicated
+// store, its address, the bound check and the counters) and written out by a short loop over the set bits.
+template <bool kTaps, bool kDeferred>
 __global__ void __launch_bounds__(kSubThreads)
 k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
               const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
@@ -268,12 +281,33 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
 #endif
   float acc = 0.f;   // sum of (h^2 - s)^3 over the support
   uint32_t cnt = 0;
-  for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4&, float s, bool inside) {
-    const float t = inside ? c.h2 - s : 0.f;
-    acc = fmaf(t * t, t, acc);
-    store_if(inside && cnt < list_rows, row + cnt, j);
-    cnt += inside ? 1u : 0u;
-  });
+  if (kDeferred) {
+    for_each_range(v, g, c, pi, [&](uint32_t begin, uint32_t end) {
+      for (uint32_t j0 = begin; j0 < end; j0 += 32u) {
+        const uint32_t chunk = min(end - j0, 32u);
+        uint32_t mask = 0u, bit = 1u;
+        for (uint32_t k = 0; k < chunk; ++k, bit <<= 1) {
+          const float4 pj = pos[j0 + k];
+          const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+          const bool inside = s < c.support_s;
+          const float t = inside ? c.h2 - s : 0.f;
+          acc = fmaf(t * t, t, acc);
+          mask |= inside ? bit : 0u;
+        }
+        for (uint32_t m = mask; m; m &= m - 1u) {  // ascending bits: list order = candidate order, as without kDeferred
+          if (cnt < list_rows) row[cnt] = j0 + (uint32_t)__ffs((int)m) - 1u;
+          ++cnt;
+        }
+      }
+    });
+  } else {
+    for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4&, float s, bool inside) {
+      const float t = inside ? c.h2 - s : 0.f;
+      acc = fmaf(t * t, t, acc);
+      store_if(inside && cnt < list_rows, row + cnt, j);
+      cnt += inside ? 1u : 0u;
+    });
+  }
   finish_density(c, acc, i, aux, pos, vel);
   ncount[i] = cnt;
   if (kTaps) {
@@ -360,15 +394,23 @@ void launch_rank_pair(const uint32_t* skey, const uint32_t* ordk, const uint32_t
 
 void launch_density_sub(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                         const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                        const DebugTaps& taps, bool debug, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+                        const DebugTaps& taps, bool debug, bool deferred, uint32_t n_launch, cudaStream_t stream,
+                        uint64_t* launches) {
   const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
-  if (debug)
-    k_density_sub<true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
-                                                            lists.entries, lists.count, lists.rows, taps.candidate_count,
-                                                            taps.support_count);
+  uint32_t* cand = debug ? taps.candidate_count : nullptr;
+  uint32_t* supp = debug ? taps.support_count : nullptr;
+if (debug && deferred)
+    k_density_sub<true, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                                  lists.entries, lists.count, lists.rows, cand, supp);
+  else if (debug)
+    k_density_sub<true, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                                   lists.entries, lists.count, lists.rows, cand, supp);
+  else if (deferred)
+    k_density_sub<false, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                                   lists.entries, lists.count, lists.rows, cand, supp);
   else
-    k_density_sub<false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
-                                                             lists.entries, lists.count, lists.rows, nullptr, nullptr);
+    k_density_sub<false, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
+                                                                    aux, lists.entries, lists.count, lists.rows, cand, supp);
   if (launches) ++*launches;
 }
 

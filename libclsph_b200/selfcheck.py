@@ -1,15 +1,14 @@
 """On-device cross-check and timing of two option sets of the CUDA library.
 
     python -m libclsph_b200.selfcheck --config config2_dambreak_1m [--particles N] [--device D]
-                                      [--candidate sub_cell_order=1 --candidate face_grid=1]
+                                      [--set sub_cell_order=1,face_grid=1 [--set ...]]
 
-Runs the same state through the library twice -- once with the default options (the organisation
-that has passed the GPU parity suite against the oracle) and once with the candidate options --
-and compares everything observable: cell keys, sort permutation, sorted keys, cell table, candidate
+Runs the same state through the library with the default options (the organisation that has passed
+the GPU parity suite against the oracle) and once with every candidate option set, and compares everything observable: cell keys, sort permutation, sorted keys, cell table, candidate
 and support counts, collision loop trips and the exported array order must be IDENTICAL; densities,
 pressures, accelerations, positions and velocities must agree within 5e-5 relative (the two
-organisations add the same terms in a different order). Then it times both, device resident.
-Prints one JSON line; exit code 0 = the candidate agrees. bench.py runs this in a subprocess before
+organisations add the same terms in a different order). Then it times each, device resident.
+Prints one JSON line; exit code 0 = at least one candidate set agrees. bench.py runs this in a subprocess before
 it adopts the candidate options, so a fault in a new kernel can neither poison the benchmark
 process nor produce a number from wrong results. No CPU code takes part in the comparison.
 """
@@ -87,25 +86,36 @@ def main(argv=None):
     ap.add_argument("--particles", type=int, default=0)
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--timed-steps", type=int, default=20)
-    ap.add_argument("--candidate", action="append", default=[], help="name=value option of the candidate set")
+    ap.add_argument("--set", action="append", default=[], dest="sets",
+                    help="one candidate option set, name=value[,name=value...]; may be repeated")
     args = ap.parse_args(argv)
     fluid, n, mass, scene_file = workloads.CONFIGS[args.config]
     n = args.particles or n
     params, terms, vol, _ = workloads.make_config(fluid=fluid, particles_count=n, particle_mass=mass)
     state = workloads.jittered_state(params, vol)
     scene = workloads.scene_arrays(scene_file)
-    cand_opts = dict((k, int(v)) for k, v in (o.split("=") for o in args.candidate)) or dict(sub_cell_order=1, face_grid=1)
-    result = {"config": args.config, "particles": n, "candidate": cand_opts, "agree": False}
+    sets = [dict((k, int(v)) for k, v in (o.split("=") for o in spec.split(","))) for spec in args.sets] or \
+        [dict(sub_cell_order=1, face_grid=1)]
+    result = {"config": args.config, "particles": n, "agree": False, "sets": []}
     try:
         # One sub-step from identical inputs: integer observables must match exactly, the rest to
         # rounding. (Later sub-steps start from states that already differ in the last bits, where a
         # key may legitimately flip for a particle on a cell boundary.)
         base, ms_base = run({}, args.device, params, terms, scene, state, 1, args.timed_steps)
-        cand, ms_cand = run(cand_opts, args.device, params, terms, scene, state, 1, args.timed_steps)
-        worst = compare(base, cand)
-        result.update(agree=True, max_rel_diff=worst, ms_per_step_default=ms_base, ms_per_step_candidate=ms_cand)
-    except BaseException as exc:  # noqa: BLE001 - reported to the caller as "does not agree"
-        result["error"] = "%s: %s" % (type(exc).__name__, exc)
+        result["ms_per_step_default"] = ms_base
+    except BaseException as exc:  # noqa: BLE001
+        result["error"] = "default options: %s: %s" % (type(exc).__name__, exc)
+        print(json.dumps(result), flush=True)
+        return 1
+    for opts in sets:
+        entry = {"options": opts, "agree": False}
+        try:
+            cand, ms_cand = run(opts, args.device, params, terms, scene, state, 1, args.timed_steps)
+            entry.update(max_rel_diff=compare(base, cand), ms_per_step=ms_cand, agree=True)
+        except BaseException as exc:  # noqa: BLE001 - reported to the caller as "does not agree"
+            entry["error"] = "%s: %s" % (type(exc).__name__, exc)
+        result["sets"].append(entry)
+    result["agree"] = any(e["agree"] for e in result["sets"])
     print(json.dumps(result), flush=True)
     return 0 if result["agree"] else 1
 

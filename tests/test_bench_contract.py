@@ -64,23 +64,33 @@ def test_organisation_choice_adopts_the_candidate_only_after_a_clean_selfcheck(m
 
     def fake(stdout, returncode=0, raises=None):
         def run_(cmd, **kw):
-            assert "libclsph_b200.selfcheck" in cmd and "--candidate" in cmd
+            assert "libclsph_b200.selfcheck" in cmd and "--set" in cmd
             if raises:
                 raise raises
             return types.SimpleNamespace(stdout=stdout, stderr="boom", returncode=returncode)
         return run_
 
     args = types.SimpleNamespace(option=[], organisation="auto", config="config2_dambreak_1m")
-    ok = json.dumps({"agree": True, "max_rel_diff": 1e-7, "ms_per_step_default": 0.9, "ms_per_step_candidate": 0.5})
+    a, b = dict(sub_cell_order=1, face_grid=1), dict(sub_cell_order=1, face_grid=1, deferred_lists=1)
+    ok = json.dumps({"agree": True, "ms_per_step_default": 0.9, "sets": [
+        {"options": a, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.5},
+        {"options": b, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.45}]})
     monkeypatch.setattr(sp, "run", fake("NCCL noise\n" + ok + "\n"))
     opts, rep = bench.choose_organisation(args, 0, 1 << 20)
-    assert opts == bench.CANDIDATE_OPTIONS and rep["adopted"] and rep["agree"]
-    slower = json.dumps({"agree": True, "max_rel_diff": 1e-7, "ms_per_step_default": 0.5, "ms_per_step_candidate": 0.9})
+    assert sorted(opts) == sorted(bench.CANDIDATE_SETS[1]) and rep["adopted"] and rep["agree"]   # the faster of the two
+    one_bad = json.dumps({"agree": True, "ms_per_step_default": 0.9, "sets": [
+        {"options": a, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.5},
+        {"options": b, "agree": False, "error": "AssertionError: support_count differs"}]})
+    monkeypatch.setattr(sp, "run", fake(one_bad))
+    assert sorted(bench.choose_organisation(args, 0, 1 << 20)[0]) == sorted(bench.CANDIDATE_OPTIONS)
+    slower = json.dumps({"agree": True, "ms_per_step_default": 0.5, "sets": [
+        {"options": a, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.9}]})
     monkeypatch.setattr(sp, "run", fake(slower))
     assert bench.choose_organisation(args, 0, 1 << 20)[0] == []
-    monkeypatch.setattr(sp, "run", fake(json.dumps({"agree": False, "error": "AssertionError: permutation differs"}), returncode=1))
+    bad = json.dumps({"agree": False, "ms_per_step_default": 0.5, "sets": [{"options": a, "agree": False, "error": "AssertionError: permutation differs"}]})
+    monkeypatch.setattr(sp, "run", fake(bad, returncode=1))
     opts, rep = bench.choose_organisation(args, 0, 1 << 20)
-    assert opts == [] and not rep["adopted"] and "permutation" in rep["error"]
+    assert opts == [] and not rep["adopted"] and "permutation" in rep["sets"][0]["error"]
     monkeypatch.setattr(sp, "run", fake("", returncode=-11))   # the subprocess crashed
     opts, rep = bench.choose_organisation(args, 0, 1 << 20)
     assert opts == [] and not rep["adopted"] and "exit code -11" in rep["error"]
