@@ -80,8 +80,10 @@ __global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t 
   for (int a = 0; a < 3; ++a) {
     mn[a] = __fsub_rn(ordered_to_float(acc->lo[a]), pad);
     mx[a] = __fadd_rn(ordered_to_float(acc->hi[a]), pad);
-    gs[a] = (int)__float2uint_rz(__fdiv_rn(__fsub_rn(mx[a], mn[a]), cell));
-    if (gs[a] >= 1024) err |= 1u;  // the reference asserts here (:247-249)
+    // saturating conversion, kept unsigned for the test: an infinite extent must not wrap to -1
+    const uint32_t cells = __float2uint_rz(__fdiv_rn(__fsub_rn(mx[a], mn[a]), cell));
+    gs[a] = (int)min(cells, 0x7fffffffu);
+    if (cells >= 1024u) err |= 1u;  // the reference asserts here (:247-249)
     acc->lo[a] = float_to_ordered(2147483648.f);
     acc->hi[a] = float_to_ordered(-2147483648.f);
   }

@@ -72,7 +72,9 @@ __device__ __forceinline__ void sub_bounds(float p, float mn, float cell, float 
   const float u = __fsub_rn(p, mn);
   const float ql = __fdiv_rn(__fsub_rn(u, hm), cell), qh = __fdiv_rn(__fadd_rn(u, hm), cell);
   lo = __float2uint_rz(__fadd_rn(ql, ql));  // negative -> 0
-  hi = __float2uint_rz(__fadd_rn(qh, qh));
+  // 2047 = last sub-cell a 10-bit cell coordinate can have: keeps the loops bounded for a particle that
+  // has blown up (infinite or huge position; the step then reports CLSPH_EGRID anyway)
+  hi = min(__float2uint_rz(__fadd_rn(qh, qh)), 2047u);
 }
 
 // *addr = v when ok, as ONE predicated store: the compiler would otherwise branch around the store

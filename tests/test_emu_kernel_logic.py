@@ -261,3 +261,29 @@ def test_edge_states(kind, options, box_scene):
     p, terms, vol = H.config("water", 1024)
     s = H.edge_state(kind, p, vol)
     G.check_against_oracle(s, p, terms, box_scene, "%s %r" % (kind, options), options=options)
+
+
+@pytest.mark.parametrize("options", [dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1)])
+def test_blown_up_particles_do_not_hang_the_kernels(options, box_scene):
+    """A particle at infinity makes the grid overflow (CLSPH_EGRID, as the reference's assert would);
+    a NaN position falls into cell 0. Either way every kernel must terminate."""
+    p, terms, vol = H.config("water", 2048)
+    s = H.state_s1(p, vol)
+    bad = s.copy()
+    bad["position"][5, 0] = np.inf
+    bad["position"][6, 1] = -np.inf
+    bad["position"][7, 2] = np.float32(3e38)
+    ctx = G.make_ctx(s.size, box_scene, p, terms, debug=False, options=options)
+    ctx.upload(bad)
+    ctx.step(2)
+    with pytest.raises(capi.ClsphError) as e:
+        ctx.synchronize()
+    assert e.value.code == capi.E_GRID
+    nan = s.copy()
+    nan["position"][9, :3] = np.nan
+    ctx.upload(nan)
+    ctx.step(2)
+    ctx.synchronize()
+    out = ctx.download()
+    assert np.isfinite(out["position"][:, :3]).sum() >= 3 * (s.size - 64)  # the NaN may spread to its neighbours, not further
+    ctx.close()
