@@ -10,6 +10,8 @@
 
 #include <functional>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "common/structures.h"
 #include "scene.h"
@@ -54,6 +56,9 @@ class sph_simulation {
   host_sync_policy host_sync;
 
   int cuda_device;          /* which GPU (default 0)                                        */
+  /* clsph_set_option(name, value) pairs applied to the device context before the scene and the
+   * particles are handed over, e.g. {"sub_cell_order", 1}, {"face_grid", 1} (include/clsph_cuda.h). */
+  std::vector<std::pair<std::string, long long> > device_options;
   bool quiet;               /* suppress the reference's console chatter (default false)     */
 
   /* State after the last simulate() call, in the reference's output order. */

@@ -11,7 +11,9 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "file_save_delegates/houdini_file_saver.h"
 #include "sph_simulation.h"
@@ -21,10 +23,12 @@ int main(int argc, char** argv) {
   int n_positional = 0, frames = 0;
   bool assume_yes = false;
   std::string sync = "";
+  std::vector<std::string> device_options;
   for (int a = 1; a < argc; ++a) {
     if (!std::strcmp(argv[a], "--yes")) assume_yes = true;
     else if (!std::strcmp(argv[a], "--frames") && a + 1 < argc) frames = std::atoi(argv[++a]);
     else if (!std::strcmp(argv[a], "--sync") && a + 1 < argc) sync = argv[++a];
+    else if (!std::strcmp(argv[a], "--option") && a + 1 < argc) device_options.push_back(argv[++a]);  // name=value
     else if (n_positional < 4) positional[n_positional++] = argv[a];
   }
   if (n_positional < 4) {
@@ -34,6 +38,14 @@ int main(int argc, char** argv) {
   }
 
   sph_simulation simulation;
+  for (size_t k = 0; k < device_options.size(); ++k) {
+    const std::string::size_type eq = device_options[k].find('=');
+    if (eq == std::string::npos) {
+      std::cerr << "--option expects name=value, got " << device_options[k] << std::endl;
+      return -1;
+    }
+    simulation.device_options.push_back(std::make_pair(device_options[k].substr(0, eq), std::atoll(device_options[k].c_str() + eq + 1)));
+  }
   houdini_file_saver saver = houdini_file_saver(positional[3]);
   try {
     simulation.load_settings("fluid_properties/" + positional[0] + ".json", "simulation_properties/" + positional[1] + ".json");

@@ -108,6 +108,8 @@ void sph_simulation::simulate(int frame_count) {
     }
   }
   clsph_context* ctx = impl_->ctx;
+  for (size_t k = 0; k < device_options.size(); ++k)
+    check_cuda_abi(ctx, clsph_set_option(ctx, device_options[k].first.c_str(), device_options[k].second));
   check_cuda_abi(ctx, clsph_set_scene(ctx, current_scene.face_normals.data(), current_scene.vertices.data(),
                                       current_scene.vertices.size(), current_scene.indices.data(), current_scene.face_count));
   check_cuda_abi(ctx, clsph_set_parameters(ctx, &parameters, &precomputed_terms));
