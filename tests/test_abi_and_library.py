@@ -64,3 +64,15 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "oracle/" not in text and "liboracle" not in text, f
+
+
+def test_product_never_loads_the_emulator_build():
+    """tests/emu/ (the CUDA sources compiled for the CPU) is test infrastructure: nothing in the product
+    package or in bench.py may import it or name its library; the only trace in the product is the pair
+    of `#ifdef CLSPH_EMU` branches around inline PTX in csrc/."""
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for dirpath, _, names in os.walk(os.path.join(ROOT, "libclsph_b200")):
+        files += [os.path.join(dirpath, f) for f in names if f.endswith((".py", ".cpp", ".h", ".hpp"))]
+    for path in files:
+        text = open(path, errors="ignore").read()
+        assert "tests.emu" not in text and "libclsph_emu" not in text and "build_emu" not in text and "cuda_emu" not in text, path
