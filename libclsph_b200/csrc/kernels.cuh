@@ -109,10 +109,11 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
                     uint64_t* launches);
 // Only particles of owned cells get an acceleration (multi-GPU: ghosts are skipped).
 // search_fallback: in list mode, also run the searching kernel for particles whose list overflowed
-// (sub-cell order has its own, launch_forces_sub_overflow).
+// (sub-cell order has its own, launch_forces_sub_overflow). dense_occupancy (sub-cell order only): the
+// instantiation compiled for four resident CTAs per SM instead of three.
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
-                   const NeighbourLists& lists, bool search_fallback, float4* accel, uint32_t n_launch,
+                   const NeighbourLists& lists, bool search_fallback, bool dense_occupancy, float4* accel, uint32_t n_launch,
                    cudaStream_t stream, uint64_t* launches);
 
 // ---- subgrid.cu: sub-cell order (arrays sorted by cell key << 3 | octant)

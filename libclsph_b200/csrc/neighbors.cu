@@ -607,9 +607,11 @@ k_density_lists(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
 // The warp first copies its 32 rows, 32 entries at a time, into a shared-memory tile with
 // coalesced 128-byte reads; each lane then walks its own row.
 // =============================================================================================
-// kFast: pair terms through add_pair_fast (sub-cell organisation).
-template <bool kFast>
-__global__ void __launch_bounds__(kFlWarps * 32, 3)
+// kFast: pair terms through add_pair_fast (sub-cell organisation). kBlocks: resident CTAs per SM the
+// register allocation aims at (3: up to 85 registers; 4: 64 registers, a third more warps to hide the
+// latency of the neighbour gathers, which is what this kernel waits for).
+template <bool kFast, int kBlocks>
+__global__ void __launch_bounds__(kFlWarps * 32, kBlocks)
 k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
                const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
                const uint32_t* __restrict__ skey, const GridState* __restrict__ grid, const SphConst c,
@@ -704,17 +706,20 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
-                   const NeighbourLists& lists, bool search_fallback, float4* accel, uint32_t n_launch,
+                   const NeighbourLists& lists, bool search_fallback, bool dense_occupancy, float4* accel, uint32_t n_launch,
                    cudaStream_t stream, uint64_t* launches) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
   if (lists.rows) {
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
     if (search_fallback)
-      k_forces_lists<false><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
-                                                                  grid, c, accel);
+      k_forces_lists<false, 3><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
+                                                                     grid, c, accel);
+    else if (dense_occupancy)  // sub-cell organisation, option forces_blocks = 4
+      k_forces_lists<true, 4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
+                                                                    grid, c, accel);
     else  // sub-cell organisation
-      k_forces_lists<true><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
-                                                                 grid, c, accel);
+      k_forces_lists<true, 3><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
+                                                                    grid, c, accel);
     if (launches) ++*launches;
     if (search_fallback) {
       // particles with more neighbours than list rows: redone with the searching kernel (exits at once elsewhere)

@@ -91,7 +91,7 @@ SUB = dict(sub_cell_order=1)
 
 @pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8),
                                      SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, deferred_lists=1),
-                                     dict(sub_cell_order=1, deferred_lists=1, list_rows=8)])
+                                     dict(sub_cell_order=1, deferred_lists=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4)])
 def test_neighbour_organisations(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
