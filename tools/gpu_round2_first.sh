@@ -10,6 +10,12 @@ for cfg in config2_dambreak_1m config3_mucus_labyrinth_4m; do
   timeout 600 python -m libclsph_b200.selfcheck --config $cfg --set sub_cell_order=1,face_grid=1 --set sub_cell_order=1,face_grid=1,deferred_lists=1 --set sub_cell_order=1,face_grid=1,forces_blocks=4 --set sub_cell_order=1,face_grid=1,deferred_lists=1,forces_blocks=4 \
       > gpurun_out/r02_selfcheck_$cfg.json 2> gpurun_out/r02_selfcheck_$cfg.err
 done
+# memcheck + racecheck of the new kernels on a small workload (established and candidate sets in one run)
+for tool in memcheck racecheck; do
+  timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -m libclsph_b200.selfcheck --config config3_mucus_labyrinth_4m \
+      --particles 30000 --timed-steps 2 --set sub_cell_order=1,face_grid=1 --set sub_cell_order=1,face_grid=1,deferred_lists=1,forces_blocks=4 \
+      > gpurun_out/r02_sanitizer_$tool.log 2>&1; echo "rc=$?" >> gpurun_out/r02_sanitizer_$tool.log
+done
 for org in default candidate; do
   timeout 600 python bench.py --organisation $org --steps 50 --warmup 10 > gpurun_out/r02_bench_cfg2_$org.json 2> gpurun_out/r02_bench_cfg2_$org.err
   timeout 600 python bench.py --organisation $org --config config3_mucus_labyrinth_4m --steps 10 --warmup 3 --e2e-steps 2 --no-cpu-baseline \
