@@ -123,8 +123,11 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
  *   "deferred_lists"   (with sub_cell_order) 1: the density pass collects the hits of up to 32 consecutive
  *                      candidates in a bit mask and writes the list entries in a short loop afterwards,
  *                      instead of one predicated store per candidate. Same lists, same order. Default 0.
- *   "forces_blocks"    (with sub_cell_order) 3 (default) or 4: resident CTAs per SM the list force kernel is
- *                      compiled for (4 = 64 registers per thread, a third more warps to hide gather latency).
+ *   "fast_pairs"       1: the list force kernel evaluates each pair with one MUFU.RSQ in place of the IEEE
+ *                      square root and divide (~2 ulp, far inside the 1e-4 bar; the |r| < 1e-7 decision
+ *                      stays exact). Default 0.
+ *   "forces_blocks"    3 (default) or 4: resident CTAs per SM the list force kernel is compiled for
+ *                      (4 = 64 registers per thread, a third more warps to hide gather latency).
  *   "face_grid"        1: the collision pass tests only the scene triangles registered in the grid
  *                      cells a particle's sub-step segment touches (conservative registration:
  *                      results are bit-identical to testing every triangle). Default 0 this round.

@@ -70,7 +70,8 @@ struct clsph_context {
   // particle in the reference's array, rr_tmp = the gathered ranks of the previous sub-step
   bool sub_order = false;
   bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
-  bool forces_dense = false;    // k_forces_lists<true, 4>: four resident CTAs per SM (option forces_blocks = 4)
+  bool forces_dense = false;    // k_forces_lists<.., 4>: four resident CTAs per SM (option forces_blocks = 4)
+  bool fast_pairs = false;      // k_forces_lists<true, ..>: add_pair_fast (option fast_pairs)
   uint32_t sub_capacity = 0;   // cells the dense sub-cell table holds (9 words each)
   uint32_t* sub_lb = nullptr;
   uint32_t* rrank = nullptr;
@@ -396,7 +397,7 @@ int enqueue_substep(clsph_context* ctx) {
                        ctx->taps, ctx->debug, ctx->deferred_lists, n, st, lc);
     if (prof) next_event(ctx);
     launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
-                  false, ctx->forces_dense, ctx->accel, n, st, lc);
+                  false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc);
     launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
                                ctx->lists, ctx->accel, n, st, lc);
     if (prof) next_event(ctx);
@@ -411,7 +412,7 @@ int enqueue_substep(clsph_context* ctx) {
                    ctx->taps, ctx->debug, n, ctx->sm_count, st, lc);
     if (prof) next_event(ctx);
     launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst,
-                  ctx->lists, true, false, ctx->accel, n, st, lc);
+                  ctx->lists, true, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc);
     if (prof) next_event(ctx);
   }
   if (ctx->debug)  // the integrator consumes the acceleration; keep a copy for the tap
@@ -635,6 +636,8 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     if (rc) return rc;
   } else if (!std::strcmp(name, "deferred_lists")) {
     ctx->deferred_lists = value != 0;
+  } else if (!std::strcmp(name, "fast_pairs")) {
+    ctx->fast_pairs = value != 0;
   } else if (!std::strcmp(name, "forces_blocks")) {
     if (value != 3 && value != 4) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: forces_blocks must be 3 or 4");
     ctx->forces_dense = value == 4;

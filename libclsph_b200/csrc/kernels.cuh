@@ -109,12 +109,12 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
                     uint64_t* launches);
 // Only particles of owned cells get an acceleration (multi-GPU: ghosts are skipped).
 // search_fallback: in list mode, also run the searching kernel for particles whose list overflowed
-// (sub-cell order has its own, launch_forces_sub_overflow). dense_occupancy (sub-cell order only): the
-// instantiation compiled for four resident CTAs per SM instead of three.
+// (sub-cell order has its own, launch_forces_sub_overflow). fast_pairs: pair terms through add_pair_fast.
+// dense_occupancy: the list kernel compiled for four resident CTAs per SM instead of three.
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
-                   const NeighbourLists& lists, bool search_fallback, bool dense_occupancy, float4* accel, uint32_t n_launch,
-                   cudaStream_t stream, uint64_t* launches);
+                   const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
+                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 
 // ---- subgrid.cu: sub-cell order (arrays sorted by cell key << 3 | octant)
 void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capacity, int sm_count, cudaStream_t stream,

@@ -706,20 +706,25 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
-                   const NeighbourLists& lists, bool search_fallback, bool dense_occupancy, float4* accel, uint32_t n_launch,
-                   cudaStream_t stream, uint64_t* launches) {
+                   const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
+                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
   if (lists.rows) {
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
-    if (search_fallback)
-      k_forces_lists<false, 3><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
-                                                                     grid, c, accel);
-    else if (dense_occupancy)  // sub-cell organisation, option forces_blocks = 4
+    // <false, 3> is the instantiation the GPU parity suite has passed; the others are selected by the options
+    // fast_pairs / forces_blocks (clsph_cuda.h)
+    if (fast_pairs && dense_occupancy)
       k_forces_lists<true, 4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
                                                                     grid, c, accel);
-    else  // sub-cell organisation
+    else if (fast_pairs)
       k_forces_lists<true, 3><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
                                                                     grid, c, accel);
+    else if (dense_occupancy)
+      k_forces_lists<false, 4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
+                                                                     grid, c, accel);
+    else
+      k_forces_lists<false, 3><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey,
+                                                                     grid, c, accel);
     if (launches) ++*launches;
     if (search_fallback) {
       // particles with more neighbours than list rows: redone with the searching kernel (exits at once elsewhere)

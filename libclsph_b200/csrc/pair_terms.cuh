@@ -47,8 +47,7 @@ __device__ __forceinline__ void add_pair(ForceSums& f, const SphConst& c, bool i
 // (about 20 of add_pair's ~80 instructions): r = s rsqrt(s) and 1/r = rsqrt(s) are good to ~2 ulp and
 // h^2 - r^2 is taken as h^2 - s, all far inside the 1e-4 bar these sums are held to. The one discrete
 // decision, smoothing.cl:23's |r| < 1e-7, is kept exact as s < degenerate_s (smallest s whose rounded
-// square root reaches 1e-7; sqrt is monotone). Used by the sub-cell organisation only; the established
-// kernels keep add_pair.
+// square root reaches 1e-7; sqrt is monotone). Selected by the option fast_pairs; the default keeps add_pair.
 __device__ __forceinline__ void add_pair_fast(ForceSums& f, const SphConst& c, bool is_self, const float4& pi,
                                               const float4& vi, float a_i, const float4& pj, const float4& vj) {
   const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;

@@ -344,7 +344,7 @@ k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   const float4 pi = pos[i], vi = vel[i];
   ForceSums sums;
   for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4& pj, float, bool inside) {
-    if (inside) add_pair_fast(sums, c, j == i, pi, vi, pi.w, pj, vel[j]);
+    if (inside) add_pair(sums, c, j == i, pi, vi, pi.w, pj, vel[j]);  // rare path: the exact pair terms
   });
   accel[i] = finish_force(sums, c, aux[i].x);
 }

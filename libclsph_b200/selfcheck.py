@@ -1,7 +1,7 @@
 """On-device cross-check and timing of two option sets of the CUDA library.
 
     python -m libclsph_b200.selfcheck --config config2_dambreak_1m [--particles N] [--device D]
-                                      [--set sub_cell_order=1,face_grid=1 [--set ...]]
+                                      [--set sub_cell_order=1,face_grid=1,fast_pairs=1 [--set ...]]
 
 Runs the same state through the library with the default options (the organisation that has passed
 the GPU parity suite against the oracle) and once with every candidate option set, and compares everything observable: cell keys, sort permutation, sorted keys, cell table, candidate
@@ -95,7 +95,7 @@ def main(argv=None):
     state = workloads.jittered_state(params, vol)
     scene = workloads.scene_arrays(scene_file)
     sets = [dict((k, int(v)) for k, v in (o.split("=") for o in spec.split(","))) for spec in args.sets] or \
-        [dict(sub_cell_order=1, face_grid=1)]
+        [dict(sub_cell_order=1, face_grid=1, fast_pairs=1)]
     result = {"config": args.config, "particles": n, "agree": False, "sets": []}
     try:
         # One sub-step from identical inputs: integer observables must match exactly, the rest to

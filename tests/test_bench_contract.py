@@ -71,7 +71,9 @@ def test_organisation_choice_adopts_the_candidate_only_after_a_clean_selfcheck(m
         return run_
 
     args = types.SimpleNamespace(option=[], organisation="auto", config="config2_dambreak_1m")
-    a, b = dict(sub_cell_order=1, face_grid=1), dict(sub_cell_order=1, face_grid=1, deferred_lists=1)
+    a = dict(kv.split("=") for kv in bench.CANDIDATE_SETS[0])
+    a = {k: int(v) for k, v in a.items()}
+    b = dict(a, deferred_lists=1)
     ok = json.dumps({"agree": True, "ms_per_step_default": 0.9, "sets": [
         {"options": a, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.5},
         {"options": b, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.45}]})

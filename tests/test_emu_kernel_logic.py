@@ -91,7 +91,8 @@ SUB = dict(sub_cell_order=1)
 
 @pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8),
                                      SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, deferred_lists=1),
-                                     dict(sub_cell_order=1, deferred_lists=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4)])
+                                     dict(sub_cell_order=1, deferred_lists=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4),
+                                     dict(sub_cell_order=1, fast_pairs=1), dict(neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1)])
 def test_neighbour_organisations(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
@@ -221,8 +222,8 @@ def test_selfcheck_module_finds_the_candidate_options_equivalent(capsys):
     import json
     from libclsph_b200 import selfcheck
     for cfg, n in (("config1_box_100k", 3000), ("config3_mucus_labyrinth_4m", 4096)):
-        rc = selfcheck.main(["--config", cfg, "--particles", str(n), "--timed-steps", "2", "--set", "sub_cell_order=1,face_grid=1",
-                             "--set", "sub_cell_order=1,face_grid=1,deferred_lists=1"])
+        rc = selfcheck.main(["--config", cfg, "--particles", str(n), "--timed-steps", "2", "--set", "sub_cell_order=1,face_grid=1,fast_pairs=1",
+                             "--set", "face_grid=1,fast_pairs=1,forces_blocks=4"])
         line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
         assert rc == 0 and line["agree"] and len(line["sets"]) == 2 and line["ms_per_step_default"] > 0, line
         for entry in line["sets"]:
@@ -254,7 +255,8 @@ def test_sub_cell_order_reports_a_grid_too_large_for_its_keys(box_scene):
 
 @pytest.mark.parametrize("kind", H.EDGE_KINDS)
 @pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1),
-                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1)])
+                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1),
+                                     dict(sub_cell_order=1, face_grid=1, fast_pairs=1)])
 def test_edge_states(kind, options, box_scene):
     """States sitting ON the path's decisions (tests/helpers.edge_state; the oracle is pinned against the
     reference's own kernels on the same states in test_oracle_vs_ref.py), in every organisation."""

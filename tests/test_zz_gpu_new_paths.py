@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 SUB = dict(sub_cell_order=1)
 GRID = dict(face_grid=1)
-BOTH = dict(sub_cell_order=1, face_grid=1)
+BOTH = dict(sub_cell_order=1, face_grid=1, fast_pairs=1)
 
 
 @pytest.mark.parametrize("n", [128, 1000, 4096, 32000])
@@ -34,7 +34,8 @@ def test_sub_cell_order_jittered(fluid, n, box_scene):
 
 @pytest.mark.parametrize("options", [SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, list_rows=24), BOTH,
                                      dict(sub_cell_order=1, deferred_lists=1), dict(sub_cell_order=1, deferred_lists=1, list_rows=8),
-                                     dict(sub_cell_order=1, forces_blocks=4)])
+                                     dict(sub_cell_order=1, forces_blocks=4),
+                                     dict(neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1)])
 def test_sub_cell_order_crowded_and_overflowing_lists(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 20000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
