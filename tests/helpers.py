@@ -133,3 +133,25 @@ def edge_state(kind, p, vol, seed=3):
 
 
 EDGE_KINDS = ("coincident", "on_support", "on_cells", "one_cell", "sparse")
+
+
+_DEVELOPED = {}
+
+
+def developed_state(fluid="water", n=4096, substeps=200, drop=0.05):
+    """State S2 of SURVEY 8(d) in small: the lattice released `drop` metres above the floor of box.obj and
+    advanced `substeps` sub-steps by the ORACLE, so that the fluid has hit the floor, spread against the
+    walls and formed a free surface (collisions, crowded and thin regions, real velocity field). Cached."""
+    from oracle import oracle as O
+    key = (fluid, n, substeps, drop)
+    if key not in _DEVELOPED:
+        p, terms, vol = config(fluid, n)
+        scene = O.load_obj(os.path.join(ROOT, "scenes", "box.obj"))
+        s = state_s0(p, vol)
+        s["position"][:, 1] += np.float32(-2.0 + drop)
+        po = p.copy()
+        for _ in range(substeps):
+            s = O.step(s, po, terms, scene, taps=False).particles
+        _DEVELOPED[key] = (p, terms, scene, s)
+    p, terms, scene, s = _DEVELOPED[key]
+    return p.copy(), terms, scene, s.copy()

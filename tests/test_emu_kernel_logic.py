@@ -289,3 +289,18 @@ def test_blown_up_particles_do_not_hang_the_kernels(options, box_scene):
     out = ctx.download()
     assert np.isfinite(out["position"][:, :3]).sum() >= 3 * (s.size - 64)  # the NaN may spread to its neighbours, not further
     ctx.close()
+
+
+@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1, fast_pairs=1),
+                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4)])
+def test_developed_state(options):
+    """State S2: fluid that has hit the floor of the box and spread -- free surface, wall
+    contacts, ~10 % of the particles colliding in the step."""
+    p, terms, scene, s = H.developed_state()
+    got, taps, want = G.check_against_oracle(s, p, terms, scene, "developed %r" % (options,), options=options)
+    assert (want.collision_iters > 1).sum() > 100
+
+
+def test_developed_state_resident_steps_in_sub_cell_order():
+    p, terms, scene, s = H.developed_state()
+    G.check_resident_steps_against_oracle(s, p, terms, scene, 4, "developed, resident", options=dict(sub_cell_order=1, face_grid=1, fast_pairs=1))

@@ -153,3 +153,14 @@ def test_edge_states(kind, options, box_scene):
     p, terms, vol = H.config("water", 4096)
     s = H.edge_state(kind, p, vol)
     G.check_against_oracle(s, p, terms, box_scene, "%s %r" % (kind, options), options=options)
+
+
+@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), BOTH,
+                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4)])
+def test_developed_state(options):
+    """State S2 in small: fluid that has hit the floor of the box and spread (free surface, wall
+    contacts, many particles colliding in the step), single step and resident steps."""
+    p, terms, scene, s = H.developed_state(n=16384)
+    got, taps, want = G.check_against_oracle(s, p, terms, scene, "developed %r" % (options,), options=options)
+    assert (want.collision_iters > 1).sum() > 100
+    G.check_resident_steps_against_oracle(s, p, terms, scene, 3, "developed, resident %r" % (options,), options=options)
