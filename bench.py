@@ -211,8 +211,8 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 CANDIDATE_OPTIONS = ["sub_cell_order=1", "face_grid=1", "fast_pairs=1"]
 # what --organisation auto lets the self-check choose from (the fastest set that agrees wins)
-CANDIDATE_SETS = [CANDIDATE_OPTIONS, CANDIDATE_OPTIONS + ["deferred_lists=1"], CANDIDATE_OPTIONS + ["forces_blocks=4"],
-                  CANDIDATE_OPTIONS + ["deferred_lists=1", "forces_blocks=4"],
+CANDIDATE_SETS = [CANDIDATE_OPTIONS, CANDIDATE_OPTIONS + ["merged_rows=1"], CANDIDATE_OPTIONS + ["merged_rows=1", "forces_blocks=4"],
+                  CANDIDATE_OPTIONS + ["deferred_lists=1", "forces_blocks=4"], CANDIDATE_OPTIONS + ["forces_blocks=4"],
                   # the established organisation with only the force-kernel and collision-pass changes
                   ["face_grid=1", "fast_pairs=1", "forces_blocks=4"]]
 _SAVED_STDOUT = None  # the real stdout while run_ours has fd 1 pointed at stderr

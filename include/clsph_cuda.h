@@ -123,6 +123,9 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
  *   "deferred_lists"   (with sub_cell_order) 1: the density pass collects the hits of up to 32 consecutive
  *                      candidates in a bit mask and writes the list entries in a short loop afterwards,
  *                      instead of one predicated store per candidate. Same lists, same order. Default 0.
+ *   "merged_rows"      (with sub_cell_order) 1: the density pass walks the two index ranges of each row of
+ *                      sub-cells in one loop, which evens out the loop lengths between the lanes of a warp
+ *                      (164 instead of 216 candidate slots per lane on the bench states). Default 0.
  *   "fast_pairs"       1: the list force kernel evaluates each pair with one MUFU.RSQ in place of the IEEE
  *                      square root and divide (~2 ulp, far inside the 1e-4 bar; the |r| < 1e-7 decision
  *                      stays exact). Default 0.

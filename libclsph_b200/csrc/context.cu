@@ -70,6 +70,7 @@ struct clsph_context {
   // particle in the reference's array, rr_tmp = the gathered ranks of the previous sub-step
   bool sub_order = false;
   bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
+  bool merged_rows = false;     // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
   bool forces_dense = false;    // k_forces_lists<.., 4>: four resident CTAs per SM (option forces_blocks = 4)
   bool fast_pairs = false;      // k_forces_lists<true, ..>: add_pair_fast (option fast_pairs)
   uint32_t sub_capacity = 0;   // cells the dense sub-cell table holds (9 words each)
@@ -394,7 +395,7 @@ int enqueue_substep(clsph_context* ctx) {
       launch_rank_pair(ctx->skey, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->wrank, ctx->sub_lb, ctx->sort, ctx->grid, n, st, lc);
     if (prof) next_event(ctx);
     launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                       ctx->taps, ctx->debug, ctx->deferred_lists, n, st, lc);
+                       ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
     if (prof) next_event(ctx);
     launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
                   false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc);
@@ -636,6 +637,8 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     if (rc) return rc;
   } else if (!std::strcmp(name, "deferred_lists")) {
     ctx->deferred_lists = value != 0;
+  } else if (!std::strcmp(name, "merged_rows")) {
+    ctx->merged_rows = value != 0;
   } else if (!std::strcmp(name, "fast_pairs")) {
     ctx->fast_pairs = value != 0;
   } else if (!std::strcmp(name, "forces_blocks")) {

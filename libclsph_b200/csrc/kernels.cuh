@@ -132,8 +132,8 @@ void launch_rank(const uint32_t* skey, const uint32_t* rr_old, uint32_t* rr_new,
                  uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 void launch_density_sub(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                         const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                        const DebugTaps& taps, bool debug, bool deferred, uint32_t n_launch, cudaStream_t stream,
-                        uint64_t* launches);
+                        const DebugTaps& taps, bool debug, bool deferred, bool merged, uint32_t n_launch,
+                        cudaStream_t stream, uint64_t* launches);
 void launch_forces_sub_overflow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                                 const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, const SphConst& c,
                                 const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream,

@@ -119,6 +119,36 @@ __device__ __forceinline__ void for_each_range(const SubView& v, const GridState
   }
 }
 
+// for_each_row: calls row(a0, a1, b0, b1) once per (z, y) row of sub-cells with the row's two index ranges
+// (the x extent of a row covers two cells; a third, which only happens within 2^-10 h of a sub-cell
+// boundary, is delivered as a row of its own). Walking both ranges in ONE loop matters in a warp: lanes
+// sit in different sub-cells, a loop runs as long as its longest lane, and the sum of two ranges varies
+// less between lanes than each of them (measured on the bench states: 164 instead of 216 candidate
+// slots per lane for 123 candidates).
+template <class Row>
+__device__ __forceinline__ void for_each_row(const SubView& v, const GridState& g, const SphConst& c, const float4& pi,
+                                             Row&& row) {
+  uint32_t xlo, xhi, ylo, yhi, zlo, zhi;
+  sub_bounds(pi.x, g.min_x, g.cell, c.h_margin, xlo, xhi);
+  sub_bounds(pi.y, g.min_y, g.cell, c.h_margin, ylo, yhi);
+  sub_bounds(pi.z, g.min_z, g.cell, c.h_margin, zlo, zhi);
+  const uint32_t cx_lo = xlo >> 1, cx_hi = xhi >> 1;
+  for (uint32_t fz = zlo; fz <= zhi; ++fz) {
+    const uint32_t kz = spread10(fz >> 1) << 2, oz = (fz & 1u) << 2;
+    for (uint32_t fy = ylo; fy <= yhi; ++fy) {
+      const uint32_t kzy = kz | (spread10(fy >> 1) << 1), ozy = oz | ((fy & 1u) << 1);
+      const uint2 a = sub_range(v, kzy | spread10(cx_lo), ozy | (xlo & 1u), ozy | (cx_hi == cx_lo ? (xhi & 1u) : 1u));
+      uint2 b = make_uint2(0u, 0u);
+      if (cx_hi > cx_lo) b = sub_range(v, kzy | spread10(cx_lo + 1u), ozy, ozy | (cx_hi == cx_lo + 1u ? (xhi & 1u) : 1u));
+      row(a.x, a.y, b.x, b.y);
+      if (cx_hi > cx_lo + 1u) {  // rare third cell of the row
+        const uint2 e = sub_range(v, kzy | spread10(cx_hi), ozy, ozy | (xhi & 1u));
+        row(e.x, e.y, 0u, 0u);
+      }
+    }
+  }
+}
+
 template <class Visit>
 __device__ __forceinline__ void for_each_neighbour(const SubView& v, const GridState& g, const SphConst& c,
                                                    const float4* pos, const float4& pi, Visit&& visit) {
@@ -257,7 +287,8 @@ k_rank_pair(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ordk
 // kDeferred: list entries are not stored candidate by candidate; the hits of up to 32 consecutive
 // candidates are collected in a bit mask (two instructions per candidate instead of six for the predicated
 // store, its address, the bound check and the counters) and written out by a short loop over the set bits.
-template <bool kTaps, bool kDeferred>
+// kMerged: both index ranges of a row of sub-cells are walked in one loop (for_each_row).
+template <bool kTaps, bool kDeferred, bool kMerged>
 __global__ void __launch_bounds__(kSubThreads)
 k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
               const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
@@ -300,6 +331,22 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
           if (cnt < list_rows) row[cnt] = j0 + (uint32_t)__ffs((int)m) - 1u;
           ++cnt;
         }
+      }
+    });
+  } else if (kMerged) {
+    for_each_row(v, g, c, pi, [&](uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+      const uint32_t total = (a1 - a0) + (b1 - b0);
+      uint32_t j = a0 < a1 ? a0 : b0;
+      for (uint32_t k = 0; k < total; ++k) {
+        const float4 pj = pos[j];
+        const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+        const bool inside = s < c.support_s;
+        const float t = inside ? c.h2 - s : 0.f;
+        acc = fmaf(t * t, t, acc);
+        store_if(inside && cnt < list_rows, row + cnt, j);
+        cnt += inside ? 1u : 0u;
+        ++j;
+        if (j == a1) j = b0;  // end of the first range: continue in the second
       }
     });
   } else {
@@ -396,23 +443,29 @@ void launch_rank_pair(const uint32_t* skey, const uint32_t* ordk, const uint32_t
 
 void launch_density_sub(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                         const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                        const DebugTaps& taps, bool debug, bool deferred, uint32_t n_launch, cudaStream_t stream,
-                        uint64_t* launches) {
+                        const DebugTaps& taps, bool debug, bool deferred, bool merged, uint32_t n_launch,
+                        cudaStream_t stream, uint64_t* launches) {
   const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
   uint32_t* cand = debug ? taps.candidate_count : nullptr;
   uint32_t* supp = debug ? taps.support_count : nullptr;
 if (debug && deferred)
-    k_density_sub<true, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
-                                                                  lists.entries, lists.count, lists.rows, cand, supp);
+    k_density_sub<true, true, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
+                                                                         aux, lists.entries, lists.count, lists.rows, cand, supp);
+  else if (debug && merged)
+    k_density_sub<true, false, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
+                                                                         aux, lists.entries, lists.count, lists.rows, cand, supp);
   else if (debug)
-    k_density_sub<true, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
-                                                                   lists.entries, lists.count, lists.rows, cand, supp);
+    k_density_sub<true, false, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
+                                                                          aux, lists.entries, lists.count, lists.rows, cand, supp);
   else if (deferred)
-    k_density_sub<false, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
-                                                                   lists.entries, lists.count, lists.rows, cand, supp);
+    k_density_sub<false, true, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
+                                                                          aux, lists.entries, lists.count, lists.rows, cand, supp);
+  else if (merged)
+    k_density_sub<false, false, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
+                                                                          aux, lists.entries, lists.count, lists.rows, cand, supp);
   else
-    k_density_sub<false, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
-                                                                    aux, lists.entries, lists.count, lists.rows, cand, supp);
+    k_density_sub<false, false, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
+                                                                           aux, lists.entries, lists.count, lists.rows, cand, supp);
   if (launches) ++*launches;
 }
 

@@ -92,7 +92,8 @@ SUB = dict(sub_cell_order=1)
 @pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8),
                                      SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, deferred_lists=1),
                                      dict(sub_cell_order=1, deferred_lists=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4),
-                                     dict(sub_cell_order=1, fast_pairs=1), dict(neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1)])
+                                     dict(sub_cell_order=1, fast_pairs=1), dict(neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
+                                     dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8)])
 def test_neighbour_organisations(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
@@ -256,7 +257,7 @@ def test_sub_cell_order_reports_a_grid_too_large_for_its_keys(box_scene):
 @pytest.mark.parametrize("kind", H.EDGE_KINDS)
 @pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1),
                                      dict(sub_cell_order=1, face_grid=1, deferred_lists=1),
-                                     dict(sub_cell_order=1, face_grid=1, fast_pairs=1)])
+                                     dict(sub_cell_order=1, face_grid=1, fast_pairs=1), dict(sub_cell_order=1, merged_rows=1)])
 def test_edge_states(kind, options, box_scene):
     """States sitting ON the path's decisions (tests/helpers.edge_state; the oracle is pinned against the
     reference's own kernels on the same states in test_oracle_vs_ref.py), in every organisation."""
@@ -292,7 +293,8 @@ def test_blown_up_particles_do_not_hang_the_kernels(options, box_scene):
 
 
 @pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1, fast_pairs=1),
-                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4)])
+                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4),
+                                     dict(sub_cell_order=1, face_grid=1, merged_rows=1, fast_pairs=1)])
 def test_developed_state(options):
     """State S2: fluid that has hit the floor of the box and spread -- free surface, wall
     contacts, ~10 % of the particles colliding in the step."""

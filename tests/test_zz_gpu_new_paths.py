@@ -35,7 +35,8 @@ def test_sub_cell_order_jittered(fluid, n, box_scene):
 @pytest.mark.parametrize("options", [SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, list_rows=24), BOTH,
                                      dict(sub_cell_order=1, deferred_lists=1), dict(sub_cell_order=1, deferred_lists=1, list_rows=8),
                                      dict(sub_cell_order=1, forces_blocks=4),
-                                     dict(neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1)])
+                                     dict(neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
+                                     dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8)])
 def test_sub_cell_order_crowded_and_overflowing_lists(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 20000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
@@ -156,7 +157,8 @@ def test_edge_states(kind, options, box_scene):
 
 
 @pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), BOTH,
-                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4)])
+                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4),
+                                     dict(sub_cell_order=1, face_grid=1, fast_pairs=1, merged_rows=1, forces_blocks=4)])
 def test_developed_state(options):
     """State S2 in small: fluid that has hit the floor of the box and spread (free surface, wall
     contacts, many particles colliding in the step), single step and resident steps."""

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 { nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv; } > gpurun_out/r02_env.log 2>&1
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_pytest_gpu.log
 for cfg in config2_dambreak_1m config3_mucus_labyrinth_4m; do
-  timeout 600 python -m libclsph_b200.selfcheck --config $cfg --set sub_cell_order=1,face_grid=1,fast_pairs=1 --set sub_cell_order=1,face_grid=1,fast_pairs=1,deferred_lists=1 --set sub_cell_order=1,face_grid=1,fast_pairs=1,forces_blocks=4 --set sub_cell_order=1,face_grid=1,fast_pairs=1,deferred_lists=1,forces_blocks=4 --set face_grid=1,fast_pairs=1,forces_blocks=4 \
+  timeout 600 python -m libclsph_b200.selfcheck --config $cfg --set sub_cell_order=1,face_grid=1,fast_pairs=1 --set sub_cell_order=1,face_grid=1,fast_pairs=1,merged_rows=1 --set sub_cell_order=1,face_grid=1,fast_pairs=1,merged_rows=1,forces_blocks=4 --set sub_cell_order=1,face_grid=1,fast_pairs=1,deferred_lists=1,forces_blocks=4 --set sub_cell_order=1,face_grid=1,fast_pairs=1,forces_blocks=4 --set face_grid=1,fast_pairs=1,forces_blocks=4 \
       > gpurun_out/r02_selfcheck_$cfg.json 2> gpurun_out/r02_selfcheck_$cfg.err
 done
 # memcheck + racecheck of the new kernels on a small workload (established and candidate sets in one run)
