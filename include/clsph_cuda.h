@@ -107,7 +107,8 @@ int clsph_set_scene(clsph_context* ctx, const float* face_normals, const float* 
 int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params,
                          const precomputed_kernel_values* terms);
 
-/* Tuning knobs; results are the same (to rounding) whatever they are set to.
+/* Tuning knobs; results are the same (to rounding) whatever they are set to. The environment variable
+ * CLSPH_OPTIONS="name=value,name=value" applies such pairs to every context at creation.
  *   "neighbour_lists"  1 (default): the density pass stores per-particle neighbour lists in HBM
  *                      and the force pass reads them; 0: both passes search on their own.
  *                      (Environment override at creation: CLSPH_NEIGHBOUR_LISTS=0/1.)

@@ -517,6 +517,26 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
     return CLSPH_ENOMEM;
   }
 #undef CREATE_TRY
+  // CLSPH_OPTIONS="name=value,name=value": clsph_set_option pairs applied to every new context, so that
+  // an unchanged application -- or the whole GPU test-suite -- can be run on another kernel organisation
+  if (const char* env = std::getenv("CLSPH_OPTIONS")) {
+    std::string spec(env);
+    size_t at = 0;
+    while (at < spec.size()) {
+      size_t end = spec.find(',', at);
+      if (end == std::string::npos) end = spec.size();
+      const std::string item = spec.substr(at, end - at);
+      at = end + 1;
+      if (item.empty()) continue;
+      const size_t eq = item.find('=');
+      int rc = eq == std::string::npos ? CLSPH_EINVAL : clsph_set_option(ctx, item.substr(0, eq).c_str(), std::atoll(item.c_str() + eq + 1));
+      if (rc != CLSPH_OK) {
+        const std::string why = eq == std::string::npos ? std::string("expected name=value") : ctx->error;
+        clsph_destroy(ctx);
+        return fail(nullptr, rc, "clsph_create: CLSPH_OPTIONS item \"%s\": %s", item.c_str(), why.c_str());
+      }
+    }
+  }
   *out = ctx;
   return CLSPH_OK;
 }
