@@ -194,16 +194,33 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
   const uint32_t* __restrict__ vals = in_b ? vals_b : vals_a;
   const uint32_t fkey = keys[r];
   const uint32_t from = vals[r];
-  dst_pos[r] = src_pos[from];
-  dst_vel[r] = src_vel[from];
-  dst_ivel[r] = src_ivel[from];
+  // Slot inside the sub-cell. The radix sort leaves the particles of a sub-cell in the order of the
+  // previous internal arrays, which depends on the history (e.g. on whether the state was re-uploaded).
+  // With the reference rank at hand (one GPU) they are put in the reference's order instead: the slot is
+  // the number of particles of the same sub-cell with a smaller rank, counted over the handful of equal
+  // keys around r. The arrays, hence every floating-point sum, then depend on the state alone: k resident
+  // sub-steps are bitwise equal to k host round trips, as in the established organisation.
+  uint32_t dest = r;
+  if (rr_src) {
+    const uint32_t mine = rr_src[from];
+    uint32_t left = 0, smaller = 0;
+    for (uint32_t q = r; q > 0 && keys[q - 1] == fkey; --q) {
+      ++left;
+      smaller += rr_src[vals[q - 1]] < mine ? 1u : 0u;
+    }
+    for (uint32_t q = r + 1; q < n && keys[q] == fkey; ++q) smaller += rr_src[vals[q]] < mine ? 1u : 0u;
+    dest = r - left + smaller;
+    rr_dst[dest] = mine;
+  }
+  dst_pos[dest] = src_pos[from];
+  dst_vel[dest] = src_vel[from];
+  dst_ivel[dest] = src_ivel[from];
   const uint32_t key = fkey >> 3, oct = fkey & 7u;
-  skey[r] = key;
-  if (rr_src) rr_dst[r] = rr_src[from];
-  if (src_pid) dst_pid[r] = src_pid[from];
+  skey[r] = key;  // the same for the whole sub-cell, whichever slot
+  if (src_pid) dst_pid[dest] = src_pid[from];
   if (src_ordk) {  // multi-GPU: order keys (cell key and rank inside the cell of the previous sub-step)
-    dst_ordk[r] = src_ordk[from];
-    dst_ordr[r] = src_ordr[from];
+    dst_ordk[dest] = src_ordk[from];
+    dst_ordr[dest] = src_ordr[from];
   }
   if (!grid->sub_dense) return;
   const uint32_t count = grid->cell_count;  // keys are < count whenever the grid fits (see k_reorder)
