@@ -166,3 +166,23 @@ def test_developed_state(options):
     got, taps, want = G.check_against_oracle(s, p, terms, scene, "developed %r" % (options,), options=options)
     assert (want.collision_iters > 1).sum() > 100
     G.check_resident_steps_against_oracle(s, p, terms, scene, 3, "developed, resident %r" % (options,), options=options)
+
+
+@pytest.mark.parametrize("options", [SUB, dict(sub_cell_order=1, merged_rows=1, fast_pairs=1, face_grid=1, forces_blocks=4)])
+def test_sub_cell_order_resident_steps_equal_host_round_trips_bitwise(options, box_scene):
+    """History independence of the sub-cell order (particles of a sub-cell are kept in the reference's
+    order): k resident sub-steps == k upload/step/download round trips, bit for bit."""
+    p, terms, vol = H.config("water", 20000)
+    s = H.state_s1(p, vol)
+    s["intermediate_velocity"][:, 0] += (2.5 * np.sign(s["position"][:, 2])).astype(np.float32)
+    ctx = G.make_ctx(s.size, box_scene, p, terms, debug=False, options=options)
+    ctx.upload(s)
+    ctx.step(4)
+    resident = ctx.download()
+    cur = s
+    for _ in range(4):
+        ctx.upload(cur)
+        ctx.step(1)
+        cur = ctx.download()
+    ctx.close()
+    assert resident.tobytes() == cur.tobytes()
