@@ -199,7 +199,9 @@ int clsph_dist_upload(clsph_context* ctx, const particle* aos, const uint32_t* i
  * particle's rank inside its cell in the REFERENCE's order: concatenating all ranks' downloads and
  * sorting by (grid_index, that word) gives exactly the array a single device -- and the reference --
  * would hold (ids passed to clsph_dist_upload must then be the indices of the initial global
- * array). Without the option the word is 0 and only per-particle values can be compared. */
+ * array), and the values themselves are bitwise those of a single-device run (every rank keeps the
+ * particles of a sub-cell in the reference's order, so all sums run in the same order). Without the
+ * option the word is 0 and per-particle values agree to rounding only. */
 int clsph_dist_download(clsph_context* ctx, particle* aos_out, uint32_t* ids_out, uint32_t capacity, uint32_t* n_out);
 
 /* ---- observation ----------------------------------------------------------------------- */

@@ -171,14 +171,18 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
     if (e < emax) { float4* r = msg_emigrants(send_right) + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f); }
     else atomicOr(&grid->error, 2u);
   }
+  // ghosts travel as (position, velocity); with order keys (sub-cell order) these ride in the two w lanes,
+  // which are free between the integrator and the density pass
+  float4 gp = p, gv = v;
+  if (wrank) { gp.w = __uint_as_float(ok_k); gv.w = __uint_as_float(ok_r); }
   e = warp_append(ghost_left, &hl->n_ghosts);
   if (ghost_left) {
-    if (e < gmax) { float4* r = msg_ghosts(send_left, emax) + (size_t)e * 2; r[0] = p; r[1] = v; }
+    if (e < gmax) { float4* r = msg_ghosts(send_left, emax) + (size_t)e * 2; r[0] = gp; r[1] = gv; }
     else atomicOr(&grid->error, 2u);
   }
   e = warp_append(ghost_right, &hr->n_ghosts);
   if (ghost_right) {
-    if (e < gmax) { float4* r = msg_ghosts(send_right, emax) + (size_t)e * 2; r[0] = p; r[1] = v; }
+    if (e < gmax) { float4* r = msg_ghosts(send_right, emax) + (size_t)e * 2; r[0] = gp; r[1] = gv; }
     else atomicOr(&grid->error, 2u);
   }
 }
@@ -197,7 +201,7 @@ k_dist_unpack(void* msg, uint32_t emax, uint32_t gmax, GridState* grid, float4* 
   const bool is_g = t >= emax && t - emax < ng;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, iv = p;
   uint32_t id = 0xFFFFFFFFu;  // ghosts carry no identity here
-  uint32_t ok_k = 0xFFFFFFFFu, ok_r = 0u;  // ... and no place in the reference's order
+  uint32_t ok_k = 0xFFFFFFFFu, ok_r = 0u;  // ... and, without order keys, no place in the reference's order
   if (is_e) {
     const float4* r = msg_emigrants(msg) + (size_t)t * 4;
     p = r[0]; v = r[1]; iv = r[2]; id = __float_as_uint(r[3].x);
@@ -205,6 +209,10 @@ k_dist_unpack(void* msg, uint32_t emax, uint32_t gmax, GridState* grid, float4* 
   } else if (is_g) {
     const float4* r = msg_ghosts(msg, emax) + (size_t)(t - emax) * 2;
     p = r[0]; v = r[1];
+    if (u_ordk) {  // the sender's order keys, see k_dist_classify
+      ok_k = __float_as_uint(p.w); ok_r = __float_as_uint(v.w);
+      p.w = 0.f; v.w = 0.f;
+    }
   }
   const uint32_t at = warp_append(is_e || is_g, u_count);
   if (is_e || is_g) {

@@ -211,6 +211,23 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
     for (uint32_t q = r + 1; q < n && keys[q] == fkey; ++q) smaller += rr_src[vals[q]] < mine ? 1u : 0u;
     dest = r - left + smaller;
     rr_dst[dest] = mine;
+  } else if (src_ordk) {
+    // multi-GPU: the same with the order keys (cell key, rank in cell of the previous sub-step), which order
+    // particles like the global reference rank does and which ghosts carry too. Every rank then holds the
+    // particles of a sub-cell in the order a single GPU would, all sums run in the same order, and the
+    // decomposition is bitwise transparent.
+    const uint32_t mk = src_ordk[from], mr = src_ordr[from];
+    uint32_t left = 0, smaller = 0;
+    for (uint32_t q = r; q > 0 && keys[q - 1] == fkey; --q) {
+      ++left;
+      const uint32_t o = vals[q - 1], jk = src_ordk[o], jr = src_ordr[o];
+      smaller += (jk < mk || (jk == mk && jr < mr)) ? 1u : 0u;
+    }
+    for (uint32_t q = r + 1; q < n && keys[q] == fkey; ++q) {
+      const uint32_t o = vals[q], jk = src_ordk[o], jr = src_ordr[o];
+      smaller += (jk < mk || (jk == mk && jr < mr)) ? 1u : 0u;
+    }
+    dest = r - left + smaller;
   }
   dst_pos[dest] = src_pos[from];
   dst_vel[dest] = src_vel[from];

@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_worker.py [n] [steps] [--sub]
 
 --sub selects the sub-cell order (+ face grid) and additionally checks that the ranks' downloads, merged by
-(grid_index, padding word), reproduce the single-GPU run's array ORDER exactly.
+(grid_index, padding word), reproduce the single-GPU run's array ORDER exactly and its values BITWISE.
 
 Every rank runs one slab of the same fluid block through the CUDA library (clsph_dist_*); rank 0
 also runs the whole block on its own GPU without decomposition and, for the first sub-step, on the
@@ -121,6 +121,12 @@ def main():
                 same_order = np.array_equal(ids[merged], ref_ids)
                 print("step %d: merged global order equals the single-GPU array order: %s" % (k, same_order), flush=True)
                 ok = ok and same_order
+                # every rank keeps the particles of a sub-cell in the reference's order (ghosts carry their order
+                # keys), so all sums run as on one GPU: the decomposition is bitwise transparent
+                bitwise = all(by_id_got[f].tobytes() == by_id_want[f].tobytes()
+                              for f in ("position", "velocity", "intermediate_velocity", "density", "pressure", "grid_index"))
+                print("step %d: bitwise equal to the single-GPU run: %s" % (k, bitwise), flush=True)
+                ok = ok and bitwise
             errs = {f: rel(by_id_got[f][:, :3] if by_id_got[f].ndim == 2 else by_id_got[f],
                            by_id_want[f][:, :3] if by_id_want[f].ndim == 2 else by_id_want[f])
                     for f in ("position", "velocity", "intermediate_velocity", "density", "pressure")}

@@ -123,6 +123,10 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
             # the latter carried in the records' padding word (clsph_dist_download)
             order = np.lexsort((parts["_pad"], parts["grid_index"]))
             assert np.array_equal(ids[order], orders[k]), "step %d: merged order differs from the single-rank array order" % k
+            # ... and, because every rank keeps the particles of a sub-cell in that order too (ghosts included),
+            # all sums run in the order a single device uses: the decomposition is BITWISE transparent
+            for f in ("position", "velocity", "intermediate_velocity", "density", "pressure", "grid_index"):
+                assert got[f].tobytes() == wants[k][f].tobytes(), "step %d: %s differs bitwise from the single-rank run" % (k, f)
         if k == 0:
             assert np.array_equal(got["grid_index"], wants[0]["grid_index"]), "keys differ from the single-rank run"
             assert np.array_equal(got["grid_index"], oracle_by_id["grid_index"]), "keys differ from the oracle"
