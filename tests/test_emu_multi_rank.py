@@ -189,3 +189,45 @@ def test_bench_multi_gpu_flow_with_its_own_capacities():
     assert not errors, errors
     assert sum(c[0] for c in counts) == world * n_per_gpu, counts
     assert sum(c[1] for c in counts) == world * n_per_gpu, counts
+
+
+def test_buffer_overflow_is_reported_and_nobody_hangs():
+    """Message buffers too small for the ghost layers (what killed the first 8-GPU run of round 1): the rank
+    that overflows reports CLSPH_ECOMM at its next synchronising call, every rank finishes its sub-steps
+    (fixed-size messages: nobody waits for data that never comes), contexts close cleanly."""
+    world = 2
+    p, terms, state, scene_file = elongated_state(2)
+    n = state.size
+    normals, vertices, indices = workloads.scene_arrays(scene_file)
+    planes = slabs.equal_count_planes(state["position"][:, 0], world)
+    owner = slabs.slab_of(state["position"][:, 0], planes)
+    uid = capi.comm_unique_id()
+    codes = [None] * world
+    errors = []
+
+    def run_rank(rank):
+        try:
+            mine = np.nonzero(owner == rank)[0].astype(np.uint32)
+            ctx = capi.Context(n)
+            ctx.set_scene(normals, vertices, indices)
+            ctx.set_parameters(p, terms)
+            ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]), emigrant_capacity=64, ghost_capacity=64)
+            ctx.dist_upload(np.ascontiguousarray(state[mine]), mine)
+            ctx.step(3)
+            try:
+                ctx.synchronize()
+                codes[rank] = 0
+            except capi.ClsphError as e:
+                codes[rank] = e.code
+            ctx.close()
+        except BaseException as exc:  # noqa: BLE001
+            errors.append((rank, exc))
+
+    threads = [threading.Thread(target=run_rank, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not errors, errors
+    assert not any(t.is_alive() for t in threads), "a rank is still waiting"
+    assert capi.E_COMM in codes, codes
