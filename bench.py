@@ -249,7 +249,7 @@ def ctx_capacity(ctx, n):
     return int(n * 1.5) + 65536
 
 
-def multi_gpu_workload(config, n_per_gpu, rank, world):
+def multi_gpu_workload(config, n_per_gpu, rank, world, sub_cell_order=False):
     """This rank's share of the weak-scaling workload: `world` x the configured count as ONE fluid block
     (same particle mass, hence same h and spacing), cut into x slabs. Returns a dict with the parameters,
     the rank's particles and ids, its slab planes and the capacities to create the context with."""
@@ -263,9 +263,51 @@ def multi_gpu_workload(config, n_per_gpu, rank, world):
     # and of bursty migration (a snapped slab boundary jumps by one cell now and then)
     per_side, side, spacing = workloads.lattice_geometry(p, vol)
     layer = int(p.particles_count / per_side * (2.0 * p.h / float(spacing))) + 1
-    emigrant_cap, ghost_cap = int(2.0 * layer) + 8192, int(4.0 * layer) + 8192
+    # Messages have a fixed size (no host-visible counts), so the capacities are what travels every sub-step:
+    # emigrants = one layer in a burst, ghosts = two cell layers (established kernels) or one (sub-cell order,
+    # two sub-cell layers), each with 50 % slack for local compression of the fluid.
+    emigrant_cap = int(1.5 * layer) + 8192
+    ghost_cap = int((1.5 if sub_cell_order else 3.0) * layer) + 8192
     return dict(params=p, terms=terms, volume=vol, state=state, ids=index, planes=planes, emigrant_capacity=emigrant_cap,
                 ghost_capacity=ghost_cap, capacity=int(1.2 * n) + 2 * layer + 2 * ghost_cap + 65536)
+
+
+def slab_invariants(w, scene, options, rank, world, unique_id, device_index, substeps=3):
+    """This rank's contribution to a few GLOBAL invariants of a short multi-GPU run of the bench workload with
+    the given options: owned particle count, sum of ids and of ids^2 (nothing lost, nothing duplicated), sums
+    of density, pressure and |position|, |velocity| components over the owned particles (float64). Summed over
+    the ranks they must not depend on the kernel organisation beyond rounding."""
+    import numpy as np
+    from libclsph_b200 import capi
+    ctx = capi.Context(w["capacity"], device=device_index)
+    for opt in options:
+        k, v = opt.split("=")
+        ctx.set_option(k, int(v))
+    ctx.set_scene(*scene)
+    ctx.set_parameters(w["params"], w["terms"])
+    ctx.dist_init(rank, world, unique_id, float(w["planes"][rank]), float(w["planes"][rank + 1]),
+                  emigrant_capacity=w["emigrant_capacity"], ghost_capacity=w["ghost_capacity"])
+    ctx.dist_upload(w["state"], w["ids"])
+    ctx.step(substeps)
+    parts, ids = ctx.dist_download()
+    ctx.close()
+    u64 = ids.astype(np.uint64)
+    with np.errstate(over="ignore"):  # sums modulo 2^64: exact and independent of the order
+        ints = np.array([parts.size, u64.sum(dtype=np.uint64), (u64 * u64).sum(dtype=np.uint64)], dtype=np.uint64).view(np.int64)
+    f = lambda a: float(np.abs(a.astype(np.float64)).sum())
+    floats = np.array([f(parts["density"]), f(parts["pressure"]), f(parts["position"][:, 0]), f(parts["position"][:, 1]),
+                       f(parts["position"][:, 2]), f(parts["velocity"][:, 0]), f(parts["velocity"][:, 1]), f(parts["velocity"][:, 2])],
+                      dtype=np.float64)
+    return ints, floats
+
+
+def invariants_agree(base, cand, n_total):
+    """base / cand: (ints, floats) of slab_invariants summed over the ranks (ints modulo 2^64) for the established
+    and the candidate options."""
+    (bi, bf), (ci, cf) = base, cand
+    exact = int(bi[0]) == int(ci[0]) == int(n_total) and int(bi[1]) == int(ci[1]) and int(bi[2]) == int(ci[2])
+    rel = max(abs(float(a) - float(b)) / max(abs(float(a)), 1e-30) for a, b in zip(bf, cf))
+    return bool(exact and rel <= 1e-5), float(rel)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -328,10 +370,39 @@ def run_ours(args, rank, world, local_rank):
         ctx = capi.Context(n, device=local_rank)
     else:
         # weak scaling: each rank generates only its own slab of the common block
-        w = multi_gpu_workload(args.config, n_cfg, rank, world)
+        w = multi_gpu_workload(args.config, n_cfg, rank, world, sub_cell_order="sub_cell_order=1" in options)
         p, terms, vol, state, ids, planes = w["params"], w["terms"], w["volume"], w["state"], w["ids"], w["planes"]
         emigrant_cap, ghost_cap = w["emigrant_capacity"], w["ghost_capacity"]
         n = state.size
+        if options and not args.option and args.organisation == "auto":
+            # The self-check ran on one GPU. Before the adopted options time a multi-GPU run, three sub-steps of
+            # this very workload are run with the established organisation and with them, and global
+            # invariants (count, id sums, sums of density / pressure / positions / velocities over the owned
+            # particles, all-reduced) must agree; otherwise every rank goes back to the established one.
+            def fresh_uid():
+                t = (torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device=device) if rank == 0
+                     else torch.zeros(128, dtype=torch.uint8, device=device))
+                dist.broadcast(t, 0)
+                return bytes(t.cpu().numpy().tolist())
+
+            def reduced(opts):
+                ints, floats = slab_invariants(w, (normals, vertices, indices), opts, rank, world, fresh_uid(), local_rank)
+                ti = torch.tensor(ints, dtype=torch.int64, device=device)      # wraps modulo 2^64 like the local sums
+                tf = torch.tensor(floats, dtype=torch.float64, device=device)
+                dist.all_reduce(ti, op=dist.ReduceOp.SUM)
+                dist.all_reduce(tf, op=dist.ReduceOp.SUM)
+                return ti.cpu().numpy(), tf.cpu().numpy()
+
+            w_sub = w
+            w = multi_gpu_workload(args.config, n_cfg, rank, world, sub_cell_order=False)  # capacities of the established kernels
+            base = reduced([])
+            w = w_sub
+            ok, rel = invariants_agree(base, reduced(options), n_cfg * world)
+            organisation["multi_gpu_crosscheck"] = {"agree": ok, "max_rel_diff": rel, "substeps": 3}
+            if not ok:
+                options = []
+                w = multi_gpu_workload(args.config, n_cfg, rank, world, sub_cell_order=False)
+                emigrant_cap, ghost_cap = w["emigrant_capacity"], w["ghost_capacity"]
         ctx = capi.Context(w["capacity"], device=local_rank)
     for opt in options:
         k, v = opt.split("=")

@@ -158,7 +158,7 @@ def test_bench_multi_gpu_flow_with_its_own_capacities():
 
     def run_rank(rank):
         try:
-            w = bench.multi_gpu_workload("config2_dambreak_1m", n_per_gpu, rank, world)
+            w = bench.multi_gpu_workload("config2_dambreak_1m", n_per_gpu, rank, world, sub_cell_order=True)
             ctx = capi.Context(w["capacity"])
             ctx.set_option("sub_cell_order", 1)
             ctx.set_option("face_grid", 1)
@@ -231,3 +231,43 @@ def test_buffer_overflow_is_reported_and_nobody_hangs():
     assert not errors, errors
     assert not any(t.is_alive() for t in threads), "a rank is still waiting"
     assert capi.E_COMM in codes, codes
+
+
+def test_bench_multi_gpu_crosscheck_of_global_invariants():
+    """bench.py, N > 1: before options chosen by the single-GPU self-check time a multi-GPU run, three sub-steps
+    of the run's own workload with the established organisation and with them must agree on global invariants.
+    Here with threads as ranks and a plain sum standing in for the all-reduce; a deliberately broken candidate
+    (ghost messages too small for the ghost layer are detected by the library itself) is not needed: the check
+    is exercised for agreement, and for disagreement with doctored numbers."""
+    import sys
+    sys.path.insert(0, H.ROOT)
+    import bench
+    world, n_per_gpu = 2, 30000
+    scene = workloads.scene_arrays("box.obj")
+    totals = {}
+    for name, options in (("established", []), ("candidate", list(bench.CANDIDATE_SETS[1]))):
+        uid = capi.comm_unique_id()
+        out = [None] * world
+        errors = []
+
+        def run_rank(rank):
+            try:
+                w = bench.multi_gpu_workload("config2_dambreak_1m", n_per_gpu, rank, world, sub_cell_order="sub_cell_order=1" in options)
+                out[rank] = bench.slab_invariants(w, scene, options, rank, world, uid, 0)
+            except BaseException as exc:  # noqa: BLE001
+                errors.append((rank, exc))
+
+        threads = [threading.Thread(target=run_rank, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=900)
+        assert not errors, errors
+        with np.errstate(over="ignore"):
+            totals[name] = (sum(o[0] for o in out), sum(o[1] for o in out))
+    ok, rel = bench.invariants_agree(totals["established"], totals["candidate"], world * n_per_gpu)
+    assert ok and rel <= 1e-5, (rel, totals)
+    lost = (totals["candidate"][0] - np.array([1, 5, 25], dtype=np.int64), totals["candidate"][1])
+    assert not bench.invariants_agree(totals["established"], lost, world * n_per_gpu)[0]
+    off = (totals["candidate"][0], totals["candidate"][1] * np.array([1.01, 1, 1, 1, 1, 1, 1, 1]))
+    assert not bench.invariants_agree(totals["established"], off, world * n_per_gpu)[0]
