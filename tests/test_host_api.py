@@ -105,6 +105,7 @@ def test_simulate_matches_oracle_steps(tmp_path, policy, callbacks):
 @pytest.mark.gpu
 def test_clsphparticles_cli_writes_frames_and_checkpoint(tmp_path):
     """The command-line driver end to end: JSON in, .geo frames and last_frame.bin out, resume."""
+    hostapi.build()  # makes libclsph_host.so and the clsphparticles binary if they are missing or stale
     wd = _workdir(tmp_path)
     sim = open(os.path.join(wd, "simulation_properties", "default.json")).read()
     sim = sim.replace('"particles_count" : 32000', '"particles_count" : 2048').replace('"serialize" : false', '"serialize" : true')
