@@ -264,9 +264,11 @@ def multi_gpu_workload(config, n_per_gpu, rank, world, sub_cell_order=False):
     per_side, side, spacing = workloads.lattice_geometry(p, vol)
     layer = int(p.particles_count / per_side * (2.0 * p.h / float(spacing))) + 1
     # Messages have a fixed size (no host-visible counts), so the capacities are what travels every sub-step:
-    # emigrants = one layer in a burst, ghosts = two cell layers (established kernels) or one (sub-cell order,
-    # two sub-cell layers), each with 50 % slack for local compression of the fluid.
-    emigrant_cap = int(1.5 * layer) + 8192
+    # emigrants = one layer in a burst (established kernels: slab boundaries snapped to cells), ghosts = two
+    # cell layers (established) or the 2h next to the plane (sub-cell order), with 50 % slack for compression.
+    # Sub-cell order: ownership follows the planes themselves, so only the particles that cross one migrate (at
+    # most vmax dt = 0.08 h of a layer per sub-step) and there are no bursts.
+    emigrant_cap = int((0.25 if sub_cell_order else 1.5) * layer) + 8192
     ghost_cap = int((1.5 if sub_cell_order else 3.0) * layer) + 8192
     return dict(params=p, terms=terms, volume=vol, state=state, ids=index, planes=planes, emigrant_capacity=emigrant_cap,
                 ghost_capacity=ghost_cap, capacity=int(1.2 * n) + 2 * layer + 2 * ghost_cap + 65536)

@@ -180,7 +180,8 @@ int clsph_comm_unique_id(void* out, size_t bytes);
 
 /* Joins the communicator. plane_lo / plane_hi = world-space x bounds of this rank's slab
  * (-INFINITY for rank 0, +INFINITY for the last rank); neighbouring ranks must pass the same
- * plane. Slabs must stay at least four grid cells (8 h) thick. Capacities are records per
+ * plane. Slabs must stay at least four grid cells (8 h) thick (two, 4 h, with sub_cell_order, where
+ * ownership follows the planes themselves instead of cells snapped to them and nothing migrates in bursts). Capacities are records per
  * message per sub-step. The planes are snapped to the cell boundaries of a grid whose origin
  * follows the fluid, so occasionally a boundary jumps by one cell and a whole cell layer
  * migrates at once: emigrant_capacity must hold one cell layer of the slab's cross-section and

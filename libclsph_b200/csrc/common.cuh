@@ -20,7 +20,8 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // run of sub-steps needs no host round trip.
 struct GridState {
   float min_x, min_y, min_z, cell;   // padded AABB minimum, cell side 2h
-  float max_x, max_y, max_z, pad0;
+  float max_x, max_y, max_z;
+  float plane_lo;                    // this rank's slab in world space: plane_lo <= x < plane_hi (-inf / +inf at the ends)
   int gx, gy, gz;                    // grid_size_*
   uint32_t cell_count;               // morton(gx, gy, gz)
   uint32_t n;                        // particles on this device
@@ -37,7 +38,7 @@ struct GridState {
   // particles of a cell are grouped by the h-sized sub-cell they are in.
   uint32_t sub;                      // 1: this sub-step sorts by sub-cell keys
   uint32_t sub_dense;                // 1: cell_count fits the dense sub-cell table; 0: binary search
-  uint32_t pad1;
+  float plane_hi;
 };
 
 // AABB accumulators: floats mapped to order-preserving unsigned so atomicMin/Max apply.
@@ -102,6 +103,18 @@ __host__ __device__ inline uint32_t compact10(uint32_t v) {
 __device__ __forceinline__ bool cell_is_owned(uint32_t key, const GridState& g) {
   const int cx = (int)compact10(key);
   return cx >= g.own_lo && cx < g.own_hi;
+}
+// Ownership of a particle. Established organisation: by the cell it is in (slab boundaries snapped to cell
+// boundaries). Sub-cell order: by the world-space planes themselves -- the kernels there work per particle,
+// so nothing forces whole cells to change owner at once, slabs stay balanced and migration is only what
+// really crosses a plane. On one GPU both say "owned".
+__device__ __forceinline__ bool owned_here(float x, uint32_t key, const GridState& g) {
+  if (g.sub) return x >= g.plane_lo && x < g.plane_hi;
+  return cell_is_owned(key, g);
+}
+__device__ __forceinline__ bool slab_is_cut(const GridState& g) {
+  if (g.sub) return g.plane_lo > -__int_as_float(0x7f800000) || g.plane_hi < __int_as_float(0x7f800000);
+  return g.own_lo > 0 || g.own_hi != 0x7fffffff;
 }
 // Owned, or in the first ghost layer on either side (whose density the force pass needs).
 __device__ __forceinline__ bool cell_needs_density(uint32_t key, const GridState& g) {

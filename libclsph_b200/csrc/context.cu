@@ -392,7 +392,8 @@ int enqueue_substep(clsph_context* ctx) {
       launch_rank(ctx->skey, ctx->rr_tmp, ctx->rrank, ctx->sub_lb, ctx->sort, ctx->grid, ctx->perm,
                   ctx->debug ? ctx->taps.keys_input : nullptr, n, st, lc);
     else         // across ranks: (cell key, rank in cell), merged at export
-      launch_rank_pair(ctx->skey, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->wrank, ctx->sub_lb, ctx->sort, ctx->grid, n, st, lc);
+      launch_rank_pair(dst.pos, ctx->skey, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->wrank, ctx->sub_lb, ctx->sort, ctx->grid, n,
+                       st, lc);
     if (prof) next_event(ctx);
     launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
                        ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);

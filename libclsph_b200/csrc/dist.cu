@@ -120,8 +120,12 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   if ((i & ~31u) >= g.n) return;  // whole warp out of range
   bool owned = i < g.n;
   if (owned && !g.fresh) {
-    const int cx_old = (int)compact10(skey[i]);
-    owned = cx_old >= g.prev_lo && cx_old < g.prev_hi;  // the rest are last step's ghost copies: dropped
+    if (g.sub) {
+      owned = ivel[i].w == 1.f;  // advanced here in the last sub-step (k_integrate's mark); the rest are ghost copies
+    } else {
+      const int cx_old = (int)compact10(skey[i]);
+      owned = cx_old >= g.prev_lo && cx_old < g.prev_hi;  // the rest are last step's ghost copies: dropped
+    }
   }
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, iv = p;
   uint32_t id = 0;
@@ -129,26 +133,32 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   // array = (its cell key, its rank inside that cell) of the previous sub-step, compared
   // lexicographically; right after an upload (0, id): ids are the indices of the uploaded global array.
   uint32_t ok_k = 0, ok_r = 0;
-  int cx = 0, fx = 0;
+  int cx = 0;
   if (owned) {
     p = pos[i]; v = vel[i]; iv = ivel[i]; id = pid[i];
     cx = (int)cell_coord(p.x, g.min_x, g.cell);
-    fx = (int)sub_coord(p.x, g.min_x, g.cell);
     if (wrank) {
       ok_k = g.fresh ? 0u : skey[i];
       ok_r = g.fresh ? id : wrank[i];
     }
   }
-  const bool has_left = g.own_lo > 0, has_right = g.own_hi != 0x7fffffff;
-  const bool go_left = owned && has_left && cx < g.own_lo;
-  const bool go_right = owned && has_right && cx >= g.own_hi;
+  // Established organisation: ownership by cell (planes snapped to cell boundaries). Sub-cell order: by the
+  // planes themselves (owned_here in common.cuh), so only particles that really cross a plane migrate.
+  const float inf = __int_as_float(0x7f800000);
+  const bool has_left = g.sub ? g.plane_lo > -inf : g.own_lo > 0;
+  const bool has_right = g.sub ? g.plane_hi < inf : g.own_hi != 0x7fffffff;
+  const bool go_left = owned && has_left && (g.sub ? p.x < g.plane_lo : cx < g.own_lo);
+  const bool go_right = owned && has_right && (g.sub ? p.x >= g.plane_hi : cx >= g.own_hi);
   const bool stay = owned && !go_left && !go_right;
+  if (g.sub) iv.w = 0.f;  // the mark is k_integrate's to set again, for what this rank advances in this sub-step
   // Ghost depth. The neighbour needs, beyond its boundary, the particles within h (candidates of its own
   // particles) whose densities it recomputes, hence those within 2h. The established kernels work on whole
   // cells of side 2h, which makes that two cell layers; the sub-cell order searches by sub-cells of side
-  // h, so two SUB-cell layers (one cell layer) are enough: half the ghost volume.
-  const bool ghost_left = stay && has_left && (g.sub ? fx < 2 * g.own_lo + 2 : cx < g.own_lo + 2);
-  const bool ghost_right = stay && has_right && (g.sub ? fx >= 2 * g.own_hi - 2 : cx >= g.own_hi - 2);
+  // h and takes roles per particle, so the particles within 2h (1 + 2^-10) of the plane are enough: half
+  // the ghost volume.
+  const float depth = g.cell * 1.0009765625f;
+  const bool ghost_left = stay && has_left && (g.sub ? p.x < g.plane_lo + depth : cx < g.own_lo + 2);
+  const bool ghost_right = stay && has_right && (g.sub ? p.x >= g.plane_hi - depth : cx >= g.own_hi - 2);
 
   // local array: stayers as owned, emigrants as ghost copies (their new key marks them as such)
   const uint32_t at = warp_append(owned, u_count);
@@ -239,7 +249,8 @@ k_dist_export(const float4* __restrict__ pos, const float4* __restrict__ vel, co
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if ((i & ~31u) >= g.n) return;
-  const bool owned = i < g.n && (g.fresh || cell_is_owned(skey[i], g));
+  // sub-cell order: owned = advanced here in the last sub-step (its position may since have left the slab)
+  const bool owned = i < g.n && (g.fresh || (g.sub ? ivel[i].w == 1.f : cell_is_owned(skey[i], g)));
   const uint32_t at = warp_append(owned, out_count);
   if (!owned) return;
   float4 p = pos[i], v = vel[i], iv = ivel[i];

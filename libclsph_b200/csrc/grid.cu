@@ -89,7 +89,9 @@ __global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t 
   }
   const uint32_t count = morton3((uint32_t)gs[0], (uint32_t)gs[1], (uint32_t)gs[2]);
   grid->min_x = mn[0]; grid->min_y = mn[1]; grid->min_z = mn[2]; grid->cell = cell;
-  grid->max_x = mx[0]; grid->max_y = mx[1]; grid->max_z = mx[2]; grid->pad0 = 0.f;
+  grid->max_x = mx[0]; grid->max_y = mx[1]; grid->max_z = mx[2];
+  grid->plane_lo = plane_lo;
+  grid->plane_hi = plane_hi;
   grid->gx = gs[0]; grid->gy = gs[1]; grid->gz = gs[2];
   grid->cell_count = count;
   if (!keep_n) grid->n = n;

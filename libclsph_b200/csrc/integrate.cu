@@ -80,13 +80,17 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
             BoundsAcc* next_bounds, uint32_t* __restrict__ iters_tap) {
   const GridState g = *grid;
   const uint32_t n = g.n;
-  const bool sliced = g.own_lo > 0 || g.own_hi != 0x7fffffff;  // multi-GPU: ghosts are not advanced
+  const bool sliced = slab_is_cut(g);  // multi-GPU: ghosts are not advanced
+  // sub-cell order across GPUs: the w lane of the half-step velocity marks "advanced here", i.e. owned in this
+  // sub-step, which is what the next exchange and the export go by (the position may since have left the slab)
+  const float owned_mark = (sliced && g.sub) ? 1.f : 0.f;
   float lo[3] = {2147483648.f, 2147483648.f, 2147483648.f};
   float hi[3] = {-2147483648.f, -2147483648.f, -2147483648.f};
 
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (sliced && !cell_is_owned(skey[i], g)) continue;
-    const float4 p4 = pos[i], iv4 = ivel[i], a4 = accel[i];
+    const float4 p4 = pos[i];
+    if (sliced && !owned_here(p4.x, skey[i], g)) continue;
+    const float4 iv4 = ivel[i], a4 = accel[i];
     V3 x = mk(p4.x, p4.y, p4.z);
     V3 v = mk(iv4.x, iv4.y, iv4.z);
     V3 acc = mk(a4.x, a4.y, a4.z);
@@ -210,7 +214,7 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
     const V3 v_out = divs(add(v_half_old, v), 2.f);
     pos[i] = make_float4(x.x, x.y, x.z, 0.f);
     vel[i] = make_float4(v_out.x, v_out.y, v_out.z, 0.f);
-    ivel[i] = make_float4(v.x, v.y, v.z, 0.f);
+    ivel[i] = make_float4(v.x, v.y, v.z, owned_mark);
     if (iters_tap) iters_tap[i] = iters;
 
     lo[0] = fminf(lo[0], x.x); hi[0] = fmaxf(hi[0], x.x);

@@ -124,7 +124,7 @@ void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const So
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,
                         uint32_t* dst_ordk, uint32_t* dst_ordr, uint32_t n_launch, cudaStream_t stream,
                         uint64_t* launches);
-void launch_rank_pair(const uint32_t* skey, const uint32_t* ordk, const uint32_t* ordr, uint32_t* wrank,
+void launch_rank_pair(const float4* pos, const uint32_t* skey, const uint32_t* ordk, const uint32_t* ordr, uint32_t* wrank,
                       const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, uint32_t n_launch,
                       cudaStream_t stream, uint64_t* launches);
 void launch_rank(const uint32_t* skey, const uint32_t* rr_old, uint32_t* rr_new, const uint32_t* sub_lb,

@@ -623,11 +623,11 @@ k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, c
   const uint32_t base = (blockIdx.x * kFlWarps + warp) * 32u;
   if (base >= n) return;
   const uint32_t i = base + lane;
-  const bool valid = i < n && cell_is_owned(skey[min(i, n - 1u)], g);  // multi-GPU: ghosts get no force
+  const float4 pi = i < n ? pos[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool valid = i < n && owned_here(pi.x, skey[min(i, n - 1u)], g);  // multi-GPU: ghosts get no force
   uint32_t count = valid ? ncount[i] : 0u;
   const bool listed = count <= list_rows;  // otherwise redone by k_forces<true>
   if (!listed) count = 0u;
-  const float4 pi = valid ? pos[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 vi = valid ? vel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   ForceSums sums;
   uint32_t* tile = s_tile[warp];

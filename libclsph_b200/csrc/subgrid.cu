@@ -291,14 +291,16 @@ k_rank(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ rr_old, u
 // count over the previous pairs, compared lexicographically. The global array, when wanted, is the
 // merge of the ranks' downloads by (grid_index, rank in cell): clsph_dist_download.
 __global__ void __launch_bounds__(kSubThreads)
-k_rank_pair(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ordk, const uint32_t* __restrict__ ordr,
-            uint32_t* __restrict__ wrank, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
-            const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid) {
+k_rank_pair(const float4* __restrict__ pos, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ordk,
+            const uint32_t* __restrict__ ordr, uint32_t* __restrict__ wrank, const uint32_t* __restrict__ sub_lb,
+            const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid) {
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   const uint32_t key = skey[i];
-  if (!cell_is_owned(key, g)) {  // ghost copies have no place in this rank's part of the order
+  // The count runs over every particle of the cell held here, owned or ghost: a cell cut by a slab plane
+  // has its other half among the ghosts (it is 2h wide, the ghosts reach 2h beyond the plane), with keys.
+  if (!owned_here(pos[i].x, key, g)) {  // ghost copies get their rank from their owner
     wrank[i] = 0u;
     return;
   }
@@ -333,13 +335,10 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
   if (i >= g.n) return;
   const SubView v = make_view(g, sub_lb, keys_a, keys_b);
   const uint32_t key = skey[i];
-  if (g.own_lo > 0 || g.own_hi != 0x7fffffff) {
-    // multi-GPU: owned sub-cells and ONE ghost sub-cell layer (side h) on either side get a density; the
-    // outer ghost sub-layer only supplies candidates (see the ghost depth in k_dist_classify)
-    const long long fx = 2ll * (long long)compact10(key) + (long long)(__ldg(v.fkeys + i) & 1u);
-    if (fx < 2ll * g.own_lo - 1 || fx > 2ll * g.own_hi) return;
-  }
   const float4 pi = pos[i];
+  // multi-GPU: the particles of the slab and the ghosts within h of it get a density (they are the
+  // neighbours of owned particles); ghosts farther out only supply candidates (ghost depth: k_dist_classify)
+  if (!(pi.x >= g.plane_lo - c.h_margin && pi.x < g.plane_hi + c.h_margin)) return;
   uint32_t* row = nlist + (size_t)i * list_rows;
 #ifndef CLSPH_EMU
   // keep the row address in registers: rebuilt from nlist + i * list_rows + cnt it costs four
@@ -420,9 +419,10 @@ k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   if (!(ncount[i] > list_rows)) return;
-  if (!cell_is_owned(skey[i], g)) return;  // multi-GPU: ghosts get no force
+  const float4 pi = pos[i];
+  if (!owned_here(pi.x, skey[i], g)) return;  // multi-GPU: ghosts get no force
   const SubView v = make_view(g, sub_lb, keys_a, keys_b);
-  const float4 pi = pos[i], vi = vel[i];
+  const float4 vi = vel[i];
   ForceSums sums;
   for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4& pj, float, bool inside) {
     if (inside) add_pair(sums, c, j == i, pi, vi, pi.w, pj, vel[j]);  // rare path: the exact pair terms
@@ -467,10 +467,10 @@ void launch_rank(const uint32_t* skey, const uint32_t* rr_old, uint32_t* rr_new,
   if (launches) ++*launches;
 }
 
-void launch_rank_pair(const uint32_t* skey, const uint32_t* ordk, const uint32_t* ordr, uint32_t* wrank,
+void launch_rank_pair(const float4* pos, const uint32_t* skey, const uint32_t* ordk, const uint32_t* ordr, uint32_t* wrank,
                       const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, uint32_t n_launch,
                       cudaStream_t stream, uint64_t* launches) {
-  k_rank_pair<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(skey, ordk, ordr, wrank, sub_lb,
+  k_rank_pair<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(pos, skey, ordk, ordr, wrank, sub_lb,
                                                                                       sort.keys_a, sort.keys_b, grid);
   if (launches) ++*launches;
 }
