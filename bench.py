@@ -232,7 +232,7 @@ def choose_organisation(args, local_rank, n_particles):
            "--particles", str(min(n_particles, 1 << 22))] + [x for o in CANDIDATE_SETS for x in ("--set", ",".join(o))]
     report = {"mode": "auto"}
     try:
-        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=240)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         report.update(json.loads(lines[-1]) if lines else {"agree": False, "error": "no output, exit code %d: %s" % (r.returncode, r.stderr[-300:])})
     except Exception as exc:  # a hang or crash of the candidate kernels must not take the benchmark down
