@@ -17,7 +17,11 @@
 //     particle has in the reference's array. The reference's next order is the stable sort of its
 //     current order by cell key, so  rrank' = cell_start + #{j in the same cell : rrank_j < rrank_i},
 //     a count over the ~40 particles of the cell (k_rank). Downloads and taps scatter through it,
-//     so everything observable is in the reference's order, bit for bit.
+//     so everything observable is in the reference's order, bit for bit;
+//   * inside a sub-cell the particles are kept in the reference's order too (k_reorder_sub), so the
+//     arrays -- and with them the order of every floating-point sum -- depend on the state alone:
+//     resident sub-steps equal host round trips bitwise, and across GPUs (order keys instead of the
+//     absolute rank, ownership by the slab planes, see dist.cu) the decomposition is bitwise transparent.
 //
 // Replaces, like neighbors.cu, kernels/sph.cl:9-62 with forces.cl:15-112; the force pass proper is
 // k_forces_lists of neighbors.cu (it only consumes the lists written here).
