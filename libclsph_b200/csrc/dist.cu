@@ -21,6 +21,14 @@
 //
 // Two ghost layers make one exchange per sub-step enough: the first layer's densities are
 // recomputed locally from the second. Slabs must be at least four cells thick.
+//
+// In the sub-cell order (subgrid.cu) the kernels take their roles per particle, and the same protocol runs
+// on the planes themselves instead of cells snapped to them: a particle belongs to the rank whose planes
+// contain it (owned_here), migrates only when it really crosses one, and the ghosts are the particles within
+// 2h of a plane. Which particles a rank advanced is marked by k_integrate in the w lane of the half-step
+// velocity. Migrating particles and ghosts carry order keys (cell key and rank in cell of the previous
+// sub-step), from which every rank keeps its arrays in the order a single GPU would: results are bitwise
+// those of a single-GPU run, and the ranks' downloads merge into the reference's global array.
 #include <dlfcn.h>
 #include <nccl.h>
 
