@@ -149,7 +149,7 @@ def test_bench_multi_gpu_flow_with_its_own_capacities():
     import sys
     sys.path.insert(0, H.ROOT)
     import bench
-    world, n_per_gpu = 2, 40000  # 80 k block: slabs ~6 cells thick (the protocol needs >= 4)
+    world, n_per_gpu = 2, 28000  # 56 k block: slabs ~5.7 cells thick (the established protocol needs >= 4)
     uid = capi.comm_unique_id()
     normals, vertices, indices = workloads.scene_arrays("box.obj")
     counts = [[None, None] for _ in range(world)]
@@ -242,7 +242,7 @@ def test_bench_multi_gpu_crosscheck_of_global_invariants():
     import sys
     sys.path.insert(0, H.ROOT)
     import bench
-    world, n_per_gpu = 2, 30000
+    world, n_per_gpu = 2, 20000
     scene = workloads.scene_arrays("box.obj")
     totals = {}
     for name, options in (("established", []), ("candidate", list(bench.CANDIDATE_SETS[1]))):
