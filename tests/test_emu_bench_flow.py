@@ -1,0 +1,115 @@
+"""bench.py's GPU arm, single GPU, run end to end on the CPU: the library is the emulator build (tests/emu/),
+torch is replaced by a stub with the handful of calls bench.py makes (events, the external stream, pinned
+host buffers), and the self-check that bench.py starts in a subprocess is run in-process. Nothing here
+measures anything; the point is that every line of the benchmark's control flow -- organisation choice,
+option plumbing, the timed regions, stage profiling, the end-to-end loop, the JSON line with its roofline and
+organisation report -- executes before the round's one real run on a B200."""
+import io
+import json
+import sys
+import time
+import types
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from libclsph_b200 import capi
+from tests import helpers as H
+from tests.emu import build_emu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulator_library():
+    saved = capi._lib
+    capi._lib = capi.load_library(build_emu.build())
+    yield capi._lib
+    capi._lib = saved
+
+
+class _Tensor:
+    def __init__(self, arr):
+        self.arr = arr
+
+    def pin_memory(self):
+        return self
+
+    def numpy(self):
+        return self.arr
+
+    def data_ptr(self):
+        return self.arr.ctypes.data
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        self.t = 0.0
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return 1e3 * (other.t - self.t)
+
+
+def fake_torch():
+    t = types.ModuleType("torch")
+    t.uint8, t.int32, t.float64, t.int64 = np.uint8, np.int32, np.float64, np.int64
+    t.empty = lambda n, dtype=np.uint8: _Tensor(np.empty(n, dtype=dtype))
+    t.from_numpy = lambda a: _Tensor(a)
+    t.device = lambda *a: "cuda:0"
+    cuda = types.ModuleType("torch.cuda")
+    cuda.set_device = lambda d: None
+    cuda.synchronize = lambda: None
+    cuda.Event = _Event
+    cuda.ExternalStream = lambda ptr, device=None: object()
+    t.cuda = cuda
+    return t, cuda
+
+
+@pytest.mark.parametrize("organisation", ["auto", "default"])
+def test_run_ours_single_gpu_prints_the_contract_line(organisation, monkeypatch, capfd):
+    sys.path.insert(0, H.ROOT)
+    import bench
+    from libclsph_b200 import selfcheck
+    torch, cuda = fake_torch()
+    monkeypatch.setitem(sys.modules, "torch", torch)
+    monkeypatch.setitem(sys.modules, "torch.cuda", cuda)
+
+    def selfcheck_in_process(cmd, **kw):  # what bench.py runs as `python -m libclsph_b200.selfcheck ...` on the GPU
+        argv = cmd[cmd.index("libclsph_b200.selfcheck") + 1:]
+        argv[argv.index("--particles") + 1] = "1500"
+        out = io.StringIO()
+        with redirect_stdout(out):
+            rc = selfcheck.main(argv + ["--timed-steps", "2"])
+        return types.SimpleNamespace(stdout=out.getvalue(), stderr="", returncode=rc)
+
+    import subprocess
+    monkeypatch.setattr(subprocess, "run", selfcheck_in_process)
+    args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, impl="ours", config="config3_mucus_labyrinth_4m", particles=1500, e2e_steps=2,
+                                 no_cpu_baseline=True, cpu_sample=4096, option=[], organisation=organisation)
+    bench.run_ours(args, 0, 1, 0)
+    out = capfd.readouterr().out
+    lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out[-2000:]
+    d = json.loads(lines[0])
+    assert d["metric"] == "particle_steps_per_sec" and d["unit"] == "particle-steps/s" and d["n_gpus"] == 1
+    assert d["steps"] == 3 and d["warmup"] == 3 and d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "config3_mucus_labyrinth_4m" and d["config"]["particles_per_gpu"] == 1500
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 1500 * 80 and d["e2e"]["d2h_bytes_per_step"] == 1500 * 80
+    assert d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["peak"] > 0 and r["achieved"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert set(r["stage_ms"]) >= {"keys", "sort", "reorder", "density", "forces", "integrate"}
+    org = d["config"]["organisation"]
+    if organisation == "auto":
+        assert org["mode"] == "auto" and org["agree"] and len(org["sets"]) == len(bench.CANDIDATE_SETS)
+        assert all(e["agree"] for e in org["sets"]), org
+        if org["adopted"]:
+            assert sorted(d["config"]["options"]) in [sorted(c) for c in bench.CANDIDATE_SETS]
+            assert r["kernel"] in ("k_density_sub", "k_density_lists", "k_forces_lists", "k_integrate", "k_onesweep", "k_reorder_sub", "k_reorder",
+                                   "k_keys_hist")
+        else:
+            assert d["config"]["options"] == []
+    else:
+        assert d["config"]["options"] == [] and org["mode"] == "default"
