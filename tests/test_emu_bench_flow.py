@@ -113,3 +113,122 @@ def test_run_ours_single_gpu_prints_the_contract_line(organisation, monkeypatch,
             assert d["config"]["options"] == []
     else:
         assert d["config"]["options"] == [] and org["mode"] == "default"
+
+
+# ---- N > 1: threads as ranks, a thread-based stand-in for torch.distributed ---------------------------------
+
+import threading
+
+
+class _DTensor(_Tensor):
+    def item(self):
+        return self.arr.reshape(-1)[0].item()
+
+    def cpu(self):
+        return self
+
+
+class _FakeDist:
+    """broadcast / all_reduce / barrier across the threads that play the ranks."""
+
+    class ReduceOp:
+        MAX, SUM = "max", "sum"
+
+    def __init__(self, world):
+        self.world = world
+        self.local = threading.local()
+        self.sync = threading.Barrier(world)
+        self.slots = [None] * world
+
+    def init_process_group(self, backend, device_id=None):
+        pass
+
+    def destroy_process_group(self):
+        pass
+
+    def barrier(self):
+        self.sync.wait(timeout=900)
+
+    def _exchange(self, arr):
+        self.slots[self.local.rank] = arr.copy()
+        self.sync.wait(timeout=900)
+        got = [s.copy() for s in self.slots]
+        self.sync.wait(timeout=900)
+        return got
+
+    def broadcast(self, t, src):
+        t.arr[...] = self._exchange(t.arr)[src]
+
+    def all_reduce(self, t, op="sum"):
+        got = self._exchange(t.arr)
+        with np.errstate(over="ignore"):
+            t.arr[...] = np.max(got, axis=0) if op == "max" else np.sum(got, axis=0, dtype=t.arr.dtype)
+
+
+def test_run_ours_two_ranks_prints_the_contract_line(monkeypatch, capsys):
+    """bench.py under torchrun with two ranks, played by two threads: organisation choice on rank 0 and its
+    broadcast, the multi-GPU cross-check of global invariants, slab workload and capacities, resident stepping,
+    stage profiling, the end-to-end loop through clsph_dist_upload / step / download, one JSON line on rank 0."""
+    sys.path.insert(0, H.ROOT)
+    import bench
+    from libclsph_b200 import selfcheck
+    world = 2
+    torch, cuda = fake_torch()
+    fdist = _FakeDist(world)
+    torch.tensor = lambda data, dtype=np.float64, device=None: _DTensor(np.array(data, dtype=dtype))
+    torch.zeros = lambda n, dtype=np.float64, device=None: _DTensor(np.zeros(n, dtype=dtype))
+    torch.from_numpy = lambda a: _DTensor(a)
+    torch.empty = lambda n, dtype=np.uint8: _DTensor(np.empty(n, dtype=dtype))
+    torch.distributed = fdist
+    monkeypatch.setitem(sys.modules, "torch", torch)
+    monkeypatch.setitem(sys.modules, "torch.cuda", cuda)
+    monkeypatch.setitem(sys.modules, "torch.distributed", fdist)
+
+    def selfcheck_in_process(cmd, **kw):
+        argv = cmd[cmd.index("libclsph_b200.selfcheck") + 1:]
+        argv[argv.index("--particles") + 1] = "2000"
+        keep = argv[: argv.index("--set")] + ["--set", ",".join(bench.CANDIDATE_SETS[1])]  # one set is enough here
+        out = io.StringIO()
+        with redirect_stdout(out):
+            rc = selfcheck.main(keep + ["--timed-steps", "2"])
+        text = out.getvalue()
+        line = json.loads(text.strip().splitlines()[-1])
+        line["ms_per_step_default"] = 1e9  # adopt the candidate whatever the emulator's clock says
+        return types.SimpleNamespace(stdout=json.dumps(line), stderr="", returncode=rc)
+
+    import subprocess
+    monkeypatch.setattr(subprocess, "run", selfcheck_in_process)
+    # the real script points fd 1 at stderr while native libraries are chatty; with two ranks in one process that
+    # juggling would race, and the line is captured from sys.stdout here anyway
+    shim = types.SimpleNamespace(**{k: getattr(bench.os, k) for k in ("path", "environ", "_exit")})
+    shim.dup = lambda fd: fd
+    shim.dup2 = lambda a, b: None
+    monkeypatch.setattr(bench, "os", shim)
+
+    errors = []
+
+    def run_rank(rank):
+        fdist.local.rank = rank
+        args = types.SimpleNamespace(gpus=world, steps=3, warmup=3, impl="ours", config="config2_dambreak_1m", particles=16000, e2e_steps=2,
+                                     no_cpu_baseline=True, cpu_sample=4096, option=[], organisation="auto")
+        try:
+            bench.run_ours(args, rank, world, 0)
+        except BaseException as exc:  # noqa: BLE001
+            errors.append((rank, repr(exc)))
+            fdist.sync.abort()
+
+    threads = [threading.Thread(target=run_rank, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=1500)
+    assert not errors, errors
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] > 0 and d["config"]["particles_total"] == 32000
+    assert sorted(d["config"]["options"]) == sorted(bench.CANDIDATE_SETS[1])
+    check = d["config"]["organisation"]["multi_gpu_crosscheck"]
+    assert check["agree"] and check["max_rel_diff"] <= 1e-5
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["roofline"]["stage_ms"]["exchange"] > 0

@@ -141,56 +141,6 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
     assert moved_total > 0, "the shear should have moved particles across a slab plane"
 
 
-def test_bench_multi_gpu_flow_with_its_own_capacities():
-    """bench.py's N>1 path, rank for rank (threads as ranks, emulator): the workload split, the
-    capacities it derives, resident stepping, then its end-to-end loop (upload + step + download per
-    sub-step). The first 8-GPU run of round 1 died on a buffer overflow; this keeps the formulas honest
-    at a scale the emulator can run. Total particle count must be conserved throughout."""
-    import sys
-    sys.path.insert(0, H.ROOT)
-    import bench
-    world, n_per_gpu = 2, 28000  # 56 k block: slabs ~5.7 cells thick (the established protocol needs >= 4)
-    uid = capi.comm_unique_id()
-    normals, vertices, indices = workloads.scene_arrays("box.obj")
-    counts = [[None, None] for _ in range(world)]
-    errors = []
-    barrier = threading.Barrier(world)
-
-    def run_rank(rank):
-        try:
-            w = bench.multi_gpu_workload("config2_dambreak_1m", n_per_gpu, rank, world, sub_cell_order=True)
-            ctx = capi.Context(w["capacity"])
-            ctx.set_option("sub_cell_order", 1)
-            ctx.set_option("face_grid", 1)
-            ctx.set_scene(normals, vertices, indices)
-            ctx.set_parameters(w["params"], w["terms"])
-            ctx.dist_init(rank, world, uid, float(w["planes"][rank]), float(w["planes"][rank + 1]),
-                          emigrant_capacity=w["emigrant_capacity"], ghost_capacity=w["ghost_capacity"])
-            ctx.dist_upload(w["state"], w["ids"])
-            ctx.step(6)
-            ctx.synchronize()
-            counts[rank][0] = ctx.dist_count()
-            for _ in range(2):  # the e2e loop of bench.py
-                ctx.dist_upload(w["state"], w["ids"])
-                ctx.step(1)
-                parts, ids = ctx.dist_download()
-            counts[rank][1] = parts.size
-            barrier.wait(timeout=600)
-            ctx.close()
-        except BaseException as exc:  # noqa: BLE001
-            errors.append((rank, exc))
-            barrier.abort()
-
-    threads = [threading.Thread(target=run_rank, args=(r,)) for r in range(world)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join(timeout=1200)
-    assert not errors, errors
-    assert sum(c[0] for c in counts) == world * n_per_gpu, counts
-    assert sum(c[1] for c in counts) == world * n_per_gpu, counts
-
-
 def test_buffer_overflow_is_reported_and_nobody_hangs():
     """Message buffers too small for the ghost layers (what killed the first 8-GPU run of round 1): the rank
     that overflows reports CLSPH_ECOMM at its next synchronising call, every rank finishes its sub-steps
@@ -233,41 +183,15 @@ def test_buffer_overflow_is_reported_and_nobody_hangs():
     assert capi.E_COMM in codes, codes
 
 
-def test_bench_multi_gpu_crosscheck_of_global_invariants():
-    """bench.py, N > 1: before options chosen by the single-GPU self-check time a multi-GPU run, three sub-steps
-    of the run's own workload with the established organisation and with them must agree on global invariants.
-    Here with threads as ranks and a plain sum standing in for the all-reduce; a deliberately broken candidate
-    (ghost messages too small for the ghost layer are detected by the library itself) is not needed: the check
-    is exercised for agreement, and for disagreement with doctored numbers."""
+def test_bench_invariants_comparison_rules():
+    """bench.invariants_agree (the N > 1 cross-check; the whole flow runs in tests/test_emu_bench_flow.py):
+    counts and id sums exact modulo 2^64, float sums to 1e-5."""
     import sys
     sys.path.insert(0, H.ROOT)
     import bench
-    world, n_per_gpu = 2, 20000
-    scene = workloads.scene_arrays("box.obj")
-    totals = {}
-    for name, options in (("established", []), ("candidate", list(bench.CANDIDATE_SETS[1]))):
-        uid = capi.comm_unique_id()
-        out = [None] * world
-        errors = []
-
-        def run_rank(rank):
-            try:
-                w = bench.multi_gpu_workload("config2_dambreak_1m", n_per_gpu, rank, world, sub_cell_order="sub_cell_order=1" in options)
-                out[rank] = bench.slab_invariants(w, scene, options, rank, world, uid, 0)
-            except BaseException as exc:  # noqa: BLE001
-                errors.append((rank, exc))
-
-        threads = [threading.Thread(target=run_rank, args=(r,)) for r in range(world)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join(timeout=900)
-        assert not errors, errors
-        with np.errstate(over="ignore"):
-            totals[name] = (sum(o[0] for o in out), sum(o[1] for o in out))
-    ok, rel = bench.invariants_agree(totals["established"], totals["candidate"], world * n_per_gpu)
-    assert ok and rel <= 1e-5, (rel, totals)
-    lost = (totals["candidate"][0] - np.array([1, 5, 25], dtype=np.int64), totals["candidate"][1])
-    assert not bench.invariants_agree(totals["established"], lost, world * n_per_gpu)[0]
-    off = (totals["candidate"][0], totals["candidate"][1] * np.array([1.01, 1, 1, 1, 1, 1, 1, 1]))
-    assert not bench.invariants_agree(totals["established"], off, world * n_per_gpu)[0]
+    ints = np.array([48000, 1151976000, -12345], dtype=np.int64)
+    floats = np.array([4.8e7, 1.2e9, 3e4, 5e4, 3e4, 1e4, 2e4, 1e4])
+    assert bench.invariants_agree((ints, floats), (ints.copy(), floats * (1 + 3e-7)), 48000) == (True, pytest.approx(3e-7, rel=1e-3))
+    assert not bench.invariants_agree((ints, floats), (ints - np.array([1, 5, 25]), floats), 48000)[0]       # a particle lost
+    assert not bench.invariants_agree((ints, floats), (ints, floats * np.array([1.01, 1, 1, 1, 1, 1, 1, 1])), 48000)[0]
+    assert not bench.invariants_agree((ints, floats), (ints, floats), 48001)[0]                                # wrong total
