@@ -237,20 +237,6 @@ def test_face_grid_in_the_full_step(plane_scene):
                                           "crowded, face grid", options=dict(face_grid=1))
 
 
-def test_selfcheck_module_finds_the_candidate_options_equivalent(capsys):
-    """libclsph_b200.selfcheck is what bench.py runs (in a subprocess, on the GPU) before adopting the
-    candidate options; here in-process against the emulator build."""
-    import json
-    from libclsph_b200 import selfcheck
-    for cfg, n in (("config3_mucus_labyrinth_4m", 4096),):
-        rc = selfcheck.main(["--config", cfg, "--particles", str(n), "--timed-steps", "2", "--set", "sub_cell_order=1,face_grid=1,fast_pairs=1",
-                             "--set", "face_grid=1,fast_pairs=1,forces_blocks=4"])
-        line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
-        assert rc == 0 and line["agree"] and len(line["sets"]) == 2 and line["ms_per_step_default"] > 0, line
-        for entry in line["sets"]:
-            assert entry["agree"] and entry["max_rel_diff"] <= 5e-5 and entry["ms_per_step"] > 0, entry
-
-
 def test_sub_cell_order_reports_a_grid_too_large_for_its_keys(box_scene):
     """With 512 to 1023 cells along z the reference still works but (Morton cell key << 3 | octant)
     no longer fits 32 bits: CLSPH_EGRID with advice, and the context stays usable."""
