@@ -18,6 +18,13 @@ box.obj, 1 Mi particles, jittered-lattice state S1). Prints ONE JSON line (rank 
              oracle port, on the host cores, on a bounded sample of the same workload
 
 --impl reference times only the CPU side (reference arm of the driver).
+
+--organisation auto (default): before anything is timed, `python -m libclsph_b200.selfcheck` runs in a subprocess
+on the GPU: one sub-step of the workload with the library's default options and with each candidate option set
+(kernels written after the last GPU session of round 1); a set qualifies if every integer
+observable and the exported order are identical and the floats agree to 5e-5; the fastest qualifying set is
+used if it beats the default. With N > 1 a multi-GPU cross-check of global invariants follows. What was
+chosen, and every timing, is in config.organisation / config.options of the JSON line.
 """
 import argparse
 import json
