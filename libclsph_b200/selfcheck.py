@@ -5,7 +5,8 @@
 
 Runs the same state through the library with the default options (the organisation that has passed
 the GPU parity suite against the oracle) and once with every candidate option set, and compares everything observable: cell keys, sort permutation, sorted keys, cell table, candidate
-and support counts, collision loop trips and the exported array order must be IDENTICAL; densities,
+and support counts, collision loop trips and the exported array order must be IDENTICAL; three resident
+sub-steps must equal three host round trips bitwise (per option set); densities,
 pressures, accelerations, positions and velocities must agree within 5e-5 relative (the two
 organisations add the same terms in a different order). Then it times each, device resident.
 Prints one JSON line; exit code 0 = at least one candidate set agrees. bench.py runs this in a subprocess before
@@ -50,6 +51,19 @@ def run(options, device, params, terms, scene, state, steps, timed_steps):
         floats = dict(density=ctx.fetch(capi.TAP_DENSITY), pressure=ctx.fetch(capi.TAP_PRESSURE),
                       acceleration=ctx.fetch(capi.TAP_ACCELERATION))
         snaps.append((ctx.download(), taps, floats))
+    # history independence: k resident sub-steps must equal k upload / step / download round trips BITWISE
+    # (every organisation keeps its arrays in an order that depends on the state alone); a difference here
+    # means some kernel's result depends on scheduling
+    ctx.set_debug(False)
+    ctx.upload(state)
+    ctx.step(3)
+    resident = ctx.download()
+    cur = state
+    for _ in range(3):
+        ctx.upload(cur)
+        ctx.step(1)
+        cur = ctx.download()
+    assert resident.tobytes() == cur.tobytes(), "resident sub-steps differ from host round trips (options %r)" % (options,)
     ms = None
     if timed_steps > 0:
         ctx.set_debug(False)
