@@ -212,7 +212,7 @@ def test_run_ours_two_ranks_prints_the_contract_line(monkeypatch, capsys):
 
     def run_rank(rank):
         fdist.local.rank = rank
-        args = types.SimpleNamespace(gpus=world, steps=3, warmup=3, impl="ours", config="config2_dambreak_1m", particles=16000, e2e_steps=2,
+        args = types.SimpleNamespace(gpus=world, steps=3, warmup=3, impl="ours", config="config2_dambreak_1m", particles=12000, e2e_steps=2,
                                      no_cpu_baseline=True, cpu_sample=4096, option=[], organisation="auto")
         try:
             bench.run_ours(args, rank, world, 0)
@@ -229,7 +229,7 @@ def test_run_ours_two_ranks_prints_the_contract_line(monkeypatch, capsys):
     lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] > 0 and d["config"]["particles_total"] == 32000
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] > 0 and d["config"]["particles_total"] == 24000
     assert sorted(d["config"]["options"]) == sorted(bench.CANDIDATE_SETS[1])
     check = d["config"]["organisation"]["multi_gpu_crosscheck"]
     assert check["agree"] and check["max_rel_diff"] <= 1e-5
