@@ -312,3 +312,15 @@ def test_developed_state(options):
 def test_developed_state_resident_steps_in_sub_cell_order():
     p, terms, scene, s = H.developed_state()
     G.check_resident_steps_against_oracle(s, p, terms, scene, 4, "developed, resident", options=dict(sub_cell_order=1, face_grid=1, fast_pairs=1))
+
+
+def test_option_validation():
+    ctx = capi.Context(1024)
+    for name, value in (("forces_blocks", 5), ("list_rows", 5000), ("no_such_option", 1)):
+        with pytest.raises(capi.ClsphError) as e:
+            ctx.set_option(name, value)
+        assert e.value.code == capi.E_INVAL, name
+    for name, value in (("forces_blocks", 4), ("forces_blocks", 3), ("fast_pairs", 1), ("merged_rows", 1), ("deferred_lists", 1),
+                        ("face_grid", 1), ("sub_cell_order", 1), ("sub_cell_order", 0), ("neighbour_lists", 0), ("list_rows", 48)):
+        ctx.set_option(name, value)
+    ctx.close()
