@@ -7,5 +7,15 @@
 #ifndef CLSPH_COMMON_STRUCTURES_H_
 #define CLSPH_COMMON_STRUCTURES_H_
 #include "../clsph_types.h"
+#ifdef __cplusplus
+/* The reference's structures.h pulls in util/cl_boilerplate.h, and with it these standard headers
+ * (util/cl_boilerplate.h:4-8). libclsph user code relies on that: example/particles.cpp uses
+ * std::ofstream and std::filebuf without including <fstream> itself. */
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+#endif
 #define COLLISION_VOLUMES_COUNT 3
 #endif

@@ -89,7 +89,12 @@ int clsph_host_simulate(const simulation_parameters* p, const precomputed_kernel
       if (full && params_out) *params_out = prm;
     };
   }
-  sim.simulate(frames);
+  try {
+    sim.simulate(frames);
+  } catch (const std::exception& e) {  // e.g. a truncated last_frame.bin (init_particles)
+    std::cerr << "clsph_host_simulate: " << e.what() << std::endl;
+    return 2;
+  }
   if (!callbacks) {
     if (states_out) std::memcpy(states_out, sim.final_particles(), sizeof(particle) * p->particles_count);
     if (params_out) *params_out = sim.parameters;

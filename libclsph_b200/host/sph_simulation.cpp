@@ -77,7 +77,13 @@ void sph_simulation::init_particles(particle* buffer, const simulation_parameter
 
   std::ifstream resume("last_frame.bin", std::ios::in | std::ios::binary);
   if (resume) {
-    resume.read(reinterpret_cast<char*>(buffer), static_cast<std::streamsize>(sizeof(particle)) * params.particles_count);
+    // The reference reads the checkpoint with cereal's loadBinary (:59-67), which throws on a short read; a
+    // truncated file must not leave the tail particles zeroed and coincident at the origin.
+    const std::streamsize want = static_cast<std::streamsize>(sizeof(particle)) * params.particles_count;
+    resume.read(reinterpret_cast<char*>(buffer), want);
+    if (resume.gcount() != want)
+      throw std::runtime_error("last_frame.bin: failed to read " + std::to_string(want) + " bytes from the checkpoint, read " +
+                               std::to_string(resume.gcount()) + " (particles_count does not match the file)");
     return;
   }
   const unsigned int ups = static_cast<unsigned int>(per_side);

@@ -49,6 +49,27 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / (scale if scale > 0 else 1.0))
 
 
+def elem_err(a, b, atol_frac=1e-3):
+    """Per-element relative error, max over elements of |a-b| / (|b| + floor). The floor is atol_frac of the
+    field's RMS magnitude: an element much smaller than the field's typical size (a velocity component that
+    happens to vanish, a pressure at its zero crossing) is held to an absolute bound instead of an empty
+    relative one. This is what "1e-4 relative" means particle by particle; rel_err only bounds the error
+    against the field's largest value."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    rms = float(np.sqrt(np.mean(b * b))) if b.size else 0.0
+    floor = atol_frac * rms if rms > 0 else 1.0
+    return float((np.abs(a - b) / (np.abs(b) + floor)).max()) if b.size else 0.0
+
+
+def assert_close_elementwise(got, want, tol=1e-4, fields=("position", "density"), what=""):
+    for f in fields:
+        g = got[f][:, :3] if got[f].ndim == 2 else got[f]
+        w = want[f][:, :3] if want[f].ndim == 2 else want[f]
+        e = elem_err(g, w)
+        assert e <= tol, "%s %s: per-element relative error %.3e > %.1e" % (what, f, e, tol)
+
+
 def assert_close_fields(got, want, tol=1e-4, fields=FIELDS_XYZ + ("density", "pressure"), what=""):
     for f in fields:
         g = got[f][:, :3] if got[f].ndim == 2 else got[f]

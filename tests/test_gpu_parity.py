@@ -65,6 +65,10 @@ def check_against_oracle(state, params, terms, scene, what, **kw):
     assert H.rel_err(taps["pressure"], want.pressure) <= TOL, what + ": pressure"
     assert H.rel_err(taps["acceleration"], want.acceleration) <= TOL, what + ": acceleration"
     H.assert_close_fields(got, want.particles, tol=TOL, what=what)
+    # ... and particle by particle (relative to each element, with a small absolute floor), not only
+    # against the field's largest value
+    assert H.elem_err(taps["density"], want.density) <= TOL, what + ": density, per element"
+    H.assert_close_elementwise(got, want.particles, tol=TOL, fields=("position", "density"), what=what)
     assert not got["acceleration"].any(), what + ": the step must export acceleration = 0 (sph.cl:97-99)"
     return got, taps, want
 
@@ -90,6 +94,7 @@ def check_resident_steps_against_oracle(state, params, terms, scene, steps, what
         assert np.array_equal(got["grid_index"], want.particles["grid_index"]), tag + ": grid_index"
         assert np.array_equal(supp, want.support_count), tag + ": support counts"
         H.assert_close_fields(got, want.particles, tol=TOL, what=tag)
+        H.assert_close_elementwise(got, want.particles, tol=TOL, fields=("position", "density"), what=tag)
         prev = got
     ctx.close()
 

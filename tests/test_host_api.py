@@ -103,6 +103,37 @@ def test_simulate_matches_oracle_steps(tmp_path, policy, callbacks):
 
 
 @pytest.mark.gpu
+def test_truncated_checkpoint_is_refused_by_the_library(tmp_path):
+    """A last_frame.bin shorter than particles_count records must raise (the reference's cereal loadBinary
+    throws, libclsph/sph_simulation.cpp:59-67), not leave the tail particles zeroed at the origin."""
+    p, terms, vol, _ = workloads.make_config(fluid="water", particles_count=4096)
+    normals, vertices, indices = hostapi.scene_load("box.obj", cwd=H.ROOT)
+    wd = _workdir(tmp_path)
+    H.state_s0(p, vol)[:1000].tofile(os.path.join(wd, "last_frame.bin"))
+    with pytest.raises(RuntimeError):
+        hostapi.simulate(p, terms, vol, normals, vertices, indices, frames=1, policy=2, callbacks=False, cwd=wd)
+
+
+REFERENCE_EXAMPLE = "/root/reference/example/particles.cpp"
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_EXAMPLE), reason="the reference tree is not present on this machine")
+def test_reference_example_compiles_and_links_unmodified(tmp_path):
+    """Drop-in claim of INTEGRATION.md: the reference's own example/particles.cpp, unmodified, compiles against
+    include/clsph (plus the reference's vendored cereal headers, which it includes itself) and links against
+    libclsph_host.so + libclsph_cuda.so."""
+    obj, exe = str(tmp_path / "particles.o"), str(tmp_path / "particles")
+    r = subprocess.run(["g++", "-std=c++14", "-c", "-I", os.path.join(H.ROOT, "include", "clsph"), "-I", "/root/reference",
+                        REFERENCE_EXAMPLE, "-o", obj], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    libdir = os.path.join(H.ROOT, "libclsph_b200")
+    r = subprocess.run(["g++", "-o", exe, obj, "-L" + libdir, "-lclsph_host", "-lclsph_cuda", "-Wl,-rpath," + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.getsize(exe) > 0
+
+
+@pytest.mark.gpu
 def test_clsphparticles_cli_writes_frames_and_checkpoint(tmp_path):
     """The command-line driver end to end: JSON in, .geo frames and last_frame.bin out, resume."""
     hostapi.build()  # makes libclsph_host.so and the clsphparticles binary if they are missing or stale
