@@ -35,7 +35,11 @@ for s in sections:
     h = s["hdr"]; iL = h.index("Line No"); iI = h.index("Instructions Executed"); iS = h.index("# Samples")
     fn = s["func"].split("(")[0][-40:]
     for r in s["rows"]:
-        if r[iL].strip().isdigit() and float(r[iI] or 0) > 0:
+        try:
+            ok = r[iL].strip().isdigit() and float(r[iI] or 0) > 0
+        except (ValueError, IndexError):
+            continue  # a source line with embedded quotes / commas (inline asm) that the CSV writer split
+        if ok:
             by.setdefault(fn, []).append((float(r[iI]), s["file"].split("/")[-1], int(r[iL]), r[1].strip()[:105], float(r[iS] or 0)))
 for fn, rows_ in by.items():
     tot = sum(r[0] for r in rows_); ts = sum(r[4] for r in rows_) or 1
