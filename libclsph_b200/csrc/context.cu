@@ -77,6 +77,10 @@ struct clsph_context {
   uint32_t* sub_lb = nullptr;
   uint32_t* rrank = nullptr;
   uint32_t* rr_tmp = nullptr;
+  // tile kernels (tiles.cu, option "tile_kernels"): the neighbour passes of the sub-cell order on blocks of 2 x 2 x 2 cells
+  bool tiles = false;
+  TileLists tl{};
+  TilePlan tile_plan{};
 
   // list mode (default): the density pass stores neighbour lists, the force pass reads them
   bool use_lists = true;
@@ -315,8 +319,31 @@ int ensure_sub(clsph_context* ctx) {
   return CLSPH_OK;
 }
 
+// Arrays of the tile kernels, allocated the first time they are selected; the staging plan follows the fluid.
+int ensure_tiles(clsph_context* ctx) {
+  if (!ctx->tiles || !ctx->sub_order) return CLSPH_OK;
+  if (!ctx->tl.masks) {
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.masks, (size_t)9 * ctx->capacity));
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.count, ctx->capacity));
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.blocks, ctx->capacity));
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.slow, ctx->capacity));
+    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.ctl, 1));
+    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tl.count, 0, sizeof(uint32_t) * ctx->capacity, ctx->stream));
+    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tl.ctl, 0, sizeof(TileCtl), ctx->stream));
+    ctx->tl.mask_stride = ctx->capacity;
+  }
+  if (ctx->have_params) {
+    const simulation_parameters& p = ctx->params;
+    const double per_sub_cell = (double)p.fluid_density / (double)p.particle_mass * (double)p.h * p.h * p.h;
+    ctx->tl.list_cap = list_rows_for(ctx);
+    ctx->tile_plan = tiles_plan(per_sub_cell, ctx->tl.list_cap);
+  }
+  return CLSPH_OK;
+}
+
 int ensure_lists(clsph_context* ctx) {
-  if (!ctx->use_lists && !ctx->sub_order) {
+  if (int rc = ensure_tiles(ctx)) return rc;
+  if ((!ctx->use_lists && !ctx->sub_order) || (ctx->tiles && ctx->sub_order)) {  // the tile kernels keep hit masks instead
     ctx->lists.rows = 0;
     return CLSPH_OK;
   }
@@ -386,7 +413,8 @@ int enqueue_substep(clsph_context* ctx) {
     launch_reorder_sub(src, dst, ctx->sort, ctx->skey, multi ? nullptr : ctx->rrank, ctx->rr_tmp, ctx->sub_lb, ctx->grid,
                        multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr,
                        multi ? ctx->ordk[ctx->cur] : nullptr, multi ? ctx->ordr[ctx->cur] : nullptr,
-                       multi ? ctx->ordk[ctx->cur ^ 1] : nullptr, multi ? ctx->ordr[ctx->cur ^ 1] : nullptr, n, st, lc);
+                       multi ? ctx->ordk[ctx->cur ^ 1] : nullptr, multi ? ctx->ordr[ctx->cur ^ 1] : nullptr,
+                       ctx->tiles ? ctx->tl.ctl : nullptr, ctx->tl.blocks, n, st, lc);
     ctx->cur ^= 1;
     if (!multi)  // one GPU: absolute index in the reference's array
       launch_rank(ctx->skey, ctx->rr_tmp, ctx->rrank, ctx->sub_lb, ctx->sort, ctx->grid, ctx->perm,
@@ -395,13 +423,28 @@ int enqueue_substep(clsph_context* ctx) {
       launch_rank_pair(dst.pos, ctx->skey, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->wrank, ctx->sub_lb, ctx->sort, ctx->grid, n,
                        st, lc);
     if (prof) next_event(ctx);
-    launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                       ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
-    if (prof) next_event(ctx);
-    launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
-                  false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc);
-    launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
-                               ctx->lists, ctx->accel, n, st, lc);
+    if (ctx->tiles) {
+      launch_density_tiles(dst.pos, dst.vel, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->tl, ctx->tile_plan,
+                           ctx->sm_count, st, lc);
+      launch_density_slow(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->tl,
+                          ctx->sm_count, st, lc);
+      if (ctx->debug)
+        launch_tile_taps(ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->tl, ctx->taps.candidate_count, ctx->taps.support_count, n,
+                         st, lc);
+      if (prof) next_event(ctx);
+      launch_forces_tiles(dst.pos, dst.vel, ctx->aux, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->tl, ctx->tile_plan,
+                          ctx->fast_pairs, ctx->accel, ctx->sm_count, st, lc);
+      launch_forces_slow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->tl, ctx->accel,
+                         ctx->sm_count, st, lc);
+    } else {
+      launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
+                         ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
+      if (prof) next_event(ctx);
+      launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
+                    false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc);
+      launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
+                                 ctx->lists, ctx->accel, n, st, lc);
+    }
     if (prof) next_event(ctx);
   } else {
     launch_clear_cells(ctx->cell_start, ctx->cell_end, ctx->grid, ctx->cell_capacity, ctx->sm_count, st, lc);
@@ -511,6 +554,7 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
   CREATE_TRY(cudaMemset(ctx->cell_start, 0, sizeof(uint32_t) * ctx->cell_capacity));
   CREATE_TRY(cudaMemset(ctx->cell_end, 0, sizeof(uint32_t) * ctx->cell_capacity));
   neighbors_init();
+  tiles_init();
   CREATE_TRY(cudaGetLastError());
   if (ctx->sub_order && ensure_sub(ctx) != CLSPH_OK) {
     g_create_error = ctx->error;
@@ -589,6 +633,11 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->sub_lb);
   cudaFree(ctx->rrank);
   cudaFree(ctx->rr_tmp);
+  cudaFree(ctx->tl.masks);
+  cudaFree(ctx->tl.count);
+  cudaFree(ctx->tl.blocks);
+  cudaFree(ctx->tl.slow);
+  cudaFree(ctx->tl.ctl);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
@@ -656,6 +705,8 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     ctx->sub_order = value != 0;
     int rc = ensure_sub(ctx);
     if (rc) return rc;
+  } else if (!std::strcmp(name, "tile_kernels")) {
+    ctx->tiles = value != 0;
   } else if (!std::strcmp(name, "deferred_lists")) {
     ctx->deferred_lists = value != 0;
   } else if (!std::strcmp(name, "merged_rows")) {

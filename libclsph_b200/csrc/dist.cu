@@ -35,6 +35,7 @@
 #include <cstdio>
 
 #include "dist.cuh"
+#include "subview.cuh"
 
 namespace clsph {
 
@@ -97,17 +98,6 @@ struct MsgHeader {
 };
 __host__ __device__ inline float4* msg_emigrants(void* msg) { return reinterpret_cast<float4*>(static_cast<char*>(msg) + 16); }
 __host__ __device__ inline float4* msg_ghosts(void* msg, uint32_t emax) { return msg_emigrants(msg) + (size_t)emax * 4; }
-
-// Slot for one element per true lane: one atomicAdd per warp, lanes get consecutive slots.
-__device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
-  const unsigned m = __ballot_sync(kFullMask, want);
-  if (m == 0u) return 0u;
-  uint32_t base = 0;
-  const int leader = __ffs(m) - 1;
-  if ((int)lane_id() == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(kFullMask, base, leader);
-  return base + __popc(m & lanemask_lt());
-}
 
 }  // namespace
 

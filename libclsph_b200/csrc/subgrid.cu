@@ -27,143 +27,13 @@
 // k_forces_lists of neighbors.cu (it only consumes the lists written here).
 #include "kernels.cuh"
 #include "pair_terms.cuh"
+#include "subview.cuh"
 
 namespace clsph {
 
 namespace {
 
 constexpr int kSubThreads = 128;
-
-// What a kernel needs to turn (cell, octant range) into an index range of the sorted arrays.
-struct SubView {
-  const uint32_t* lb;     // dense table: lb[cell * 9 + o] = first index of the cell's octant >= o; [8] = end
-  const uint32_t* fkeys;  // sorted sub-cell keys (binary-search fallback)
-  uint32_t n, cell_count;
-  bool dense;
-};
-
-__device__ __forceinline__ SubView make_view(const GridState& g, const uint32_t* sub_lb, const uint32_t* keys_a,
-                                             const uint32_t* keys_b) {
-  SubView v;
-  v.lb = sub_lb;
-  v.fkeys = (g.sort_passes & 1u) ? keys_b : keys_a;  // an odd number of passes ends in the "b" buffers
-  v.n = g.n;
-  v.cell_count = g.cell_count;
-  v.dense = g.sub_dense != 0u;
-  return v;
-}
-
-// Particles of cell `key` whose octant is in [o_lo, o_hi]: one contiguous range.
-__device__ __forceinline__ uint2 sub_range(const SubView& v, uint32_t key, uint32_t o_lo, uint32_t o_hi) {
-  if (key >= v.cell_count) return make_uint2(0u, 0u);
-  if (v.dense) {
-    const uint32_t* row = v.lb + (size_t)key * 9u;
-    return make_uint2(__ldg(row + o_lo), __ldg(row + o_hi + 1u));
-  }
-  const uint32_t base = key << 3;  // key < 2^29 in sub-cell mode
-  const uint32_t a = lower_bound_key(v.fkeys, v.n, base + o_lo);
-  const uint32_t b = (base + o_hi == 0xFFFFFFFFu) ? v.n : lower_bound_key(v.fkeys, v.n, base + o_hi + 1u);
-  return make_uint2(a, b);
-}
-
-// Sub-cell coordinates [lo, hi] along one axis that can hold a particle within the support of a
-// particle at offset u = p - min. A pair inside the support has |dx| < h (1 + 2^-21); u itself
-// carries up to 2^-13 h of rounding (u < 2048 h). Both are covered by searching
-// [u - hm, u + hm] with hm = h (1 + 2^-10), mapped to sub-cells by the SAME monotone rounding
-// sequence as sub_coord: every neighbour's sub-cell lies in [lo, hi]. Usually hi - lo = 2; 3 when
-// the particle is within 2^-10 h of a sub-cell boundary.
-__device__ __forceinline__ void sub_bounds(float p, float mn, float cell, float hm, uint32_t& lo, uint32_t& hi) {
-  const float u = __fsub_rn(p, mn);
-  const float ql = __fdiv_rn(__fsub_rn(u, hm), cell), qh = __fdiv_rn(__fadd_rn(u, hm), cell);
-  lo = __float2uint_rz(__fadd_rn(ql, ql));  // negative -> 0
-  // 2047 = last sub-cell a 10-bit cell coordinate can have: keeps the loops bounded for a particle that
-  // has blown up (infinite or huge position; the step then reports CLSPH_EGRID anyway)
-  hi = min(__float2uint_rz(__fadd_rn(qh, qh)), 2047u);
-}
-
-// *addr = v when ok, as ONE predicated store: the compiler would otherwise branch around the store
-// and its address arithmetic, and in a warp that branch is nearly always taken by some lane.
-__device__ __forceinline__ void store_if(bool ok, uint32_t* addr, uint32_t v) {
-#ifdef CLSPH_EMU  // tests/emu: CPU build of the kernels for logic tests, no PTX
-  if (ok) *addr = v;
-#else
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)ok),
-               "l"(__cvta_generic_to_global(addr)), "r"(v)
-               : "memory");
-#endif
-}
-
-// for_each_range: calls range(begin, end) for every index range of candidates of the sub-cells around pi.
-// for_each_neighbour, on top of it:
-// Calls visit(j, pos[j], s, inside) for every candidate j of the sub-cells around pi, z outermost /
-// x innermost; inside = (s = |pi - pj|^2) < support_s is the reference's window test (self included).
-// The visitor gets every candidate so that it can stay branch-free: about one candidate in seven is
-// inside, so in a warp some lane nearly always is, and a divergent "inside" branch would run for all.
-template <class Range>
-__device__ __forceinline__ void for_each_range(const SubView& v, const GridState& g, const SphConst& c, const float4& pi,
-                                               Range&& range) {
-  uint32_t xlo, xhi, ylo, yhi, zlo, zhi;
-  sub_bounds(pi.x, g.min_x, g.cell, c.h_margin, xlo, xhi);
-  sub_bounds(pi.y, g.min_y, g.cell, c.h_margin, ylo, yhi);
-  sub_bounds(pi.z, g.min_z, g.cell, c.h_margin, zlo, zhi);
-  const uint32_t cx_lo = xlo >> 1, cx_hi = xhi >> 1;
-  for (uint32_t fz = zlo; fz <= zhi; ++fz) {
-    const uint32_t kz = spread10(fz >> 1) << 2, oz = (fz & 1u) << 2;
-    for (uint32_t fy = ylo; fy <= yhi; ++fy) {
-      const uint32_t kzy = kz | (spread10(fy >> 1) << 1), ozy = oz | ((fy & 1u) << 1);
-      // the x extent of the row covers two (rarely three) cells; inside a cell the octants with
-      // x bit 0 and 1 are adjacent, so each cell contributes one range
-      for (uint32_t cx = cx_lo; cx <= cx_hi; ++cx) {
-        const uint32_t o_lo = ozy | (cx == cx_lo ? (xlo & 1u) : 0u);
-        const uint32_t o_hi = ozy | (cx == cx_hi ? (xhi & 1u) : 1u);
-        const uint2 r = sub_range(v, kzy | spread10(cx), o_lo, o_hi);
-        range(r.x, r.y);
-      }
-    }
-  }
-}
-
-// for_each_row: calls row(a0, a1, b0, b1) once per (z, y) row of sub-cells with the row's two index ranges
-// (the x extent of a row covers two cells; a third, which only happens within 2^-10 h of a sub-cell
-// boundary, is delivered as a row of its own). Walking both ranges in ONE loop matters in a warp: lanes
-// sit in different sub-cells, a loop runs as long as its longest lane, and the sum of two ranges varies
-// less between lanes than each of them (measured on the bench states: 164 instead of 216 candidate
-// slots per lane for 123 candidates).
-template <class Row>
-__device__ __forceinline__ void for_each_row(const SubView& v, const GridState& g, const SphConst& c, const float4& pi,
-                                             Row&& row) {
-  uint32_t xlo, xhi, ylo, yhi, zlo, zhi;
-  sub_bounds(pi.x, g.min_x, g.cell, c.h_margin, xlo, xhi);
-  sub_bounds(pi.y, g.min_y, g.cell, c.h_margin, ylo, yhi);
-  sub_bounds(pi.z, g.min_z, g.cell, c.h_margin, zlo, zhi);
-  const uint32_t cx_lo = xlo >> 1, cx_hi = xhi >> 1;
-  for (uint32_t fz = zlo; fz <= zhi; ++fz) {
-    const uint32_t kz = spread10(fz >> 1) << 2, oz = (fz & 1u) << 2;
-    for (uint32_t fy = ylo; fy <= yhi; ++fy) {
-      const uint32_t kzy = kz | (spread10(fy >> 1) << 1), ozy = oz | ((fy & 1u) << 1);
-      const uint2 a = sub_range(v, kzy | spread10(cx_lo), ozy | (xlo & 1u), ozy | (cx_hi == cx_lo ? (xhi & 1u) : 1u));
-      uint2 b = make_uint2(0u, 0u);
-      if (cx_hi > cx_lo) b = sub_range(v, kzy | spread10(cx_lo + 1u), ozy, ozy | (cx_hi == cx_lo + 1u ? (xhi & 1u) : 1u));
-      row(a.x, a.y, b.x, b.y);
-      if (cx_hi > cx_lo + 1u) {  // rare third cell of the row
-        const uint2 e = sub_range(v, kzy | spread10(cx_hi), ozy, ozy | (xhi & 1u));
-        row(e.x, e.y, 0u, 0u);
-      }
-    }
-  }
-}
-
-template <class Visit>
-__device__ __forceinline__ void for_each_neighbour(const SubView& v, const GridState& g, const SphConst& c,
-                                                   const float4* pos, const float4& pi, Visit&& visit) {
-  for_each_range(v, g, c, pi, [&](uint32_t begin, uint32_t end) {
-    for (uint32_t j = begin; j < end; ++j) {
-      const float4 pj = pos[j];
-      const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
-      visit(j, pj, s, s < c.support_s);
-    }
-  });
-}
 
 }  // namespace
 
@@ -189,7 +59,8 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
               const uint32_t* __restrict__ vals_b, uint32_t* __restrict__ skey, const uint32_t* __restrict__ rr_src,
               uint32_t* __restrict__ rr_dst, uint32_t* __restrict__ sub_lb, const GridState* __restrict__ grid,
               const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid, const uint32_t* __restrict__ src_ordk,
-              const uint32_t* __restrict__ src_ordr, uint32_t* __restrict__ dst_ordk, uint32_t* __restrict__ dst_ordr) {
+              const uint32_t* __restrict__ src_ordr, uint32_t* __restrict__ dst_ordk, uint32_t* __restrict__ dst_ordr,
+              TileCtl* tile_ctl, uint32_t* __restrict__ tile_blocks) {
   const uint32_t n = grid->n;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -238,6 +109,10 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
   dst_ivel[dest] = src_ivel[from];
   const uint32_t key = fkey >> 3, oct = fkey & 7u;
   skey[r] = key;  // the same for the whole sub-cell, whichever slot
+  // tile kernels (tiles.cu): a block is 8 consecutive Morton cells (2 x 2 x 2); the first particle of each
+  // non-empty block announces it. The list order is arbitrary and does not influence any result.
+  if (tile_ctl && key < grid->cell_count && (r == 0 || (keys[r - 1] >> 6) != (fkey >> 6)))
+    tile_blocks[atomicAdd(&tile_ctl->n_blocks, 1u)] = fkey >> 6;
   if (src_pid) dst_pid[dest] = src_pid[from];
   if (src_ordk) {  // multi-GPU: order keys (cell key and rank inside the cell of the previous sub-step)
     dst_ordk[dest] = src_ordk[from];
@@ -434,6 +309,77 @@ k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   accel[i] = finish_force(sums, c, aux[i].x);
 }
 
+// ---- per-particle kernels behind the tile kernels (tiles.cu): the particles of TileLists::slow ----------------
+// Density, pressure and support count by the walk of k_density_sub (search window of sub_bounds, global memory).
+// No masks are written: kNoMasks in the count sends the force pass of these particles to k_forces_slow.
+__global__ void __launch_bounds__(kSubThreads)
+k_density_slow(float4* pos, float4* vel, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
+               const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const SphConst c, float4* __restrict__ aux,
+               uint32_t* __restrict__ ncount, const uint32_t* __restrict__ slow, const TileCtl* __restrict__ ctl) {
+  const GridState g = *grid;
+  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const uint32_t n_slow = ctl->n_slow;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slow; k += gridDim.x * blockDim.x) {
+    const uint32_t i = slow[k];
+    const float4 pi = pos[i];
+    float acc = 0.f;
+    uint32_t cnt = 0;
+    for_each_neighbour(v, g, c, pos, pi, [&](uint32_t, const float4&, float s, bool inside) {
+      const float t = inside ? c.h2 - s : 0.f;
+      acc = fmaf(t * t, t, acc);
+      cnt += inside ? 1u : 0u;
+    });
+    finish_density(c, acc, i, aux, pos, vel);
+    ncount[i] = cnt | kNoMasks;
+  }
+}
+
+__global__ void __launch_bounds__(kSubThreads)
+k_forces_slow(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
+              const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
+              const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const SphConst c,
+              const uint32_t* __restrict__ slow, const TileCtl* __restrict__ ctl, float4* __restrict__ accel) {
+  const GridState g = *grid;
+  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const uint32_t n_slow = ctl->n_slow;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slow; k += gridDim.x * blockDim.x) {
+    const uint32_t i = slow[k];
+    const float4 pi = pos[i];
+    if (!owned_here(pi.x, skey[i], g)) continue;  // multi-GPU: ghosts get no force
+    const float4 vi = vel[i];
+    ForceSums sums;
+    for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4& pj, float, bool inside) {
+      if (inside) add_pair(sums, c, j == i, pi, vi, pi.w, pj, vel[j]);  // rare path: the exact pair terms
+    });
+    accel[i] = finish_force(sums, c, aux[i].x);
+  }
+}
+
+// Debug taps of the tile organisation, in the internal order (the caller scatters through rrank).
+__global__ void __launch_bounds__(kSubThreads)
+k_tile_taps(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
+            const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const uint32_t* __restrict__ ncount,
+            uint32_t* __restrict__ cand_count, uint32_t* __restrict__ supp_count) {
+  const GridState g = *grid;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const uint32_t key = skey[i];
+  // the reference's candidate count: every particle of the 27 cells around this one (forces.cl:25-40)
+  const uint32_t cx = compact10(key), cy = compact10(key >> 1), cz = compact10(key >> 2);
+  uint32_t total = 0;
+  if (cx != 0u && cy != 0u && cz != 0u) {  // with a 0 coordinate the reference's unsigned loop does not run
+    for (uint32_t z = cz - 1u; z <= cz + 1u; ++z)
+      for (uint32_t y = cy - 1u; y <= cy + 1u; ++y)
+        for (uint32_t x = cx - 1u; x <= cx + 1u; ++x) {
+          const uint2 r = sub_range(v, morton3(x, y, z), 0u, 7u);
+          total += r.y - r.x;
+        }
+  }
+  cand_count[i] = total;
+  supp_count[i] = ncount[i] & ~kNoMasks;
+}
+
 // dst[rrank[i]] = src[i], `words` 32-bit words per item: internal order -> the reference's order.
 __global__ void __launch_bounds__(256) k_scatter_words(const uint32_t* __restrict__ src, const uint32_t* __restrict__ rrank,
                                                        uint32_t* __restrict__ dst, uint32_t n, uint32_t words) {
@@ -455,11 +401,13 @@ void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capa
 void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                         const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,
-                        uint32_t* dst_ordk, uint32_t* dst_ordr, uint32_t n_launch, cudaStream_t stream,
-                        uint64_t* launches) {
+                        uint32_t* dst_ordk, uint32_t* dst_ordr, TileCtl* tile_ctl, uint32_t* tile_blocks, uint32_t n_launch,
+                        cudaStream_t stream, uint64_t* launches) {
+  if (tile_ctl) cudaMemsetAsync(tile_ctl, 0, sizeof(TileCtl), stream);
   k_reorder_sub<<<(n_launch + 255) / 256, 256, 0, stream>>>(src.pos, src.vel, src.ivel, dst.pos, dst.vel, dst.ivel, sort.keys_a,
                                                             sort.keys_b, sort.vals_a, sort.vals_b, skey, rr_src, rr_dst, sub_lb,
-                                                            grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr);
+                                                            grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr,
+                                                            tile_ctl, tile_blocks);
   if (launches) ++*launches;
 }
 
@@ -513,6 +461,31 @@ void launch_forces_sub_overflow(const float4* pos, const float4* vel, const floa
                                 uint64_t* launches) {
   k_forces_sub<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(
       pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, lists.count, lists.rows, accel);
+  if (launches) ++*launches;
+}
+
+void launch_density_slow(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
+                         const GridState* grid, const SphConst& c, float4* aux, const TileLists& tl, int sm_count,
+                         cudaStream_t stream, uint64_t* launches) {
+  (void)skey;
+  k_density_slow<<<sm_count * 2, kSubThreads, 0, stream>>>(pos, vel, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, tl.count, tl.slow,
+                                                           tl.ctl);
+  if (launches) ++*launches;
+}
+
+void launch_forces_slow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey, const uint32_t* sub_lb,
+                        const SortBuffers& sort, const GridState* grid, const SphConst& c, const TileLists& tl, float4* accel,
+                        int sm_count, cudaStream_t stream, uint64_t* launches) {
+  k_forces_slow<<<sm_count * 2, kSubThreads, 0, stream>>>(pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, tl.slow,
+                                                          tl.ctl, accel);
+  if (launches) ++*launches;
+}
+
+void launch_tile_taps(const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
+                      const TileLists& tl, uint32_t* cand_count, uint32_t* supp_count, uint32_t n_launch, cudaStream_t stream,
+                      uint64_t* launches) {
+  k_tile_taps<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(skey, sub_lb, sort.keys_a, sort.keys_b, grid,
+                                                                                      tl.count, cand_count, supp_count);
   if (launches) ++*launches;
 }
 

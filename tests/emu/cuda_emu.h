@@ -173,6 +173,12 @@ struct cudaDeviceProp {
   char name[64];
 };
 
+enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaDevAttrMaxSharedMemoryPerMultiprocessor = 81 };
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {  // the B200's figures
+  *v = a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 227 * 1024 : 228 * 1024;
+  return cudaSuccess;
+}
 cudaError_t cudaGetDeviceCount(int* n);
 cudaError_t cudaSetDevice(int d);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int d);
