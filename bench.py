@@ -63,12 +63,15 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=0, help="override the particle count of the config")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=102400)
+    ap.add_argument("--cpu-sample", type=int, default=102400,
+                    help="particles of the cpu_baseline sample; given explicitly it also bounds the --impl reference run")
     ap.add_argument("--option", action="append", default=[], help="name=value passed to clsph_set_option (tuning)")
     ap.add_argument("--organisation", default="auto", choices=["auto", "default", "candidate"],
                     help="auto: adopt the candidate kernel organisation (sub-cell order + face grid) only if a subprocess "
                          "self-check on this GPU finds it identical to the default one and faster; default / candidate: no check")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.cpu_sample_given = any(a == "--cpu-sample" or a.startswith("--cpu-sample=") for a in sys.argv[1:])
+    return args
 
 
 def measured_traffic(config, world, kernel):
@@ -159,10 +162,15 @@ def cpu_run(args, n, substeps, warmup):
     from oracle import oracle as O, ref as R
     p, terms, vol, scene_file, state = sample_workload(args, n_override=n)
     scene = O.load_obj(os.path.join(ROOT, "scenes", scene_file))
+    # every host core this process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # make the CPU side 1 / cores of what the box can do
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if R.available():
+        R.set_num_threads(cores)
         _, _, secs = R.simulate(p, terms, vol, scene, initial=state, substeps=warmup + substeps, record_all=False)
         elapsed = float(secs[warmup:].sum())
         return n * substeps / elapsed, "reference", R.num_threads(), elapsed
+    O.set_num_threads(cores)
     cur = state
     po = p.copy()
     for _ in range(warmup):
@@ -192,20 +200,27 @@ def run_reference(args, rank):
         return
     fluid, n_full, mass, scene = __import__("libclsph_b200.workloads", fromlist=["CONFIGS"]).CONFIGS[args.config]
     n_full = (args.particles or n_full) * max(1, args.gpus)  # the GPU arm runs gpus x the configured count as one block
-    # bounded sample: calibrate, then size N so that K+W sub-steps take about two minutes
-    n_cal = min(16384, n_full)
+    # The configured particle count itself when K+W sub-steps of it fit about four minutes on this box's cores
+    # (config 2 on 16 cores: ~2 s per sub-step); otherwise a bounded sample of the same fluid, sized to that budget
+    # (same_config false). --cpu-sample N forces a sample.
+    n_cal = min(65536, n_full)
     rate, kind, cores, _ = cpu_run(args, n_cal, 2, 1)
     total = max(1, args.steps + args.warmup)
-    n = int(min(n_full, args.cpu_sample, max(4096, rate * 120.0 / total)))
-    n -= n % 4096 if n >= 4096 else 0
+    budget_n = int(rate * 240.0 / total)
+    n = n_full if (budget_n >= n_full and not args.cpu_sample_given) else int(min(n_full, args.cpu_sample if args.cpu_sample_given else n_full,
+                                                                                  max(4096, budget_n)))
+    if n != n_full:
+        n -= n % 4096 if n >= 4096 else 0
     t_wall = time.perf_counter()
     rate, kind, cores, elapsed = cpu_run(args, n, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config, "particles_per_step_sample": n, "particles_full": n_full,
-                   "state": "S1 jittered lattice, seed 20261017", "note": "each step is a bounded sample of the workload (same fluid, same spacing)"},
+        "config": {"workload": args.config, "particles_per_step_sample": n, "particles_full": n_full, "same_config": n == n_full,
+                   "state": "S1 jittered lattice, seed 20261017",
+                   "note": ("each step is one sub-step of the configured workload at its full particle count" if n == n_full else
+                            "each step is a bounded sample of the workload (same fluid, same spacing)")},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": "%d particles x %d sub-steps, %.1f s wall" % (n, args.steps, time.perf_counter() - t_wall)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -557,9 +572,8 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
-    # NCCL prints its version banner on stdout at some debug levels; stdout must carry the JSON line only
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # (NCCL_DEBUG is left as the caller set it: run_ours points fd 1 at stderr while native libraries may print,
+    # so NCCL's communicator log cannot reach the JSON line on stdout)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

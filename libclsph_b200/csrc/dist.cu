@@ -119,7 +119,9 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   bool owned = i < g.n;
   if (owned && !g.fresh) {
     if (g.sub) {
-      owned = ivel[i].w == 1.f;  // advanced here in the last sub-step (k_integrate's mark); the rest are ghost copies
+      // advanced here in the last sub-step (k_integrate's mark); the rest are ghost copies. A slab that is not
+      // cut at all (world size 1) has no ghosts and k_integrate writes no marks: everything is owned.
+      owned = ivel[i].w == 1.f || !slab_is_cut(g);
     } else {
       const int cx_old = (int)compact10(skey[i]);
       owned = cx_old >= g.prev_lo && cx_old < g.prev_hi;  // the rest are last step's ghost copies: dropped
@@ -248,7 +250,7 @@ k_dist_export(const float4* __restrict__ pos, const float4* __restrict__ vel, co
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if ((i & ~31u) >= g.n) return;
   // sub-cell order: owned = advanced here in the last sub-step (its position may since have left the slab)
-  const bool owned = i < g.n && (g.fresh || (g.sub ? ivel[i].w == 1.f : cell_is_owned(skey[i], g)));
+  const bool owned = i < g.n && (g.fresh || (g.sub ? (ivel[i].w == 1.f || !slab_is_cut(g)) : cell_is_owned(skey[i], g)));
   const uint32_t at = warp_append(owned, out_count);
   if (!owned) return;
   float4 p = pos[i], v = vel[i], iv = ivel[i];

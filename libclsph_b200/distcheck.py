@@ -1,0 +1,135 @@
+"""Bitwise parity of the slab decomposition against a single-GPU run, on the ranks of a running job.
+
+    report = distcheck.bitwise_parity(dist, rank, world, local_rank, n_total=60000 * world, steps=4)
+
+Every rank runs its slab of one fluid block through the CUDA library (clsph_dist_*); rank 0 also runs the
+whole block on its own GPU without decomposition. After every sub-step the ranks' owned particles are
+gathered on rank 0 and compared with the single-GPU array:
+  * nothing lost, nothing duplicated (the persistent ids are a permutation of 0..n-1);
+  * the ranks' downloads merged by (grid_index, rank inside the cell) reproduce the single-GPU array ORDER;
+  * position, velocity, half-step velocity, density, pressure and grid_index of every particle are equal
+    BIT FOR BIT (each rank keeps the particles of a sub-cell in the order a single GPU does, ghosts carry
+    their order keys, so every floating-point sum runs in the same order).
+The state is a sheared block (the upper half moves right, the lower half left, 2.5 m/s) so that particles
+really cross the slab planes during the check.
+
+Used by bench.py before it times a multi-GPU run (`multi_gpu_parity` in its JSON line) and by
+tests/dist_worker.py. No CPU code takes part: the single-GPU run is the product's own kernels, which the GPU
+parity suite pins to the oracle.
+"""
+import numpy as np
+
+from . import abi, capi, slabs, workloads
+
+FIELDS = ("position", "velocity", "intermediate_velocity", "density", "pressure", "grid_index")
+
+
+def _gather_owned(dist, torch, ctx, rank, world, device):
+    """All ranks' owned particles and ids on rank 0 (padded all_gather)."""
+    parts, ids = ctx.dist_download()
+    n = torch.tensor([parts.size], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    cap = max(counts)
+    buf = torch.zeros(cap * 84, dtype=torch.uint8, device=device)
+    raw = np.concatenate([parts.view(np.uint8).reshape(-1), ids.view(np.uint8).reshape(-1)])
+    buf[: raw.size] = torch.from_numpy(raw).to(device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    if rank != 0:
+        return None, None, counts
+    all_p, all_i = [], []
+    for r in range(world):
+        b = bufs[r].cpu().numpy()
+        all_p.append(b[: counts[r] * 80].view(abi.PARTICLE).copy())
+        all_i.append(b[counts[r] * 80: counts[r] * 84].view(np.uint32).copy())
+    return np.concatenate(all_p), np.concatenate(all_i), counts
+
+
+def sheared_block(n_total):
+    p, terms, vol, scene_file = workloads.make_config(fluid="water", particles_count=n_total, particle_mass=0.05)
+    state = workloads.jittered_state(p, vol)
+    state["intermediate_velocity"][:, 0] += (2.5 * np.sign(state["position"][:, 2])).astype(np.float32)
+    state["velocity"][:, 0] = state["intermediate_velocity"][:, 0]
+    return p, terms, vol, scene_file, state
+
+
+def bitwise_parity(dist, rank, world, local_rank, n_total, steps=4, options=(), verbose=False):
+    """Returns the report dict (identical on every rank). `options`: "name=value" strings for both runs."""
+    import torch
+    device = torch.device("cuda", local_rank)
+    p, terms, vol, scene_file, state = sheared_block(n_total)
+    normals, vertices, indices = workloads.scene_arrays(scene_file)
+    planes = slabs.equal_count_planes(state["position"][:, 0], world)
+    owner = slabs.slab_of(state["position"][:, 0], planes)
+    mine = np.nonzero(owner == rank)[0].astype(np.uint32)
+
+    uid = (torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device=device) if rank == 0
+           else torch.zeros(128, dtype=torch.uint8, device=device))
+    dist.broadcast(uid, 0)
+    uid = bytes(uid.cpu().numpy().tolist())
+
+    def make(capacity):
+        ctx = capi.Context(capacity, device=local_rank)
+        for opt in options:
+            k, v = opt.split("=")
+            ctx.set_option(k, int(v))
+        ctx.set_scene(normals, vertices, indices)
+        ctx.set_parameters(p, terms)
+        return ctx
+
+    ctx = make(int(n_total * (1.0 / world + 0.5)) + 4096)  # owned + ghost layers on both sides, with slack
+    ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
+    ctx.dist_upload(np.ascontiguousarray(state[mine]), mine)
+    single = None
+    if rank == 0:
+        single = make(n_total)
+        single.upload(state)
+
+    report = {"particles": int(n_total), "world": int(world), "substeps": int(steps), "bitwise": True, "order": True,
+              "ids_exact": True, "migrated": 0, "first_failure": None}
+    ref_ids = np.arange(n_total, dtype=np.uint32)
+    for k in range(steps):
+        ctx.step(1)
+        ctx.synchronize()
+        got, ids, counts = _gather_owned(dist, torch, ctx, rank, world, device)
+        if rank != 0:
+            continue
+        single.step(1)
+        want = single.download()
+        ref_ids = ref_ids[single.fetch(capi.TAP_PERMUTATION)]  # id of the particle at each position of the single run
+        exact = sum(counts) == n_total and np.array_equal(np.sort(ids), np.arange(n_total, dtype=np.uint32))
+        report["ids_exact"] = report["ids_exact"] and bool(exact)
+        if not exact:
+            report["bitwise"] = report["order"] = False
+            report["first_failure"] = report["first_failure"] or "sub-step %d: particles lost or duplicated, counts %r" % (k, counts)
+            break
+        by_id_got = np.empty(n_total, dtype=abi.PARTICLE)
+        by_id_got[ids] = got
+        by_id_want = np.empty(n_total, dtype=abi.PARTICLE)
+        by_id_want[ref_ids] = want
+        merged = np.lexsort((got["_pad"], got["grid_index"]))
+        same_order = bool(np.array_equal(ids[merged], ref_ids))
+        bad = [f for f in FIELDS if by_id_got[f].tobytes() != by_id_want[f].tobytes()]
+        report["order"] = report["order"] and same_order
+        report["bitwise"] = report["bitwise"] and not bad
+        if (bad or not same_order) and not report["first_failure"]:
+            report["first_failure"] = "sub-step %d: %s" % (k, ("fields differ: " + ",".join(bad)) if bad else "merged order differs")
+        holder = np.empty(n_total, dtype=np.int64)
+        holder[ids] = np.concatenate([np.full(c, r) for r, c in enumerate(counts)])
+        report["migrated"] = int((holder != owner).sum())
+        if verbose:
+            print("distcheck sub-step %d: counts %r order %s bitwise %s migrated %d" % (k, counts, same_order, not bad, report["migrated"]),
+                  flush=True)
+    ctx.close()
+    if single is not None:
+        single.close()
+    # the verdict travels to every rank
+    flags = torch.tensor([int(report["bitwise"]), int(report["order"]), int(report["ids_exact"]), report["migrated"]],
+                         dtype=torch.int64, device=device)
+    dist.broadcast(flags, 0)
+    if rank != 0:
+        report.update(bitwise=bool(flags[0].item()), order=bool(flags[1].item()), ids_exact=bool(flags[2].item()),
+                      migrated=int(flags[3].item()))
+    return report

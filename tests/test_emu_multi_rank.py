@@ -50,7 +50,7 @@ def by_id(parts, ids, n):
     return out
 
 
-@pytest.mark.parametrize("world,copies,sub", [(2, 2, 0), (3, 3, 1)])
+@pytest.mark.parametrize("world,copies,sub", [(2, 2, 0), (3, 3, 1), (1, 2, 1)])  # world 1: a slab that is not cut at all
 def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
     steps = 3
     p, terms, state, scene_file = elongated_state(copies)
@@ -138,7 +138,7 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
             g = got[f][:, :3] if got[f].ndim == 2 else got[f]
             w = wants[k][f][:, :3] if wants[k][f].ndim == 2 else wants[k][f]
             assert rel(g, w) <= (1e-4 if k == 0 else 2e-3), (k, f, rel(g, w))
-    assert moved_total > 0, "the shear should have moved particles across a slab plane"
+    assert moved_total > 0 or world == 1, "the shear should have moved particles across a slab plane"
 
 
 def test_buffer_overflow_is_reported_and_nobody_hangs():
