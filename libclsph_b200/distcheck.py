@@ -24,27 +24,17 @@ from . import abi, capi, slabs, workloads
 FIELDS = ("position", "velocity", "intermediate_velocity", "density", "pressure", "grid_index")
 
 
-def _gather_owned(dist, torch, ctx, rank, world, device):
-    """All ranks' owned particles and ids on rank 0 (padded all_gather)."""
+def _gather_owned(dist, ctx, rank, world):
+    """All ranks' owned particles and ids, concatenated in rank order (only rank 0 uses them)."""
     parts, ids = ctx.dist_download()
-    n = torch.tensor([parts.size], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
-    cap = max(counts)
-    buf = torch.zeros(cap * 84, dtype=torch.uint8, device=device)
-    raw = np.concatenate([parts.view(np.uint8).reshape(-1), ids.view(np.uint8).reshape(-1)])
-    buf[: raw.size] = torch.from_numpy(raw).to(device)
-    bufs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(bufs, buf)
+    got = [None] * world
+    dist.all_gather_object(got, (parts.tobytes(), ids.tobytes()))
+    counts = [len(i) // 4 for _, i in got]
     if rank != 0:
         return None, None, counts
-    all_p, all_i = [], []
-    for r in range(world):
-        b = bufs[r].cpu().numpy()
-        all_p.append(b[: counts[r] * 80].view(abi.PARTICLE).copy())
-        all_i.append(b[counts[r] * 80: counts[r] * 84].view(np.uint32).copy())
-    return np.concatenate(all_p), np.concatenate(all_i), counts
+    all_p = np.concatenate([np.frombuffer(p, dtype=abi.PARTICLE) for p, _ in got])
+    all_i = np.concatenate([np.frombuffer(i, dtype=np.uint32) for _, i in got])
+    return all_p, all_i, counts
 
 
 def sheared_block(n_total):
@@ -57,18 +47,15 @@ def sheared_block(n_total):
 
 def bitwise_parity(dist, rank, world, local_rank, n_total, steps=4, options=(), verbose=False):
     """Returns the report dict (identical on every rank). `options`: "name=value" strings for both runs."""
-    import torch
-    device = torch.device("cuda", local_rank)
     p, terms, vol, scene_file, state = sheared_block(n_total)
     normals, vertices, indices = workloads.scene_arrays(scene_file)
     planes = slabs.equal_count_planes(state["position"][:, 0], world)
     owner = slabs.slab_of(state["position"][:, 0], planes)
     mine = np.nonzero(owner == rank)[0].astype(np.uint32)
 
-    uid = (torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device=device) if rank == 0
-           else torch.zeros(128, dtype=torch.uint8, device=device))
-    dist.broadcast(uid, 0)
-    uid = bytes(uid.cpu().numpy().tolist())
+    box = [capi.comm_unique_id() if rank == 0 else None]  # one NCCL id for the library's own communicator
+    dist.broadcast_object_list(box, 0)
+    uid = bytes(box[0])
 
     def make(capacity):
         ctx = capi.Context(capacity, device=local_rank)
@@ -93,7 +80,7 @@ def bitwise_parity(dist, rank, world, local_rank, n_total, steps=4, options=(), 
     for k in range(steps):
         ctx.step(1)
         ctx.synchronize()
-        got, ids, counts = _gather_owned(dist, torch, ctx, rank, world, device)
+        got, ids, counts = _gather_owned(dist, ctx, rank, world)
         if rank != 0:
             continue
         single.step(1)
@@ -101,10 +88,10 @@ def bitwise_parity(dist, rank, world, local_rank, n_total, steps=4, options=(), 
         ref_ids = ref_ids[single.fetch(capi.TAP_PERMUTATION)]  # id of the particle at each position of the single run
         exact = sum(counts) == n_total and np.array_equal(np.sort(ids), np.arange(n_total, dtype=np.uint32))
         report["ids_exact"] = report["ids_exact"] and bool(exact)
-        if not exact:
+        if not exact:  # (no early exit: the other ranks keep calling the collectives of the remaining sub-steps)
             report["bitwise"] = report["order"] = False
             report["first_failure"] = report["first_failure"] or "sub-step %d: particles lost or duplicated, counts %r" % (k, counts)
-            break
+            continue
         by_id_got = np.empty(n_total, dtype=abi.PARTICLE)
         by_id_got[ids] = got
         by_id_want = np.empty(n_total, dtype=abi.PARTICLE)
@@ -125,11 +112,6 @@ def bitwise_parity(dist, rank, world, local_rank, n_total, steps=4, options=(), 
     ctx.close()
     if single is not None:
         single.close()
-    # the verdict travels to every rank
-    flags = torch.tensor([int(report["bitwise"]), int(report["order"]), int(report["ids_exact"]), report["migrated"]],
-                         dtype=torch.int64, device=device)
-    dist.broadcast(flags, 0)
-    if rank != 0:
-        report.update(bitwise=bool(flags[0].item()), order=bool(flags[1].item()), ids_exact=bool(flags[2].item()),
-                      migrated=int(flags[3].item()))
-    return report
+    box = [report if rank == 0 else None]  # the verdict travels to every rank
+    dist.broadcast_object_list(box, 0)
+    return box[0]

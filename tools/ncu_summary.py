@@ -40,7 +40,7 @@ for s in sections:
         except (ValueError, IndexError):
             continue  # a source line with embedded quotes / commas (inline asm) that the CSV writer split
         if ok:
-            by.setdefault(fn, []).append((float(r[iI]), s["file"].split("/")[-1], int(r[iL]), r[1].strip()[:105], float(r[iS] or 0)))
+            by.setdefault(fn, []).append((float(r[iI]), s["file"].split("/")[-1], int(r[iL]), r[1].strip()[:105], float(r[iS] or 0) if r[iS] not in ('-', '') else 0.0))
 for fn, rows_ in by.items():
     tot = sum(r[0] for r in rows_); ts = sum(r[4] for r in rows_) or 1
     print("==== %s: %.3e warp-instructions attributed (inlined lines are double counted)" % (fn, tot))
