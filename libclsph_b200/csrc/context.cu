@@ -322,28 +322,23 @@ int ensure_sub(clsph_context* ctx) {
 // Arrays of the tile kernels, allocated the first time they are selected; the staging plan follows the fluid.
 int ensure_tiles(clsph_context* ctx) {
   if (!ctx->tiles || !ctx->sub_order) return CLSPH_OK;
-  if (!ctx->tl.masks) {
-    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.masks, (size_t)9 * ctx->capacity));
-    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.count, ctx->capacity));
+  if (!ctx->tl.blocks) {
     CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.blocks, ctx->capacity));
     CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.slow, ctx->capacity));
     CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.ctl, 1));
-    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tl.count, 0, sizeof(uint32_t) * ctx->capacity, ctx->stream));
     CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tl.ctl, 0, sizeof(TileCtl), ctx->stream));
-    ctx->tl.mask_stride = ctx->capacity;
   }
   if (ctx->have_params) {
     const simulation_parameters& p = ctx->params;
     const double per_sub_cell = (double)p.fluid_density / (double)p.particle_mass * (double)p.h * p.h * p.h;
-    ctx->tl.list_cap = list_rows_for(ctx);
-    ctx->tile_plan = tiles_plan(per_sub_cell, ctx->tl.list_cap);
+    ctx->tile_plan = tiles_plan(per_sub_cell);
   }
   return CLSPH_OK;
 }
 
 int ensure_lists(clsph_context* ctx) {
   if (int rc = ensure_tiles(ctx)) return rc;
-  if ((!ctx->use_lists && !ctx->sub_order) || (ctx->tiles && ctx->sub_order)) {  // the tile kernels keep hit masks instead
+  if (!ctx->use_lists && !ctx->sub_order) {
     ctx->lists.rows = 0;
     return CLSPH_OK;
   }
@@ -424,18 +419,18 @@ int enqueue_substep(clsph_context* ctx) {
                        st, lc);
     if (prof) next_event(ctx);
     if (ctx->tiles) {
-      launch_density_tiles(dst.pos, dst.vel, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->tl, ctx->tile_plan,
-                           ctx->sm_count, st, lc);
-      launch_density_slow(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->tl,
+      launch_density_tiles(dst.pos, dst.vel, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists, ctx->tl,
+                           ctx->tile_plan, ctx->sm_count, st, lc);
+      launch_density_slow(dst.pos, dst.vel, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists, ctx->tl,
                           ctx->sm_count, st, lc);
       if (ctx->debug)
-        launch_tile_taps(ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->tl, ctx->taps.candidate_count, ctx->taps.support_count, n,
-                         st, lc);
+        launch_tile_taps(dst.pos, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->lists, ctx->taps.candidate_count,
+                         ctx->taps.support_count, n, st, lc);
       if (prof) next_event(ctx);
-      launch_forces_tiles(dst.pos, dst.vel, ctx->aux, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->tl, ctx->tile_plan,
-                          ctx->fast_pairs, ctx->accel, ctx->sm_count, st, lc);
-      launch_forces_slow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->tl, ctx->accel,
-                         ctx->sm_count, st, lc);
+      launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
+                    false, true, ctx->forces_dense, ctx->accel, n, st, lc, true);
+      launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
+                                 ctx->lists, ctx->accel, n, st, lc);
     } else {
       launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
                          ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
@@ -633,8 +628,6 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->sub_lb);
   cudaFree(ctx->rrank);
   cudaFree(ctx->rr_tmp);
-  cudaFree(ctx->tl.masks);
-  cudaFree(ctx->tl.count);
   cudaFree(ctx->tl.blocks);
   cudaFree(ctx->tl.slow);
   cudaFree(ctx->tl.ctl);

@@ -114,7 +114,7 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
                    const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
-                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool tile_lists = false);
 
 struct TileCtl;
 // ---- subgrid.cu: sub-cell order (arrays sorted by cell key << 3 | octant)
@@ -142,48 +142,38 @@ void launch_forces_sub_overflow(const float4* pos, const float4* vel, const floa
 void launch_scatter_words(const void* src, const uint32_t* rrank, void* dst, uint32_t n, uint32_t words,
                           cudaStream_t stream, uint64_t* launches);
 
-// ---- tiles.cu: the neighbour passes of the sub-cell order as tile kernels (blocks of 2 x 2 x 2 cells)
-constexpr uint32_t kNoMasks = 0x80000000u;  // ncount bit: the particle has no hit masks (per-particle kernels serve it)
+// ---- tiles.cu: the density pass of the sub-cell order as a tile kernel (blocks of 2 x 2 x 2 cells)
 // Device-side bookkeeping of one sub-step, zeroed before the gather kernel appends the block list.
 struct TileCtl {
   uint32_t n_blocks;      // non-empty blocks, appended by k_reorder_sub
-  uint32_t next_density;  // work counters of the persistent tile kernels
-  uint32_t next_forces;
-  uint32_t n_slow;        // particles handed to the per-particle kernels (TileLists::slow)
+  uint32_t next_density;  // work counter of the persistent tile kernel
+  uint32_t next_slow;     // work counter of k_density_slow
+  uint32_t n_slow;        // particles handed to k_density_slow (TileLists::slow)
   uint32_t pad[4];
 };
 struct TileLists {
-  unsigned long long* masks = nullptr;  // [9][mask_stride]: hit bits of particle i in row r at masks[r * mask_stride + i]
-  size_t mask_stride = 0;
-  uint32_t* count = nullptr;            // [capacity] support count; kNoMasks set = no masks
-  uint32_t list_cap = 0;                // neighbours per particle the force pass lists (more: per-particle kernel)
   uint32_t* blocks = nullptr;           // [capacity] ids (cell key >> 3) of the non-empty blocks, any order
-  uint32_t* slow = nullptr;             // [capacity] particles for the per-particle kernels
+  uint32_t* slow = nullptr;             // [capacity] particles for k_density_slow
   TileCtl* ctl = nullptr;
 };
 struct TilePlan {
-  uint32_t density_slots = 0, forces_slots = 0;  // staging capacity (particles of a region) per CTA
-  size_t density_smem = 0, forces_smem = 0;      // dynamic shared memory per CTA
+  uint32_t density_slots = 0;  // staging capacity (particles of a region) per CTA
+  size_t density_smem = 0;     // dynamic shared memory per CTA
 };
 void tiles_init();
-TilePlan tiles_plan(double particles_per_sub_cell, uint32_t list_cap);
+TilePlan tiles_plan(double particles_per_sub_cell);
+// Densities, pressures and neighbour lists (the particle itself not listed; lists.count = neighbours found).
 void launch_density_tiles(float4* pos, float4* vel, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
-                          const SphConst& c, float4* aux, const TileLists& tl, const TilePlan& plan, int sm_count,
-                          cudaStream_t stream, uint64_t* launches);
-void launch_forces_tiles(const float4* pos, const float4* vel, const float4* aux, const uint32_t* sub_lb, const SortBuffers& sort,
-                         const GridState* grid, const SphConst& c, const TileLists& tl, const TilePlan& plan, bool fast_pairs,
-                         float4* accel, int sm_count, cudaStream_t stream, uint64_t* launches);
-// subgrid.cu: the particles of TileLists::slow, one thread each, searching in global memory
-void launch_density_slow(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
-                         const GridState* grid, const SphConst& c, float4* aux, const TileLists& tl, int sm_count,
+                          const SphConst& c, float4* aux, const NeighbourLists& lists, const TileLists& tl, const TilePlan& plan,
+                          int sm_count, cudaStream_t stream, uint64_t* launches);
+// subgrid.cu: the particles of TileLists::slow, one warp each, searching in global memory; same outputs, same bits
+void launch_density_slow(float4* pos, float4* vel, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
+                         const SphConst& c, float4* aux, const NeighbourLists& lists, const TileLists& tl, int sm_count,
                          cudaStream_t stream, uint64_t* launches);
-void launch_forces_slow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey, const uint32_t* sub_lb,
-                        const SortBuffers& sort, const GridState* grid, const SphConst& c, const TileLists& tl, float4* accel,
-                        int sm_count, cudaStream_t stream, uint64_t* launches);
 // debug taps of the tile organisation: the reference's candidate count (27 cells) and the support count
-void launch_tile_taps(const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
-                      const TileLists& tl, uint32_t* cand_count, uint32_t* supp_count, uint32_t n_launch, cudaStream_t stream,
-                      uint64_t* launches);
+void launch_tile_taps(const float4* pos, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
+                      const GridState* grid, const SphConst& c, const NeighbourLists& lists, uint32_t* cand_count,
+                      uint32_t* supp_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 
 // ---- integrate.cu
 void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,

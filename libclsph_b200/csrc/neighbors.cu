@@ -665,6 +665,86 @@ k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, c
   if (valid && listed) accel[i] = finish_force(sums, c, aux[i].x);
 }
 
+// The same pass for the lists of the tile kernel (tiles.cu): the particle itself is not listed (its own term is
+// added by tile_finish_force), and the pair terms are tile_pair_ops / tile_pair_add -- constants factored out of
+// the sums, one MUFU.RSQ per pair, no branch: ~46 instead of ~71 instructions per pair. A particle with a
+// degenerate pair (coincident particles, smoothing.cl:23; found by the exact test on s) is redone on the spot
+// with the reference's formulas.
+template <int kBlocks>
+__global__ void __launch_bounds__(kFlWarps * 32, kBlocks)
+k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
+                    const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
+                    const uint32_t* __restrict__ skey, const GridState* __restrict__ grid, const SphConst c,
+                    float4* __restrict__ accel) {
+  __shared__ uint32_t s_tile[kFlWarps][32 * kTileStride];
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const GridState g = *grid;
+  const uint32_t n = g.n;
+  const uint32_t base = (blockIdx.x * kFlWarps + warp) * 32u;
+  if (base >= n) return;
+  const uint32_t i = base + lane;
+  const float4 pi = i < n ? pos[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool valid = i < n && owned_here(pi.x, skey[min(i, n - 1u)], g);  // multi-GPU: ghosts get no force
+  uint32_t count = valid ? ncount[i] : 0u;
+  const bool listed = count <= list_rows;  // otherwise redone by k_forces_sub
+  if (!listed) count = 0u;
+  const float4 vi = valid ? vel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  ForceSums sums;
+  bool degenerate = false;
+  uint32_t* tile = s_tile[warp];
+  const uint32_t max_count = warp_max_u32(count);
+  for (uint32_t e0 = 0; e0 < max_count; e0 += 32u) {
+#pragma unroll
+    for (int p0 = 0; p0 < 32; p0 += 8) {  // rows p of the tile <- entries e0 .. e0+31 of particle base+p, 8 loads in flight
+      uint32_t v[8];
+      bool ok[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        ok[k] = e0 + lane < __shfl_sync(kFullMask, count, p0 + k);
+        v[k] = ok[k] ? nlist[(size_t)(base + p0 + k) * list_rows + e0 + lane] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (ok[k]) tile[(p0 + k) * kTileStride + lane] = v[k];
+    }
+    __syncwarp();
+    const uint32_t mine = count > e0 ? min(count - e0, 32u) : 0u;
+    const uint32_t* row = tile + lane * kTileStride;
+    uint32_t e = 0;
+    for (; e + 2 <= mine; e += 2) {  // two neighbours per trip: four independent gathers in flight
+      const uint32_t ja = row[e], jb = row[e + 1];
+      const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb];
+      float sa, sb;
+      const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa);
+      const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb);
+      degenerate |= (sa < c.degenerate_s) | (sb < c.degenerate_s);
+      tile_pair_add(sums, oa);
+      tile_pair_add(sums, ob);
+    }
+    if (e < mine) {
+      const uint32_t j = row[e];
+      float s;
+      const TilePair o = tile_pair_ops(c, pi, vi, pos[j], vel[j], s);
+      degenerate |= s < c.degenerate_s;
+      tile_pair_add(sums, o);
+    }
+    __syncwarp();
+  }
+  if (!(valid && listed)) return;
+  if (!degenerate) {
+    accel[i] = tile_finish_force(sums, c, aux[i].x, vi.w);
+    return;
+  }
+  ForceSums exact;
+  const uint32_t* mine = nlist + (size_t)i * list_rows;
+  for (uint32_t e = 0; e < count; ++e) {
+    const uint32_t j = mine[e];
+    add_pair(exact, c, false, pi, vi, pi.w, pos[j], vel[j]);
+  }
+  add_pair(exact, c, true, pi, vi, pi.w, pi, vi);
+  accel[i] = finish_force(exact, c, aux[i].x);
+}
+
 // ---------------------------------------------------------------------------------------------
 void neighbors_init() {
   cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDensitySmem);
@@ -707,9 +787,18 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
                    const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
-                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool tile_lists) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
-  if (lists.rows) {
+  if (lists.rows && tile_lists) {  // lists of the tile kernel: the particle itself is not listed
+    const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
+    if (dense_occupancy)
+      k_forces_lists_tile<4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid,
+                                                                   c, accel);
+    else
+      k_forces_lists_tile<3><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid,
+                                                                   c, accel);
+    if (launches) ++*launches;
+  } else if (lists.rows) {
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
     // <false, 3> is the instantiation the GPU parity suite has passed; the others are selected by the options
     // fast_pairs / forces_blocks (clsph_cuda.h)

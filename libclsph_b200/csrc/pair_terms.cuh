@@ -93,6 +93,71 @@ __device__ __forceinline__ float4 finish_force(const ForceSums& f, const SphCons
   return make_float4(fx / rho + c.gx, fy / rho + c.gy, fz / rho + c.gz, 0.f);
 }
 
+// ---- pair terms of the tile kernels (tiles.cu) and of the per-particle kernels behind them (subgrid.cu) ----------
+// Same formulas with the per-run constants factored out of the sums (they are applied once per particle in
+// tile_finish_force) and one MUFU.RSQ for r and 1/r: 36 floating-point instructions per pair, no branch.
+//   P += (p_j/rho_j^2 + p_i/rho_i^2) (h - r)^2 / r * d        pressure      x m c_spiky
+//   W += (v_j - v_i) (m/rho_j) (h - r)                        viscosity     x c_visc
+//   N += (m/rho_j) (h^2 - s)^2 * d                            colour normal x c_poly6_grad
+//   L += (m/rho_j) (h^2 - s) (3 h^2 - 7 s)                    colour laplacian x c_poly6_lap
+// Valid for j != i and s >= degenerate_s; the callers exclude the particle itself (its only contribution, to L,
+// is tile_self_lap) and hand particles with a degenerate pair (coincident particles, smoothing.cl:23) to the
+// exact add_pair. Both kernels evaluate operands and sums with THESE functions in the same order, so a particle
+// gets the same bits whichever kernel serves it.
+struct TilePair {
+  float kp, dx, dy, dz, vc, ux, uy, uz, gc, lw;
+};
+__device__ __forceinline__ float rsqrt_fast(float s) {
+#ifdef CLSPH_EMU
+  return 1.0f / sqrtf(s);
+#else
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+  return r;
+#endif
+}
+__device__ __forceinline__ TilePair tile_pair_ops(const SphConst& c, const float4& pi, const float4& vi, const float4& pj,
+                                                  const float4& vj, float& s_out) {
+  TilePair o;
+  o.dx = pi.x - pj.x; o.dy = pi.y - pj.y; o.dz = pi.z - pj.z;
+  const float s = fmaf(o.dz, o.dz, fmaf(o.dy, o.dy, o.dx * o.dx));
+  s_out = s;
+  const float inv_r = rsqrt_fast(s);
+  const float hr = c.h - s * inv_r;
+  o.kp = (pj.w + pi.w) * (hr * hr * inv_r);
+  o.vc = vj.w * hr;
+  o.ux = vj.x - vi.x; o.uy = vj.y - vi.y; o.uz = vj.z - vi.z;
+  const float t = c.h2 - s;
+  o.gc = vj.w * (t * t);
+  o.lw = vj.w * (t * fmaf(-7.f, s, 3.f * c.h2));
+  return o;
+}
+__device__ __forceinline__ void tile_pair_add(ForceSums& f, const TilePair& o) {
+  f.px = fmaf(o.kp, o.dx, f.px); f.py = fmaf(o.kp, o.dy, f.py); f.pz = fmaf(o.kp, o.dz, f.pz);
+  f.wx = fmaf(o.ux, o.vc, f.wx); f.wy = fmaf(o.uy, o.vc, f.wy); f.wz = fmaf(o.uz, o.vc, f.wz);
+  f.nx = fmaf(o.gc, o.dx, f.nx); f.ny = fmaf(o.gc, o.dy, f.ny); f.nz = fmaf(o.gc, o.dz, f.nz);
+  f.lap += o.lw;
+}
+// The particle's own term (s = 0: only the laplacian of the colour field is non-zero), then the constants, then
+// finish_force. mor_i = m / rho_i.
+__device__ __forceinline__ float4 tile_finish_force(ForceSums f, const SphConst& c, float rho, float mor_i) {
+  f.lap += mor_i * (c.h2 * (3.f * c.h2));
+  const float kp = c.mass * c.c_spiky;
+  f.px *= kp; f.py *= kp; f.pz *= kp;
+  f.wx *= c.c_visc; f.wy *= c.c_visc; f.wz *= c.c_visc;
+  f.nx *= c.c_poly6_grad; f.ny *= c.c_poly6_grad; f.nz *= c.c_poly6_grad;
+  f.lap *= c.c_poly6_lap;
+  return finish_force(f, c, rho);
+}
+
+// The particle's own term of the density sum, added last by the tile kernel and the kernel behind it (s = 0; NaN
+// for a particle that has blown up, which then fails the support test as it does in the reference).
+__device__ __forceinline__ float tile_self_density(float acc, const float4& pi, const SphConst& c) {
+  const float s = dist2_contract(pi.x, pi.y, pi.z, pi.x, pi.y, pi.z);
+  const float t = s < c.support_s ? c.h2 - s : 0.f;
+  return fmaf(t * t, t, acc);
+}
+
 // forces.cl:33-36 / smoothing.cl:1-4: rho = sum m C6 (h^2 - r^2)^3; sph.cl:37-39: Tait pressure.
 // Writes (rho, p) to aux[i] and the two per-neighbour factors the force pass gathers.
 __device__ __forceinline__ void finish_density(const SphConst& c, float sum_cubed, uint32_t i, float4* __restrict__ aux,

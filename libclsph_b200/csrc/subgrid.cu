@@ -309,57 +309,60 @@ k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   accel[i] = finish_force(sums, c, aux[i].x);
 }
 
-// ---- per-particle kernels behind the tile kernels (tiles.cu): the particles of TileLists::slow ----------------
-// Density, pressure and support count by the walk of k_density_sub (search window of sub_bounds, global memory).
-// No masks are written: kNoMasks in the count sends the force pass of these particles to k_forces_slow.
+// ---- the kernel behind the tile kernel (tiles.cu): the particles of TileLists::slow, one WARP each -------------
+// Density, pressure, neighbour list and count by the walk of k_density_sub (search window of sub_bounds, global
+// memory), lanes across the candidates of a range. The list entries and the density terms are taken in candidate
+// order (ballot + prefix count; the terms are broadcast one by one and every lane keeps the same running sum), and
+// the particle's own term comes last: the same order, hence the same bits, as k_density_tiles.
 __global__ void __launch_bounds__(kSubThreads)
 k_density_slow(float4* pos, float4* vel, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
                const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const SphConst c, float4* __restrict__ aux,
-               uint32_t* __restrict__ ncount, const uint32_t* __restrict__ slow, const TileCtl* __restrict__ ctl) {
+               uint32_t* __restrict__ nlist, uint32_t* __restrict__ ncount, uint32_t list_rows, const uint32_t* __restrict__ slow,
+               const TileCtl* __restrict__ ctl) {
   const GridState g = *grid;
   const SubView v = make_view(g, sub_lb, keys_a, keys_b);
   const uint32_t n_slow = ctl->n_slow;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slow; k += gridDim.x * blockDim.x) {
+  const unsigned lane = lane_id();
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_slow; k += n_warps) {
     const uint32_t i = slow[k];
     const float4 pi = pos[i];
+    uint32_t* row = nlist + (size_t)i * list_rows;
     float acc = 0.f;
     uint32_t cnt = 0;
-    for_each_neighbour(v, g, c, pos, pi, [&](uint32_t, const float4&, float s, bool inside) {
-      const float t = inside ? c.h2 - s : 0.f;
-      acc = fmaf(t * t, t, acc);
-      cnt += inside ? 1u : 0u;
+    for_each_range(v, g, c, pi, [&](uint32_t begin, uint32_t end) {
+      for (uint32_t j0 = begin; j0 < end; j0 += 32u) {
+        const uint32_t j = j0 + lane;
+        const bool ok = j < end;
+        const float4 pj = pos[ok ? j : i];
+        const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+        const bool inside = ok && j != i && s < c.support_s;
+        const float t = c.h2 - s;
+        unsigned m = __ballot_sync(kFullMask, inside);
+        const uint32_t at = cnt + (uint32_t)__popc(m & lanemask_lt());
+        if (inside && at < list_rows) row[at] = j;
+        cnt += (uint32_t)__popc(m);
+        while (m) {
+          const int src = __ffs((int)m) - 1;
+          m &= m - 1u;
+          const float tk = __shfl_sync(kFullMask, t, src);
+          acc = fmaf(tk * tk, tk, acc);
+        }
+      }
     });
-    finish_density(c, acc, i, aux, pos, vel);
-    ncount[i] = cnt | kNoMasks;
-  }
-}
-
-__global__ void __launch_bounds__(kSubThreads)
-k_forces_slow(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
-              const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
-              const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const SphConst c,
-              const uint32_t* __restrict__ slow, const TileCtl* __restrict__ ctl, float4* __restrict__ accel) {
-  const GridState g = *grid;
-  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
-  const uint32_t n_slow = ctl->n_slow;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slow; k += gridDim.x * blockDim.x) {
-    const uint32_t i = slow[k];
-    const float4 pi = pos[i];
-    if (!owned_here(pi.x, skey[i], g)) continue;  // multi-GPU: ghosts get no force
-    const float4 vi = vel[i];
-    ForceSums sums;
-    for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4& pj, float, bool inside) {
-      if (inside) add_pair(sums, c, j == i, pi, vi, pi.w, pj, vel[j]);  // rare path: the exact pair terms
-    });
-    accel[i] = finish_force(sums, c, aux[i].x);
+    if (lane == 0u) {
+      finish_density(c, tile_self_density(acc, pi, c), i, aux, pos, vel);
+      ncount[i] = cnt;
+    }
   }
 }
 
 // Debug taps of the tile organisation, in the internal order (the caller scatters through rrank).
 __global__ void __launch_bounds__(kSubThreads)
-k_tile_taps(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
-            const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const uint32_t* __restrict__ ncount,
-            uint32_t* __restrict__ cand_count, uint32_t* __restrict__ supp_count) {
+k_tile_taps(const float4* __restrict__ pos, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
+            const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
+            const SphConst c, const uint32_t* __restrict__ ncount, uint32_t* __restrict__ cand_count,
+            uint32_t* __restrict__ supp_count) {
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
@@ -377,7 +380,10 @@ k_tile_taps(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_
         }
   }
   cand_count[i] = total;
-  supp_count[i] = ncount[i] & ~kNoMasks;
+  // the support count includes the particle itself (unless it has blown up: NaN fails the test as in the reference)
+  const float4 pi = pos[i];
+  const bool self = dist2_contract(pi.x, pi.y, pi.z, pi.x, pi.y, pi.z) < c.support_s;
+  supp_count[i] = ncount[i] + (self ? 1u : 0u);
 }
 
 // dst[rrank[i]] = src[i], `words` 32-bit words per item: internal order -> the reference's order.
@@ -464,28 +470,19 @@ void launch_forces_sub_overflow(const float4* pos, const float4* vel, const floa
   if (launches) ++*launches;
 }
 
-void launch_density_slow(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
-                         const GridState* grid, const SphConst& c, float4* aux, const TileLists& tl, int sm_count,
+void launch_density_slow(float4* pos, float4* vel, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
+                         const SphConst& c, float4* aux, const NeighbourLists& lists, const TileLists& tl, int sm_count,
                          cudaStream_t stream, uint64_t* launches) {
-  (void)skey;
-  k_density_slow<<<sm_count * 2, kSubThreads, 0, stream>>>(pos, vel, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, tl.count, tl.slow,
-                                                           tl.ctl);
+  k_density_slow<<<sm_count * 2, kSubThreads, 0, stream>>>(pos, vel, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries,
+                                                           lists.count, lists.rows, tl.slow, tl.ctl);
   if (launches) ++*launches;
 }
 
-void launch_forces_slow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey, const uint32_t* sub_lb,
-                        const SortBuffers& sort, const GridState* grid, const SphConst& c, const TileLists& tl, float4* accel,
-                        int sm_count, cudaStream_t stream, uint64_t* launches) {
-  k_forces_slow<<<sm_count * 2, kSubThreads, 0, stream>>>(pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, tl.slow,
-                                                          tl.ctl, accel);
-  if (launches) ++*launches;
-}
-
-void launch_tile_taps(const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
-                      const TileLists& tl, uint32_t* cand_count, uint32_t* supp_count, uint32_t n_launch, cudaStream_t stream,
-                      uint64_t* launches) {
-  k_tile_taps<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(skey, sub_lb, sort.keys_a, sort.keys_b, grid,
-                                                                                      tl.count, cand_count, supp_count);
+void launch_tile_taps(const float4* pos, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
+                      const GridState* grid, const SphConst& c, const NeighbourLists& lists, uint32_t* cand_count,
+                      uint32_t* supp_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+  k_tile_taps<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(pos, skey, sub_lb, sort.keys_a, sort.keys_b, grid,
+                                                                                      c, lists.count, cand_count, supp_count);
   if (launches) ++*launches;
 }
 

@@ -43,6 +43,9 @@ inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; ret
 struct uint3 {
   unsigned x, y, z;
 };
+struct alignas(16) uint4 {
+  unsigned x, y, z, w;
+};
 struct dim3 {
   unsigned x, y, z;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
