@@ -19,12 +19,10 @@ box.obj, 1 Mi particles, jittered-lattice state S1). Prints ONE JSON line (rank 
 
 --impl reference times only the CPU side (reference arm of the driver).
 
---organisation auto (default): before anything is timed, `python -m libclsph_b200.selfcheck` runs in a subprocess
-on the GPU: one sub-step of the workload with the library's default options and with each candidate option set
-(kernels written after the last GPU session of round 1); a set qualifies if every integer
-observable and the exported order are identical and the floats agree to 5e-5; the fastest qualifying set is
-used if it beats the default. With N > 1 a multi-GPU cross-check of global invariants follows. What was
-chosen, and every timing, is in config.organisation / config.options of the JSON line.
+The library's default kernel organisation is what gets timed (sub-cell order, merged rows, face grid);
+--option name=value overrides single options for tuning runs. With N > 1 the run starts with a bitwise parity
+check of the slab decomposition against a single-GPU run on the job's own ranks (libclsph_b200.distcheck,
+`multi_gpu_parity` in the JSON line). `repeats` holds four more timed regions of K sub-steps and the median.
 """
 import argparse
 import json
@@ -66,9 +64,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=102400,
                     help="particles of the cpu_baseline sample; given explicitly it also bounds the --impl reference run")
     ap.add_argument("--option", action="append", default=[], help="name=value passed to clsph_set_option (tuning)")
-    ap.add_argument("--organisation", default="auto", choices=["auto", "default", "candidate"],
-                    help="auto: adopt the candidate kernel organisation (sub-cell order + face grid) only if a subprocess "
-                         "self-check on this GPU finds it identical to the default one and faster; default / candidate: no check")
+    ap.add_argument("--repeats", type=int, default=4, help="further timed regions of K sub-steps after the one `value` is taken from")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the bitwise multi-GPU parity check before timing")
     args = ap.parse_args()
     args.cpu_sample_given = any(a == "--cpu-sample" or a.startswith("--cpu-sample=") for a in sys.argv[1:])
     return args
@@ -77,12 +74,12 @@ def parse_args():
 def measured_traffic(config, world, kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture, when this run matches the capture."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
             t = json.load(fh)
         if world != 1 or t["config"] != config or kernel not in t["kernels"]:
             return None, None
         k = t["kernels"][kernel]
-        return (k["read_mb"] + k["write_mb"]) * 1e6, "ncu --set full, %s (profiles/r01_traffic.json)" % k["capture"]
+        return (k["read_mb"] + k["write_mb"]) * 1e6, "ncu --set full, %s (profiles/r02_traffic.json)" % k["capture"]
     except Exception:
         return None, None
 
@@ -231,47 +228,15 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
-CANDIDATE_OPTIONS = ["sub_cell_order=1", "face_grid=1", "fast_pairs=1"]
-# what --organisation auto lets the self-check choose from (the fastest set that agrees wins)
-CANDIDATE_SETS = [CANDIDATE_OPTIONS, CANDIDATE_OPTIONS + ["merged_rows=1"], CANDIDATE_OPTIONS + ["merged_rows=1", "forces_blocks=4"],
-                  CANDIDATE_OPTIONS + ["deferred_lists=1", "forces_blocks=4"], CANDIDATE_OPTIONS + ["forces_blocks=4"],
-                  # the established organisation with only the force-kernel and collision-pass changes
-                  ["face_grid=1", "fast_pairs=1", "forces_blocks=4"]]
 _SAVED_STDOUT = None  # the real stdout while run_ours has fd 1 pointed at stderr
 
 
-def choose_organisation(args, local_rank, n_particles):
-    """(options, report). The candidate options select kernels that were written after the last GPU
-    session of round 1; they are adopted only when libclsph_b200.selfcheck, run in a SUBPROCESS on
-    this GPU, finds every integer observable identical to the default organisation's (which passed
-    the GPU parity suite against the oracle), the rest equal to rounding, and the step faster."""
-    if args.option or args.organisation == "default":
-        return list(args.option), {"mode": "as given" if args.option else "default"}
-    if args.organisation == "candidate":
-        return list(CANDIDATE_OPTIONS), {"mode": "candidate, unchecked"}
-    import subprocess
-    cmd = [sys.executable, "-m", "libclsph_b200.selfcheck", "--config", args.config, "--device", str(local_rank),
-           "--particles", str(min(n_particles, 1 << 22))] + [x for o in CANDIDATE_SETS for x in ("--set", ",".join(o))]
-    report = {"mode": "auto"}
-    try:
-        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=240)
-        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-        report.update(json.loads(lines[-1]) if lines else {"agree": False, "error": "no output, exit code %d: %s" % (r.returncode, r.stderr[-300:])})
-    except Exception as exc:  # a hang or crash of the candidate kernels must not take the benchmark down
-        report.update({"agree": False, "error": repr(exc)})
-    best = None
-    for entry in report.get("sets", []):
-        if entry.get("agree") and entry.get("ms_per_step", 1e30) < report.get("ms_per_step_default", 0.0):
-            if best is None or entry["ms_per_step"] < best["ms_per_step"]:
-                best = entry
-    report["adopted"] = best is not None
-    return (["%s=%d" % kv for kv in best["options"].items()] if best else []), report
 def ctx_capacity(ctx, n):
     """Room for a rank's download: its own particles plus what may have migrated in."""
     return int(n * 1.5) + 65536
 
 
-def multi_gpu_workload(config, n_per_gpu, rank, world, sub_cell_order=False):
+def multi_gpu_workload(config, n_per_gpu, rank, world, sub_cell_order=True):
     """This rank's share of the weak-scaling workload: `world` x the configured count as ONE fluid block
     (same particle mass, hence same h and spacing), cut into x slabs. Returns a dict with the parameters,
     the rank's particles and ids, its slab planes and the capacities to create the context with."""
@@ -294,44 +259,6 @@ def multi_gpu_workload(config, n_per_gpu, rank, world, sub_cell_order=False):
     ghost_cap = int((1.5 if sub_cell_order else 3.0) * layer) + 8192
     return dict(params=p, terms=terms, volume=vol, state=state, ids=index, planes=planes, emigrant_capacity=emigrant_cap,
                 ghost_capacity=ghost_cap, capacity=int(1.2 * n) + 2 * layer + 2 * ghost_cap + 65536)
-
-
-def slab_invariants(w, scene, options, rank, world, unique_id, device_index, substeps=3):
-    """This rank's contribution to a few GLOBAL invariants of a short multi-GPU run of the bench workload with
-    the given options: owned particle count, sum of ids and of ids^2 (nothing lost, nothing duplicated), sums
-    of density, pressure and |position|, |velocity| components over the owned particles (float64). Summed over
-    the ranks they must not depend on the kernel organisation beyond rounding."""
-    import numpy as np
-    from libclsph_b200 import capi
-    ctx = capi.Context(w["capacity"], device=device_index)
-    for opt in options:
-        k, v = opt.split("=")
-        ctx.set_option(k, int(v))
-    ctx.set_scene(*scene)
-    ctx.set_parameters(w["params"], w["terms"])
-    ctx.dist_init(rank, world, unique_id, float(w["planes"][rank]), float(w["planes"][rank + 1]),
-                  emigrant_capacity=w["emigrant_capacity"], ghost_capacity=w["ghost_capacity"])
-    ctx.dist_upload(w["state"], w["ids"])
-    ctx.step(substeps)
-    parts, ids = ctx.dist_download()
-    ctx.close()
-    u64 = ids.astype(np.uint64)
-    with np.errstate(over="ignore"):  # sums modulo 2^64: exact and independent of the order
-        ints = np.array([parts.size, u64.sum(dtype=np.uint64), (u64 * u64).sum(dtype=np.uint64)], dtype=np.uint64).view(np.int64)
-    f = lambda a: float(np.abs(a.astype(np.float64)).sum())
-    floats = np.array([f(parts["density"]), f(parts["pressure"]), f(parts["position"][:, 0]), f(parts["position"][:, 1]),
-                       f(parts["position"][:, 2]), f(parts["velocity"][:, 0]), f(parts["velocity"][:, 1]), f(parts["velocity"][:, 2])],
-                      dtype=np.float64)
-    return ints, floats
-
-
-def invariants_agree(base, cand, n_total):
-    """base / cand: (ints, floats) of slab_invariants summed over the ranks (ints modulo 2^64) for the established
-    and the candidate options."""
-    (bi, bf), (ci, cf) = base, cand
-    exact = int(bi[0]) == int(ci[0]) == int(n_total) and int(bi[1]) == int(ci[1]) and int(bi[2]) == int(ci[2])
-    rel = max(abs(float(a) - float(b)) / max(abs(float(a)), 1e-30) for a, b in zip(bf, cf))
-    return bool(exact and rel <= 1e-5), float(rel)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -374,18 +301,8 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     fluid, n_cfg, mass, scene_file = workloads.CONFIGS[args.config]
     n_cfg = args.particles or n_cfg
-    # kernel organisation: decided once (rank 0), the same on every rank
-    if rank == 0:
-        options, organisation = choose_organisation(args, local_rank, n_cfg)
-    else:
-        options, organisation = [], {}
-    if dist is not None:
-        # the choice travels as an index: 0 = as given on the command line, k = CANDIDATE_SETS[k - 1]
-        index = 1 + [sorted(c) for c in CANDIDATE_SETS].index(sorted(options)) if sorted(options) in [sorted(c) for c in CANDIDATE_SETS] else 0
-        flag = torch.tensor([index], dtype=torch.int32, device=device)
-        dist.broadcast(flag, 0)
-        if rank != 0:
-            options = list(CANDIDATE_SETS[int(flag.item()) - 1]) if int(flag.item()) else list(args.option)
+    options = list(args.option)
+    sub = "sub_cell_order=0" not in options
     normals, vertices, indices = workloads.scene_arrays(scene_file)
     if world == 1:
         p, terms, vol, _, state = sample_workload(args)
@@ -393,40 +310,16 @@ def run_ours(args, rank, world, local_rank):
         n = state.size
         ctx = capi.Context(n, device=local_rank)
     else:
+        # bitwise parity of the slab decomposition on this job's own ranks, before anything is timed
+        parity = None
+        if not args.no_parity and sub:
+            from libclsph_b200 import distcheck
+            parity = distcheck.bitwise_parity(dist, rank, world, local_rank, n_total=60000 * world, steps=4, options=options)
         # weak scaling: each rank generates only its own slab of the common block
-        w = multi_gpu_workload(args.config, n_cfg, rank, world, sub_cell_order="sub_cell_order=1" in options)
+        w = multi_gpu_workload(args.config, n_cfg, rank, world, sub_cell_order=sub)
         p, terms, vol, state, ids, planes = w["params"], w["terms"], w["volume"], w["state"], w["ids"], w["planes"]
         emigrant_cap, ghost_cap = w["emigrant_capacity"], w["ghost_capacity"]
         n = state.size
-        if options and not args.option and args.organisation == "auto":
-            # The self-check ran on one GPU. Before the adopted options time a multi-GPU run, three sub-steps of
-            # this very workload are run with the established organisation and with them, and global
-            # invariants (count, id sums, sums of density / pressure / positions / velocities over the owned
-            # particles, all-reduced) must agree; otherwise every rank goes back to the established one.
-            def fresh_uid():
-                t = (torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device=device) if rank == 0
-                     else torch.zeros(128, dtype=torch.uint8, device=device))
-                dist.broadcast(t, 0)
-                return bytes(t.cpu().numpy().tolist())
-
-            def reduced(opts):
-                ints, floats = slab_invariants(w, (normals, vertices, indices), opts, rank, world, fresh_uid(), local_rank)
-                ti = torch.tensor(ints, dtype=torch.int64, device=device)      # wraps modulo 2^64 like the local sums
-                tf = torch.tensor(floats, dtype=torch.float64, device=device)
-                dist.all_reduce(ti, op=dist.ReduceOp.SUM)
-                dist.all_reduce(tf, op=dist.ReduceOp.SUM)
-                return ti.cpu().numpy(), tf.cpu().numpy()
-
-            w_sub = w
-            w = multi_gpu_workload(args.config, n_cfg, rank, world, sub_cell_order=False)  # capacities of the established kernels
-            base = reduced([])
-            w = w_sub
-            ok, rel = invariants_agree(base, reduced(options), n_cfg * world)
-            organisation["multi_gpu_crosscheck"] = {"agree": ok, "max_rel_diff": rel, "substeps": 3}
-            if not ok:
-                options = []
-                w = multi_gpu_workload(args.config, n_cfg, rank, world, sub_cell_order=False)
-                emigrant_cap, ghost_cap = w["emigrant_capacity"], w["ghost_capacity"]
         ctx = capi.Context(w["capacity"], device=local_rank)
     for opt in options:
         k, v = opt.split("=")
@@ -458,16 +351,21 @@ def run_ours(args, rank, world, local_rank):
     ctx.profile_enable(False)  # resets the launch counter
     barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    ctx.step(args.steps)
-    e1.record(stream)
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.finish()
+    def timed_region():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.step(args.steps)
+        e1.record(stream)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    ms_total = timed_region()
     launches = ctx.profile_read()["kernel_launches"]
+    # BASELINE.md section 3 asks for the median of 5: four more regions of K sub-steps on the evolving state
+    regions = [ms_total] + [timed_region() for _ in range(max(0, args.repeats))]
+    clocks = sampler.finish()
     n_total = sum_over_ranks(float(n))
     value = n_total * args.steps / (ms_total * 1e-3)
     grid = ctx.parameters()
@@ -485,12 +383,13 @@ def run_ours(args, rank, world, local_rank):
     dominant = max((k for k in kb), key=lambda k: per.get(k, 0.0))
     peak, peak_src = measured_peak()
     achieved = n * kb[dominant] / (per[dominant] * 1e-3) / 1e9
-    sub = "sub_cell_order=1" in options
-    kernel_name = {"density": "k_density_sub" if sub else "k_density_lists", "forces": "k_forces_lists",
+    tiles = sub and "tile_kernels=1" in options
+    kernel_name = {"density": ("k_density_tiles" if tiles else "k_density_sub") if sub else "k_density_lists",
+                   "forces": "k_forces_lists_tile" if tiles else "k_forces_lists",
                    "reorder": "k_reorder_sub" if sub else "k_reorder", "sort": "k_onesweep", "keys": "k_keys_hist",
                    "integrate": "k_integrate"}[dominant]
-    # the committed ncu capture is of the established organisation only
-    traffic, traffic_src = (None, None) if options else measured_traffic(args.config if not args.particles else None, world, "k_" + dominant)
+    # the committed ncu capture is of the default options
+    traffic, traffic_src = (None, None) if options else measured_traffic(args.config if not args.particles else None, world, kernel_name)
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": n * kb[dominant], "peak_source": peak_src,
@@ -555,9 +454,13 @@ def run_ours(args, rank, world, local_rank):
                    "all-reduce, migration + two ghost cell layers per side in one NCCL send/recv group" % (world, world),
                    "l2": "per-step working set ~%d MB vs 126 MB L2, no flush: sub-steps form a dependent chain" % (n * 200 // (1 << 20)),
                    "grid": [grid.grid_size_x, grid.grid_size_y, grid.grid_size_z], "grid_cell_count": grid.grid_cell_count,
-                   "options": options, "organisation": organisation},
+                   "options": options},
+        "repeats": {"ms_per_step": [m / args.steps for m in regions],
+                    "median_value": n_total * args.steps / (sorted(regions)[len(regions) // 2] * 1e-3)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
+    if world > 1:
+        line["multi_gpu_parity"] = parity if parity is not None else {"skipped": True}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args)
@@ -595,17 +498,6 @@ def main():
         import traceback
         traceback.print_exc()
         sys.stderr.flush()
-        if world == 1 and args.organisation == "auto" and not args.option:
-            # The candidate organisation passed its self-check but the run failed later (the CUDA context of
-            # this process may be unusable now): measure the established organisation in a fresh process.
-            import subprocess
-            sys.stderr.write("bench: re-running with --organisation default in a fresh process\n")
-            sys.stderr.flush()
-            sys.stdout.flush()
-            if _SAVED_STDOUT is not None:
-                os.dup2(_SAVED_STDOUT, 1)  # the child must inherit the real stdout for its JSON line
-            rc = subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--organisation", "default"])
-            os._exit(rc)
         os._exit(1)
 
 

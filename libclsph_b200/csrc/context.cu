@@ -58,7 +58,7 @@ struct clsph_context {
   Face* faces = nullptr;
   uint32_t face_count = 0;
   // face grid (option "face_grid"): cell lists of the scene's triangles for the collision pass
-  bool use_face_grid = false;
+  bool use_face_grid = true;   // option "face_grid"
   FaceGrid face_grid{};
   uint32_t* fg_cell_start = nullptr;
   uint32_t* fg_ids = nullptr;
@@ -68,11 +68,11 @@ struct clsph_context {
 
   // sub-cell order (subgrid.cu): arrays sorted by (cell key << 3 | octant); rrank = index of each
   // particle in the reference's array, rr_tmp = the gathered ranks of the previous sub-step
-  bool sub_order = false;
+  bool sub_order = true;        // option "sub_cell_order"
   bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
-  bool merged_rows = false;     // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
-  bool forces_dense = false;    // k_forces_lists<.., 4>: four resident CTAs per SM (option forces_blocks = 4)
-  bool fast_pairs = false;      // k_forces_lists<true, ..>: add_pair_fast (option fast_pairs)
+  bool merged_rows = true;      // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
+  bool forces_dense = true;     // k_forces_lists<.., 4>: four resident CTAs per SM (option forces_blocks = 4)
+  bool fast_pairs = true;       // k_forces_lists<true, ..>: add_pair_fast (option fast_pairs)
   uint32_t sub_capacity = 0;   // cells the dense sub-cell table holds (9 words each)
   uint32_t* sub_lb = nullptr;
   uint32_t* rrank = nullptr;

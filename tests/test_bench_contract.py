@@ -54,52 +54,3 @@ def test_kernel_byte_table_matches_the_survey_total():
         # = 304 + 16 P; SURVEY 8(d) fuses force+integrate (104) and counts the cell table read (4): 256 + 16 P
         assert sum(kb.values()) == 304 + 16 * passes
         assert bench.step_bytes(passes) == 256 + 16 * passes
-
-
-def test_organisation_choice_adopts_the_candidate_only_after_a_clean_selfcheck(monkeypatch):
-    sys.path.insert(0, H.ROOT)
-    import subprocess as sp
-    import types
-    import bench
-
-    def fake(stdout, returncode=0, raises=None):
-        def run_(cmd, **kw):
-            assert "libclsph_b200.selfcheck" in cmd and "--set" in cmd
-            if raises:
-                raise raises
-            return types.SimpleNamespace(stdout=stdout, stderr="boom", returncode=returncode)
-        return run_
-
-    args = types.SimpleNamespace(option=[], organisation="auto", config="config2_dambreak_1m")
-    a = dict(kv.split("=") for kv in bench.CANDIDATE_SETS[0])
-    a = {k: int(v) for k, v in a.items()}
-    b = dict(a, deferred_lists=1)
-    ok = json.dumps({"agree": True, "ms_per_step_default": 0.9, "sets": [
-        {"options": a, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.5},
-        {"options": b, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.45}]})
-    monkeypatch.setattr(sp, "run", fake("NCCL noise\n" + ok + "\n"))
-    opts, rep = bench.choose_organisation(args, 0, 1 << 20)
-    assert sorted(opts) == sorted("%s=%d" % kv for kv in b.items()) and rep["adopted"] and rep["agree"]   # the faster of the two
-    one_bad = json.dumps({"agree": True, "ms_per_step_default": 0.9, "sets": [
-        {"options": a, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.5},
-        {"options": b, "agree": False, "error": "AssertionError: support_count differs"}]})
-    monkeypatch.setattr(sp, "run", fake(one_bad))
-    assert sorted(bench.choose_organisation(args, 0, 1 << 20)[0]) == sorted(bench.CANDIDATE_OPTIONS)
-    slower = json.dumps({"agree": True, "ms_per_step_default": 0.5, "sets": [
-        {"options": a, "agree": True, "max_rel_diff": 1e-7, "ms_per_step": 0.9}]})
-    monkeypatch.setattr(sp, "run", fake(slower))
-    assert bench.choose_organisation(args, 0, 1 << 20)[0] == []
-    bad = json.dumps({"agree": False, "ms_per_step_default": 0.5, "sets": [{"options": a, "agree": False, "error": "AssertionError: permutation differs"}]})
-    monkeypatch.setattr(sp, "run", fake(bad, returncode=1))
-    opts, rep = bench.choose_organisation(args, 0, 1 << 20)
-    assert opts == [] and not rep["adopted"] and "permutation" in rep["sets"][0]["error"]
-    monkeypatch.setattr(sp, "run", fake("", returncode=-11))   # the subprocess crashed
-    opts, rep = bench.choose_organisation(args, 0, 1 << 20)
-    assert opts == [] and not rep["adopted"] and "exit code -11" in rep["error"]
-    monkeypatch.setattr(sp, "run", fake("", raises=sp.TimeoutExpired("selfcheck", 600)))   # ... or hung
-    assert bench.choose_organisation(args, 0, 1 << 20)[0] == []
-    # explicit choices bypass the check
-    args.organisation = "default"
-    assert bench.choose_organisation(args, 0, 1 << 20)[0] == []
-    args.organisation, args.option = "auto", ["list_rows=48"]
-    assert bench.choose_organisation(args, 0, 1 << 20)[0] == ["list_rows=48"]

@@ -1,9 +1,8 @@
 """bench.py's GPU arm, single GPU, run end to end on the CPU: the library is the emulator build (tests/emu/),
 torch is replaced by a stub with the handful of calls bench.py makes (events, the external stream, pinned
-host buffers), and the self-check that bench.py starts in a subprocess is run in-process. Nothing here
-measures anything; the point is that every line of the benchmark's control flow -- organisation choice,
-option plumbing, the timed regions, stage profiling, the end-to-end loop, the JSON line with its roofline and
-organisation report -- executes before the round's one real run on a B200."""
+host buffers). Nothing here measures anything; the point is that every line of the benchmark's control flow --
+option plumbing, the timed regions and their repeats, stage profiling, the end-to-end loop, the multi-GPU parity
+check, the JSON line with its roofline -- executes before a real run on a B200."""
 import io
 import json
 import sys
@@ -67,30 +66,15 @@ def fake_torch():
     return t, cuda
 
 
-@pytest.mark.parametrize("organisation", ["auto", "default"])
-def test_run_ours_single_gpu_prints_the_contract_line(organisation, monkeypatch, capfd):
+@pytest.mark.parametrize("options", [[], ["sub_cell_order=0"]])
+def test_run_ours_single_gpu_prints_the_contract_line(options, monkeypatch, capfd):
     sys.path.insert(0, H.ROOT)
     import bench
-    from libclsph_b200 import selfcheck
     torch, cuda = fake_torch()
     monkeypatch.setitem(sys.modules, "torch", torch)
     monkeypatch.setitem(sys.modules, "torch.cuda", cuda)
-
-    def selfcheck_in_process(cmd, **kw):  # what bench.py runs as `python -m libclsph_b200.selfcheck ...` on the GPU
-        argv = cmd[cmd.index("libclsph_b200.selfcheck") + 1:]
-        argv[argv.index("--particles") + 1] = "1500"
-        assert argv.count("--set") == len(bench.CANDIDATE_SETS)
-        # two of the sets are enough to exercise the choice (all of them run in the kernel-logic tests)
-        argv = argv[: argv.index("--set")] + ["--set", ",".join(bench.CANDIDATE_SETS[1]), "--set", ",".join(bench.CANDIDATE_SETS[-1])]
-        out = io.StringIO()
-        with redirect_stdout(out):
-            rc = selfcheck.main(argv + ["--timed-steps", "2"])
-        return types.SimpleNamespace(stdout=out.getvalue(), stderr="", returncode=rc)
-
-    import subprocess
-    monkeypatch.setattr(subprocess, "run", selfcheck_in_process)
     args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, impl="ours", config="config3_mucus_labyrinth_4m", particles=1500, e2e_steps=2,
-                                 no_cpu_baseline=True, cpu_sample=4096, option=[], organisation=organisation)
+                                 no_cpu_baseline=True, cpu_sample=4096, option=list(options), repeats=2, no_parity=False)
     bench.run_ours(args, 0, 1, 0)
     out = capfd.readouterr().out
     lines = [ln for ln in out.splitlines() if ln.startswith("{")]
@@ -99,23 +83,15 @@ def test_run_ours_single_gpu_prints_the_contract_line(organisation, monkeypatch,
     assert d["metric"] == "particle_steps_per_sec" and d["unit"] == "particle-steps/s" and d["n_gpus"] == 1
     assert d["steps"] == 3 and d["warmup"] == 3 and d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["config"]["workload"] == "config3_mucus_labyrinth_4m" and d["config"]["particles_per_gpu"] == 1500
+    assert d["config"]["options"] == list(options)
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 1500 * 80 and d["e2e"]["d2h_bytes_per_step"] == 1500 * 80
     assert d["gpu_launches"] > 0
+    assert len(d["repeats"]["ms_per_step"]) == 3 and d["repeats"]["median_value"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["peak"] > 0 and r["achieved"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert set(r["stage_ms"]) >= {"keys", "sort", "reorder", "density", "forces", "integrate"}
-    org = d["config"]["organisation"]
-    if organisation == "auto":
-        assert org["mode"] == "auto" and org["agree"] and len(org["sets"]) == 2
-        assert all(e["agree"] for e in org["sets"]), org
-        if org["adopted"]:
-            assert sorted(d["config"]["options"]) in [sorted(c) for c in bench.CANDIDATE_SETS]
-            assert r["kernel"] in ("k_density_sub", "k_density_lists", "k_forces_lists", "k_integrate", "k_onesweep", "k_reorder_sub", "k_reorder",
-                                   "k_keys_hist")
-        else:
-            assert d["config"]["options"] == []
-    else:
-        assert d["config"]["options"] == [] and org["mode"] == "default"
+    assert r["kernel"] in ("k_density_sub", "k_density_lists", "k_forces_lists", "k_integrate", "k_onesweep", "k_reorder_sub", "k_reorder",
+                           "k_keys_hist")
 
 
 # ---- N > 1: threads as ranks, a thread-based stand-in for torch.distributed ---------------------------------
@@ -162,6 +138,19 @@ class _FakeDist:
     def broadcast(self, t, src):
         t.arr[...] = self._exchange(t.arr)[src]
 
+    def _exchange_objects(self, obj):
+        self.slots[self.local.rank] = obj
+        self.sync.wait(timeout=900)
+        got = list(self.slots)
+        self.sync.wait(timeout=900)
+        return got
+
+    def all_gather_object(self, out, obj):
+        out[:] = self._exchange_objects(obj)
+
+    def broadcast_object_list(self, box, src):
+        box[:] = self._exchange_objects(list(box))[src]
+
     def all_reduce(self, t, op="sum"):
         got = self._exchange(t.arr)
         with np.errstate(over="ignore"):
@@ -169,12 +158,12 @@ class _FakeDist:
 
 
 def test_run_ours_two_ranks_prints_the_contract_line(monkeypatch, capsys):
-    """bench.py under torchrun with two ranks, played by two threads: organisation choice on rank 0 and its
-    broadcast, the multi-GPU cross-check of global invariants, slab workload and capacities, resident stepping,
+    """bench.py under torchrun with two ranks, played by two threads: the bitwise parity check of the slab
+    decomposition (libclsph_b200.distcheck) on the job's own ranks, slab workload and capacities, resident stepping,
     stage profiling, the end-to-end loop through clsph_dist_upload / step / download, one JSON line on rank 0."""
     sys.path.insert(0, H.ROOT)
     import bench
-    from libclsph_b200 import selfcheck
+    from libclsph_b200 import distcheck
     world = 2
     torch, cuda = fake_torch()
     fdist = _FakeDist(world)
@@ -186,21 +175,11 @@ def test_run_ours_two_ranks_prints_the_contract_line(monkeypatch, capsys):
     monkeypatch.setitem(sys.modules, "torch", torch)
     monkeypatch.setitem(sys.modules, "torch.cuda", cuda)
     monkeypatch.setitem(sys.modules, "torch.distributed", fdist)
-
-    def selfcheck_in_process(cmd, **kw):
-        argv = cmd[cmd.index("libclsph_b200.selfcheck") + 1:]
-        argv[argv.index("--particles") + 1] = "2000"
-        keep = argv[: argv.index("--set")] + ["--set", ",".join(bench.CANDIDATE_SETS[1])]  # one set is enough here
-        out = io.StringIO()
-        with redirect_stdout(out):
-            rc = selfcheck.main(keep + ["--timed-steps", "2"])
-        text = out.getvalue()
-        line = json.loads(text.strip().splitlines()[-1])
-        line["ms_per_step_default"] = 1e9  # adopt the candidate whatever the emulator's clock says
-        return types.SimpleNamespace(stdout=json.dumps(line), stderr="", returncode=rc)
-
-    import subprocess
-    monkeypatch.setattr(subprocess, "run", selfcheck_in_process)
+    # the check itself at a size the emulator finishes in seconds
+    real_parity = distcheck.bitwise_parity
+    monkeypatch.setattr(distcheck, "bitwise_parity",
+                        lambda dist, rank, world, local_rank, n_total, steps=4, options=(), verbose=False:
+                        real_parity(dist, rank, world, local_rank, n_total=6000, steps=2, options=options))
     # the real script points fd 1 at stderr while native libraries are chatty; with two ranks in one process that
     # juggling would race, and the line is captured from sys.stdout here anyway
     shim = types.SimpleNamespace(**{k: getattr(bench.os, k) for k in ("path", "environ", "_exit")})
@@ -213,11 +192,12 @@ def test_run_ours_two_ranks_prints_the_contract_line(monkeypatch, capsys):
     def run_rank(rank):
         fdist.local.rank = rank
         args = types.SimpleNamespace(gpus=world, steps=3, warmup=3, impl="ours", config="config2_dambreak_1m", particles=12000, e2e_steps=2,
-                                     no_cpu_baseline=True, cpu_sample=4096, option=[], organisation="auto")
+                                     no_cpu_baseline=True, cpu_sample=4096, option=[], repeats=1, no_parity=False)
         try:
             bench.run_ours(args, rank, world, 0)
         except BaseException as exc:  # noqa: BLE001
-            errors.append((rank, repr(exc)))
+            import traceback
+            errors.append((rank, traceback.format_exc()))
             fdist.sync.abort()
 
     threads = [threading.Thread(target=run_rank, args=(r,)) for r in range(world)]
@@ -230,8 +210,7 @@ def test_run_ours_two_ranks_prints_the_contract_line(monkeypatch, capsys):
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] > 0 and d["config"]["particles_total"] == 24000
-    assert sorted(d["config"]["options"]) == sorted(bench.CANDIDATE_SETS[1])
-    check = d["config"]["organisation"]["multi_gpu_crosscheck"]
-    assert check["agree"] and check["max_rel_diff"] <= 1e-5
+    par = d["multi_gpu_parity"]
+    assert par["bitwise"] and par["order"] and par["ids_exact"] and par["world"] == 2, par
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
     assert d["roofline"]["stage_ms"]["exchange"] > 0
