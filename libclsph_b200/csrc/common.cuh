@@ -144,6 +144,53 @@ __device__ __forceinline__ float dist2_contract(float ax, float ay, float az, fl
   return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
+// ---- packed fp32 (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE fp32 lanes per instruction) -------------------
+// Each lane rounds exactly like the scalar _rn operation, so results are bit-identical to scalar code; what
+// changes is the issue slots: one instruction per two lanes. A scalar operand broadcast to both lanes costs
+// nothing (the SASS operand form R.F32 next to R.F32x2.HI_LO).
+#ifdef CLSPH_EMU
+struct f32x2 { float lo, hi; };
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) { return f32x2{lo, hi}; }
+__device__ __forceinline__ float f2_lo(f32x2 a) { return a.lo; }
+__device__ __forceinline__ float f2_hi(f32x2 a) { return a.hi; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { return f32x2{__fsub_rn(a.lo, b.lo), __fsub_rn(a.hi, b.hi)}; }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { return f32x2{__fmul_rn(a.lo, b.lo), __fmul_rn(a.hi, b.hi)}; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { return f32x2{__fmaf_rn(a.lo, b.lo, c.lo), __fmaf_rn(a.hi, b.hi, c.hi)}; }
+#else
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float f2_lo(f32x2 a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+  return lo;
+}
+__device__ __forceinline__ float f2_hi(f32x2 a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+  return hi;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+#endif
+__device__ __forceinline__ f32x2 f2_bcast(float v) { return f2_make(v, v); }
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
 #ifdef CLSPH_EMU  // tests/emu: CPU build of the kernels for logic tests, no PTX

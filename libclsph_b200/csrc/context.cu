@@ -71,6 +71,9 @@ struct clsph_context {
   bool sub_order = true;        // option "sub_cell_order"
   bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
   bool merged_rows = true;      // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
+  bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
+  uint32_t* pair_items = nullptr;   // [capacity] items written by k_reorder_sub
+  uint32_t* pair_count = nullptr;
   bool forces_dense = true;     // k_forces_lists<.., 4>: four resident CTAs per SM (option forces_blocks = 4)
   bool fast_pairs = true;       // k_forces_lists<true, ..>: add_pair_fast (option fast_pairs)
   uint32_t sub_capacity = 0;   // cells the dense sub-cell table holds (9 words each)
@@ -315,6 +318,9 @@ int ensure_sub(clsph_context* ctx) {
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->sub_lb, (size_t)ctx->sub_capacity * 9u));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->rrank, ctx->capacity));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->rr_tmp, ctx->capacity));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pair_items, ctx->capacity));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pair_count, 1));
+  CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pair_count, 0, sizeof(uint32_t), ctx->stream));
   CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sub_lb, 0, sizeof(uint32_t) * 9u * (size_t)ctx->sub_capacity, ctx->stream));
   return CLSPH_OK;
 }
@@ -403,13 +409,14 @@ int enqueue_substep(clsph_context* ctx) {
   launch_sort_passes(ctx->sort, ctx->grid, n, st, lc);
   if (prof) next_event(ctx);
 
+  const bool pairs = sub && ctx->pair_density && !ctx->tiles && !ctx->deferred_lists;
   if (sub) {
     launch_clear_sub(ctx->sub_lb, ctx->grid, ctx->sub_capacity, ctx->sm_count, st, lc);
     launch_reorder_sub(src, dst, ctx->sort, ctx->skey, multi ? nullptr : ctx->rrank, ctx->rr_tmp, ctx->sub_lb, ctx->grid,
                        multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr,
                        multi ? ctx->ordk[ctx->cur] : nullptr, multi ? ctx->ordr[ctx->cur] : nullptr,
                        multi ? ctx->ordk[ctx->cur ^ 1] : nullptr, multi ? ctx->ordr[ctx->cur ^ 1] : nullptr,
-                       ctx->tiles ? ctx->tl.ctl : nullptr, ctx->tl.blocks, n, st, lc);
+                       ctx->tiles ? ctx->tl.ctl : nullptr, ctx->tl.blocks, pairs ? ctx->pair_items : nullptr, ctx->pair_count, n, st, lc);
     ctx->cur ^= 1;
     if (!multi)  // one GPU: absolute index in the reference's array
       launch_rank(ctx->skey, ctx->rr_tmp, ctx->rrank, ctx->sub_lb, ctx->sort, ctx->grid, ctx->perm,
@@ -432,8 +439,12 @@ int enqueue_substep(clsph_context* ctx) {
       launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
                                  ctx->lists, ctx->accel, n, st, lc);
     } else {
-      launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                         ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
+      if (pairs)
+        launch_density_pairs(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
+                             ctx->taps, ctx->debug, ctx->pair_items, ctx->pair_count, n, st, lc);
+      else
+        launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
+                           ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
       if (prof) next_event(ctx);
       launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
                     false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc);
@@ -628,6 +639,8 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->sub_lb);
   cudaFree(ctx->rrank);
   cudaFree(ctx->rr_tmp);
+  cudaFree(ctx->pair_items);
+  cudaFree(ctx->pair_count);
   cudaFree(ctx->tl.blocks);
   cudaFree(ctx->tl.slow);
   cudaFree(ctx->tl.ctl);
@@ -704,6 +717,8 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     ctx->deferred_lists = value != 0;
   } else if (!std::strcmp(name, "merged_rows")) {
     ctx->merged_rows = value != 0;
+  } else if (!std::strcmp(name, "pair_density")) {
+    ctx->pair_density = value != 0;
   } else if (!std::strcmp(name, "fast_pairs")) {
     ctx->fast_pairs = value != 0;
   } else if (!std::strcmp(name, "forces_blocks")) {

@@ -123,8 +123,13 @@ void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capa
 void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                         const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,
-                        uint32_t* dst_ordk, uint32_t* dst_ordr, TileCtl* tile_ctl, uint32_t* tile_blocks, uint32_t n_launch,
-                        cudaStream_t stream, uint64_t* launches);
+                        uint32_t* dst_ordk, uint32_t* dst_ordr, TileCtl* tile_ctl, uint32_t* tile_blocks, uint32_t* pair_items,
+                        uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+// Density + pressure + neighbour lists, two particles of a sub-cell per thread (packed fp32: FADD2 / FFMA2).
+void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
+                          const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
+                          const DebugTaps& taps, bool debug, const uint32_t* pair_items, const uint32_t* pair_count,
+                          uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 void launch_rank_pair(const float4* pos, const uint32_t* skey, const uint32_t* ordk, const uint32_t* ordr, uint32_t* wrank,
                       const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, uint32_t n_launch,
                       cudaStream_t stream, uint64_t* launches);

@@ -52,18 +52,16 @@ __global__ void __launch_bounds__(256) k_clear_sub(uint32_t* __restrict__ sub_lb
 // sub-step. Slots where the sub-cell key changes fill the octant boundaries of the dense table:
 // lb[cell][o] = first index whose octant is >= o, lb[cell][8] = end of the cell; untouched (empty)
 // cells stay [0, 0).
-__global__ void __launch_bounds__(256)
-k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src_vel, const float4* __restrict__ src_ivel,
-              float4* __restrict__ dst_pos, float4* __restrict__ dst_vel, float4* __restrict__ dst_ivel,
-              const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const uint32_t* __restrict__ vals_a,
-              const uint32_t* __restrict__ vals_b, uint32_t* __restrict__ skey, const uint32_t* __restrict__ rr_src,
-              uint32_t* __restrict__ rr_dst, uint32_t* __restrict__ sub_lb, const GridState* __restrict__ grid,
-              const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid, const uint32_t* __restrict__ src_ordk,
-              const uint32_t* __restrict__ src_ordr, uint32_t* __restrict__ dst_ordk, uint32_t* __restrict__ dst_ordr,
-              TileCtl* tile_ctl, uint32_t* __restrict__ tile_blocks) {
-  const uint32_t n = grid->n;
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
+// (the body of k_reorder_sub for one sorted slot r < n; *left_out = slots of the same sub-cell before r)
+__device__ __forceinline__ void
+reorder_sub_slot(uint32_t r, uint32_t n, const float4* __restrict__ src_pos, const float4* __restrict__ src_vel,
+                 const float4* __restrict__ src_ivel, float4* __restrict__ dst_pos, float4* __restrict__ dst_vel,
+                 float4* __restrict__ dst_ivel, const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b,
+                 const uint32_t* __restrict__ vals_a, const uint32_t* __restrict__ vals_b, uint32_t* __restrict__ skey,
+                 const uint32_t* __restrict__ rr_src, uint32_t* __restrict__ rr_dst, uint32_t* __restrict__ sub_lb,
+                 const GridState* __restrict__ grid, const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid,
+                 const uint32_t* __restrict__ src_ordk, const uint32_t* __restrict__ src_ordr, uint32_t* __restrict__ dst_ordk,
+                 uint32_t* __restrict__ dst_ordr, TileCtl* tile_ctl, uint32_t* __restrict__ tile_blocks, uint32_t* left_out) {
   const bool in_b = (grid->sort_passes & 1u) != 0u;
   const uint32_t* __restrict__ keys = in_b ? keys_b : keys_a;
   const uint32_t* __restrict__ vals = in_b ? vals_b : vals_a;
@@ -86,6 +84,7 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
     for (uint32_t q = r + 1; q < n && keys[q] == fkey; ++q) smaller += rr_src[vals[q]] < mine ? 1u : 0u;
     dest = r - left + smaller;
     rr_dst[dest] = mine;
+    *left_out = left;
   } else if (src_ordk) {
     // multi-GPU: the same with the order keys (cell key, rank in cell of the previous sub-step), which order
     // particles like the global reference rank does and which ghosts carry too. Every rank then holds the
@@ -103,6 +102,11 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
       smaller += (jk < mk || (jk == mk && jr < mr)) ? 1u : 0u;
     }
     dest = r - left + smaller;
+    *left_out = left;
+  } else {
+    uint32_t left = 0;
+    for (uint32_t q = r; q > 0 && keys[q - 1] == fkey; --q) ++left;
+    *left_out = left;
   }
   dst_pos[dest] = src_pos[from];
   dst_vel[dest] = src_vel[from];
@@ -140,6 +144,36 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
   }
   if (r == n - 1 && key < count)
     for (uint32_t o = oct + 1u; o <= 8u; ++o) row[o] = n;
+}
+
+// Pair items (k_density_pairs): the particles of a sub-cell are handled two at a time by one thread, so every
+// slot at an even offset inside its sub-cell announces the pair (itself, the next slot if that is in the same
+// sub-cell). The list order is arbitrary -- warps append in arrival order -- and does not influence any result.
+__global__ void __launch_bounds__(256)
+k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src_vel, const float4* __restrict__ src_ivel,
+              float4* __restrict__ dst_pos, float4* __restrict__ dst_vel, float4* __restrict__ dst_ivel,
+              const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const uint32_t* __restrict__ vals_a,
+              const uint32_t* __restrict__ vals_b, uint32_t* __restrict__ skey, const uint32_t* __restrict__ rr_src,
+              uint32_t* __restrict__ rr_dst, uint32_t* __restrict__ sub_lb, const GridState* __restrict__ grid,
+              const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid, const uint32_t* __restrict__ src_ordk,
+              const uint32_t* __restrict__ src_ordr, uint32_t* __restrict__ dst_ordk, uint32_t* __restrict__ dst_ordr,
+              TileCtl* tile_ctl, uint32_t* __restrict__ tile_blocks, uint32_t* __restrict__ pair_items,
+              uint32_t* __restrict__ pair_count) {
+  const uint32_t n = grid->n;
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((r & ~31u) >= n) return;  // whole warp out of range
+  uint32_t left = 1u;
+  if (r < n)
+    reorder_sub_slot(r, n, src_pos, src_vel, src_ivel, dst_pos, dst_vel, dst_ivel, keys_a, keys_b, vals_a, vals_b, skey, rr_src,
+                     rr_dst, sub_lb, grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr, tile_ctl, tile_blocks, &left);
+  if (!pair_items) return;
+  const bool leader = r < n && (left & 1u) == 0u;
+  const uint32_t at = warp_append(leader, pair_count);
+  if (leader) {
+    const uint32_t* __restrict__ keys = (grid->sort_passes & 1u) ? keys_b : keys_a;
+    const bool second = r + 1u < n && keys[r + 1u] == keys[r];
+    pair_items[at] = r | (second ? 0x80000000u : 0u);
+  }
 }
 
 // Reference rank after this sub-step's sort (see the header comment). Also writes the permutation
@@ -288,6 +322,119 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
   }
 }
 
+// =============================================================================================
+// The same pass with TWO particles of a sub-cell per thread (items of k_reorder_sub). Both see the same rows of
+// sub-cells, so every candidate is loaded once and tested against both with packed fp32 instructions (FADD2,
+// FMUL2, FFMA2: one issue slot per two tests, the candidate a broadcast scalar operand). Each lane rounds like
+// the scalar code and every particle still meets its candidates in the same order, so densities, lists and
+// counts are BITWISE those of k_density_sub<.., kMerged>. The search window is the union of the two particles'
+// windows (they differ only within 2^-10 h of a sub-cell boundary); a candidate outside a particle's own window
+// is outside its support and adds an exact zero.
+// =============================================================================================
+template <bool kTaps>
+__global__ void __launch_bounds__(kSubThreads)
+k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
+                const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
+                const SphConst c, float4* __restrict__ aux, uint32_t* __restrict__ nlist, uint32_t* __restrict__ ncount,
+                uint32_t list_rows, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ supp_count,
+                const uint32_t* __restrict__ pair_items, const uint32_t* __restrict__ pair_count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *pair_count) return;
+  const GridState g = *grid;
+  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
+  const uint32_t item = pair_items[t];
+  const uint32_t i0 = item & 0x7FFFFFFFu;
+  const bool two = (item >> 31) != 0u;
+  const uint32_t i1 = two ? i0 + 1u : i0;
+  const float4 p0 = pos[i0], p1 = pos[i1];
+  // multi-GPU: the particles of the slab and the ghosts within h of it get a density (k_density_sub)
+  const bool need0 = p0.x >= g.plane_lo - c.h_margin && p0.x < g.plane_hi + c.h_margin;
+  const bool need1 = two && p1.x >= g.plane_lo - c.h_margin && p1.x < g.plane_hi + c.h_margin;
+  if (!need0 && !need1) return;
+  uint32_t* row0 = nlist + (size_t)i0 * list_rows;
+#ifndef CLSPH_EMU
+  asm volatile("" : "+l"(row0));  // keep the row address in registers (see k_density_sub)
+#endif
+  uint32_t* row1 = row0 + (two ? list_rows : 0u);
+#ifndef CLSPH_EMU
+  asm volatile("" : "+l"(row1));
+#endif
+  // union of the two search windows
+  uint32_t xlo, xhi, ylo, yhi, zlo, zhi;
+  sub_bounds(p0.x, g.min_x, g.cell, c.h_margin, xlo, xhi);
+  sub_bounds(p0.y, g.min_y, g.cell, c.h_margin, ylo, yhi);
+  sub_bounds(p0.z, g.min_z, g.cell, c.h_margin, zlo, zhi);
+  if (two) {
+    uint32_t lo, hi;
+    sub_bounds(p1.x, g.min_x, g.cell, c.h_margin, lo, hi); xlo = min(xlo, lo); xhi = max(xhi, hi);
+    sub_bounds(p1.y, g.min_y, g.cell, c.h_margin, lo, hi); ylo = min(ylo, lo); yhi = max(yhi, hi);
+    sub_bounds(p1.z, g.min_z, g.cell, c.h_margin, lo, hi); zlo = min(zlo, lo); zhi = max(zhi, hi);
+  }
+  const f32x2 X = f2_make(p0.x, p1.x), Y = f2_make(p0.y, p1.y), Z = f2_make(p0.z, p1.z);
+  const f32x2 H2 = f2_bcast(c.h2);
+  f32x2 acc = f2_make(0.f, 0.f);  // sums of (h^2 - s)^3 over the two supports
+  uint32_t cnt0 = 0, cnt1 = 0;
+  auto walk = [&](uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+    const uint32_t total = (a1 - a0) + (b1 - b0);
+    uint32_t j = a0 < a1 ? a0 : b0;
+    for (uint32_t k = 0; k < total; ++k) {
+      const float4 pj = pos[j];
+      const f32x2 dx = f2_sub(X, f2_bcast(pj.x)), dy = f2_sub(Y, f2_bcast(pj.y)), dz = f2_sub(Z, f2_bcast(pj.z));
+      const f32x2 s = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+      const f32x2 d = f2_sub(H2, s);
+      const bool in0 = f2_lo(s) < c.support_s, in1 = f2_hi(s) < c.support_s;
+      const f32x2 w = f2_make(in0 ? f2_lo(d) : 0.f, in1 ? f2_hi(d) : 0.f);
+      acc = f2_fma(f2_mul(w, w), w, acc);
+      store_if(in0 && cnt0 < list_rows, row0 + cnt0, j);
+      cnt0 += in0 ? 1u : 0u;
+      store_if(in1 && cnt1 < list_rows, row1 + cnt1, j);
+      cnt1 += in1 ? 1u : 0u;
+      ++j;
+      if (j == a1) j = b0;  // end of the first range: continue in the second
+    }
+  };
+  const uint32_t cx_lo = xlo >> 1, cx_hi = xhi >> 1;
+  for (uint32_t fz = zlo; fz <= zhi; ++fz) {
+    const uint32_t kz = spread10(fz >> 1) << 2, oz = (fz & 1u) << 2;
+    for (uint32_t fy = ylo; fy <= yhi; ++fy) {
+      const uint32_t kzy = kz | (spread10(fy >> 1) << 1), ozy = oz | ((fy & 1u) << 1);
+      const uint2 a = sub_range(v, kzy | spread10(cx_lo), ozy | (xlo & 1u), ozy | (cx_hi == cx_lo ? (xhi & 1u) : 1u));
+      uint2 b = make_uint2(0u, 0u);
+      if (cx_hi > cx_lo) b = sub_range(v, kzy | spread10(cx_lo + 1u), ozy, ozy | (cx_hi == cx_lo + 1u ? (xhi & 1u) : 1u));
+      walk(a.x, a.y, b.x, b.y);
+      if (cx_hi > cx_lo + 1u) {  // rare third cell of the row
+        const uint2 e = sub_range(v, kzy | spread10(cx_hi), ozy, ozy | (xhi & 1u));
+        walk(e.x, e.y, 0u, 0u);
+      }
+    }
+  }
+  if (need0) {
+    finish_density(c, f2_lo(acc), i0, aux, pos, vel);
+    ncount[i0] = cnt0;
+  }
+  if (need1) {
+    finish_density(c, f2_hi(acc), i1, aux, pos, vel);
+    ncount[i1] = cnt1;
+  }
+  if (kTaps) {
+    // the reference's candidate count: every particle of the 27 cells around this one (forces.cl:25-40);
+    // both particles are in the same cell
+    const uint32_t key = skey[i0];
+    const uint32_t cx = compact10(key), cy = compact10(key >> 1), cz = compact10(key >> 2);
+    uint32_t total = 0;
+    if (cx != 0u && cy != 0u && cz != 0u) {  // with a 0 coordinate the reference's unsigned loop does not run
+      for (uint32_t z = cz - 1u; z <= cz + 1u; ++z)
+        for (uint32_t y = cy - 1u; y <= cy + 1u; ++y)
+          for (uint32_t x = cx - 1u; x <= cx + 1u; ++x) {
+            const uint2 r = sub_range(v, morton3(x, y, z), 0u, 7u);
+            total += r.y - r.x;
+          }
+    }
+    if (need0) { cand_count[i0] = total; supp_count[i0] = cnt0; }
+    if (need1) { cand_count[i1] = total; supp_count[i1] = cnt1; }
+  }
+}
+
 // Forces for the particles whose list overflowed: same traversal, pair terms evaluated in place.
 __global__ void __launch_bounds__(kSubThreads)
 k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
@@ -407,13 +554,14 @@ void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capa
 void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                         const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,
-                        uint32_t* dst_ordk, uint32_t* dst_ordr, TileCtl* tile_ctl, uint32_t* tile_blocks, uint32_t n_launch,
-                        cudaStream_t stream, uint64_t* launches) {
+                        uint32_t* dst_ordk, uint32_t* dst_ordr, TileCtl* tile_ctl, uint32_t* tile_blocks, uint32_t* pair_items,
+                        uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
   if (tile_ctl) cudaMemsetAsync(tile_ctl, 0, sizeof(TileCtl), stream);
+  if (pair_items) cudaMemsetAsync(pair_count, 0, sizeof(uint32_t), stream);
   k_reorder_sub<<<(n_launch + 255) / 256, 256, 0, stream>>>(src.pos, src.vel, src.ivel, dst.pos, dst.vel, dst.ivel, sort.keys_a,
                                                             sort.keys_b, sort.vals_a, sort.vals_b, skey, rr_src, rr_dst, sub_lb,
                                                             grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr,
-                                                            tile_ctl, tile_blocks);
+                                                            tile_ctl, tile_blocks, pair_items, pair_count);
   if (launches) ++*launches;
 }
 
@@ -458,6 +606,22 @@ if (debug && deferred)
   else
     k_density_sub<false, false, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
                                                                            aux, lists.entries, lists.count, lists.rows, cand, supp);
+  if (launches) ++*launches;
+}
+
+void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
+                          const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
+                          const DebugTaps& taps, bool debug, const uint32_t* pair_items, const uint32_t* pair_count,
+                          uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+  // the item count lives on the device (between n / 2 and n): sized for the worst case, surplus blocks leave at once
+  const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
+  if (debug)
+    k_density_pairs<true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries,
+                                                              lists.count, lists.rows, taps.candidate_count, taps.support_count,
+                                                              pair_items, pair_count);
+  else
+    k_density_pairs<false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries,
+                                                               lists.count, lists.rows, nullptr, nullptr, pair_items, pair_count);
   if (launches) ++*launches;
 }
 

@@ -44,7 +44,7 @@ def random_case(rng, n_max=2500):
 def test_random_configuration_single_step(seed):
     rng = np.random.default_rng(seed)
     what, p, terms, scene, s = random_case(rng)
-    for options in (dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1, fast_pairs=1),
+    for options in (dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=1, face_grid=1, fast_pairs=1),
                     dict(sub_cell_order=1, list_rows=int(rng.choice([8, 16]))), dict(sub_cell_order=1, merged_rows=1)):
         G.check_against_oracle(s, p, terms, scene, "%s %r" % (what, options), options=options)
 

@@ -89,10 +89,10 @@ def test_binary_search_fallback_matches_dense_table(box_scene):
 SUB = dict(sub_cell_order=1)
 
 
-@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8),
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=0, neighbour_lists=1, list_rows=8),
                                      SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, deferred_lists=1),
                                      dict(sub_cell_order=1, deferred_lists=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4),
-                                     dict(sub_cell_order=1, fast_pairs=1), dict(neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
+                                     dict(sub_cell_order=1, fast_pairs=1), dict(sub_cell_order=0, neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
                                      dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8)])
 def test_neighbour_organisations(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
@@ -152,7 +152,7 @@ def test_sub_cell_order_binary_search_fallback(box_scene):
     G.check_against_oracle(s, p, terms, box_scene, "sub, binary search", cell_table_capacity=8, options=SUB)
 
 
-@pytest.mark.parametrize("options", [dict(neighbour_lists=1), SUB])
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=1), SUB])
 def test_resident_steps_keep_the_reference_order(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     s = H.state_s1(p, vol)
@@ -181,6 +181,25 @@ def test_sub_cell_order_resident_steps_equal_host_round_trips_bitwise(options, b
         cur = ctx.download()
     ctx.close()
     assert resident.tobytes() == cur.tobytes()
+
+
+@pytest.mark.parametrize("fluid,n", [("water", 6000), ("mucus", 3000)])
+def test_pair_density_is_bitwise_the_per_particle_kernel(fluid, n, box_scene):
+    """k_density_pairs (two particles of a sub-cell per thread, packed fp32) against k_density_sub<merged>: each packed
+    lane rounds like the scalar code and every particle meets its candidates in the same order, so after several
+    resident sub-steps every byte of the state and every tap is the same."""
+    p, terms, vol = H.config(fluid, n)
+    s = H.state_s1(p, vol)
+    s["intermediate_velocity"][:, 0] += (2.5 * np.sign(s["position"][:, 2])).astype(np.float32)
+    outs = []
+    for pair in (1, 0):
+        ctx = G.make_ctx(s.size, box_scene, p, terms, debug=True, options=dict(pair_density=pair, merged_rows=1))
+        ctx.upload(s)
+        ctx.step(3)
+        outs.append((ctx.download().tobytes(), ctx.fetch(capi.TAP_SUPPORT_COUNT).tobytes(), ctx.fetch(capi.TAP_CANDIDATE_COUNT).tobytes(),
+                     ctx.fetch(capi.TAP_ACCELERATION).tobytes()))
+        ctx.close()
+    assert outs[0] == outs[1]
 
 
 def test_sub_cell_order_host_round_trip_and_option_rules(box_scene):
@@ -261,7 +280,7 @@ def test_sub_cell_order_reports_a_grid_too_large_for_its_keys(box_scene):
 
 
 @pytest.mark.parametrize("kind", H.EDGE_KINDS)
-@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1),
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=1, face_grid=1),
                                      dict(sub_cell_order=1, face_grid=1, deferred_lists=1),
                                      dict(sub_cell_order=1, face_grid=1, fast_pairs=1), dict(sub_cell_order=1, merged_rows=1)])
 def test_edge_states(kind, options, box_scene):
@@ -272,7 +291,7 @@ def test_edge_states(kind, options, box_scene):
     G.check_against_oracle(s, p, terms, box_scene, "%s %r" % (kind, options), options=options)
 
 
-@pytest.mark.parametrize("options", [dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1)])
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=1, face_grid=1)])
 def test_blown_up_particles_do_not_hang_the_kernels(options, box_scene):
     """A particle at infinity makes the grid overflow (CLSPH_EGRID, as the reference's assert would);
     a NaN position falls into cell 0. Either way every kernel must terminate."""
@@ -298,7 +317,7 @@ def test_blown_up_particles_do_not_hang_the_kernels(options, box_scene):
     ctx.close()
 
 
-@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(sub_cell_order=1, face_grid=1, fast_pairs=1),
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=1, face_grid=1, fast_pairs=1),
                                      dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4),
                                      dict(sub_cell_order=1, face_grid=1, merged_rows=1, fast_pairs=1)])
 def test_developed_state(options):

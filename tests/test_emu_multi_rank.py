@@ -181,17 +181,3 @@ def test_buffer_overflow_is_reported_and_nobody_hangs():
     assert not errors, errors
     assert not any(t.is_alive() for t in threads), "a rank is still waiting"
     assert capi.E_COMM in codes, codes
-
-
-def test_bench_invariants_comparison_rules():
-    """bench.invariants_agree (the N > 1 cross-check; the whole flow runs in tests/test_emu_bench_flow.py):
-    counts and id sums exact modulo 2^64, float sums to 1e-5."""
-    import sys
-    sys.path.insert(0, H.ROOT)
-    import bench
-    ints = np.array([48000, 1151976000, -12345], dtype=np.int64)
-    floats = np.array([4.8e7, 1.2e9, 3e4, 5e4, 3e4, 1e4, 2e4, 1e4])
-    assert bench.invariants_agree((ints, floats), (ints.copy(), floats * (1 + 3e-7)), 48000) == (True, pytest.approx(3e-7, rel=1e-3))
-    assert not bench.invariants_agree((ints, floats), (ints - np.array([1, 5, 25]), floats), 48000)[0]       # a particle lost
-    assert not bench.invariants_agree((ints, floats), (ints, floats * np.array([1.01, 1, 1, 1, 1, 1, 1, 1])), 48000)[0]
-    assert not bench.invariants_agree((ints, floats), (ints, floats), 48001)[0]                                # wrong total

@@ -161,8 +161,8 @@ def test_binary_search_fallback_matches_dense_table(box_scene):
     assert dense.tobytes() == sparse.tobytes()
 
 
-@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), dict(neighbour_lists=1, list_rows=8),
-                                     dict(neighbour_lists=1, list_rows=24)])
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=0, neighbour_lists=1, list_rows=8),
+                                     dict(sub_cell_order=0, neighbour_lists=1, list_rows=24)])
 def test_neighbour_organisations_agree_with_the_oracle(options, box_scene, plane_scene):
     """Two-pass search, stored neighbour lists, and lists too short for most particles (which
     sends them through the fallback kernel) all meet the same bar."""

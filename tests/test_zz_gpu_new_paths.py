@@ -35,7 +35,7 @@ def test_sub_cell_order_jittered(fluid, n, box_scene):
 @pytest.mark.parametrize("options", [SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, list_rows=24), BOTH,
                                      dict(sub_cell_order=1, deferred_lists=1), dict(sub_cell_order=1, deferred_lists=1, list_rows=8),
                                      dict(sub_cell_order=1, forces_blocks=4),
-                                     dict(neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
+                                     dict(sub_cell_order=0, neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
                                      dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8)])
 def test_sub_cell_order_crowded_and_overflowing_lists(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 20000)
@@ -129,6 +129,25 @@ def test_organisations_agree_on_the_device_at_four_million():
     H.assert_close_fields(b, a, tol=1e-4, what="4 Mi, new paths vs established")
 
 
+@pytest.mark.parametrize("fluid,n", [("water", 200000), ("mucus", 100000)])
+def test_pair_density_is_bitwise_the_per_particle_kernel(fluid, n, box_scene):
+    """k_density_pairs (two particles of a sub-cell per thread, packed fp32) against k_density_sub<merged>: each packed
+    lane rounds like the scalar code and every particle meets its candidates in the same order, so after several
+    resident sub-steps every byte of the state and every tap is the same."""
+    p, terms, vol = H.config(fluid, n)
+    s = H.state_s1(p, vol)
+    s["intermediate_velocity"][:, 0] += (2.5 * np.sign(s["position"][:, 2])).astype(np.float32)
+    outs = []
+    for pair in (1, 0):
+        ctx = G.make_ctx(s.size, box_scene, p, terms, debug=True, options=dict(pair_density=pair, merged_rows=1))
+        ctx.upload(s)
+        ctx.step(3)
+        outs.append((ctx.download().tobytes(), ctx.fetch(capi.TAP_SUPPORT_COUNT).tobytes(), ctx.fetch(capi.TAP_CANDIDATE_COUNT).tobytes(),
+                     ctx.fetch(capi.TAP_ACCELERATION).tobytes()))
+        ctx.close()
+    assert outs[0] == outs[1]
+
+
 @pytest.mark.parametrize("world,n", [(2, 60000), (4, 120000)])
 def test_slab_decomposition_in_sub_cell_order_reproduces_the_global_array_order(world, n):
     import subprocess
@@ -145,7 +164,7 @@ def test_slab_decomposition_in_sub_cell_order_reproduces_the_global_array_order(
 
 
 @pytest.mark.parametrize("kind", H.EDGE_KINDS)
-@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), BOTH])
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), BOTH])
 def test_edge_states(kind, options, box_scene):
     """States sitting ON the path's decisions (coincident particles / erratum E3, pairs at distance h,
     positions on cell and sub-cell boundaries, the whole fluid in one cell, isolated particles), in every
@@ -156,7 +175,7 @@ def test_edge_states(kind, options, box_scene):
     G.check_against_oracle(s, p, terms, box_scene, "%s %r" % (kind, options), options=options)
 
 
-@pytest.mark.parametrize("options", [dict(neighbour_lists=0), dict(neighbour_lists=1), BOTH,
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), BOTH,
                                      dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4),
                                      dict(sub_cell_order=1, face_grid=1, fast_pairs=1, merged_rows=1, forces_blocks=4)])
 def test_developed_state(options):
