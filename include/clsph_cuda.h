@@ -191,6 +191,12 @@ int clsph_comm_unique_id(void* out, size_t bytes);
 int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_id, float plane_lo, float plane_hi,
                     uint32_t emigrant_capacity, uint32_t ghost_capacity);
 
+/* How the ranks exchange particles and the AABB every sub-step: "peer stores ..." (each rank stores its records
+ * straight into the neighbours' memory over NVLink, CUDA IPC between the processes; no collective per sub-step) or
+ * "nccl ..." (send/recv + all-reduce: chosen when peer access is unavailable or CLSPH_DIST_TRANSPORT=nccl).
+ * "none" before clsph_dist_init. Results are bitwise the same either way. */
+const char* clsph_dist_transport(const clsph_context* ctx);
+
 /* This rank's particles with their global ids (any unique 32-bit labels below 2^32-1). */
 int clsph_dist_upload(clsph_context* ctx, const particle* aos, const uint32_t* ids, uint32_t n);
 

@@ -17,7 +17,7 @@ SYMBOLS = [
     "clsph_set_parameters", "clsph_set_option", "clsph_upload_particles", "clsph_step", "clsph_synchronize",
     "clsph_get_parameters", "clsph_download_particles", "clsph_simulate_single_frame", "clsph_set_debug",
     "clsph_debug_fetch", "clsph_kernel_advection_collision", "clsph_comm_unique_id", "clsph_dist_init",
-    "clsph_dist_upload", "clsph_dist_download", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_stream",
+    "clsph_dist_upload", "clsph_dist_download", "clsph_dist_transport", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_stream",
 ]
 
 TAP_SORTED_KEYS, TAP_PERMUTATION, TAP_CELL_TABLE, TAP_KEYS_INPUT, TAP_CANDIDATE_COUNT = 0, 1, 2, 3, 4
@@ -81,8 +81,10 @@ def load_library(path=None):
     L.clsph_particle_count.argtypes = [vp, ctypes.POINTER(u32)]
     L.clsph_stream.argtypes = [vp]
     L.clsph_stream.restype = vp
+    L.clsph_dist_transport.argtypes = [vp]
+    L.clsph_dist_transport.restype = ctypes.c_char_p
     for name in SYMBOLS:
-        if name not in ("clsph_destroy", "clsph_last_error", "clsph_stream"):
+        if name not in ("clsph_destroy", "clsph_last_error", "clsph_stream", "clsph_dist_transport"):
             getattr(L, name).restype = ctypes.c_int
     if path == _build.LIB_PATH:
         _lib = L
@@ -195,6 +197,10 @@ class Context:
         buf = ctypes.create_string_buffer(bytes(unique_id), 128)
         self._check(self._lib.clsph_dist_init(self._h, rank, world, buf, plane_lo, plane_hi, emigrant_capacity,
                                               ghost_capacity))
+
+    def dist_transport(self):
+        """How the ranks exchange particles: "peer stores ..." (NVLink, no collective per sub-step) or "nccl ..."."""
+        return self._lib.clsph_dist_transport(self._h).decode()
 
     def dist_upload(self, particles, ids):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)

@@ -243,6 +243,11 @@ int check_device_flags(clsph_context* ctx) {
   GridState g;
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&g, ctx->grid, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
   CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (g.error & 8u) {
+    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(&ctx->grid->error, 0, sizeof(uint32_t), ctx->stream));
+    return fail(ctx, CLSPH_ECOMM, "multi-GPU exchange: a neighbouring rank did not deliver its AABB or its particles in time "
+                "(peer transport; did every rank call clsph_step the same number of times?)");
+  }
   if (g.error & 2u) {
     CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(&ctx->grid->error, 0, sizeof(uint32_t), ctx->stream));
     return fail(ctx, CLSPH_ECOMM, "multi-GPU buffer overflow: more local, migrating or ghost particles than the capacities given "
@@ -385,7 +390,7 @@ int enqueue_substep(clsph_context* ctx) {
     launch_bounds(ctx->state[ctx->cur].pos, ctx->n, ctx->bounds, ctx->sm_count, st, lc);
     ctx->bounds_valid = true;
   }
-  if (multi && dist_allreduce_bounds(&ctx->dist, ctx->bounds, st)) return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
+  if (multi && dist_reduce_bounds(&ctx->dist, ctx->bounds, ctx->grid, st, lc)) return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
   const bool sub = ctx->sub_order;
   launch_grid_setup(ctx->bounds, ctx->grid, ctx->params.h, ctx->n, ctx->cell_capacity, multi ? ctx->dist.plane_lo : -inf,
                     multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, st, lc);
@@ -471,6 +476,7 @@ int enqueue_substep(clsph_context* ctx) {
                                         cudaMemcpyDeviceToDevice, st));
   launch_integrate(dst, ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->face_grid, ctx->grid, ctx->konst, ctx->bounds,
                    ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, lc);
+  if (multi) dist_publish_bounds(&ctx->dist, ctx->bounds, st, lc);
   if (prof) next_event(ctx);
   CLSPH_CUDA_TRY(ctx, cudaGetLastError());
   return CLSPH_OK;
@@ -753,6 +759,7 @@ int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) 
   ctx->n = n;
   ctx->have_particles = true;
   ctx->bounds_valid = false;
+  if (ctx->dist.active) dist_invalidate_bounds(&ctx->dist);
   return CLSPH_OK;
 }
 
@@ -787,6 +794,8 @@ int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_
   return CLSPH_OK;
 }
 
+const char* clsph_dist_transport(const clsph_context* ctx) { return ctx ? dist_transport(&ctx->dist) : "none"; }
+
 int clsph_dist_upload(clsph_context* ctx, const particle* aos, const uint32_t* ids, uint32_t n) {
   if (!ctx) return CLSPH_EINVAL;
   if (!ctx->dist.active) return fail(ctx, CLSPH_ESTATE, "clsph_dist_upload: call clsph_dist_init first");
@@ -804,6 +813,7 @@ int clsph_dist_upload(clsph_context* ctx, const particle* aos, const uint32_t* i
   ctx->n = n;
   ctx->have_particles = true;
   ctx->bounds_valid = false;
+  if (ctx->dist.active) dist_invalidate_bounds(&ctx->dist);
   return CLSPH_OK;
 }
 

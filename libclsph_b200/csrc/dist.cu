@@ -29,10 +29,29 @@
 // velocity. Migrating particles and ghosts carry order keys (cell key and rank in cell of the previous
 // sub-step), from which every rank keeps its arrays in the order a single GPU would: results are bitwise
 // those of a single-GPU run, and the ranks' downloads merge into the reference's global array.
+//
+// Transport. On a box where the GPUs reach each other's memory (NVLink / NVSwitch, CUDA IPC between the rank
+// processes) steps 1 and 3 do not call NCCL at all: every rank owns a MAILBOX in its HBM that the others map.
+//   * k_dist_classify stores the emigrant and ghost records straight into the neighbour's mailbox while it
+//     compacts the local array -- the transfer is the kernel's own stores, overlapping its other work, and only the
+//     records that exist travel; k_dist_signal then publishes the counts and the sub-step's sequence number
+//     (release at system scope), k_dist_unpack waits for that number (acquire) before it reads;
+//   * the AABB travels the same way: k_bounds_publish stores the six accumulators of a rank into a slot of every
+//     mailbox right after the integrator has produced them (the end of the PREVIOUS sub-step, so the stores are long
+//     done when they are needed), k_bounds_gather waits for the slots of all ranks and reduces them.
+// No rank ever waits for a rank that waits for it: a kernel that stores never waits, a kernel that waits only needs
+// kernels that precede it in the other ranks' streams. Slots are double-buffered by the parity of the sequence
+// number (a rank two slabs away may run ahead by part of a sub-step); the record areas need no second buffer
+// because a neighbour can only store sub-step k's records after this rank has published its AABB for k, i.e. after
+// it has unpacked k - 1. Waits give up after ~10 s and flag CLSPH_ECOMM instead of hanging the GPU.
+// NCCL remains for the start-up (exchange of the IPC handles) and as the transport when peer access is unavailable
+// (CLSPH_DIST_TRANSPORT=nccl forces it).
 #include <dlfcn.h>
 #include <nccl.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "dist.cuh"
 #include "subview.cuh"
@@ -99,6 +118,32 @@ struct MsgHeader {
 __host__ __device__ inline float4* msg_emigrants(void* msg) { return reinterpret_cast<float4*>(static_cast<char*>(msg) + 16); }
 __host__ __device__ inline float4* msg_ghosts(void* msg, uint32_t emax) { return msg_emigrants(msg) + (size_t)emax * 4; }
 
+// Where k_dist_classify puts what goes to one neighbour.
+struct MsgOut {
+  uint32_t* counts;   // [0] emigrants, [1] ghosts appended so far (local memory)
+  float4* emigrants;  // records: the local send buffer (NCCL) or the neighbour's mailbox (peer stores)
+  float4* ghosts;
+};
+
+// Mailbox of a rank (peer transport), mapped by every other rank:
+//   [0, 2048)     AABB slots [parity][source rank][8 words]: lo[3], hi[3], sequence number, pad
+//   [2048, 2112)  message headers [side][8 words]: emigrants, ghosts, sequence number; side 0 = from the left neighbour
+//   [4096, ...)   records of side 0, then of side 1: emigrants (emax x 64 B), ghosts (gmax x 32 B)
+constexpr int kMaxPeers = 32;
+constexpr size_t kMailboxRecords = 4096;
+__host__ __device__ inline uint32_t* mailbox_bounds(void* box, uint32_t parity, uint32_t rank) {
+  return static_cast<uint32_t*>(box) + ((size_t)parity * kMaxPeers + rank) * 8u;
+}
+__host__ __device__ inline const uint32_t* mailbox_bounds(const void* box, uint32_t parity, uint32_t rank) {
+  return static_cast<const uint32_t*>(box) + ((size_t)parity * kMaxPeers + rank) * 8u;
+}
+__host__ __device__ inline uint32_t* mailbox_header(void* box, int side) { return static_cast<uint32_t*>(box) + 512 + side * 8; }
+inline size_t side_bytes(uint32_t emax, uint32_t gmax) { return (size_t)emax * 64 + (size_t)gmax * 32; }
+inline float4* mailbox_emigrants(void* box, int side, uint32_t emax, uint32_t gmax) {
+  return reinterpret_cast<float4*>(static_cast<char*>(box) + kMailboxRecords + (size_t)side * side_bytes(emax, gmax));
+}
+inline float4* mailbox_ghosts(void* box, int side, uint32_t emax, uint32_t gmax) { return mailbox_emigrants(box, side, emax, gmax) + (size_t)emax * 4; }
+
 }  // namespace
 
 const char* dist_last_error() { return g_nccl_error; }
@@ -111,7 +156,7 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
                 const uint32_t* __restrict__ pid, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ wrank,
                 GridState* grid, float4* __restrict__ u_pos, float4* __restrict__ u_vel, float4* __restrict__ u_ivel,
                 uint32_t* __restrict__ u_pid, uint32_t* __restrict__ u_ordk, uint32_t* __restrict__ u_ordr,
-                uint32_t* __restrict__ u_count, uint32_t capacity, void* send_left, void* send_right, uint32_t emax,
+                uint32_t* __restrict__ u_count, uint32_t capacity, const MsgOut left, const MsgOut right, uint32_t emax,
                 uint32_t gmax) {
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,57 +213,133 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
       if (u_ordk) { u_ordk[at] = ok_k; u_ordr[at] = ok_r; }
     } else atomicOr(&grid->error, 2u);
   }
-  MsgHeader* hl = static_cast<MsgHeader*>(send_left);
-  MsgHeader* hr = static_cast<MsgHeader*>(send_right);
+  // the records go where the transport wants them: the local send buffer (NCCL) or the neighbour's mailbox (peer
+  // stores over NVLink); the counters are local either way
   uint32_t e;
-  e = warp_append(go_left, &hl->n_emigrants);
+  e = warp_append(go_left, left.counts);
   if (go_left) {
-    if (e < emax) { float4* r = msg_emigrants(send_left) + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f); }
+    if (e < emax) { float4* r = left.emigrants + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f); }
     else atomicOr(&grid->error, 2u);
   }
-  e = warp_append(go_right, &hr->n_emigrants);
+  e = warp_append(go_right, right.counts);
   if (go_right) {
-    if (e < emax) { float4* r = msg_emigrants(send_right) + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f); }
+    if (e < emax) { float4* r = right.emigrants + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f); }
     else atomicOr(&grid->error, 2u);
   }
   // ghosts travel as (position, velocity); with order keys (sub-cell order) these ride in the two w lanes,
   // which are free between the integrator and the density pass
   float4 gp = p, gv = v;
   if (wrank) { gp.w = __uint_as_float(ok_k); gv.w = __uint_as_float(ok_r); }
-  e = warp_append(ghost_left, &hl->n_ghosts);
+  e = warp_append(ghost_left, left.counts + 1);
   if (ghost_left) {
-    if (e < gmax) { float4* r = msg_ghosts(send_left, emax) + (size_t)e * 2; r[0] = gp; r[1] = gv; }
+    if (e < gmax) { float4* r = left.ghosts + (size_t)e * 2; r[0] = gp; r[1] = gv; }
     else atomicOr(&grid->error, 2u);
   }
-  e = warp_append(ghost_right, &hr->n_ghosts);
+  e = warp_append(ghost_right, right.counts + 1);
   if (ghost_right) {
-    if (e < gmax) { float4* r = msg_ghosts(send_right, emax) + (size_t)e * 2; r[0] = gp; r[1] = gv; }
+    if (e < gmax) { float4* r = right.ghosts + (size_t)e * 2; r[0] = gp; r[1] = gv; }
     else atomicOr(&grid->error, 2u);
   }
 }
 
+// ---- peer transport: flags and waits ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_flag(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void store_flag(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+// Waits until *flag == want. Gives up after kSpinLimit clock ticks (a peer that died must not hang this GPU).
+constexpr long long kSpinLimit = 20000000000ll;
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t want, long long limit = kSpinLimit) {
+  const long long t0 = clock64();
+  while (load_flag(flag) != want)
+    if (clock64() - t0 > limit) return false;
+  __threadfence_system();  // acquire: what the peer stored before the flag is visible from here on
+  return true;
+}
+
+// After k_dist_classify (stream order): the records are stored, now the counts and the sequence number.
+__global__ void k_dist_signal(const uint32_t* counts_left, const uint32_t* counts_right, uint32_t* header_left,
+                              uint32_t* header_right, uint32_t seq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __threadfence_system();  // release: everything this rank has stored so far precedes the flags
+  if (header_left) { store_flag(header_left, counts_left[0]); store_flag(header_left + 1, counts_left[1]); }
+  if (header_right) { store_flag(header_right, counts_right[0]); store_flag(header_right + 1, counts_right[1]); }
+  __threadfence_system();
+  if (header_left) store_flag(header_left + 2, seq);
+  if (header_right) store_flag(header_right + 2, seq);
+}
+
+// The six AABB accumulators of this rank into slot [parity of seq][rank] of every rank's mailbox (its own too).
+__global__ void k_bounds_publish(const BoundsAcc* acc, void* const* mailboxes, int rank, int world, uint32_t seq) {
+  const int r = (int)threadIdx.x;
+  if (blockIdx.x != 0 || r >= world) return;
+  uint32_t* slot = mailbox_bounds(mailboxes[r], seq & 1u, (uint32_t)rank);
+  for (int a = 0; a < 3; ++a) { store_flag(slot + a, acc->lo[a]); store_flag(slot + 3 + a, acc->hi[a]); }
+  __threadfence_system();
+  store_flag(slot + 6, seq);
+}
+
+// Teardown: tells every rank that this one has finished storing (its stream is drained), then waits until all
+// others have said so too: only then may a mailbox be freed. A few seconds at most, in case a peer is gone.
+constexpr uint32_t kClosed = 0xC105ED00u;
+__global__ void k_dist_close(void* const* mailboxes, void* mailbox, int rank, int world) {
+  const int r = (int)threadIdx.x;
+  if (blockIdx.x != 0 || r >= world) return;
+  __threadfence_system();
+  store_flag(mailbox_bounds(mailboxes[r], 0u, (uint32_t)rank) + 7, kClosed);
+  wait_flag(mailbox_bounds(mailbox, 0u, (uint32_t)r) + 7, kClosed, kSpinLimit / 4);
+}
+
+// Waits for the slots of all ranks and leaves the global AABB in acc (what the all-reduce of the NCCL transport does).
+__global__ void k_bounds_gather(BoundsAcc* acc, void* mailbox, int world, uint32_t seq, GridState* grid) {
+  const unsigned r = threadIdx.x;  // one warp
+  uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+  if ((int)r < world) {
+    const uint32_t* slot = mailbox_bounds(mailbox, seq & 1u, r);
+    if (!wait_flag(slot + 6, seq)) atomicOr(&grid->error, 8u);
+    for (int a = 0; a < 3; ++a) { lo[a] = load_flag(slot + a); hi[a] = load_flag(slot + 3 + a); }
+  }
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(kFullMask, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(kFullMask, hi[a], o));
+    }
+  if (r == 0)
+    for (int a = 0; a < 3; ++a) { acc->lo[a] = lo[a]; acc->hi[a] = hi[a]; }
+}
+
 // Appends one received message: its emigrants become owned particles here, its ghosts are
 // candidates for the neighbour passes. Thread t < emax handles emigrant t, the rest ghost t - emax.
+// wait_seq != 0 (peer transport): the message is complete when header[2] == wait_seq.
 __global__ void __launch_bounds__(256)
-k_dist_unpack(void* msg, uint32_t emax, uint32_t gmax, GridState* grid, float4* __restrict__ u_pos,
+k_dist_unpack(const uint32_t* header, const float4* emigrants, const float4* ghosts, uint32_t wait_seq, uint32_t emax, uint32_t gmax,
+              GridState* grid, float4* __restrict__ u_pos,
               float4* __restrict__ u_vel, float4* __restrict__ u_ivel, uint32_t* __restrict__ u_pid,
               uint32_t* __restrict__ u_ordk, uint32_t* __restrict__ u_ordr, uint32_t* __restrict__ u_count,
               uint32_t capacity) {
-  const MsgHeader h = *static_cast<const MsgHeader*>(msg);
+  __shared__ uint32_t s_counts[2];
+  if (threadIdx.x == 0) {
+    bool ok = true;
+    if (wait_seq) ok = wait_flag(header + 2, wait_seq);
+    if (!ok) atomicOr(&grid->error, 8u);
+    s_counts[0] = ok ? load_flag(header) : 0u;
+    s_counts[1] = ok ? load_flag(header + 1) : 0u;
+  }
+  __syncthreads();
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t ne = min(h.n_emigrants, emax), ng = min(h.n_ghosts, gmax);
+  const uint32_t ne = min(s_counts[0], emax), ng = min(s_counts[1], gmax);
   const bool is_e = t < ne;
   const bool is_g = t >= emax && t - emax < ng;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, iv = p;
   uint32_t id = 0xFFFFFFFFu;  // ghosts carry no identity here
   uint32_t ok_k = 0xFFFFFFFFu, ok_r = 0u;  // ... and, without order keys, no place in the reference's order
   if (is_e) {
-    const float4* r = msg_emigrants(msg) + (size_t)t * 4;
-    p = r[0]; v = r[1]; iv = r[2]; id = __float_as_uint(r[3].x);
-    ok_k = __float_as_uint(r[3].y); ok_r = __float_as_uint(r[3].z);
+    const float4* r = emigrants + (size_t)t * 4;  // (L2 loads: the lines were written from outside this SM's L1)
+    p = __ldcg(r); v = __ldcg(r + 1); iv = __ldcg(r + 2);
+    const float4 tag = __ldcg(r + 3);
+    id = __float_as_uint(tag.x);
+    ok_k = __float_as_uint(tag.y); ok_r = __float_as_uint(tag.z);
   } else if (is_g) {
-    const float4* r = msg_ghosts(msg, emax) + (size_t)(t - emax) * 2;
-    p = r[0]; v = r[1];
+    const float4* r = ghosts + (size_t)(t - emax) * 2;
+    p = __ldcg(r); v = __ldcg(r + 1);
     if (u_ordk) {  // the sender's order keys, see k_dist_classify
       ok_k = __float_as_uint(p.w); ok_r = __float_as_uint(v.w);
       p.w = 0.f; v.w = 0.f;
@@ -281,6 +402,61 @@ int dist_unique_id(void* out, size_t bytes) {
   return 0;
 }
 
+// Peer transport set-up: one mailbox per rank, its IPC handle all-gathered (as an all-reduce(max) over a zeroed
+// table in which every rank fills its own row: the one collective dist.cu already uses), every mailbox mapped.
+// All ranks agree on the outcome (a second all-reduce), so either all use peer stores or all use NCCL.
+static bool setup_peer_transport(DistState* d) {
+  const char* env = getenv("CLSPH_DIST_TRANSPORT");
+  bool want = !(env && !strcmp(env, "nccl")) && d->world <= kMaxPeers;
+  ncclComm_t comm = static_cast<ncclComm_t>(d->comm);
+  const size_t words_per_rank = sizeof(cudaIpcMemHandle_t) / 4;
+  uint32_t* table = nullptr;   // device: world rows of handle words, then one word of "this rank is fine"
+  const size_t table_words = words_per_rank * d->world;
+  if (cudaMalloc(&table, (table_words + 1) * 4) != cudaSuccess) return false;
+  cudaMemset(table, 0, (table_words + 1) * 4);
+  d->mailbox_bytes = kMailboxRecords + 2 * side_bytes(d->emax, d->gmax);
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (want) {
+    want = cudaMalloc(&d->mailbox, d->mailbox_bytes) == cudaSuccess && cudaMemset(d->mailbox, 0, kMailboxRecords) == cudaSuccess &&
+           cudaIpcGetMemHandle(&mine, d->mailbox) == cudaSuccess;
+    cudaGetLastError();
+  }
+  if (want) cudaMemcpy(table + words_per_rank * d->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+  bool ok = nccl_check(nccl().AllReduce(table, table, table_words, ncclUint32, ncclMax, comm, nullptr), "ncclAllReduce(handles)");
+  ok = ok && cudaStreamSynchronize(nullptr) == cudaSuccess;
+  std::vector<cudaIpcMemHandle_t> handles(d->world);
+  if (ok) cudaMemcpy(handles.data(), table, table_words * 4, cudaMemcpyDeviceToHost);
+  bool mapped = ok && want;
+  for (int r = 0; r < d->world && mapped; ++r) {
+    if (r == d->rank) { d->peer_mailbox[r] = d->mailbox; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mapped = false; break; }
+    d->peer_mailbox[r] = p;
+  }
+  // 1 = this rank cannot: max over ranks tells everybody
+  const uint32_t bad = mapped ? 0u : 1u;
+  cudaMemcpy(table + table_words, &bad, 4, cudaMemcpyHostToDevice);
+  uint32_t any_bad = 1u;
+  if (ok && nccl_check(nccl().AllReduce(table + table_words, table + table_words, 1, ncclUint32, ncclMax, comm, nullptr), "ncclAllReduce(transport)") &&
+      cudaStreamSynchronize(nullptr) == cudaSuccess)
+    cudaMemcpy(&any_bad, table + table_words, 4, cudaMemcpyDeviceToHost);
+  cudaFree(table);
+  if (any_bad) {
+    for (int r = 0; r < d->world; ++r) {
+      if (r != d->rank && d->peer_mailbox[r]) cudaIpcCloseMemHandle(d->peer_mailbox[r]);
+      d->peer_mailbox[r] = nullptr;
+    }
+    cudaFree(d->mailbox);
+    d->mailbox = nullptr;
+    cudaGetLastError();
+    return false;
+  }
+  if (cudaMalloc(&d->peer_table, sizeof(void*) * kMaxPeers) != cudaSuccess) return false;
+  cudaMemcpy(d->peer_table, d->peer_mailbox, sizeof(void*) * d->world, cudaMemcpyHostToDevice);
+  return true;
+}
+
 int dist_init(DistState* d, int rank, int world, const void* id_bytes, float plane_lo, float plane_hi, uint32_t emax,
               uint32_t gmax) {
   if (!nccl().ok) { snprintf(g_nccl_error, sizeof(g_nccl_error), "libnccl.so.2 could not be loaded"); return 1; }
@@ -296,18 +472,28 @@ int dist_init(DistState* d, int rank, int world, const void* id_bytes, float pla
   d->emax = emax;
   d->gmax = gmax;
   d->msg_bytes = 16 + (size_t)emax * 64 + (size_t)gmax * 32;
-  for (int s = 0; s < 2; ++s) {
-    if (cudaMalloc(&d->send[s], d->msg_bytes) != cudaSuccess || cudaMalloc(&d->recv[s], d->msg_bytes) != cudaSuccess) {
-      snprintf(g_nccl_error, sizeof(g_nccl_error), "cudaMalloc of %zu-byte message buffers failed", d->msg_bytes);
-      return 1;
-    }
-    cudaMemset(d->send[s], 0, 16);
-    cudaMemset(d->recv[s], 0, 16);
-  }
+  d->seq = 0;
+  d->bounds_published = false;
   if (cudaMalloc(&d->counters, 64) != cudaSuccess) return 1;
   cudaMemset(d->counters, 0, 64);
+  d->peer = setup_peer_transport(d);
+  if (!d->peer) {  // NCCL messages: local send and receive buffers
+    for (int s = 0; s < 2; ++s) {
+      if (cudaMalloc(&d->send[s], d->msg_bytes) != cudaSuccess || cudaMalloc(&d->recv[s], d->msg_bytes) != cudaSuccess) {
+        snprintf(g_nccl_error, sizeof(g_nccl_error), "cudaMalloc of %zu-byte message buffers failed", d->msg_bytes);
+        return 1;
+      }
+      cudaMemset(d->send[s], 0, 16);
+      cudaMemset(d->recv[s], 0, 16);
+    }
+  }
   d->active = true;
   return 0;
+}
+
+const char* dist_transport(const DistState* d) {
+  if (!d->active) return "none";
+  return d->peer ? "peer stores into the neighbours' mailboxes (CUDA IPC over NVLink), no collective per sub-step" : "nccl send/recv + all-reduce";
 }
 
 void dist_destroy(DistState* d) {
@@ -316,12 +502,34 @@ void dist_destroy(DistState* d) {
     cudaFree(d->send[s]);
     cudaFree(d->recv[s]);
   }
+  if (d->peer) {
+    // the other ranks may still be storing into this mailbox (the AABB they publish at the end of their last
+    // sub-step): leave together
+    k_dist_close<<<1, 32>>>(d->peer_table, d->mailbox, d->rank, d->world);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < d->world; ++r)
+      if (r != d->rank && d->peer_mailbox[r]) cudaIpcCloseMemHandle(d->peer_mailbox[r]);
+    cudaFree(d->peer_table);
+    cudaFree(d->mailbox);
+  }
   cudaFree(d->counters);
   if (d->comm && nccl().ok) nccl().CommDestroy(static_cast<ncclComm_t>(d->comm));
   d->active = false;
 }
 
-int dist_allreduce_bounds(DistState* d, BoundsAcc* acc, cudaStream_t stream) {
+// Start of a sub-step: the global AABB into acc. Advances the sequence number.
+int dist_reduce_bounds(DistState* d, BoundsAcc* acc, GridState* grid, cudaStream_t stream, uint64_t* launches) {
+  ++d->seq;
+  if (d->peer) {
+    if (!d->bounds_published) {  // first sub-step after an upload: nothing was published at the end of a previous one
+      k_bounds_publish<<<1, 32, 0, stream>>>(acc, d->peer_table, d->rank, d->world, d->seq);
+      if (launches) ++*launches;
+    }
+    d->bounds_published = false;
+    k_bounds_gather<<<1, 32, 0, stream>>>(acc, d->mailbox, d->world, d->seq, grid);
+    if (launches) ++*launches;
+    return 0;
+  }
   ncclComm_t comm = static_cast<ncclComm_t>(d->comm);
   if (!nccl_check(nccl().GroupStart(), "ncclGroupStart")) return 1;
   bool ok = nccl_check(nccl().AllReduce(acc->lo, acc->lo, 3, ncclUint32, ncclMin, comm, stream), "ncclAllReduce(min)");
@@ -330,19 +538,61 @@ int dist_allreduce_bounds(DistState* d, BoundsAcc* acc, cudaStream_t stream) {
   return ok ? 0 : 1;
 }
 
+// End of a sub-step (the integrator has accumulated the next AABB of this rank's particles): peer transport
+// sends it on its way now, a whole neighbour-search ahead of when it is needed.
+void dist_publish_bounds(DistState* d, const BoundsAcc* acc, cudaStream_t stream, uint64_t* launches) {
+  if (!d->peer) return;
+  k_bounds_publish<<<1, 32, 0, stream>>>(acc, d->peer_table, d->rank, d->world, d->seq + 1u);
+  d->bounds_published = true;
+  if (launches) ++*launches;
+}
+
+// The particles were replaced (upload): what was published for the next sub-step is stale. Skipping two
+// sequence numbers keeps the slot parity and makes every rank wait for the fresh values.
+void dist_invalidate_bounds(DistState* d) {
+  if (d->bounds_published) d->seq += 2u;
+  d->bounds_published = false;
+}
+
 int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pid, const uint32_t* skey,
                   const uint32_t* wrank, GridState* grid, const StateArrays& u, uint32_t* u_pid, uint32_t* u_ordk,
                   uint32_t* u_ordr, uint32_t capacity, cudaStream_t stream, uint64_t* launches) {
   ncclComm_t comm = static_cast<ncclComm_t>(d->comm);
   uint32_t* u_count = d->counters;
+  const bool has_left = d->rank > 0, has_right = d->rank + 1 < d->world;
+  const unsigned blocks = (capacity + 255) / 256;
+  const unsigned ublocks = (d->emax + d->gmax + 255) / 256;
+  if (d->peer) {
+    // counters: [0] local count, [1] export count, [4..5] to the left, [6..7] to the right
+    cudaMemsetAsync(d->counters, 0, 32, stream);
+    // my left neighbour receives "from its right" (side 1), my right neighbour "from its left" (side 0)
+    void* lbox = has_left ? d->peer_mailbox[d->rank - 1] : d->mailbox;  // (without a neighbour nothing is ever appended)
+    void* rbox = has_right ? d->peer_mailbox[d->rank + 1] : d->mailbox;
+    const MsgOut left{d->counters + 4, mailbox_emigrants(lbox, 1, d->emax, d->gmax), mailbox_ghosts(lbox, 1, d->emax, d->gmax)};
+    const MsgOut right{d->counters + 6, mailbox_emigrants(rbox, 0, d->emax, d->gmax), mailbox_ghosts(rbox, 0, d->emax, d->gmax)};
+    k_dist_classify<<<blocks, 256, 0, stream>>>(prev.pos, prev.vel, prev.ivel, prev_pid, skey, wrank, grid, u.pos, u.vel, u.ivel,
+                                                u_pid, u_ordk, u_ordr, u_count, capacity, left, right, d->emax, d->gmax);
+    k_dist_signal<<<1, 32, 0, stream>>>(d->counters + 4, d->counters + 6, has_left ? mailbox_header(lbox, 1) : nullptr,
+                                        has_right ? mailbox_header(rbox, 0) : nullptr, d->seq);
+    if (has_left)
+      k_dist_unpack<<<ublocks, 256, 0, stream>>>(mailbox_header(d->mailbox, 0), mailbox_emigrants(d->mailbox, 0, d->emax, d->gmax),
+                                                 mailbox_ghosts(d->mailbox, 0, d->emax, d->gmax), d->seq, d->emax, d->gmax, grid, u.pos,
+                                                 u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
+    if (has_right)
+      k_dist_unpack<<<ublocks, 256, 0, stream>>>(mailbox_header(d->mailbox, 1), mailbox_emigrants(d->mailbox, 1, d->emax, d->gmax),
+                                                 mailbox_ghosts(d->mailbox, 1, d->emax, d->gmax), d->seq, d->emax, d->gmax, grid, u.pos,
+                                                 u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
+    k_dist_finish<<<1, 32, 0, stream>>>(grid, u_count, capacity);
+    if (launches) *launches += 3 + (has_left ? 1 : 0) + (has_right ? 1 : 0);
+    return 0;
+  }
   cudaMemsetAsync(u_count, 0, sizeof(uint32_t), stream);
   cudaMemsetAsync(d->send[0], 0, 16, stream);
   cudaMemsetAsync(d->send[1], 0, 16, stream);
-  const unsigned blocks = (capacity + 255) / 256;
+  const MsgOut left{static_cast<uint32_t*>(d->send[0]), msg_emigrants(d->send[0]), msg_ghosts(d->send[0], d->emax)};
+  const MsgOut right{static_cast<uint32_t*>(d->send[1]), msg_emigrants(d->send[1]), msg_ghosts(d->send[1], d->emax)};
   k_dist_classify<<<blocks, 256, 0, stream>>>(prev.pos, prev.vel, prev.ivel, prev_pid, skey, wrank, grid, u.pos, u.vel, u.ivel,
-                                              u_pid, u_ordk, u_ordr, u_count, capacity, d->send[0], d->send[1], d->emax,
-                                              d->gmax);
-  const bool has_left = d->rank > 0, has_right = d->rank + 1 < d->world;
+                                              u_pid, u_ordk, u_ordr, u_count, capacity, left, right, d->emax, d->gmax);
   if (!nccl_check(nccl().GroupStart(), "ncclGroupStart")) return 1;
   bool ok = true;
   if (has_left) {
@@ -354,13 +604,12 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
     ok = ok && nccl_check(nccl().Recv(d->recv[1], d->msg_bytes, ncclUint8, d->rank + 1, comm, stream), "ncclRecv(right)");
   }
   if (!nccl_check(nccl().GroupEnd(), "ncclGroupEnd") || !ok) return 1;
-  const unsigned ublocks = (d->emax + d->gmax + 255) / 256;
   if (has_left)
-    k_dist_unpack<<<ublocks, 256, 0, stream>>>(d->recv[0], d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk, u_ordr,
-                                               u_count, capacity);
+    k_dist_unpack<<<ublocks, 256, 0, stream>>>(static_cast<const uint32_t*>(d->recv[0]), msg_emigrants(d->recv[0]), msg_ghosts(d->recv[0], d->emax),
+                                               0u, d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
   if (has_right)
-    k_dist_unpack<<<ublocks, 256, 0, stream>>>(d->recv[1], d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk, u_ordr,
-                                               u_count, capacity);
+    k_dist_unpack<<<ublocks, 256, 0, stream>>>(static_cast<const uint32_t*>(d->recv[1]), msg_emigrants(d->recv[1]), msg_ghosts(d->recv[1], d->emax),
+                                               0u, d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
   k_dist_finish<<<1, 32, 0, stream>>>(grid, u_count, capacity);
   if (launches) *launches += 2 + (has_left ? 1 : 0) + (has_right ? 1 : 0);
   return 0;

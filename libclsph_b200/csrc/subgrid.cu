@@ -161,18 +161,29 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
               uint32_t* __restrict__ pair_count) {
   const uint32_t n = grid->n;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((r & ~31u) >= n) return;  // whole warp out of range
   uint32_t left = 1u;
   if (r < n)
     reorder_sub_slot(r, n, src_pos, src_vel, src_ivel, dst_pos, dst_vel, dst_ivel, keys_a, keys_b, vals_a, vals_b, skey, rr_src,
                      rr_dst, sub_lb, grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr, tile_ctl, tile_blocks, &left);
   if (!pair_items) return;
+  // one append per CTA: the items of 256 consecutive slots stay together and in order, which keeps the threads
+  // of a density CTA on neighbouring sub-cells (L1 reuse of the candidate rows)
+  __shared__ uint32_t s_warp[8], s_base;
   const bool leader = r < n && (left & 1u) == 0u;
-  const uint32_t at = warp_append(leader, pair_count);
+  const unsigned m = __ballot_sync(kFullMask, leader);
+  const unsigned warp = threadIdx.x >> 5;
+  if (lane_id() == 0u) s_warp[warp] = (uint32_t)__popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int w = 0; w < 8; ++w) { const uint32_t c = s_warp[w]; s_warp[w] = total; total += c; }
+    s_base = total ? atomicAdd(pair_count, total) : 0u;
+  }
+  __syncthreads();
   if (leader) {
     const uint32_t* __restrict__ keys = (grid->sort_passes & 1u) ? keys_b : keys_a;
     const bool second = r + 1u < n && keys[r + 1u] == keys[r];
-    pair_items[at] = r | (second ? 0x80000000u : 0u);
+    pair_items[s_base + s_warp[warp] + (uint32_t)__popc(m & lanemask_lt())] = r | (second ? 0x80000000u : 0u);
   }
 }
 
@@ -374,23 +385,36 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
   const f32x2 H2 = f2_bcast(c.h2);
   f32x2 acc = f2_make(0.f, 0.f);  // sums of (h^2 - s)^3 over the two supports
   uint32_t cnt0 = 0, cnt1 = 0;
+  auto test = [&](const float4& pj, uint32_t j) {
+    const f32x2 dx = f2_sub(X, f2_bcast(pj.x)), dy = f2_sub(Y, f2_bcast(pj.y)), dz = f2_sub(Z, f2_bcast(pj.z));
+    const f32x2 s = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+    const f32x2 d = f2_sub(H2, s);
+    const bool in0 = f2_lo(s) < c.support_s, in1 = f2_hi(s) < c.support_s;
+    const f32x2 w = f2_make(in0 ? f2_lo(d) : 0.f, in1 ? f2_hi(d) : 0.f);
+    acc = f2_fma(f2_mul(w, w), w, acc);
+    store_if(in0 && cnt0 < list_rows, row0 + cnt0, j);
+    cnt0 += in0 ? 1u : 0u;
+    store_if(in1 && cnt1 < list_rows, row1 + cnt1, j);
+    cnt1 += in1 ? 1u : 0u;
+  };
+  // Candidate k of the row's two index ranges laid end to end. Four loads are issued before the first test: a
+  // thread walks ~160 candidates one after the other, and with one load in flight the pass waits on L1 / L2 latency.
   auto walk = [&](uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
-    const uint32_t total = (a1 - a0) + (b1 - b0);
-    uint32_t j = a0 < a1 ? a0 : b0;
-    for (uint32_t k = 0; k < total; ++k) {
-      const float4 pj = pos[j];
-      const f32x2 dx = f2_sub(X, f2_bcast(pj.x)), dy = f2_sub(Y, f2_bcast(pj.y)), dz = f2_sub(Z, f2_bcast(pj.z));
-      const f32x2 s = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
-      const f32x2 d = f2_sub(H2, s);
-      const bool in0 = f2_lo(s) < c.support_s, in1 = f2_hi(s) < c.support_s;
-      const f32x2 w = f2_make(in0 ? f2_lo(d) : 0.f, in1 ? f2_hi(d) : 0.f);
-      acc = f2_fma(f2_mul(w, w), w, acc);
-      store_if(in0 && cnt0 < list_rows, row0 + cnt0, j);
-      cnt0 += in0 ? 1u : 0u;
-      store_if(in1 && cnt1 < list_rows, row1 + cnt1, j);
-      cnt1 += in1 ? 1u : 0u;
-      ++j;
-      if (j == a1) j = b0;  // end of the first range: continue in the second
+    const uint32_t la = a1 - a0, total = la + (b1 - b0);
+    const uint32_t shift = b0 - la;  // index = k + shift in the second range
+    uint32_t k = 0;
+    for (; k + 4u <= total; k += 4u) {
+      const uint32_t j0 = k < la ? a0 + k : k + shift, j1 = k + 1u < la ? a0 + k + 1u : k + 1u + shift,
+                     j2 = k + 2u < la ? a0 + k + 2u : k + 2u + shift, j3 = k + 3u < la ? a0 + k + 3u : k + 3u + shift;
+      const float4 q0 = pos[j0], q1 = pos[j1], q2 = pos[j2], q3 = pos[j3];
+      test(q0, j0);
+      test(q1, j1);
+      test(q2, j2);
+      test(q3, j3);
+    }
+    for (; k < total; ++k) {
+      const uint32_t j = k < la ? a0 + k : k + shift;
+      test(pos[j], j);
     }
   };
   const uint32_t cx_lo = xlo >> 1, cx_hi = xhi >> 1;

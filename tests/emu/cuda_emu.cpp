@@ -389,3 +389,8 @@ cudaError_t cudaEventDestroy(cudaEvent_t e) {
   delete e;
   return cudaSuccess;
 }
+
+#include <chrono>
+long long clock64() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}

@@ -177,6 +177,24 @@ struct cudaDeviceProp {
 };
 
 enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaDevAttrMaxSharedMemoryPerMultiprocessor = 81 };
+// ---- peer memory between ranks: in the emulator every rank is a thread of one process, a handle is the pointer
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  std::memset(h, 0, sizeof(*h));
+  std::memcpy(h->reserved, &p, sizeof(p));
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  std::memcpy(p, h.reserved, sizeof(*p));
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T>
+inline T __ldcg(const T* p) { return *p; }
+long long clock64();  // nanoseconds (the product code only compares differences with a generous limit)
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {  // the B200's figures
   *v = a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 227 * 1024 : 228 * 1024;
@@ -197,6 +215,7 @@ cudaError_t cudaMemset(void* dst, int v, size_t bytes);
 cudaError_t cudaMemsetAsync(void* dst, int v, size_t bytes, cudaStream_t s = nullptr);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaEventCreate(cudaEvent_t* e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr);

@@ -50,9 +50,12 @@ def by_id(parts, ids, n):
     return out
 
 
-@pytest.mark.parametrize("world,copies,sub", [(2, 2, 0), (3, 3, 1), (1, 2, 1)])  # world 1: a slab that is not cut at all
-def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
+# world 1: a slab that is not cut at all; transport: stores into the neighbours' mailboxes (default) or NCCL messages
+@pytest.mark.parametrize("world,copies,sub,transport", [(2, 2, 0, "peer"), (3, 3, 1, "peer"), (1, 2, 1, "peer"), (3, 3, 1, "nccl")])
+def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub, transport, monkeypatch):
     steps = 3
+    if transport == "nccl":
+        monkeypatch.setenv("CLSPH_DIST_TRANSPORT", "nccl")
     p, terms, state, scene_file = elongated_state(copies)
     n = state.size
     normals, vertices, indices = workloads.scene_arrays(scene_file)
@@ -72,6 +75,7 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub):
             ctx.set_scene(normals, vertices, indices)
             ctx.set_parameters(p, terms)
             ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
+            assert ctx.dist_transport().startswith("peer stores" if transport == "peer" else "nccl")
             ctx.dist_upload(np.ascontiguousarray(state[mine]), mine)
             for k in range(steps):
                 ctx.step(1)
