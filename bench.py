@@ -35,6 +35,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# configurations whose particle count is the TOTAL of the job (BASELINE config 4: 16 Mi over 8 GPUs); every other
+# configuration is per GPU when N > 1 (weak scaling: N x the configured count as one block)
+FIXED_TOTAL = {"config4_river_16m"}
 METRIC = "particle_steps_per_sec"
 UNIT = "particle-steps/s"
 # Algorithmic bytes per particle-step (SURVEY 8d / DESIGN.md): 256 + 16 P, P = radix passes.
@@ -196,7 +199,9 @@ def run_reference(args, rank):
     if rank != 0:
         return
     fluid, n_full, mass, scene = __import__("libclsph_b200.workloads", fromlist=["CONFIGS"]).CONFIGS[args.config]
-    n_full = (args.particles or n_full) * max(1, args.gpus)  # the GPU arm runs gpus x the configured count as one block
+    n_full = args.particles or n_full
+    if not (args.config in FIXED_TOTAL and not args.particles):
+        n_full *= max(1, args.gpus)  # the GPU arm runs gpus x the configured count as one block
     # The configured particle count itself when K+W sub-steps of it fit about four minutes on this box's cores
     # (config 2 on 16 cores: ~2 s per sub-step); otherwise a bounded sample of the same fluid, sized to that budget
     # (same_config false). --cpu-sample N forces a sample.
@@ -301,6 +306,9 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     fluid, n_cfg, mass, scene_file = workloads.CONFIGS[args.config]
     n_cfg = args.particles or n_cfg
+    fixed_total = args.config in FIXED_TOTAL and not args.particles
+    if fixed_total and world > 1:
+        n_cfg //= world
     options = list(args.option)
     sub = "sub_cell_order=0" not in options
     normals, vertices, indices = workloads.scene_arrays(scene_file)
@@ -334,6 +342,7 @@ def run_ours(args, rank, world, local_rank):
         dist.broadcast(uid, 0)
         ctx.dist_init(rank, world, bytes(uid.cpu().numpy().tolist()), float(planes[rank]), float(planes[rank + 1]),
                       emigrant_capacity=emigrant_cap, ghost_capacity=ghost_cap)
+    transport = ctx.dist_transport() if world > 1 else "none"
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
 
     def upload_state():
@@ -445,13 +454,13 @@ def run_ours(args, rank, world, local_rank):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if fixed_total else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.config, "particles_per_gpu": n, "particles_total": int(n_total), "fluid": fluid,
                    "scene": scene_file, "state": "S1 jittered lattice, seed 20261017",
                    "parallelism": "single GPU" if world == 1 else
-                   "one fluid block of %d x the configured count, slab-decomposed along x over %d GPUs; per sub-step: AABB "
-                   "all-reduce, migration + two ghost cell layers per side in one NCCL send/recv group" % (world, world),
+                   "one fluid block of %d x the configured count, slab-decomposed along x over %d GPUs; per sub-step: global AABB, "
+                   "migration + ghosts within 2h of each plane; transport: %s" % (world, world, transport),
                    "l2": "per-step working set ~%d MB vs 126 MB L2, no flush: sub-steps form a dependent chain" % (n * 200 // (1 << 20)),
                    "grid": [grid.grid_size_x, grid.grid_size_y, grid.grid_size_z], "grid_cell_count": grid.grid_cell_count,
                    "options": options},

@@ -735,7 +735,7 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     if (int rc = refresh_face_grid(ctx)) return rc;
   } else if (!std::strcmp(name, "list_rows")) {
     if (value < 0 || value > 1024) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: list_rows must be in [0, 1024]");
-    ctx->list_rows_override = (uint32_t)value;
+    ctx->list_rows_override = ((uint32_t)value + 1u) & ~1u;  // even: k_density_pairs stores entries two at a time
   } else {
     return fail(ctx, CLSPH_EINVAL, "clsph_set_option: unknown option \"%s\"", name);
   }

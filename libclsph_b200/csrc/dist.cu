@@ -402,6 +402,39 @@ int dist_unique_id(void* out, size_t bytes) {
   return 0;
 }
 
+// CLSPH_DIST_TIMING=1 (diagnostics): CUDA events around the pieces of the exchange of up to 256 sub-steps,
+// averaged and printed to stderr when the context is destroyed.
+namespace {
+struct ExchangeTiming {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // 5 per sub-step: start, after classify, after signal, after unpack, end
+  size_t used = 0;
+};
+ExchangeTiming g_timing;
+void timing_mark(cudaStream_t stream) {
+  if (!g_timing.on || g_timing.used >= g_timing.ev.size()) return;
+  cudaEventRecord(g_timing.ev[g_timing.used++], stream);
+}
+void timing_report(int rank) {
+  if (!g_timing.on) return;
+  cudaDeviceSynchronize();
+  double sum[4] = {0, 0, 0, 0};
+  size_t steps = g_timing.used / 5;
+  const size_t skip = steps > 20 ? 10 : 0;  // warm-up sub-steps
+  for (size_t k = skip; k < steps; ++k)
+    for (int p = 0; p < 4; ++p) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_timing.ev[k * 5 + p], g_timing.ev[k * 5 + p + 1]);
+      sum[p] += ms;
+    }
+  const double n = steps > skip ? (double)(steps - skip) : 1.0;
+  fprintf(stderr, "clsph dist timing rank %d over %zu sub-steps (us): classify %.1f, signal %.1f, unpack+wait %.1f, finish %.1f\n", rank,
+          steps - skip, 1e3 * sum[0] / n, 1e3 * sum[1] / n, 1e3 * sum[2] / n, 1e3 * sum[3] / n);
+  for (cudaEvent_t e : g_timing.ev) cudaEventDestroy(e);
+  g_timing = ExchangeTiming{};
+}
+}  // namespace
+
 // Peer transport set-up: one mailbox per rank, its IPC handle all-gathered (as an all-reduce(max) over a zeroed
 // table in which every rank fills its own row: the one collective dist.cu already uses), every mailbox mapped.
 // All ranks agree on the outcome (a second all-reduce), so either all use peer stores or all use NCCL.
@@ -477,6 +510,13 @@ int dist_init(DistState* d, int rank, int world, const void* id_bytes, float pla
   if (cudaMalloc(&d->counters, 64) != cudaSuccess) return 1;
   cudaMemset(d->counters, 0, 64);
   d->peer = setup_peer_transport(d);
+  if (const char* t = getenv("CLSPH_DIST_TIMING")) {
+    if (atoi(t) != 0 && !g_timing.on) {
+      g_timing.on = true;
+      g_timing.ev.resize(5 * 256);
+      for (cudaEvent_t& e : g_timing.ev) cudaEventCreate(&e);
+    }
+  }
   if (!d->peer) {  // NCCL messages: local send and receive buffers
     for (int s = 0; s < 2; ++s) {
       if (cudaMalloc(&d->send[s], d->msg_bytes) != cudaSuccess || cudaMalloc(&d->recv[s], d->msg_bytes) != cudaSuccess) {
@@ -498,6 +538,7 @@ const char* dist_transport(const DistState* d) {
 
 void dist_destroy(DistState* d) {
   if (!d->active) return;
+  timing_report(d->rank);
   for (int s = 0; s < 2; ++s) {
     cudaFree(d->send[s]);
     cudaFree(d->recv[s]);
@@ -564,6 +605,7 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
   const unsigned ublocks = (d->emax + d->gmax + 255) / 256;
   if (d->peer) {
     // counters: [0] local count, [1] export count, [4..5] to the left, [6..7] to the right
+    timing_mark(stream);
     cudaMemsetAsync(d->counters, 0, 32, stream);
     // my left neighbour receives "from its right" (side 1), my right neighbour "from its left" (side 0)
     void* lbox = has_left ? d->peer_mailbox[d->rank - 1] : d->mailbox;  // (without a neighbour nothing is ever appended)
@@ -572,8 +614,10 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
     const MsgOut right{d->counters + 6, mailbox_emigrants(rbox, 0, d->emax, d->gmax), mailbox_ghosts(rbox, 0, d->emax, d->gmax)};
     k_dist_classify<<<blocks, 256, 0, stream>>>(prev.pos, prev.vel, prev.ivel, prev_pid, skey, wrank, grid, u.pos, u.vel, u.ivel,
                                                 u_pid, u_ordk, u_ordr, u_count, capacity, left, right, d->emax, d->gmax);
+    timing_mark(stream);
     k_dist_signal<<<1, 32, 0, stream>>>(d->counters + 4, d->counters + 6, has_left ? mailbox_header(lbox, 1) : nullptr,
                                         has_right ? mailbox_header(rbox, 0) : nullptr, d->seq);
+    timing_mark(stream);
     if (has_left)
       k_dist_unpack<<<ublocks, 256, 0, stream>>>(mailbox_header(d->mailbox, 0), mailbox_emigrants(d->mailbox, 0, d->emax, d->gmax),
                                                  mailbox_ghosts(d->mailbox, 0, d->emax, d->gmax), d->seq, d->emax, d->gmax, grid, u.pos,
@@ -582,7 +626,9 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
       k_dist_unpack<<<ublocks, 256, 0, stream>>>(mailbox_header(d->mailbox, 1), mailbox_emigrants(d->mailbox, 1, d->emax, d->gmax),
                                                  mailbox_ghosts(d->mailbox, 1, d->emax, d->gmax), d->seq, d->emax, d->gmax, grid, u.pos,
                                                  u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
+    timing_mark(stream);
     k_dist_finish<<<1, 32, 0, stream>>>(grid, u_count, capacity);
+    timing_mark(stream);
     if (launches) *launches += 3 + (has_left ? 1 : 0) + (has_right ? 1 : 0);
     return 0;
   }

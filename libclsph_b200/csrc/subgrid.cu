@@ -384,7 +384,7 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
   const f32x2 X = f2_make(p0.x, p1.x), Y = f2_make(p0.y, p1.y), Z = f2_make(p0.z, p1.z);
   const f32x2 H2 = f2_bcast(c.h2);
   f32x2 acc = f2_make(0.f, 0.f);  // sums of (h^2 - s)^3 over the two supports
-  uint32_t cnt0 = 0, cnt1 = 0;
+  uint32_t cnt0 = 0, cnt1 = 0, held0 = 0, held1 = 0;
   auto test = [&](const float4& pj, uint32_t j) {
     const f32x2 dx = f2_sub(X, f2_bcast(pj.x)), dy = f2_sub(Y, f2_bcast(pj.y)), dz = f2_sub(Z, f2_bcast(pj.z));
     const f32x2 s = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
@@ -392,9 +392,15 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     const bool in0 = f2_lo(s) < c.support_s, in1 = f2_hi(s) < c.support_s;
     const f32x2 w = f2_make(in0 ? f2_lo(d) : 0.f, in1 ? f2_hi(d) : 0.f);
     acc = f2_fma(f2_mul(w, w), w, acc);
-    store_if(in0 && cnt0 < list_rows, row0 + cnt0, j);
+    // List entries leave two at a time: the pass is bound by L1 wavefronts, and every lane's store is a wavefront
+    // of its own (each lane writes its own row), so one 8-byte store per two hits halves that share. The first
+    // hit of a pair waits in a register (list_rows is even, rows are 8-byte aligned).
+    const bool odd0 = (cnt0 & 1u) != 0u, odd1 = (cnt1 & 1u) != 0u;
+    store2_if(in0 && odd0 && cnt0 < list_rows, row0 + (cnt0 - 1u), held0, j);
+    held0 = (in0 && !odd0) ? j : held0;
     cnt0 += in0 ? 1u : 0u;
-    store_if(in1 && cnt1 < list_rows, row1 + cnt1, j);
+    store2_if(in1 && odd1 && cnt1 < list_rows, row1 + (cnt1 - 1u), held1, j);
+    held1 = (in1 && !odd1) ? j : held1;
     cnt1 += in1 ? 1u : 0u;
   };
   // Candidate k of the row's two index ranges laid end to end. Four loads are issued before the first test: a
@@ -432,6 +438,9 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
       }
     }
   }
+  // the last hit of an odd count is still held
+  if ((cnt0 & 1u) && cnt0 - 1u < list_rows) row0[cnt0 - 1u] = held0;
+  if (two && (cnt1 & 1u) && cnt1 - 1u < list_rows) row1[cnt1 - 1u] = held1;
   if (need0) {
     finish_density(c, f2_lo(acc), i0, aux, pos, vel);
     ncount[i0] = cnt0;

@@ -67,6 +67,17 @@ __device__ __forceinline__ void store_if(bool ok, uint32_t* addr, uint32_t v) {
 #endif
 }
 
+// Two consecutive words at an 8-byte aligned address, as ONE predicated store.
+__device__ __forceinline__ void store2_if(bool ok, uint32_t* addr, uint32_t a, uint32_t b) {
+#ifdef CLSPH_EMU
+  if (ok) { addr[0] = a; addr[1] = b; }
+#else
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v2.u32 [%1], {%2, %3};\n\t}" ::"r"((uint32_t)ok),
+               "l"(__cvta_generic_to_global(addr)), "r"(a), "r"(b)
+               : "memory");
+#endif
+}
+
 // for_each_range: calls range(begin, end) for every index range of candidates of the sub-cells around pi.
 // for_each_neighbour, on top of it:
 // Calls visit(j, pos[j], s, inside) for every candidate j of the sub-cells around pi, z outermost /

@@ -1,8 +1,8 @@
 """Multi-GPU worker, launched by tests/test_multi_gpu.py (or by hand) under torchrun:
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_worker.py [n] [steps] [--sub]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_worker.py [n] [steps] [--no-sub]
 
---sub selects the sub-cell order (+ face grid) and additionally checks that the ranks' downloads, merged by
+The library's default organisation (sub-cell order) is additionally checked for this:  that the ranks' downloads, merged by
 (grid_index, padding word), reproduce the single-GPU run's array ORDER exactly and its values BITWISE.
 
 Every rank runs one slab of the same fluid block through the CUDA library (clsph_dist_*); rank 0
@@ -50,7 +50,7 @@ def rel(a, b):
 
 def main():
     argv = [a for a in sys.argv[1:] if not a.startswith("--")]
-    sub = "--sub" in sys.argv
+    sub = "--no-sub" not in sys.argv  # (--sub is accepted and is the default)
     n = int(argv[0]) if len(argv) > 0 else 60000
     steps = int(argv[1]) if len(argv) > 1 else 3
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -79,20 +79,20 @@ def main():
 
     cap = int(n * (1.0 / world + 0.5)) + 4096  # owned + two ghost layers per side with slack
     ctx = capi.Context(cap, device=local)
-    if sub:
-        ctx.set_option("sub_cell_order", 1)
-        ctx.set_option("face_grid", 1)
+    if not sub:
+        ctx.set_option("sub_cell_order", 0)
     ctx.set_scene(normals, vertices, indices)
     ctx.set_parameters(p, terms)
     ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
+    if rank == 0:
+        print("transport: %s" % ctx.dist_transport(), flush=True)
     ctx.dist_upload(np.ascontiguousarray(state[mine]), mine)
 
     single = None
     if rank == 0:
         single = capi.Context(n, device=local)
-        if sub:
-            single.set_option("sub_cell_order", 1)
-            single.set_option("face_grid", 1)
+        if not sub:
+            single.set_option("sub_cell_order", 0)
         single.set_scene(normals, vertices, indices)
         single.set_parameters(p, terms)
         single.upload(state)
