@@ -266,6 +266,25 @@ def multi_gpu_workload(config, n_per_gpu, rank, world, sub_cell_order=True):
                 ghost_capacity=ghost_cap, capacity=int(1.2 * n) + 2 * layer + 2 * ghost_cap + 65536)
 
 
+def bind_to_gpu_numa(local_rank):
+    """Keeps this rank's threads (and with them its pinned host buffers, first touch) on the CPUs next to its GPU:
+    with eight ranks on one box the end-to-end copies otherwise all cross to one NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1}
+        allowed = set(os.sched_getaffinity(0)) & near
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     # stdout must carry exactly one JSON line: native libraries (NCCL's version banner) write to fd 1 too,
     # so everything goes to stderr until the line is ready
@@ -278,6 +297,7 @@ def run_ours(args, rank, world, local_rank):
     from libclsph_b200 import capi, workloads
 
     dist = None
+    near_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
@@ -446,7 +466,8 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * (80 if world == 1 else 84),
                "d2h_bytes_per_step": n * (80 if world == 1 else 84), "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "path": ("clsph_simulate_single_frame(host AoS in, host AoS out)" if world == 1 else
-                        "clsph_dist_upload + clsph_step + clsph_dist_download per rank") + ", pinned buffers"}
+                        "clsph_dist_upload + clsph_step + clsph_dist_download per rank") + ", pinned buffers",
+               "cpus_near_gpu": near_cpus}
     else:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "steps": 0,
                "path": "skipped (--e2e-steps 0)"}

@@ -72,6 +72,7 @@ struct clsph_context {
   bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
   bool merged_rows = true;      // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
   bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
+  int pair_variant = 5;             // option "pair_variant" (tuning): walk 0/1/2 + 3 x (entries stored two at a time)
   uint32_t* pair_items = nullptr;   // [capacity] items written by k_reorder_sub
   uint32_t* pair_count = nullptr;
   bool forces_dense = true;     // k_forces_lists<.., 4>: four resident CTAs per SM (option forces_blocks = 4)
@@ -446,7 +447,7 @@ int enqueue_substep(clsph_context* ctx) {
     } else {
       if (pairs)
         launch_density_pairs(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                             ctx->taps, ctx->debug, ctx->pair_items, ctx->pair_count, n, st, lc);
+                             ctx->taps, ctx->debug, ctx->pair_variant, ctx->pair_items, ctx->pair_count, n, st, lc);
       else
         launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
                            ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
@@ -725,6 +726,9 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     ctx->merged_rows = value != 0;
   } else if (!std::strcmp(name, "pair_density")) {
     ctx->pair_density = value != 0;
+  } else if (!std::strcmp(name, "pair_variant")) {
+    if (value < 0 || value > 5) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: pair_variant must be in [0, 5]");
+    ctx->pair_variant = (int)value;
   } else if (!std::strcmp(name, "fast_pairs")) {
     ctx->fast_pairs = value != 0;
   } else if (!std::strcmp(name, "forces_blocks")) {

@@ -342,7 +342,10 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
 // windows (they differ only within 2^-10 h of a sub-cell boundary); a candidate outside a particle's own window
 // is outside its support and adds an exact zero.
 // =============================================================================================
-template <bool kTaps>
+// kWalk: how a thread walks a row's candidates -- 0: one after the other; 1: the same with the next candidate's
+// load issued before the current one is tested; 2: four loads issued, then four tests. kStore2: list entries are
+// stored two at a time (one 8-byte store per two hits) instead of one by one.
+template <bool kTaps, int kWalk, bool kStore2>
 __global__ void __launch_bounds__(kSubThreads)
 k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
                 const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
@@ -392,35 +395,62 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     const bool in0 = f2_lo(s) < c.support_s, in1 = f2_hi(s) < c.support_s;
     const f32x2 w = f2_make(in0 ? f2_lo(d) : 0.f, in1 ? f2_hi(d) : 0.f);
     acc = f2_fma(f2_mul(w, w), w, acc);
-    // List entries leave two at a time: the pass is bound by L1 wavefronts, and every lane's store is a wavefront
-    // of its own (each lane writes its own row), so one 8-byte store per two hits halves that share. The first
-    // hit of a pair waits in a register (list_rows is even, rows are 8-byte aligned).
-    const bool odd0 = (cnt0 & 1u) != 0u, odd1 = (cnt1 & 1u) != 0u;
-    store2_if(in0 && odd0 && cnt0 < list_rows, row0 + (cnt0 - 1u), held0, j);
-    held0 = (in0 && !odd0) ? j : held0;
+    if (kStore2) {
+      // List entries leave two at a time: every lane's store is an L1 wavefront and a 32-byte L2 sector write of its
+      // own (each lane writes its own row), so one 8-byte store per two hits halves that. The first hit of a pair
+      // waits in a register (list_rows is even, rows are 8-byte aligned).
+      const bool odd0 = (cnt0 & 1u) != 0u, odd1 = (cnt1 & 1u) != 0u;
+      store2_if(in0 && odd0 && cnt0 < list_rows, row0 + (cnt0 - 1u), held0, j);
+      held0 = (in0 && !odd0) ? j : held0;
+      store2_if(in1 && odd1 && cnt1 < list_rows, row1 + (cnt1 - 1u), held1, j);
+      held1 = (in1 && !odd1) ? j : held1;
+    } else {
+      store_if(in0 && cnt0 < list_rows, row0 + cnt0, j);
+      store_if(in1 && cnt1 < list_rows, row1 + cnt1, j);
+    }
     cnt0 += in0 ? 1u : 0u;
-    store2_if(in1 && odd1 && cnt1 < list_rows, row1 + (cnt1 - 1u), held1, j);
-    held1 = (in1 && !odd1) ? j : held1;
     cnt1 += in1 ? 1u : 0u;
   };
-  // Candidate k of the row's two index ranges laid end to end. Four loads are issued before the first test: a
-  // thread walks ~160 candidates one after the other, and with one load in flight the pass waits on L1 / L2 latency.
+  // The row's two index ranges laid end to end. A thread walks ~160 candidates one after the other; with one load
+  // in flight the pass waits on L1 / L2 latency, hence the variants.
   auto walk = [&](uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
     const uint32_t la = a1 - a0, total = la + (b1 - b0);
-    const uint32_t shift = b0 - la;  // index = k + shift in the second range
-    uint32_t k = 0;
-    for (; k + 4u <= total; k += 4u) {
-      const uint32_t j0 = k < la ? a0 + k : k + shift, j1 = k + 1u < la ? a0 + k + 1u : k + 1u + shift,
-                     j2 = k + 2u < la ? a0 + k + 2u : k + 2u + shift, j3 = k + 3u < la ? a0 + k + 3u : k + 3u + shift;
-      const float4 q0 = pos[j0], q1 = pos[j1], q2 = pos[j2], q3 = pos[j3];
-      test(q0, j0);
-      test(q1, j1);
-      test(q2, j2);
-      test(q3, j3);
-    }
-    for (; k < total; ++k) {
-      const uint32_t j = k < la ? a0 + k : k + shift;
-      test(pos[j], j);
+    if (kWalk == 2) {
+      const uint32_t shift = b0 - la;  // index = k + shift in the second range
+      uint32_t k = 0;
+      for (; k + 4u <= total; k += 4u) {
+        const uint32_t j0 = k < la ? a0 + k : k + shift, j1 = k + 1u < la ? a0 + k + 1u : k + 1u + shift,
+                       j2 = k + 2u < la ? a0 + k + 2u : k + 2u + shift, j3 = k + 3u < la ? a0 + k + 3u : k + 3u + shift;
+        const float4 q0 = pos[j0], q1 = pos[j1], q2 = pos[j2], q3 = pos[j3];
+        test(q0, j0);
+        test(q1, j1);
+        test(q2, j2);
+        test(q3, j3);
+      }
+      for (; k < total; ++k) {
+        const uint32_t j = k < la ? a0 + k : k + shift;
+        test(pos[j], j);
+      }
+    } else if (kWalk == 1) {
+      if (total == 0u) return;
+      uint32_t j = a0 < a1 ? a0 : b0;
+      float4 cur = pos[j];
+      for (uint32_t k = 1; k < total; ++k) {
+        uint32_t jn = j + 1u;
+        if (jn == a1) jn = b0;  // end of the first range: continue in the second
+        const float4 nxt = pos[jn];
+        test(cur, j);
+        cur = nxt;
+        j = jn;
+      }
+      test(cur, j);
+    } else {
+      uint32_t j = a0 < a1 ? a0 : b0;
+      for (uint32_t k = 0; k < total; ++k) {
+        test(pos[j], j);
+        ++j;
+        if (j == a1) j = b0;
+      }
     }
   };
   const uint32_t cx_lo = xlo >> 1, cx_hi = xhi >> 1;
@@ -438,9 +468,10 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
       }
     }
   }
-  // the last hit of an odd count is still held
-  if ((cnt0 & 1u) && cnt0 - 1u < list_rows) row0[cnt0 - 1u] = held0;
-  if (two && (cnt1 & 1u) && cnt1 - 1u < list_rows) row1[cnt1 - 1u] = held1;
+  if (kStore2) {  // the last hit of an odd count is still held
+    if ((cnt0 & 1u) && cnt0 - 1u < list_rows) row0[cnt0 - 1u] = held0;
+    if (two && (cnt1 & 1u) && cnt1 - 1u < list_rows) row1[cnt1 - 1u] = held1;
+  }
   if (need0) {
     finish_density(c, f2_lo(acc), i0, aux, pos, vel);
     ncount[i0] = cnt0;
@@ -644,17 +675,29 @@ if (debug && deferred)
 
 void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                           const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                          const DebugTaps& taps, bool debug, const uint32_t* pair_items, const uint32_t* pair_count,
+                          const DebugTaps& taps, bool debug, int variant, const uint32_t* pair_items, const uint32_t* pair_count,
                           uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
   // the item count lives on the device (between n / 2 and n): sized for the worst case, surplus blocks leave at once
   const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
-  if (debug)
-    k_density_pairs<true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries,
-                                                              lists.count, lists.rows, taps.candidate_count, taps.support_count,
-                                                              pair_items, pair_count);
-  else
-    k_density_pairs<false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries,
-                                                               lists.count, lists.rows, nullptr, nullptr, pair_items, pair_count);
+  uint32_t* cand = debug ? taps.candidate_count : nullptr;
+  uint32_t* supp = debug ? taps.support_count : nullptr;
+#define CLSPH_PAIRS(TAPS, WALK, ST2)                                                                                               \
+  k_density_pairs<TAPS, WALK, ST2><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, \
+                                                                       lists.entries, lists.count, lists.rows, cand, supp, pair_items, \
+                                                                       pair_count)
+  if (debug) {
+    CLSPH_PAIRS(true, 2, true);
+  } else {
+    switch (variant) {
+      case 0: CLSPH_PAIRS(false, 0, false); break;
+      case 1: CLSPH_PAIRS(false, 1, false); break;
+      case 2: CLSPH_PAIRS(false, 2, false); break;
+      case 3: CLSPH_PAIRS(false, 0, true); break;
+      case 4: CLSPH_PAIRS(false, 1, true); break;
+      default: CLSPH_PAIRS(false, 2, true); break;
+    }
+  }
+#undef CLSPH_PAIRS
   if (launches) ++*launches;
 }
 
