@@ -108,34 +108,39 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
                          const precomputed_kernel_values* terms);
 
 /* Tuning knobs; results are the same (to rounding) whatever they are set to. The environment variable
- * CLSPH_OPTIONS="name=value,name=value" applies such pairs to every context at creation.
- *   "neighbour_lists"  1 (default): the density pass stores per-particle neighbour lists in HBM
- *                      and the force pass reads them; 0: both passes search on their own.
- *                      (Environment override at creation: CLSPH_NEIGHBOUR_LISTS=0/1.)
- *   "list_rows"        list entries kept per particle (0 = derive from the rest density);
- *                      particles with more neighbours fall back to the searching force kernel.
- *   "sub_cell_order"   1: keep the arrays in HBM sorted by (cell key << 3 | octant of the cell), so
+ * CLSPH_OPTIONS="name=value,name=value" applies such pairs to every context at creation. The defaults are the
+ * organisation measured fastest on a B200 (profiles/r02_*); the others are kept as fallbacks and for A/B runs.
+ *   "sub_cell_order"   1 (default): keep the arrays in HBM sorted by (cell key << 3 | octant of the cell), so
  *                      that each particle searches the ~27 sub-cells of side h around it (~130
  *                      candidates) instead of the 27 cells of side 2h (~1000). The reference's array
  *                      order is carried as a per-particle rank; downloads and taps are in the
- *                      reference's order exactly as with 0 (default this round: 0).
- *                      Needs a grid whose Morton cell count stays below 2^29 (z axis < 512 cells);
- *                      set it before particles are uploaded. (Environment: CLSPH_SUB_CELL_ORDER.)
- *   "deferred_lists"   (with sub_cell_order) 1: the density pass collects the hits of up to 32 consecutive
- *                      candidates in a bit mask and writes the list entries in a short loop afterwards,
- *                      instead of one predicated store per candidate. Same lists, same order. Default 0.
- *   "merged_rows"      (with sub_cell_order) 1: the density pass walks the two index ranges of each row of
- *                      sub-cells in one loop, which evens out the loop lengths between the lanes of a warp
- *                      (164 instead of 216 candidate slots per lane on the bench states). Default 0.
- *   "fast_pairs"       1: the list force kernel evaluates each pair with one MUFU.RSQ in place of the IEEE
+ *                      reference's order exactly as with 0.
+ *                      Needs a grid whose Morton cell count stays below 2^29 (z axis < 512 cells; larger grids
+ *                      report CLSPH_EGRID and want 0); set it before particles are uploaded.
+ *                      0: the established organisation on whole cells (k_density_lists / k_forces_lists).
+ *   "pair_density"     (with sub_cell_order) 1 (default): the density pass handles two particles of a sub-cell per
+ *                      thread with packed fp32 arithmetic (FADD2 / FFMA2), bitwise the same results as 0
+ *                      (one particle per thread). "pair_variant" 0..5 selects how a thread walks its candidates
+ *                      (one by one / next load ahead / four loads ahead) and whether list entries are stored
+ *                      one or two at a time; 5 (default) = four ahead, in twos.
+ *   "merged_rows"      (pair_density = 0) 1 (default): the density pass walks the two index ranges of each row of
+ *                      sub-cells in one loop, which evens out the loop lengths between the lanes of a warp.
+ *   "deferred_lists"   (pair_density = 0) 1: hits of up to 32 consecutive candidates are collected in a bit mask
+ *                      and the list entries written in a short loop afterwards. Same lists. Default 0.
+ *   "tile_kernels"     1: density pass on blocks of 2 x 2 x 2 cells staged in shared memory by bulk copies
+ *                      (tiles.cu). Correct, not faster than the default on a B200 (profiles/r02_b, r02_d). Default 0.
+ *   "neighbour_lists"  (sub_cell_order = 0) 1 (default): the density pass stores per-particle neighbour lists in HBM
+ *                      and the force pass reads them; 0: both passes search on their own.
+ *   "list_rows"        list entries kept per particle (0 = derive from the rest density; rounded up to even);
+ *                      particles with more neighbours fall back to the searching force kernel.
+ *   "fast_pairs"       1 (default): the list force kernel evaluates each pair with one MUFU.RSQ in place of the IEEE
  *                      square root and divide (~2 ulp, far inside the 1e-4 bar; the |r| < 1e-7 decision
- *                      stays exact). Default 0.
- *   "forces_blocks"    3 (default) or 4: resident CTAs per SM the list force kernel is compiled for
+ *                      stays exact). 0: the reference's operation sequence.
+ *   "forces_blocks"    4 (default) or 3: resident CTAs per SM the list force kernel is compiled for
  *                      (4 = 64 registers per thread, a third more warps to hide gather latency).
- *   "face_grid"        1: the collision pass tests only the scene triangles registered in the grid
+ *   "face_grid"        1 (default): the collision pass tests only the scene triangles registered in the grid
  *                      cells a particle's sub-step segment touches (conservative registration:
- *                      results are bit-identical to testing every triangle). Default 0 this round.
- *                      (Environment: CLSPH_FACE_GRID.) */
+ *                      results are bit-identical to testing every triangle, 0). */
 int clsph_set_option(clsph_context* ctx, const char* name, long long value);
 
 /* Host AoS (80-byte records) -> device SoA. n must be >= 128 (sort.cl:9-20, erratum E8) and

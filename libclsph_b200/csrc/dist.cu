@@ -160,7 +160,7 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
                 uint32_t gmax) {
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((i & ~31u) >= g.n) return;  // whole warp out of range
+  if (blockIdx.x * blockDim.x >= g.n) return;  // whole CTA out of range
   bool owned = i < g.n;
   if (owned && !g.fresh) {
     if (g.sub) {
@@ -206,7 +206,7 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   const bool ghost_right = stay && has_right && (g.sub ? p.x >= g.plane_hi - depth : cx >= g.own_hi - 2);
 
   // local array: stayers as owned, emigrants as ghost copies (their new key marks them as such)
-  const uint32_t at = warp_append(owned, u_count);
+  const uint32_t at = block256_append(owned, u_count);
   if (owned) {
     if (at < capacity) {
       u_pos[at] = p; u_vel[at] = v; u_ivel[at] = iv; u_pid[at] = id;

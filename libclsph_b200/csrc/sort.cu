@@ -15,6 +15,8 @@
 //
 // Algorithmic traffic per particle: keys 16 B read + 4 B write + 4 B re-read for the histogram
 // accounting of SURVEY 8(d) (here fused: the key never leaves registers), then 16 B per pass.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace clsph {
@@ -111,13 +113,18 @@ __global__ void __launch_bounds__(256) k_scan_hist(const uint32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // One onesweep pass.
 // ---------------------------------------------------------------------------------------------
+// kItems keys per thread: tiles of 256 * kItems keys. 16 amortises the look-back best when the pass is bandwidth
+// bound (tens of millions of keys); 8 doubles the CTAs and halves each CTA's chain of ranking steps, which is what
+// a pass over one or two million keys -- a single wave of CTAs, latency bound -- is made of.
+template <int kItems>
 __global__ void __launch_bounds__(kSortThreads)
 k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out, const GridState* __restrict__ grid, const uint32_t* __restrict__ digit_base,
            uint32_t* __restrict__ tile_counter, volatile uint32_t* status, int pass) {
   constexpr int kWarps = kSortThreads / 32;
-  __shared__ uint32_t s_keys[kSortTile];
-  __shared__ uint32_t s_vals[kSortTile];
+  constexpr int kTile = kSortThreads * kItems;
+  __shared__ uint32_t s_keys[kTile];
+  __shared__ uint32_t s_vals[kTile];
   __shared__ uint32_t s_warp_hist[kWarps][kRadix];
   __shared__ uint32_t s_digit_start[kRadix];
   __shared__ uint32_t s_digit_global[kRadix];
@@ -133,26 +140,26 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
   for (int i = tid; i < kWarps * kRadix; i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
-  const uint64_t tile_base64 = (uint64_t)tile * kSortTile;
+  const uint64_t tile_base64 = (uint64_t)tile * kTile;
   if (tile_base64 >= n) return;
   const uint32_t tile_base = (uint32_t)tile_base64;
   const int shift = 8 * pass;
   digit_base += pass * kRadix;
   status += (size_t)pass * gridDim.x * kRadix;
 
-  // Each warp owns a contiguous run of 32*kSortItems keys and walks it 32 at a time: tile order
+  // Each warp owns a contiguous run of 32*kItems keys and walks it 32 at a time: tile order
   // = (warp, round, lane), which is what makes the ranks stable.
-  uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
-  const uint32_t warp_base = tile_base + warp * (32 * kSortItems);
+  uint32_t key[kItems], val[kItems], rank[kItems];
+  const uint32_t warp_base = tile_base + warp * (32 * kItems);
 #pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
+  for (int k = 0; k < kItems; ++k) {
     const uint32_t idx = warp_base + k * 32 + lane;
     const bool ok = idx < n;
     key[k] = ok ? keys_in[idx] : 0xFFFFFFFFu;  // padding sorts to the very end of the tile
     val[k] = (vals_in != nullptr && ok) ? vals_in[idx] : idx;
   }
 #pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
+  for (int k = 0; k < kItems; ++k) {
     const uint32_t d = (key[k] >> shift) & 0xFFu;
     const unsigned peers = __match_any_sync(kFullMask, d);
     const int leader = __ffs(peers) - 1;
@@ -202,14 +209,14 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
 
   // Scatter inside shared memory to tile-sorted order, then stream out coalesced runs.
 #pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
+  for (int k = 0; k < kItems; ++k) {
     const uint32_t d = (key[k] >> shift) & 0xFFu;
     const uint32_t at = s_digit_start[d] + s_warp_hist[warp][d] + rank[k];
     s_keys[at] = key[k];
     s_vals[at] = val[k];
   }
   __syncthreads();
-  const uint32_t tile_n = min((uint32_t)kSortTile, n - tile_base);
+  const uint32_t tile_n = min((uint32_t)kTile, n - tile_base);
   for (uint32_t i = tid; i < tile_n; i += kSortThreads) {
     const uint32_t k = s_keys[i];
     const uint32_t at = s_digit_global[(k >> shift) & 0xFFu] + i;
@@ -221,11 +228,21 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
 // ---------------------------------------------------------------------------------------------
 // Host-side launchers
 // ---------------------------------------------------------------------------------------------
-uint32_t sort_tiles_for(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
+// Keys per thread of a onesweep tile for n keys (see k_onesweep). CLSPH_SORT_ITEMS=8|16 overrides (tuning).
+static int sort_items_for(uint32_t n) {
+  static const int forced = [] { const char* e = getenv("CLSPH_SORT_ITEMS"); return e ? atoi(e) : 0; }();
+  if (forced == 8 || forced == 16) return forced;
+  return n <= (1u << 22) ? 8 : 16;
+}
+uint32_t sort_tiles_for(uint32_t n) {
+  const uint32_t tile = (uint32_t)kSortThreads * (uint32_t)sort_items_for(n);
+  return (n + tile - 1) / tile;
+}
 
 size_t sort_scratch_words(uint32_t max_particles) {
   // hist[4][256] + digit_base[4][256] + tile_counter[4] (padded to 64) + status[4][tiles][256]
-  return (size_t)2 * kMaxSortPasses * kRadix + 64 + (size_t)kMaxSortPasses * sort_tiles_for(max_particles) * kRadix;
+  const uint32_t most_tiles = (max_particles + kSortThreads * 8u - 1u) / (kSortThreads * 8u);  // the smaller tile
+  return (size_t)2 * kMaxSortPasses * kRadix + 64 + (size_t)kMaxSortPasses * most_tiles * kRadix;
 }
 
 namespace {
@@ -266,10 +283,14 @@ void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_
   // pass 0: a -> b (identity payload), pass 1: b -> a, pass 2: a -> b, pass 3: b -> a
   for (int pass = 0; pass < kMaxSortPasses; ++pass) {
     const bool even = (pass & 1) == 0;
-    k_onesweep<<<tiles, kSortThreads, 0, stream>>>(even ? b.keys_a : b.keys_b,
-                                                   pass == 0 ? nullptr : (even ? b.vals_a : b.vals_b),
-                                                   even ? b.keys_b : b.keys_a, even ? b.vals_b : b.vals_a, grid,
-                                                   l.digit_base, l.tile_counter, l.status, pass);
+    if (sort_items_for(n_launch) == 8)
+      k_onesweep<8><<<tiles, kSortThreads, 0, stream>>>(even ? b.keys_a : b.keys_b, pass == 0 ? nullptr : (even ? b.vals_a : b.vals_b),
+                                                        even ? b.keys_b : b.keys_a, even ? b.vals_b : b.vals_a, grid, l.digit_base,
+                                                        l.tile_counter, l.status, pass);
+    else
+      k_onesweep<16><<<tiles, kSortThreads, 0, stream>>>(even ? b.keys_a : b.keys_b, pass == 0 ? nullptr : (even ? b.vals_a : b.vals_b),
+                                                         even ? b.keys_b : b.keys_a, even ? b.vals_b : b.vals_a, grid, l.digit_base,
+                                                         l.tile_counter, l.status, pass);
   }
   if (launches) *launches += 1 + kMaxSortPasses;
 }

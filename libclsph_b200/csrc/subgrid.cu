@@ -673,6 +673,28 @@ if (debug && deferred)
   if (launches) ++*launches;
 }
 
+namespace {
+struct PairArgs {
+  float4 *pos, *vel;
+  const uint32_t *skey, *sub_lb, *keys_a, *keys_b;
+  const GridState* grid;
+  SphConst c;
+  float4* aux;
+  uint32_t *nlist, *ncount;
+  uint32_t list_rows;
+  uint32_t *cand, *supp;
+  const uint32_t *pair_items, *pair_count;
+  unsigned blocks;
+  cudaStream_t stream;
+};
+template <bool kTaps, int kWalk, bool kStore2>
+void launch_pairs_variant(const PairArgs& a) {
+  k_density_pairs<kTaps, kWalk, kStore2><<<a.blocks, kSubThreads, 0, a.stream>>>(a.pos, a.vel, a.skey, a.sub_lb, a.keys_a, a.keys_b, a.grid, a.c, a.aux,
+                                                                                 a.nlist, a.ncount, a.list_rows, a.cand, a.supp, a.pair_items,
+                                                                                 a.pair_count);
+}
+}  // namespace
+
 void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                           const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
                           const DebugTaps& taps, bool debug, int variant, const uint32_t* pair_items, const uint32_t* pair_count,
@@ -681,23 +703,20 @@ void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const 
   const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
   uint32_t* cand = debug ? taps.candidate_count : nullptr;
   uint32_t* supp = debug ? taps.support_count : nullptr;
-#define CLSPH_PAIRS(TAPS, WALK, ST2)                                                                                               \
-  k_density_pairs<TAPS, WALK, ST2><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, \
-                                                                       lists.entries, lists.count, lists.rows, cand, supp, pair_items, \
-                                                                       pair_count)
+  const PairArgs a{pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries, lists.count, lists.rows, cand, supp,
+                   pair_items, pair_count, blocks, stream};
   if (debug) {
-    CLSPH_PAIRS(true, 2, true);
+    launch_pairs_variant<true, 2, true>(a);
   } else {
     switch (variant) {
-      case 0: CLSPH_PAIRS(false, 0, false); break;
-      case 1: CLSPH_PAIRS(false, 1, false); break;
-      case 2: CLSPH_PAIRS(false, 2, false); break;
-      case 3: CLSPH_PAIRS(false, 0, true); break;
-      case 4: CLSPH_PAIRS(false, 1, true); break;
-      default: CLSPH_PAIRS(false, 2, true); break;
+      case 0: launch_pairs_variant<false, 0, false>(a); break;
+      case 1: launch_pairs_variant<false, 1, false>(a); break;
+      case 2: launch_pairs_variant<false, 2, false>(a); break;
+      case 3: launch_pairs_variant<false, 0, true>(a); break;
+      case 4: launch_pairs_variant<false, 1, true>(a); break;
+      default: launch_pairs_variant<false, 2, true>(a); break;
     }
   }
-#undef CLSPH_PAIRS
   if (launches) ++*launches;
 }
 

@@ -162,4 +162,24 @@ __device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
   return base + __popc(m & lanemask_lt());
 }
 
+// The same for a whole CTA of 256 threads (all of them must call it): ONE atomicAdd per CTA. With a million
+// appending threads the per-warp form sends tens of thousands of atomics to one address, and that queue, not
+// the copy, is what the kernel then waits for. Slots follow thread order inside the CTA.
+__device__ __forceinline__ uint32_t block256_append(bool want, uint32_t* counter) {
+  __shared__ uint32_t s_warp[8], s_base;
+  const unsigned m = __ballot_sync(kFullMask, want);
+  const unsigned warp = threadIdx.x >> 5;
+  if (lane_id() == 0u) s_warp[warp] = (uint32_t)__popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int w = 0; w < 8; ++w) { const uint32_t c = s_warp[w]; s_warp[w] = total; total += c; }
+    s_base = total ? atomicAdd(counter, total) : 0u;
+  }
+  __syncthreads();
+  const uint32_t at = s_base + s_warp[warp] + (uint32_t)__popc(m & lanemask_lt());
+  __syncthreads();  // the shared words are reused by the next call
+  return at;
+}
+
 }  // namespace clsph

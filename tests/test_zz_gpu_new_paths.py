@@ -99,6 +99,36 @@ def test_one_million_particles_config2_sub_cell_order(box_scene):
     assert np.array_equal(np.sort(taps["permutation"]), np.arange(s.size, dtype=np.uint32))
 
 
+def _scene(name):
+    return O.load_obj(os.path.join(H.ROOT, "scenes", name))
+
+
+def test_river_scene_full_step_against_the_oracle():
+    """Config 4's scene (river.obj) at a size the oracle steps in seconds: the whole sub-step, every integer
+    observable bit-exact, floats within 1e-4 (also per element)."""
+    p, terms, vol, scene_file = workloads.make_config(fluid="water", particles_count=98304, particle_mass=0.05)
+    s = workloads.jittered_state(p, vol)
+    G.check_against_oracle(s, p, terms, _scene("river.obj"), "river.obj, 96 Ki water")
+
+
+def test_plane_scene_sweep_state_against_the_oracle():
+    """The scaling sweep's workload (uniform block over plane.obj, config 5) at 256 Ki particles, several resident steps."""
+    p, terms, vol, scene_file = workloads.make_config(fluid="water", particles_count=262144, particle_mass=0.05)
+    s = workloads.jittered_state(p, vol)
+    scene = _scene("plane.obj")
+    G.check_against_oracle(s, p, terms, scene, "plane.obj sweep block, 256 Ki")
+    G.check_resident_steps_against_oracle(s, p, terms, scene, 3, "plane.obj sweep block, resident")
+
+
+def test_four_million_mucus_in_the_labyrinth_against_the_oracle():
+    """Config 3 at its full size against the ORACLE (about half a minute of host time): keys, permutation, cell
+    table, candidate / support counts, collision trips bit-exact; densities, accelerations, positions within 1e-4."""
+    p, terms, vol, scene_file = workloads.make_config("config3_mucus_labyrinth_4m")
+    s = workloads.jittered_state(p, vol)
+    got, taps, want = G.check_against_oracle(s, p, terms, _scene(scene_file), "config 3, 4 Mi mucus in labyrinth.obj")
+    assert np.array_equal(np.sort(taps["permutation"]), np.arange(s.size, dtype=np.uint32))
+
+
 def test_organisations_agree_on_the_device_at_four_million():
     """Config 3 size (4 Mi, mucus, labyrinth): the new paths against the established one, bit for bit
     on every integer observable and the exported order, to rounding on the rest."""
