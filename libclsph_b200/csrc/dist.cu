@@ -34,7 +34,7 @@
 // processes) steps 1 and 3 do not call NCCL at all: every rank owns a MAILBOX in its HBM that the others map.
 //   * k_dist_classify stores the emigrant and ghost records straight into the neighbour's mailbox while it
 //     compacts the local array -- the transfer is the kernel's own stores, overlapping its other work, and only the
-//     records that exist travel; k_dist_signal then publishes the counts and the sub-step's sequence number
+//     records that exist travel; its last CTA then publishes the counts and the sub-step's sequence number
 //     (release at system scope), k_dist_unpack waits for that number (acquire) before it reads;
 //   * the AABB travels the same way: k_bounds_publish stores the six accumulators of a rank into a slot of every
 //     mailbox right after the integrator has produced them (the end of the PREVIOUS sub-step, so the stores are long
@@ -125,6 +125,20 @@ struct MsgOut {
   float4* ghosts;
 };
 
+// Peer transport: the last CTA of k_dist_classify to finish publishes the counts and the sequence number.
+struct PeerSignal {
+  uint32_t* done;          // ticket counter (null: NCCL transport, nothing to publish)
+  uint32_t* header_left;   // header of my message in the left / right neighbour's mailbox (null: no such neighbour)
+  uint32_t* header_right;
+  uint32_t seq;
+};
+// One received message for k_dist_unpack.
+struct MsgIn {
+  const uint32_t* header;  // emigrants, ghosts, sequence number (null: no neighbour on this side)
+  const float4* emigrants;
+  const float4* ghosts;
+};
+
 // Mailbox of a rank (peer transport), mapped by every other rank:
 //   [0, 2048)     AABB slots [parity][source rank][8 words]: lo[3], hi[3], sequence number, pad
 //   [2048, 2112)  message headers [side][8 words]: emigrants, ghosts, sequence number; side 0 = from the left neighbour
@@ -151,16 +165,30 @@ const char* dist_last_error() { return g_nccl_error; }
 // ---------------------------------------------------------------------------------------------
 // Kernels
 // ---------------------------------------------------------------------------------------------
+// ---- peer transport: flags and waits ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_flag(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void store_flag(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+// Waits until *flag == want. Gives up after kSpinLimit clock ticks (a peer that died must not hang this GPU).
+constexpr long long kSpinLimit = 20000000000ll;
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t want, long long limit = kSpinLimit) {
+  const long long t0 = clock64();
+  while (load_flag(flag) != want)
+    if (clock64() - t0 > limit) return false;
+  __threadfence_system();  // acquire: what the peer stored before the flag is visible from here on
+  return true;
+}
+
 __global__ void __launch_bounds__(256)
 k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ ivel,
                 const uint32_t* __restrict__ pid, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ wrank,
                 GridState* grid, float4* __restrict__ u_pos, float4* __restrict__ u_vel, float4* __restrict__ u_ivel,
                 uint32_t* __restrict__ u_pid, uint32_t* __restrict__ u_ordk, uint32_t* __restrict__ u_ordr,
                 uint32_t* __restrict__ u_count, uint32_t capacity, const MsgOut left, const MsgOut right, uint32_t emax,
-                uint32_t gmax) {
+                uint32_t gmax, const PeerSignal sig) {
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x * blockDim.x >= g.n) return;  // whole CTA out of range
+  bool stored_remotely = false;
+  if (blockIdx.x * blockDim.x < g.n) {  // (a CTA wholly out of range only takes part in the signalling below)
   bool owned = i < g.n;
   if (owned && !g.fresh) {
     if (g.sub) {
@@ -240,31 +268,22 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
     if (e < gmax) { float4* r = right.ghosts + (size_t)e * 2; r[0] = gp; r[1] = gv; }
     else atomicOr(&grid->error, 2u);
   }
-}
-
-// ---- peer transport: flags and waits ---------------------------------------------------------------------
-__device__ __forceinline__ uint32_t load_flag(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
-__device__ __forceinline__ void store_flag(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
-// Waits until *flag == want. Gives up after kSpinLimit clock ticks (a peer that died must not hang this GPU).
-constexpr long long kSpinLimit = 20000000000ll;
-__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t want, long long limit = kSpinLimit) {
-  const long long t0 = clock64();
-  while (load_flag(flag) != want)
-    if (clock64() - t0 > limit) return false;
-  __threadfence_system();  // acquire: what the peer stored before the flag is visible from here on
-  return true;
-}
-
-// After k_dist_classify (stream order): the records are stored, now the counts and the sequence number.
-__global__ void k_dist_signal(const uint32_t* counts_left, const uint32_t* counts_right, uint32_t* header_left,
-                              uint32_t* header_right, uint32_t seq) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  __threadfence_system();  // release: everything this rank has stored so far precedes the flags
-  if (header_left) { store_flag(header_left, counts_left[0]); store_flag(header_left + 1, counts_left[1]); }
-  if (header_right) { store_flag(header_right, counts_right[0]); store_flag(header_right + 1, counts_right[1]); }
+  stored_remotely = go_left || go_right || ghost_left || ghost_right;
+  }
+  if (!sig.done) return;
+  // Peer transport: the records are in the neighbours' mailboxes once every CTA has passed this point; the last
+  // one to arrive publishes the counts, then the sequence number the receivers wait for (release at system scope).
+  if (stored_remotely) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   __threadfence_system();
-  if (header_left) store_flag(header_left + 2, seq);
-  if (header_right) store_flag(header_right + 2, seq);
+  if (atomicAdd(sig.done, 1u) != gridDim.x - 1u) return;
+  __threadfence_system();
+  if (sig.header_left) { store_flag(sig.header_left, atomicAdd(left.counts, 0u)); store_flag(sig.header_left + 1, atomicAdd(left.counts + 1, 0u)); }
+  if (sig.header_right) { store_flag(sig.header_right, atomicAdd(right.counts, 0u)); store_flag(sig.header_right + 1, atomicAdd(right.counts + 1, 0u)); }
+  __threadfence_system();
+  if (sig.header_left) store_flag(sig.header_left + 2, sig.seq);
+  if (sig.header_right) store_flag(sig.header_right + 2, sig.seq);
 }
 
 // The six AABB accumulators of this rank into slot [parity of seq][rank] of every rank's mailbox (its own too).
@@ -306,25 +325,34 @@ __global__ void k_bounds_gather(BoundsAcc* acc, void* mailbox, int world, uint32
     for (int a = 0; a < 3; ++a) { acc->lo[a] = lo[a]; acc->hi[a] = hi[a]; }
 }
 
-// Appends one received message: its emigrants become owned particles here, its ghosts are
-// candidates for the neighbour passes. Thread t < emax handles emigrant t, the rest ghost t - emax.
-// wait_seq != 0 (peer transport): the message is complete when header[2] == wait_seq.
+// Appends the received messages: their emigrants become owned particles here, their ghosts are candidates for
+// the neighbour passes. The first half of the grid serves the message from the left, the second half the one from
+// the right; in a message, thread t < emax handles emigrant t, the rest ghost t - emax.
+// wait_seq != 0 (peer transport): a message is complete when header[2] == wait_seq.
+// The last CTA to finish publishes the local particle count (what k_dist_finish does otherwise) and re-arms the
+// counters of the exchange for the next sub-step.
 __global__ void __launch_bounds__(256)
-k_dist_unpack(const uint32_t* header, const float4* emigrants, const float4* ghosts, uint32_t wait_seq, uint32_t emax, uint32_t gmax,
+k_dist_unpack(const MsgIn from_left, const MsgIn from_right, uint32_t wait_seq, uint32_t emax, uint32_t gmax,
               GridState* grid, float4* __restrict__ u_pos,
               float4* __restrict__ u_vel, float4* __restrict__ u_ivel, uint32_t* __restrict__ u_pid,
-              uint32_t* __restrict__ u_ordk, uint32_t* __restrict__ u_ordr, uint32_t* __restrict__ u_count,
+              uint32_t* __restrict__ u_ordk, uint32_t* __restrict__ u_ordr, uint32_t* counters,
               uint32_t capacity) {
   __shared__ uint32_t s_counts[2];
+  uint32_t* u_count = counters;
+  const unsigned half = gridDim.x >> 1;
+  const bool right = blockIdx.x >= half;
+  const MsgIn msg = right ? from_right : from_left;
   if (threadIdx.x == 0) {
-    bool ok = true;
-    if (wait_seq) ok = wait_flag(header + 2, wait_seq);
-    if (!ok) atomicOr(&grid->error, 8u);
-    s_counts[0] = ok ? load_flag(header) : 0u;
-    s_counts[1] = ok ? load_flag(header + 1) : 0u;
+    bool ok = msg.header != nullptr;
+    if (ok && wait_seq) {
+      ok = wait_flag(msg.header + 2, wait_seq);
+      if (!ok) atomicOr(&grid->error, 8u);
+    }
+    s_counts[0] = ok ? load_flag(msg.header) : 0u;
+    s_counts[1] = ok ? load_flag(msg.header + 1) : 0u;
   }
   __syncthreads();
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = (blockIdx.x - (right ? half : 0u)) * blockDim.x + threadIdx.x;
   const uint32_t ne = min(s_counts[0], emax), ng = min(s_counts[1], gmax);
   const bool is_e = t < ne;
   const bool is_g = t >= emax && t - emax < ng;
@@ -332,13 +360,13 @@ k_dist_unpack(const uint32_t* header, const float4* emigrants, const float4* gho
   uint32_t id = 0xFFFFFFFFu;  // ghosts carry no identity here
   uint32_t ok_k = 0xFFFFFFFFu, ok_r = 0u;  // ... and, without order keys, no place in the reference's order
   if (is_e) {
-    const float4* r = emigrants + (size_t)t * 4;  // (L2 loads: the lines were written from outside this SM's L1)
+    const float4* r = msg.emigrants + (size_t)t * 4;  // (L2 loads: the lines were written from outside this SM's L1)
     p = __ldcg(r); v = __ldcg(r + 1); iv = __ldcg(r + 2);
     const float4 tag = __ldcg(r + 3);
     id = __float_as_uint(tag.x);
     ok_k = __float_as_uint(tag.y); ok_r = __float_as_uint(tag.z);
   } else if (is_g) {
-    const float4* r = ghosts + (size_t)(t - emax) * 2;
+    const float4* r = msg.ghosts + (size_t)(t - emax) * 2;
     p = __ldcg(r); v = __ldcg(r + 1);
     if (u_ordk) {  // the sender's order keys, see k_dist_classify
       ok_k = __float_as_uint(p.w); ok_r = __float_as_uint(v.w);
@@ -352,12 +380,24 @@ k_dist_unpack(const uint32_t* header, const float4* emigrants, const float4* gho
       if (u_ordk) { u_ordk[at] = ok_k; u_ordr[at] = ok_r; }
     } else atomicOr(&grid->error, 2u);
   }
+  // the last CTA: local particle count, counters back to zero (counters[1], the export count, is not ours)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (atomicAdd(counters + 3, 1u) != gridDim.x - 1u) return;
+  __threadfence();
+  grid->n = min(atomicAdd(u_count, 0u), capacity);
+  grid->fresh = 0u;
+  counters[0] = 0u; counters[2] = 0u; counters[3] = 0u;
+  counters[4] = 0u; counters[5] = 0u; counters[6] = 0u; counters[7] = 0u;
 }
 
-__global__ void k_dist_finish(GridState* grid, const uint32_t* u_count, uint32_t capacity) {
+__global__ void k_dist_finish(GridState* grid, uint32_t* counters, uint32_t capacity) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    grid->n = min(*u_count, capacity);
+    grid->n = min(counters[0], capacity);
     grid->fresh = 0u;
+    counters[0] = 0u; counters[2] = 0u; counters[3] = 0u;
+    counters[4] = 0u; counters[5] = 0u; counters[6] = 0u; counters[7] = 0u;
   }
 }
 
@@ -599,46 +639,47 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
                   const uint32_t* wrank, GridState* grid, const StateArrays& u, uint32_t* u_pid, uint32_t* u_ordk,
                   uint32_t* u_ordr, uint32_t capacity, cudaStream_t stream, uint64_t* launches) {
   ncclComm_t comm = static_cast<ncclComm_t>(d->comm);
+  // counters (zero at the start of every exchange: the last kernel of the previous one re-arms them):
+  // [0] local count, [1] export count (clsph_dist_download), [2] / [3] CTAs done in classify / unpack,
+  // [4..5] emigrants, ghosts to the left, [6..7] to the right
   uint32_t* u_count = d->counters;
   const bool has_left = d->rank > 0, has_right = d->rank + 1 < d->world;
   const unsigned blocks = (capacity + 255) / 256;
   const unsigned ublocks = (d->emax + d->gmax + 255) / 256;
   if (d->peer) {
-    // counters: [0] local count, [1] export count, [4..5] to the left, [6..7] to the right
     timing_mark(stream);
-    cudaMemsetAsync(d->counters, 0, 32, stream);
     // my left neighbour receives "from its right" (side 1), my right neighbour "from its left" (side 0)
     void* lbox = has_left ? d->peer_mailbox[d->rank - 1] : d->mailbox;  // (without a neighbour nothing is ever appended)
     void* rbox = has_right ? d->peer_mailbox[d->rank + 1] : d->mailbox;
     const MsgOut left{d->counters + 4, mailbox_emigrants(lbox, 1, d->emax, d->gmax), mailbox_ghosts(lbox, 1, d->emax, d->gmax)};
     const MsgOut right{d->counters + 6, mailbox_emigrants(rbox, 0, d->emax, d->gmax), mailbox_ghosts(rbox, 0, d->emax, d->gmax)};
+    const PeerSignal sig{d->counters + 2, has_left ? mailbox_header(lbox, 1) : nullptr, has_right ? mailbox_header(rbox, 0) : nullptr, d->seq};
     k_dist_classify<<<blocks, 256, 0, stream>>>(prev.pos, prev.vel, prev.ivel, prev_pid, skey, wrank, grid, u.pos, u.vel, u.ivel,
-                                                u_pid, u_ordk, u_ordr, u_count, capacity, left, right, d->emax, d->gmax);
+                                                u_pid, u_ordk, u_ordr, u_count, capacity, left, right, d->emax, d->gmax, sig);
     timing_mark(stream);
-    k_dist_signal<<<1, 32, 0, stream>>>(d->counters + 4, d->counters + 6, has_left ? mailbox_header(lbox, 1) : nullptr,
-                                        has_right ? mailbox_header(rbox, 0) : nullptr, d->seq);
     timing_mark(stream);
-    if (has_left)
-      k_dist_unpack<<<ublocks, 256, 0, stream>>>(mailbox_header(d->mailbox, 0), mailbox_emigrants(d->mailbox, 0, d->emax, d->gmax),
-                                                 mailbox_ghosts(d->mailbox, 0, d->emax, d->gmax), d->seq, d->emax, d->gmax, grid, u.pos,
-                                                 u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
-    if (has_right)
-      k_dist_unpack<<<ublocks, 256, 0, stream>>>(mailbox_header(d->mailbox, 1), mailbox_emigrants(d->mailbox, 1, d->emax, d->gmax),
-                                                 mailbox_ghosts(d->mailbox, 1, d->emax, d->gmax), d->seq, d->emax, d->gmax, grid, u.pos,
-                                                 u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
+    if (has_left || has_right) {
+      const MsgIn from_left{has_left ? mailbox_header(d->mailbox, 0) : nullptr, mailbox_emigrants(d->mailbox, 0, d->emax, d->gmax),
+                            mailbox_ghosts(d->mailbox, 0, d->emax, d->gmax)};
+      const MsgIn from_right{has_right ? mailbox_header(d->mailbox, 1) : nullptr, mailbox_emigrants(d->mailbox, 1, d->emax, d->gmax),
+                             mailbox_ghosts(d->mailbox, 1, d->emax, d->gmax)};
+      k_dist_unpack<<<2 * ublocks, 256, 0, stream>>>(from_left, from_right, d->seq, d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid,
+                                                     u_ordk, u_ordr, d->counters, capacity);
+    } else {
+      k_dist_finish<<<1, 32, 0, stream>>>(grid, d->counters, capacity);
+    }
     timing_mark(stream);
-    k_dist_finish<<<1, 32, 0, stream>>>(grid, u_count, capacity);
     timing_mark(stream);
-    if (launches) *launches += 3 + (has_left ? 1 : 0) + (has_right ? 1 : 0);
+    if (launches) *launches += 2;
     return 0;
   }
-  cudaMemsetAsync(u_count, 0, sizeof(uint32_t), stream);
   cudaMemsetAsync(d->send[0], 0, 16, stream);
   cudaMemsetAsync(d->send[1], 0, 16, stream);
   const MsgOut left{static_cast<uint32_t*>(d->send[0]), msg_emigrants(d->send[0]), msg_ghosts(d->send[0], d->emax)};
   const MsgOut right{static_cast<uint32_t*>(d->send[1]), msg_emigrants(d->send[1]), msg_ghosts(d->send[1], d->emax)};
+  const PeerSignal none{nullptr, nullptr, nullptr, 0u};
   k_dist_classify<<<blocks, 256, 0, stream>>>(prev.pos, prev.vel, prev.ivel, prev_pid, skey, wrank, grid, u.pos, u.vel, u.ivel,
-                                              u_pid, u_ordk, u_ordr, u_count, capacity, left, right, d->emax, d->gmax);
+                                              u_pid, u_ordk, u_ordr, u_count, capacity, left, right, d->emax, d->gmax, none);
   if (!nccl_check(nccl().GroupStart(), "ncclGroupStart")) return 1;
   bool ok = true;
   if (has_left) {
@@ -650,14 +691,15 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
     ok = ok && nccl_check(nccl().Recv(d->recv[1], d->msg_bytes, ncclUint8, d->rank + 1, comm, stream), "ncclRecv(right)");
   }
   if (!nccl_check(nccl().GroupEnd(), "ncclGroupEnd") || !ok) return 1;
-  if (has_left)
-    k_dist_unpack<<<ublocks, 256, 0, stream>>>(static_cast<const uint32_t*>(d->recv[0]), msg_emigrants(d->recv[0]), msg_ghosts(d->recv[0], d->emax),
-                                               0u, d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
-  if (has_right)
-    k_dist_unpack<<<ublocks, 256, 0, stream>>>(static_cast<const uint32_t*>(d->recv[1]), msg_emigrants(d->recv[1]), msg_ghosts(d->recv[1], d->emax),
-                                               0u, d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk, u_ordr, u_count, capacity);
-  k_dist_finish<<<1, 32, 0, stream>>>(grid, u_count, capacity);
-  if (launches) *launches += 2 + (has_left ? 1 : 0) + (has_right ? 1 : 0);
+  if (has_left || has_right) {
+    const MsgIn from_left{has_left ? static_cast<const uint32_t*>(d->recv[0]) : nullptr, msg_emigrants(d->recv[0]), msg_ghosts(d->recv[0], d->emax)};
+    const MsgIn from_right{has_right ? static_cast<const uint32_t*>(d->recv[1]) : nullptr, msg_emigrants(d->recv[1]), msg_ghosts(d->recv[1], d->emax)};
+    k_dist_unpack<<<2 * ublocks, 256, 0, stream>>>(from_left, from_right, 0u, d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid, u_ordk,
+                                                   u_ordr, d->counters, capacity);
+  } else {
+    k_dist_finish<<<1, 32, 0, stream>>>(grid, d->counters, capacity);
+  }
+  if (launches) *launches += 2;
   return 0;
 }
 
