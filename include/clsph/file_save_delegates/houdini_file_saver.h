@@ -22,7 +22,12 @@ class houdini_file_saver {
    * at most two frames in flight. */
   int writeFrameToFile(particle* particles, const simulation_parameters& parameters);
 
-  /* Blocks until every frame handed to writeFrameToFile is on disk. */
+  /* The same frame from what the file actually needs of each particle: n records of seven floats (position,
+   * velocity, density) in the order of the particle array -- what clsph_frame_begin packs on the GPU (28 instead of
+   * 80 bytes per particle over the host link). sph_simulation::frame_saver uses it. Same files, byte for byte. */
+  int writeFramePoints(const float* points, unsigned int count, float particle_mass);
+
+  /* Blocks until every frame handed to writeFrameToFile / writeFramePoints is on disk. */
   void wait();
 
   std::string frames_folder_prefix;
@@ -30,6 +35,7 @@ class houdini_file_saver {
 
  private:
   struct writer;
+  int submit_job(void* frame_job);
   int frame_count;
   writer* writer_;
 };

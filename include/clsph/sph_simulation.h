@@ -16,6 +16,8 @@
 #include "common/structures.h"
 #include "scene.h"
 
+class houdini_file_saver;
+
 class sph_simulation {
  public:
   sph_simulation();
@@ -60,6 +62,12 @@ class sph_simulation {
    * particles are handed over, e.g. {"sub_cell_order", 1}, {"face_grid", 1} (include/clsph_cuda.h). */
   std::vector<std::pair<std::string, long long> > device_options;
   bool quiet;               /* suppress the reference's console chatter (default false)     */
+  /* Frame export off the critical path: when set (and host_sync != sync_every_substep), simulate() itself hands the
+   * state at the start of every frame -- the moment example/particles.cpp:93-96 writes it from its pre_frame
+   * callback -- to this saver, packed on the GPU to the 28 bytes per particle a frame file needs and copied while
+   * the frame's sub-steps already run (clsph_frame_begin / clsph_frame_end). Files are byte for byte those of
+   * writeFrameToFile on the downloaded array. */
+  houdini_file_saver* frame_saver;
 
   /* State after the last simulate() call, in the reference's output order. */
   const particle* final_particles() const;

@@ -168,6 +168,18 @@ int clsph_get_parameters(clsph_context* ctx, simulation_parameters* out);
  * writes them, acceleration = 0 (sph.cl:97-99). Synchronises. Replaces sph_simulation.cpp:339. */
 int clsph_download_particles(clsph_context* ctx, particle* aos_out);
 
+/* Frame export off the critical path. A frame file needs seven floats of a particle -- position, velocity, density
+ * (libclsph/file_save_delegates/houdini_file_saver.cpp:39-62 reads exactly these; colour and mass follow from the
+ * density and the parameters) -- not its 80 bytes. clsph_frame_begin packs them on the device, in the reference's
+ * output order, and starts the copy into `points` (n x 7 floats; page-locked memory, e.g. from clsph_host_alloc,
+ * lets the copy run while further sub-steps are enqueued and computed) on a stream of its own; it does not wait.
+ * clsph_frame_end waits until `points` is complete. One frame may be pending at a time. */
+int clsph_frame_begin(clsph_context* ctx, float* points, uint32_t capacity);
+int clsph_frame_end(clsph_context* ctx);
+/* Page-locked host memory for the above (cudaHostAlloc / cudaFreeHost without a CUDA header on the caller's side). */
+int clsph_host_alloc(void** out, size_t bytes);
+void clsph_host_free(void* p);
+
 /* One sub-step with host buffers on both sides, the exact shape of
  * sph_simulation::simulate_single_frame(in, out): upload, step, download, and the grid
  * block of *params rewritten. `in` may equal `out`. `terms` may be NULL to keep the ones set. */

@@ -17,7 +17,7 @@ SYMBOLS = [
     "clsph_set_parameters", "clsph_set_option", "clsph_upload_particles", "clsph_step", "clsph_synchronize",
     "clsph_get_parameters", "clsph_download_particles", "clsph_simulate_single_frame", "clsph_set_debug",
     "clsph_debug_fetch", "clsph_kernel_advection_collision", "clsph_comm_unique_id", "clsph_dist_init",
-    "clsph_dist_upload", "clsph_dist_download", "clsph_dist_transport", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_stream",
+    "clsph_dist_upload", "clsph_dist_download", "clsph_dist_transport", "clsph_frame_begin", "clsph_frame_end", "clsph_host_alloc", "clsph_host_free", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_stream",
 ]
 
 TAP_SORTED_KEYS, TAP_PERMUTATION, TAP_CELL_TABLE, TAP_KEYS_INPUT, TAP_CANDIDATE_COUNT = 0, 1, 2, 3, 4
@@ -81,10 +81,15 @@ def load_library(path=None):
     L.clsph_particle_count.argtypes = [vp, ctypes.POINTER(u32)]
     L.clsph_stream.argtypes = [vp]
     L.clsph_stream.restype = vp
+    L.clsph_frame_begin.argtypes = [vp, vp, u32]
+    L.clsph_frame_end.argtypes = [vp]
+    L.clsph_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), sz]
+    L.clsph_host_free.argtypes = [vp]
+    L.clsph_host_free.restype = None
     L.clsph_dist_transport.argtypes = [vp]
     L.clsph_dist_transport.restype = ctypes.c_char_p
     for name in SYMBOLS:
-        if name not in ("clsph_destroy", "clsph_last_error", "clsph_stream", "clsph_dist_transport"):
+        if name not in ("clsph_destroy", "clsph_last_error", "clsph_stream", "clsph_dist_transport", "clsph_host_free"):
             getattr(L, name).restype = ctypes.c_int
     if path == _build.LIB_PATH:
         _lib = L
@@ -197,6 +202,15 @@ class Context:
         buf = ctypes.create_string_buffer(bytes(unique_id), 128)
         self._check(self._lib.clsph_dist_init(self._h, rank, world, buf, plane_lo, plane_hi, emigrant_capacity,
                                               ghost_capacity))
+
+    def frame_points(self):
+        """(n, 7) float32: position, velocity, density of every particle in the reference's output order, packed on
+        the device (clsph_frame_begin / clsph_frame_end)."""
+        import numpy as np
+        out = np.empty((self.particle_count(), 7), dtype=np.float32)
+        self._check(self._lib.clsph_frame_begin(self._h, _vp(out), out.shape[0]))
+        self._check(self._lib.clsph_frame_end(self._h))
+        return out
 
     def dist_transport(self):
         """How the ranks exchange particles: "peer stores ..." (NVLink, no collective per sub-step) or "nccl ..."."""

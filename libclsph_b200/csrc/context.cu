@@ -33,6 +33,15 @@ struct clsph_context {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  // side stream: work of a sub-step that nothing later in the same sub-step reads (k_rank) runs next to the
+  // neighbour passes instead of in front of them; forked and joined with events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // frame export (clsph_frame_begin / clsph_frame_end): packed records leave on a copy stream while the next
+  // sub-steps run
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_copied = nullptr;
+  bool frame_pending = false;
   uint32_t capacity = 0;       // max particles
   uint32_t cell_capacity = 0;  // dense table entries
   uint32_t n = 0;              // particles held
@@ -325,8 +334,8 @@ int ensure_sub(clsph_context* ctx) {
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->rrank, ctx->capacity));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->rr_tmp, ctx->capacity));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pair_items, ctx->capacity));
-  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pair_count, 1));
-  CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pair_count, 0, sizeof(uint32_t), ctx->stream));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pair_count, 2));  // [0] items, [1] lists that overflowed in the density pass
+  CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pair_count, 0, 2 * sizeof(uint32_t), ctx->stream));
   CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sub_lb, 0, sizeof(uint32_t) * 9u * (size_t)ctx->sub_capacity, ctx->stream));
   return CLSPH_OK;
 }
@@ -415,6 +424,7 @@ int enqueue_substep(clsph_context* ctx) {
   launch_sort_passes(ctx->sort, ctx->grid, n, st, lc);
   if (prof) next_event(ctx);
 
+  bool join_side = false;  // the side stream has work of this sub-step
   const bool pairs = sub && ctx->pair_density && !ctx->tiles && !ctx->deferred_lists;
   if (sub) {
     launch_clear_sub(ctx->sub_lb, ctx->grid, ctx->sub_capacity, ctx->sm_count, st, lc);
@@ -424,10 +434,21 @@ int enqueue_substep(clsph_context* ctx) {
                        multi ? ctx->ordk[ctx->cur ^ 1] : nullptr, multi ? ctx->ordr[ctx->cur ^ 1] : nullptr,
                        ctx->tiles ? ctx->tl.ctl : nullptr, ctx->tl.blocks, pairs ? ctx->pair_items : nullptr, ctx->pair_count, n, st, lc);
     ctx->cur ^= 1;
-    if (!multi)  // one GPU: absolute index in the reference's array
+    if (!multi) {  // one GPU: absolute index in the reference's array
+      // Nothing in this sub-step reads the new ranks, and the pass (a count over the ~40 particles of each cell,
+      // latency bound) fits into the issue slots the density pass leaves free: side stream, joined at the end.
+      const bool rank_on_side = !ctx->debug && !prof;
+      join_side = rank_on_side;
+      cudaStream_t rs = st;
+      if (rank_on_side) {
+        CLSPH_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+        CLSPH_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        rs = ctx->side;
+      }
       launch_rank(ctx->skey, ctx->rr_tmp, ctx->rrank, ctx->sub_lb, ctx->sort, ctx->grid, ctx->perm,
-                  ctx->debug ? ctx->taps.keys_input : nullptr, n, st, lc);
-    else         // across ranks: (cell key, rank in cell), merged at export
+                  ctx->debug ? ctx->taps.keys_input : nullptr, n, rs, lc);
+      if (rank_on_side) CLSPH_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+    } else         // across ranks: (cell key, rank in cell), merged at export
       launch_rank_pair(dst.pos, ctx->skey, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->wrank, ctx->sub_lb, ctx->sort, ctx->grid, n,
                        st, lc);
     if (prof) next_event(ctx);
@@ -443,7 +464,7 @@ int enqueue_substep(clsph_context* ctx) {
       launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
                     false, true, ctx->forces_dense, ctx->accel, n, st, lc, true);
       launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
-                                 ctx->lists, ctx->accel, n, st, lc);
+                                 ctx->lists, ctx->accel, nullptr, n, st, lc);
     } else {
       if (pairs)
         launch_density_pairs(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
@@ -455,7 +476,7 @@ int enqueue_substep(clsph_context* ctx) {
       launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
                     false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc);
       launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
-                                 ctx->lists, ctx->accel, n, st, lc);
+                                 ctx->lists, ctx->accel, pairs ? ctx->pair_count + 1 : nullptr, n, st, lc);
     }
     if (prof) next_event(ctx);
   } else {
@@ -478,6 +499,7 @@ int enqueue_substep(clsph_context* ctx) {
   launch_integrate(dst, ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->face_grid, ctx->grid, ctx->konst, ctx->bounds,
                    ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, lc);
   if (multi) dist_publish_bounds(&ctx->dist, ctx->bounds, st, lc);
+  if (join_side) CLSPH_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));  // whatever follows sees the new ranks
   if (prof) next_event(ctx);
   CLSPH_CUDA_TRY(ctx, cudaGetLastError());
   return CLSPH_OK;
@@ -537,6 +559,12 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
   CREATE_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
   CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+  CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_packed, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   const size_t cap = max_particles;
   for (int s = 0; s < 2; ++s) {
     CREATE_TRY(dev_alloc(&ctx->state[s].pos, cap));
@@ -652,6 +680,14 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->tl.slow);
   cudaFree(ctx->tl.ctl);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->copy) cudaStreamSynchronize(ctx->copy);
+  if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->copy) cudaStreamDestroy(ctx->copy);
+  if (ctx->side) cudaStreamSynchronize(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
   delete ctx;
@@ -752,6 +788,7 @@ int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) 
   if (n < 128u) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: need at least 128 particles, got %u (sort.cl:9-20)", n);
   if (n > ctx->capacity) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: %u particles exceed the capacity %u", n, ctx->capacity);
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->frame_pending) CLSPH_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));  // the staging area is in use
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, aos, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, ctx->sub_order ? ctx->rrank : nullptr, n,
                     ctx->stream, &ctx->launches);
@@ -892,10 +929,56 @@ int clsph_download_particles(clsph_context* ctx, particle* aos_out) {
   if (!aos_out) return fail(ctx, CLSPH_EINVAL, "clsph_download_particles: aos_out is null");
   if (!ctx->have_particles) return fail(ctx, CLSPH_ESTATE, "clsph_download_particles: no particles uploaded");
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->frame_pending) CLSPH_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));  // the staging area is in use
   launch_soa_to_aos(ctx->state[ctx->cur], ctx->aux, ctx->skey, (ctx->sub_order && !ctx->dist.active) ? ctx->rrank : nullptr,
                     ctx->aos_stage, ctx->n, ctx->stream, &ctx->launches);
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(aos_out, ctx->aos_stage, sizeof(particle) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   return clsph_synchronize(ctx);
+}
+
+/* ---- frame export ------------------------------------------------------------------------- */
+
+int clsph_frame_begin(clsph_context* ctx, float* points, uint32_t capacity) {
+  if (!ctx || !points) return CLSPH_EINVAL;
+  if (!ctx->have_particles) return fail(ctx, CLSPH_ESTATE, "clsph_frame_begin: no particles uploaded");
+  if (ctx->dist.active) return fail(ctx, CLSPH_ESTATE, "clsph_frame_begin: single-GPU contexts only (use clsph_dist_download)");
+  if (ctx->frame_pending) return fail(ctx, CLSPH_ESTATE, "clsph_frame_begin: the previous frame was not collected with clsph_frame_end");
+  if (capacity < ctx->n) return fail(ctx, CLSPH_EINVAL, "clsph_frame_begin: %u particles, room for %u", ctx->n, capacity);
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // the 28-byte records are packed on the compute stream (the state must not move on before they are taken: 20 us
+  // at a million particles) into the staging area; the copy to the host then runs on its own stream
+  float* staged = static_cast<float*>(ctx->aos_stage);
+  launch_pack_frame(ctx->state[ctx->cur], ctx->aux, ctx->sub_order ? ctx->rrank : nullptr, staged, ctx->n, ctx->stream, &ctx->launches);
+  CLSPH_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_packed, ctx->stream));
+  CLSPH_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_packed, 0));
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(points, staged, sizeof(float) * 7u * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->copy));
+  CLSPH_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copied, ctx->copy));
+  ctx->frame_pending = true;
+  return CLSPH_OK;
+}
+
+int clsph_frame_end(clsph_context* ctx) {
+  if (!ctx) return CLSPH_EINVAL;
+  if (!ctx->frame_pending) return CLSPH_OK;
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy));
+  ctx->frame_pending = false;
+  return CLSPH_OK;
+}
+
+int clsph_host_alloc(void** out, size_t bytes) {
+  if (!out) return CLSPH_EINVAL;
+  *out = nullptr;
+  if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(nullptr, CLSPH_ENOMEM, "clsph_host_alloc: %zu bytes of page-locked memory", bytes);
+  }
+  return CLSPH_OK;
+}
+
+void clsph_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+  cudaGetLastError();
 }
 
 int clsph_simulate_single_frame(clsph_context* ctx, const particle* in, particle* out, simulation_parameters* params,

@@ -271,6 +271,27 @@ void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uin
   if (launches) ++*launches;
 }
 
+// What a frame file needs of a particle (file_save_delegates/houdini_file_saver.cpp:39-62 of the reference reads
+// position, velocity and density; colour and mass follow from the density and the parameters): seven floats, in
+// the reference's output order.
+__global__ void __launch_bounds__(256) k_pack_frame(const float4* __restrict__ pos, const float4* __restrict__ vel,
+                                                    const float4* __restrict__ aux, const uint32_t* __restrict__ rrank,
+                                                    float* __restrict__ out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pos[i], v = vel[i];
+  float* rec = out + (size_t)(rrank ? rrank[i] : i) * 7;
+  rec[0] = p.x; rec[1] = p.y; rec[2] = p.z;
+  rec[3] = v.x; rec[4] = v.y; rec[5] = v.z;
+  rec[6] = aux[i].x;
+}
+
+void launch_pack_frame(const StateArrays& src, const float4* aux, const uint32_t* rrank, float* out, uint32_t n, cudaStream_t stream,
+                       uint64_t* launches) {
+  k_pack_frame<<<blocks_for(n, 256), 256, 0, stream>>>(src.pos, src.vel, aux, rrank, out, n);
+  if (launches) ++*launches;
+}
+
 void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, const uint32_t* rrank, void* aos,
                        uint32_t n, cudaStream_t stream, uint64_t* launches) {
   k_soa_to_aos<<<blocks_for(n, 256), 256, 0, stream>>>(src.pos, src.vel, src.ivel, aux, skey, rrank, (float4*)aos, n);

@@ -88,6 +88,9 @@ void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uin
                        uint32_t* rrank, uint32_t n, cudaStream_t stream, uint64_t* launches);
 void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, const uint32_t* rrank, void* aos,
                        uint32_t n, cudaStream_t stream, uint64_t* launches);
+// Seven floats per particle (position, velocity, density) in the reference's order: what a frame file needs.
+void launch_pack_frame(const StateArrays& src, const float4* aux, const uint32_t* rrank, float* out, uint32_t n, cudaStream_t stream,
+                       uint64_t* launches);
 void launch_reference_cell_table(const uint32_t* skey, const GridState* grid, uint32_t* table, uint32_t n_launch,
                                  cudaStream_t stream, uint64_t* launches);
 void launch_copy_u32(const uint32_t* src, uint32_t* dst, uint32_t n, cudaStream_t stream, uint64_t* launches);
@@ -142,8 +145,8 @@ void launch_density_sub(float4* pos, float4* vel, const uint32_t* skey, const ui
                         cudaStream_t stream, uint64_t* launches);
 void launch_forces_sub_overflow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                                 const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, const SphConst& c,
-                                const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream,
-                                uint64_t* launches);
+                                const NeighbourLists& lists, float4* accel, const uint32_t* overflowed, uint32_t n_launch,
+                                cudaStream_t stream, uint64_t* launches);
 void launch_scatter_words(const void* src, const uint32_t* rrank, void* dst, uint32_t n, uint32_t words,
                           cudaStream_t stream, uint64_t* launches);
 

@@ -480,6 +480,8 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     finish_density(c, f2_hi(acc), i1, aux, pos, vel);
     ncount[i1] = cnt1;
   }
+  // lists that did not fit (rare): k_forces_sub only looks for them when there are any
+  if ((need0 && cnt0 > list_rows) || (need1 && cnt1 > list_rows)) atomicAdd(const_cast<uint32_t*>(pair_count) + 1, 1u);
   if (kTaps) {
     // the reference's candidate count: every particle of the 27 cells around this one (forces.cl:25-40);
     // both particles are in the same cell
@@ -504,7 +506,9 @@ __global__ void __launch_bounds__(kSubThreads)
 k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
              const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
              const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const SphConst c,
-             const uint32_t* __restrict__ ncount, uint32_t list_rows, float4* __restrict__ accel) {
+             const uint32_t* __restrict__ ncount, uint32_t list_rows, float4* __restrict__ accel,
+             const uint32_t* __restrict__ overflowed) {
+  if (overflowed && *overflowed == 0u) return;  // the density pass found no list that overflowed
   const GridState g = *grid;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
@@ -621,7 +625,7 @@ void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const So
                         uint32_t* dst_ordk, uint32_t* dst_ordr, TileCtl* tile_ctl, uint32_t* tile_blocks, uint32_t* pair_items,
                         uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
   if (tile_ctl) cudaMemsetAsync(tile_ctl, 0, sizeof(TileCtl), stream);
-  if (pair_items) cudaMemsetAsync(pair_count, 0, sizeof(uint32_t), stream);
+  if (pair_items) cudaMemsetAsync(pair_count, 0, 2 * sizeof(uint32_t), stream);  // items, overflowing lists
   k_reorder_sub<<<(n_launch + 255) / 256, 256, 0, stream>>>(src.pos, src.vel, src.ivel, dst.pos, dst.vel, dst.ivel, sort.keys_a,
                                                             sort.keys_b, sort.vals_a, sort.vals_b, skey, rr_src, rr_dst, sub_lb,
                                                             grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr,
@@ -722,10 +726,10 @@ void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const 
 
 void launch_forces_sub_overflow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                                 const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, const SphConst& c,
-                                const NeighbourLists& lists, float4* accel, uint32_t n_launch, cudaStream_t stream,
-                                uint64_t* launches) {
+                                const NeighbourLists& lists, float4* accel, const uint32_t* overflowed, uint32_t n_launch,
+                                cudaStream_t stream, uint64_t* launches) {
   k_forces_sub<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(
-      pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, lists.count, lists.rows, accel);
+      pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, lists.count, lists.rows, accel, overflowed);
   if (launches) ++*launches;
 }
 

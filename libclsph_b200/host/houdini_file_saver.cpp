@@ -385,6 +385,21 @@ int houdini_file_saver::writeFrameToFile(particle* particles, const simulation_p
     o.vx = q.velocity.s[0]; o.vy = q.velocity.s[1]; o.vz = q.velocity.s[2];
     o.rho = q.density;
   }
+  return submit_job(&job);
+}
+
+int houdini_file_saver::writeFramePoints(const float* points, unsigned int count, float particle_mass) {
+  static_assert(sizeof(FramePoint) == 7 * sizeof(float), "FramePoint is the packed record of clsph_frame_begin");
+  FrameJob job;
+  job.file_name = frames_folder_prefix + "frames/frame" + frame_suffix(++frame_count) + ".geo";
+  job.mass = particle_mass;
+  job.points.resize(count);
+  if (count) std::memcpy(job.points.data(), points, sizeof(FramePoint) * static_cast<size_t>(count));
+  return submit_job(&job);
+}
+
+int houdini_file_saver::submit_job(void* job_ptr) {
+  FrameJob& job = *static_cast<FrameJob*>(job_ptr);
   if (!asynchronous) {
     const unsigned hw = std::thread::hardware_concurrency();
     write_job(job, static_cast<int>(hw ? hw : 4));

@@ -6,7 +6,10 @@
 // optionally serialises last_frame.bin, resumes from it when its size matches, prints the settings
 // and a progress bar. Extra flag: --yes skips the "press a key" prompt; --frames N limits the run;
 // --sync full|substep chooses when the host array is refreshed (default: substep if
-// write_all_frames or serialize, else full).
+// write_all_frames or serialize, else full). --frame-export device|host: who prepares a frame -- `device` (default
+// with --sync full): the GPU packs the 28 bytes per particle a frame needs and copies them while the next sub-steps
+// run (sph_simulation::frame_saver), the 80-byte array is not downloaded at all; `host`: the reference's way, the
+// pre_frame callback writes the downloaded array. Same files, byte for byte.
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -22,12 +25,13 @@ int main(int argc, char** argv) {
   std::string positional[4];
   int n_positional = 0, frames = 0;
   bool assume_yes = false;
-  std::string sync = "";
+  std::string sync = "", frame_export = "";
   std::vector<std::string> device_options;
   for (int a = 1; a < argc; ++a) {
     if (!std::strcmp(argv[a], "--yes")) assume_yes = true;
     else if (!std::strcmp(argv[a], "--frames") && a + 1 < argc) frames = std::atoi(argv[++a]);
     else if (!std::strcmp(argv[a], "--sync") && a + 1 < argc) sync = argv[++a];
+    else if (!std::strcmp(argv[a], "--frame-export") && a + 1 < argc) frame_export = argv[++a];
     else if (!std::strcmp(argv[a], "--option") && a + 1 < argc) device_options.push_back(argv[++a]);  // name=value
     else if (n_positional < 4) positional[n_positional++] = argv[a];
   }
@@ -57,11 +61,17 @@ int main(int argc, char** argv) {
   const bool every_substep = simulation.write_intermediate_frames || simulation.serialize;
   simulation.host_sync = (sync == "substep" || (sync.empty() && every_substep)) ? sph_simulation::sync_every_substep
                                                                                  : sph_simulation::sync_full_frames;
+  // frames straight from the device: only when the array is not needed on the host between frames
+  const bool device_frames = simulation.host_sync != sph_simulation::sync_every_substep && frame_export != "host";
+  if (device_frames) {
+    simulation.frame_saver = &saver;
+    simulation.host_sync = sph_simulation::sync_never;  // the callback below only draws the progress bar
+  }
   int calls = 0;
   bool array_is_current = true;  // the initial state is on the host before the first callback
   simulation.pre_frame = [&](particle* particles, const simulation_parameters& params, bool full_frame) {
     const bool current = simulation.host_sync == sph_simulation::sync_every_substep || full_frame || array_is_current;
-    if (simulation.write_intermediate_frames != full_frame && current) saver.writeFrameToFile(particles, params);
+    if (!device_frames && simulation.write_intermediate_frames != full_frame && current) saver.writeFrameToFile(particles, params);
     if (simulation.serialize && current) {
       std::ofstream file_out("last_frame.bin", std::ios::binary);
       file_out.write(reinterpret_cast<const char*>(particles), static_cast<std::streamsize>(sizeof(particle)) * params.particles_count);

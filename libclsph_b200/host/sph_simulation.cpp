@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "clsph_cuda.h"
+#include "file_save_delegates/houdini_file_saver.h"
 #include "mini_json.h"
 
 namespace {
@@ -54,7 +55,7 @@ struct sph_simulation::impl {
 
 sph_simulation::sph_simulation()
     : parameters(), precomputed_terms(), write_intermediate_frames(false), serialize(false), initial_volume(0.f),
-      host_sync(sync_every_substep), cuda_device(0), quiet(false), impl_(new impl) {}
+      host_sync(sync_every_substep), cuda_device(0), quiet(false), frame_saver(nullptr), impl_(new impl) {}
 
 sph_simulation::~sph_simulation() {
   if (impl_->ctx) clsph_destroy(impl_->ctx);
@@ -128,7 +129,28 @@ void sph_simulation::simulate(int frame_count) {
   const bool any_callback = static_cast<bool>(pre_frame) || static_cast<bool>(post_frame);
   const host_sync_policy policy = any_callback ? host_sync : sync_never;
 
+  // frame export by the library itself: two page-locked buffers, the copy of frame i overlaps its sub-steps
+  const bool export_frames = frame_saver != nullptr && policy != sync_every_substep && frame_count > 0;
+  float* frame_points[2] = {nullptr, nullptr};
+  bool frame_in_flight = false;
+  if (export_frames)
+    for (int b = 0; b < 2; ++b) {
+      void* mem = nullptr;
+      check_cuda_abi(nullptr, clsph_host_alloc(&mem, sizeof(float) * 7u * static_cast<size_t>(n)));
+      frame_points[b] = static_cast<float*>(mem);
+    }
+  auto collect_frame = [&](int buffer) {
+    check_cuda_abi(ctx, clsph_frame_end(ctx));
+    frame_saver->writeFramePoints(frame_points[buffer], n, parameters.particle_mass);
+    frame_in_flight = false;
+  };
+
   for (int i = 0; i < frame_count; ++i) {
+    if (export_frames) {
+      if (frame_in_flight) collect_frame((i + 1) & 1);
+      check_cuda_abi(ctx, clsph_frame_begin(ctx, frame_points[i & 1], n));
+      frame_in_flight = true;
+    }
     if (pre_frame) pre_frame(particles, parameters, true);
 
     for (int j = 0; static_cast<float>(j) < (1.f / parameters.simulation_scale); ++j) {
@@ -151,6 +173,12 @@ void sph_simulation::simulate(int frame_count) {
     if (post_frame) post_frame(particles, parameters, true);
   }
 
+  if (export_frames) {
+    if (frame_in_flight) collect_frame((frame_count + 1) & 1);
+    frame_saver->wait();  // the saver copies what it is given, but leave nothing behind that points into the buffers
+    clsph_host_free(frame_points[0]);
+    clsph_host_free(frame_points[1]);
+  }
   if (policy != sync_every_substep) {
     check_cuda_abi(ctx, clsph_download_particles(ctx, particles));
     check_cuda_abi(ctx, clsph_get_parameters(ctx, &parameters));

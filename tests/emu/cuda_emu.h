@@ -216,8 +216,14 @@ cudaError_t cudaMemsetAsync(void* dst, int v, size_t bytes, cudaStream_t s = nul
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+enum { cudaHostAllocDefault = 0 };
+inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { *p = std::malloc(bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaEventCreate(cudaEvent_t* e);
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }  // launches are synchronous here
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr);
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaEventDestroy(cudaEvent_t e);

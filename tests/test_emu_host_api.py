@@ -45,3 +45,32 @@ def test_cli_with_device_options_writes_frames_under_the_emulator(tmp_path):
     assert lines[0] == "PGEOMETRY V5" and lines[1] == "NPoints 1024 NPrims 1" and lines[-1] == "endExtra"
     bad = subprocess.run(base + ["--option", "no_such_option=1"], cwd=wd, env=_env(), capture_output=True, text=True, timeout=600)
     assert bad.returncode != 0 and "unknown option" in bad.stderr
+
+
+def _cli_frames(wd_root, name, extra, frames=3, particles=2048):
+    wd = os.path.join(str(wd_root), name)
+    os.makedirs(wd)
+    for d in ("fluid_properties", "simulation_properties", "scenes"):
+        shutil.copytree(os.path.join(H.ROOT, d), os.path.join(wd, d))
+    os.makedirs(os.path.join(wd, "frames"))
+    sim = open(os.path.join(wd, "simulation_properties", "default.json")).read()
+    open(os.path.join(wd, "simulation_properties", "small.json"), "w").write(
+        sim.replace('"particles_count" : 32000', '"particles_count" : %d' % particles))
+    r = subprocess.run([hostapi.CLI_PATH, "water", "small", "box.obj", "", "--yes", "--frames", str(frames)] + extra, cwd=wd, env=_env(),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-1500:]
+    names = sorted(os.listdir(os.path.join(wd, "frames")))
+    return {n: open(os.path.join(wd, "frames", n), "rb").read() for n in names}
+
+
+def test_frames_packed_on_the_device_are_byte_identical_under_the_emulator(tmp_path):
+    """--frame-export device (default with --sync full: clsph_frame_begin packs 28 bytes per particle on the GPU, the
+    copy overlaps the next sub-steps, nothing else is downloaded) against --frame-export host (the reference's way:
+    the pre_frame callback writes the downloaded 80-byte array): same file names, same bytes."""
+    hostapi.build()
+    dev = _cli_frames(tmp_path, "device", [])
+    host = _cli_frames(tmp_path, "host", ["--frame-export", "host"])
+    assert sorted(dev) == sorted(host) == ["frame0000001.geo", "frame0000002.geo", "frame0000003.geo"]
+    for name in dev:
+        assert dev[name] == host[name], name
+    assert dev["frame0000001.geo"] != dev["frame0000003.geo"]  # the fluid moved

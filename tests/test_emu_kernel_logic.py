@@ -343,3 +343,19 @@ def test_option_validation():
                         ("face_grid", 1), ("sub_cell_order", 1), ("sub_cell_order", 0), ("neighbour_lists", 0), ("list_rows", 48)):
         ctx.set_option(name, value)
     ctx.close()
+
+
+def test_frame_points_are_the_downloaded_fields(box_scene):
+    """clsph_frame_begin / clsph_frame_end: the seven floats per particle a frame file needs, packed on the device in
+    the reference's output order, equal the same fields of the full download bit for bit."""
+    p, terms, vol = H.config("water", 3000)
+    s = H.state_s1(p, vol)
+    ctx = G.make_ctx(s.size, box_scene, p, terms, debug=False)
+    ctx.upload(s)
+    ctx.step(2)
+    pts = ctx.frame_points()
+    got = ctx.download()
+    ctx.close()
+    assert pts.shape == (s.size, 7)
+    assert np.array_equal(pts[:, 0:3], got["position"][:, :3]) and np.array_equal(pts[:, 3:6], got["velocity"][:, :3])
+    assert np.array_equal(pts[:, 6], got["density"])

@@ -162,6 +162,26 @@ def test_clsphparticles_cli_writes_frames_and_checkpoint(tmp_path):
     assert "incorrect size" in r.stdout
 
 
+@pytest.mark.gpu
+def test_frames_packed_on_the_device_are_byte_identical(tmp_path):
+    """clsphparticles --frame-export device (default: 28 bytes per particle packed on the GPU, copied while the next
+    sub-steps run) against --frame-export host (the downloaded 80-byte array written by the callback): same bytes."""
+    hostapi.build()
+    out = {}
+    for mode, extra in (("device", []), ("host", ["--frame-export", "host"])):
+        wd = _workdir(tmp_path / mode)
+        sim = open(os.path.join(wd, "simulation_properties", "default.json")).read()
+        open(os.path.join(wd, "simulation_properties", "small.json"), "w").write(sim.replace('"particles_count" : 32000', '"particles_count" : 20000'))
+        r = subprocess.run([hostapi.CLI_PATH, "water", "small", "box.obj", "", "--yes", "--frames", "3"] + extra, cwd=wd,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        names = sorted(os.listdir(os.path.join(wd, "frames")))
+        out[mode] = {n: open(os.path.join(wd, "frames", n), "rb").read() for n in names}
+    assert sorted(out["device"]) == sorted(out["host"]) == ["frame0000001.geo", "frame0000002.geo", "frame0000003.geo"]
+    for name in out["device"]:
+        assert out["device"][name] == out["host"][name], name
+
+
 def test_geo_numbers_match_printf_g_on_adversarial_values(tmp_path):
     """The frame writer formats with std::to_chars on worker threads; every number must still read
     exactly like the reference's iostream output (printf %g): checked against Python's %g over
