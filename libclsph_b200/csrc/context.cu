@@ -81,6 +81,7 @@ struct clsph_context {
   bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
   bool merged_rows = true;      // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
   bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
+  bool factored_forces = true;      // option "factored_forces": k_forces_lists_tile on lists that leave the particle itself out
   int pair_variant = 5;             // option "pair_variant" (tuning): walk 0/1/2 + 3 x (entries stored two at a time)
   uint32_t* pair_items = nullptr;   // [capacity] items written by k_reorder_sub
   uint32_t* pair_count = nullptr;
@@ -425,6 +426,8 @@ int enqueue_substep(clsph_context* ctx) {
   if (prof) next_event(ctx);
 
   bool join_side = false;  // the side stream has work of this sub-step
+  // lists without the particle itself + the list force kernel with factored pair terms (option "factored_forces")
+  const bool factored = sub && ctx->pair_density && !ctx->tiles && !ctx->deferred_lists && ctx->factored_forces && ctx->fast_pairs;
   const bool pairs = sub && ctx->pair_density && !ctx->tiles && !ctx->deferred_lists;
   if (sub) {
     launch_clear_sub(ctx->sub_lb, ctx->grid, ctx->sub_capacity, ctx->sm_count, st, lc);
@@ -468,13 +471,13 @@ int enqueue_substep(clsph_context* ctx) {
     } else {
       if (pairs)
         launch_density_pairs(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                             ctx->taps, ctx->debug, ctx->pair_variant, ctx->pair_items, ctx->pair_count, n, st, lc);
+                             ctx->taps, ctx->debug, ctx->pair_variant, factored, ctx->pair_items, ctx->pair_count, n, st, lc);
       else
         launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
                            ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
       if (prof) next_event(ctx);
       launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
-                    false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc);
+                    false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc, factored);
       launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
                                  ctx->lists, ctx->accel, pairs ? ctx->pair_count + 1 : nullptr, n, st, lc);
     }
@@ -762,6 +765,8 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     ctx->merged_rows = value != 0;
   } else if (!std::strcmp(name, "pair_density")) {
     ctx->pair_density = value != 0;
+  } else if (!std::strcmp(name, "factored_forces")) {
+    ctx->factored_forces = value != 0;
   } else if (!std::strcmp(name, "pair_variant")) {
     if (value < 0 || value > 5) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: pair_variant must be in [0, 5]");
     ctx->pair_variant = (int)value;

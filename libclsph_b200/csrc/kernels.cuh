@@ -131,8 +131,8 @@ void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const So
 // Density + pressure + neighbour lists, two particles of a sub-cell per thread (packed fp32: FADD2 / FFMA2).
 void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                           const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                          const DebugTaps& taps, bool debug, int variant, const uint32_t* pair_items, const uint32_t* pair_count,
-                          uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+                          const DebugTaps& taps, bool debug, int variant, bool no_self, const uint32_t* pair_items,
+                          const uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 void launch_rank_pair(const float4* pos, const uint32_t* skey, const uint32_t* ordk, const uint32_t* ordr, uint32_t* wrank,
                       const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, uint32_t n_launch,
                       cudaStream_t stream, uint64_t* launches);

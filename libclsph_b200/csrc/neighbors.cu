@@ -29,6 +29,8 @@
 // All of these are FP32-issue / shared-memory bound, not HBM bound (SURVEY hard part 1); their
 // HBM traffic is the 16-32 B/particle of coalesced reads, L2-resident candidate gathers and, in
 // list mode, about 2 x 4 B x (neighbours per particle) of list traffic.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "pair_terms.cuh"
 
@@ -670,7 +672,9 @@ k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, c
 // the sums, one MUFU.RSQ per pair, no branch: ~46 instead of ~71 instructions per pair. A particle with a
 // degenerate pair (coincident particles, smoothing.cl:23; found by the exact test on s) is redone on the spot
 // with the reference's formulas.
-template <int kBlocks>
+// kTrip neighbours per trip of the walk: 2 (four gathers in flight) or 4 (eight; the pass is bound by the latency
+// of those gathers, L1 hit rate ~60 %).
+template <int kBlocks, int kTrip>
 __global__ void __launch_bounds__(kFlWarps * 32, kBlocks)
 k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
                     const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
@@ -711,6 +715,22 @@ k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ v
     const uint32_t mine = count > e0 ? min(count - e0, 32u) : 0u;
     const uint32_t* row = tile + lane * kTileStride;
     uint32_t e = 0;
+    if (kTrip == 4) {
+      for (; e + 4 <= mine; e += 4) {  // four neighbours per trip: eight independent gathers in flight
+        const uint32_t ja = row[e], jb = row[e + 1], jc = row[e + 2], jd = row[e + 3];
+        const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb], pc = pos[jc], vc = vel[jc], pd = pos[jd], vd = vel[jd];
+        float sa, sb, sc, sd;
+        const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa);
+        tile_pair_add(sums, oa);
+        const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb);
+        tile_pair_add(sums, ob);
+        const TilePair oc = tile_pair_ops(c, pi, vi, pc, vc, sc);
+        tile_pair_add(sums, oc);
+        const TilePair od = tile_pair_ops(c, pi, vi, pd, vd, sd);
+        tile_pair_add(sums, od);
+        degenerate |= (sa < c.degenerate_s) | (sb < c.degenerate_s) | (sc < c.degenerate_s) | (sd < c.degenerate_s);
+      }
+    }
     for (; e + 2 <= mine; e += 2) {  // two neighbours per trip: four independent gathers in flight
       const uint32_t ja = row[e], jb = row[e + 1];
       const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb];
@@ -791,12 +811,15 @@ void launch_forces(const float4* pos, const float4* vel, const float4* aux, cons
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
   if (lists.rows && tile_lists) {  // lists of the tile kernel: the particle itself is not listed
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
-    if (dense_occupancy)
-      k_forces_lists_tile<4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid,
-                                                                   c, accel);
+    static const int trip = [] { const char* e = getenv("CLSPH_FORCES_TRIP"); return e ? atoi(e) : 2; }();  // tuning
+    if (dense_occupancy && trip == 4)
+      k_forces_lists_tile<4, 4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    else if (dense_occupancy)
+      k_forces_lists_tile<4, 2><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    else if (trip == 4)
+      k_forces_lists_tile<3, 4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     else
-      k_forces_lists_tile<3><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid,
-                                                                   c, accel);
+      k_forces_lists_tile<3, 2><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     if (launches) ++*launches;
   } else if (lists.rows) {
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);

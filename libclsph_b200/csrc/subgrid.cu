@@ -345,7 +345,9 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
 // kWalk: how a thread walks a row's candidates -- 0: one after the other; 1: the same with the next candidate's
 // load issued before the current one is tested; 2: four loads issued, then four tests. kStore2: list entries are
 // stored two at a time (one 8-byte store per two hits) instead of one by one.
-template <bool kTaps, int kWalk, bool kStore2>
+// kNoSelf: the particle itself is not listed (it still counts in the density and in the support tap): the form the
+// list force kernel with factored pair terms (k_forces_lists_tile) wants.
+template <bool kTaps, int kWalk, bool kStore2, bool kNoSelf>
 __global__ void __launch_bounds__(kSubThreads)
 k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
                 const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
@@ -392,9 +394,10 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     const f32x2 dx = f2_sub(X, f2_bcast(pj.x)), dy = f2_sub(Y, f2_bcast(pj.y)), dz = f2_sub(Z, f2_bcast(pj.z));
     const f32x2 s = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
     const f32x2 d = f2_sub(H2, s);
-    const bool in0 = f2_lo(s) < c.support_s, in1 = f2_hi(s) < c.support_s;
-    const f32x2 w = f2_make(in0 ? f2_lo(d) : 0.f, in1 ? f2_hi(d) : 0.f);
+    const bool hit0 = f2_lo(s) < c.support_s, hit1 = f2_hi(s) < c.support_s;
+    const f32x2 w = f2_make(hit0 ? f2_lo(d) : 0.f, hit1 ? f2_hi(d) : 0.f);
     acc = f2_fma(f2_mul(w, w), w, acc);
+    const bool in0 = kNoSelf ? (hit0 && j != i0) : hit0, in1 = kNoSelf ? (hit1 && j != i1) : hit1;  // what goes into the lists
     if (kStore2) {
       // List entries leave two at a time: every lane's store is an L1 wavefront and a 32-byte L2 sector write of its
       // own (each lane writes its own row), so one 8-byte store per two hits halves that. The first hit of a pair
@@ -496,8 +499,11 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
             total += r.y - r.x;
           }
     }
-    if (need0) { cand_count[i0] = total; supp_count[i0] = cnt0; }
-    if (need1) { cand_count[i1] = total; supp_count[i1] = cnt1; }
+    // the support count includes the particle itself (unless it has blown up: NaN fails the test as in the reference)
+    const uint32_t self0 = (kNoSelf && dist2_contract(p0.x, p0.y, p0.z, p0.x, p0.y, p0.z) < c.support_s) ? 1u : 0u;
+    const uint32_t self1 = (kNoSelf && dist2_contract(p1.x, p1.y, p1.z, p1.x, p1.y, p1.z) < c.support_s) ? 1u : 0u;
+    if (need0) { cand_count[i0] = total; supp_count[i0] = cnt0 + self0; }
+    if (need1) { cand_count[i1] = total; supp_count[i1] = cnt1 + self1; }
   }
 }
 
@@ -691,9 +697,9 @@ struct PairArgs {
   unsigned blocks;
   cudaStream_t stream;
 };
-template <bool kTaps, int kWalk, bool kStore2>
+template <bool kTaps, int kWalk, bool kStore2, bool kNoSelf>
 void launch_pairs_variant(const PairArgs& a) {
-  k_density_pairs<kTaps, kWalk, kStore2><<<a.blocks, kSubThreads, 0, a.stream>>>(a.pos, a.vel, a.skey, a.sub_lb, a.keys_a, a.keys_b, a.grid, a.c, a.aux,
+  k_density_pairs<kTaps, kWalk, kStore2, kNoSelf><<<a.blocks, kSubThreads, 0, a.stream>>>(a.pos, a.vel, a.skey, a.sub_lb, a.keys_a, a.keys_b, a.grid, a.c, a.aux,
                                                                                  a.nlist, a.ncount, a.list_rows, a.cand, a.supp, a.pair_items,
                                                                                  a.pair_count);
 }
@@ -701,24 +707,27 @@ void launch_pairs_variant(const PairArgs& a) {
 
 void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                           const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                          const DebugTaps& taps, bool debug, int variant, const uint32_t* pair_items, const uint32_t* pair_count,
-                          uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+                          const DebugTaps& taps, bool debug, int variant, bool no_self, const uint32_t* pair_items,
+                          const uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
   // the item count lives on the device (between n / 2 and n): sized for the worst case, surplus blocks leave at once
   const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
   uint32_t* cand = debug ? taps.candidate_count : nullptr;
   uint32_t* supp = debug ? taps.support_count : nullptr;
   const PairArgs a{pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries, lists.count, lists.rows, cand, supp,
                    pair_items, pair_count, blocks, stream};
-  if (debug) {
-    launch_pairs_variant<true, 2, true>(a);
+  if (no_self) {  // lists for k_forces_lists_tile; the measured-best walk only
+    if (debug) launch_pairs_variant<true, 2, true, true>(a);
+    else launch_pairs_variant<false, 2, true, true>(a);
+  } else if (debug) {
+    launch_pairs_variant<true, 2, true, false>(a);
   } else {
     switch (variant) {
-      case 0: launch_pairs_variant<false, 0, false>(a); break;
-      case 1: launch_pairs_variant<false, 1, false>(a); break;
-      case 2: launch_pairs_variant<false, 2, false>(a); break;
-      case 3: launch_pairs_variant<false, 0, true>(a); break;
-      case 4: launch_pairs_variant<false, 1, true>(a); break;
-      default: launch_pairs_variant<false, 2, true>(a); break;
+      case 0: launch_pairs_variant<false, 0, false, false>(a); break;
+      case 1: launch_pairs_variant<false, 1, false, false>(a); break;
+      case 2: launch_pairs_variant<false, 2, false, false>(a); break;
+      case 3: launch_pairs_variant<false, 0, true, false>(a); break;
+      case 4: launch_pairs_variant<false, 1, true, false>(a); break;
+      default: launch_pairs_variant<false, 2, true, false>(a); break;
     }
   }
   if (launches) ++*launches;
