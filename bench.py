@@ -413,8 +413,10 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     achieved = n * kb[dominant] / (per[dominant] * 1e-3) / 1e9
     tiles = sub and "tile_kernels=1" in options
-    kernel_name = {"density": ("k_density_tiles" if tiles else "k_density_sub") if sub else "k_density_lists",
-                   "forces": "k_forces_lists_tile" if tiles else "k_forces_lists",
+    pairs = sub and not tiles and "pair_density=0" not in options and "deferred_lists=1" not in options
+    factored = sub and not tiles and "factored_forces=0" not in options and "fast_pairs=0" not in options
+    kernel_name = {"density": ("k_density_tiles" if tiles else "k_density_pairs" if pairs else "k_density_sub") if sub else "k_density_lists",
+                   "forces": "k_forces_lists_tile" if (tiles or factored) else "k_forces_lists",
                    "reorder": "k_reorder_sub" if sub else "k_reorder", "sort": "k_onesweep", "keys": "k_keys_hist",
                    "integrate": "k_integrate"}[dominant]
     # the committed ncu capture is of the default options

@@ -426,8 +426,9 @@ int enqueue_substep(clsph_context* ctx) {
   if (prof) next_event(ctx);
 
   bool join_side = false;  // the side stream has work of this sub-step
-  // lists without the particle itself + the list force kernel with factored pair terms (option "factored_forces")
-  const bool factored = sub && ctx->pair_density && !ctx->tiles && !ctx->deferred_lists && ctx->factored_forces && ctx->fast_pairs;
+  // the list force kernel with factored pair terms on the lists of the per-particle / pair density kernels, which
+  // contain the particle itself (option "factored_forces")
+  const bool factored = sub && !ctx->tiles && ctx->factored_forces && ctx->fast_pairs;
   const bool pairs = sub && ctx->pair_density && !ctx->tiles && !ctx->deferred_lists;
   if (sub) {
     launch_clear_sub(ctx->sub_lb, ctx->grid, ctx->sub_capacity, ctx->sm_count, st, lc);
@@ -465,19 +466,19 @@ int enqueue_substep(clsph_context* ctx) {
                          ctx->taps.support_count, n, st, lc);
       if (prof) next_event(ctx);
       launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
-                    false, true, ctx->forces_dense, ctx->accel, n, st, lc, true);
+                    false, true, ctx->forces_dense, ctx->accel, n, st, lc, 1);
       launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
                                  ctx->lists, ctx->accel, nullptr, n, st, lc);
     } else {
       if (pairs)
         launch_density_pairs(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                             ctx->taps, ctx->debug, ctx->pair_variant, factored, ctx->pair_items, ctx->pair_count, n, st, lc);
+                             ctx->taps, ctx->debug, ctx->pair_variant, false, ctx->pair_items, ctx->pair_count, n, st, lc);
       else
         launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
                            ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
       if (prof) next_event(ctx);
       launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
-                    false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc, factored);
+                    false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc, factored ? 2 : 0);
       launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
                                  ctx->lists, ctx->accel, pairs ? ctx->pair_count + 1 : nullptr, n, st, lc);
     }

@@ -117,7 +117,7 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
                    const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
-                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool tile_lists = false);
+                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, int tile_lists = 0);
 
 struct TileCtl;
 // ---- subgrid.cu: sub-cell order (arrays sorted by cell key << 3 | octant)

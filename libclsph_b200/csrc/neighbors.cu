@@ -674,7 +674,8 @@ k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, c
 // with the reference's formulas.
 // kTrip neighbours per trip of the walk: 2 (four gathers in flight) or 4 (eight; the pass is bound by the latency
 // of those gathers, L1 hit rate ~60 %).
-template <int kBlocks, int kTrip>
+// kSelfListed: the lists contain the particle itself (k_density_pairs / k_density_sub write them that way).
+template <int kBlocks, int kTrip, bool kSelfListed>
 __global__ void __launch_bounds__(kFlWarps * 32, kBlocks)
 k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
                     const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
@@ -720,13 +721,13 @@ k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ v
         const uint32_t ja = row[e], jb = row[e + 1], jc = row[e + 2], jd = row[e + 3];
         const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb], pc = pos[jc], vc = vel[jc], pd = pos[jd], vd = vel[jd];
         float sa, sb, sc, sd;
-        const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa);
+        const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa, kSelfListed && ja == i);
         tile_pair_add(sums, oa);
-        const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb);
+        const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb, kSelfListed && jb == i);
         tile_pair_add(sums, ob);
-        const TilePair oc = tile_pair_ops(c, pi, vi, pc, vc, sc);
+        const TilePair oc = tile_pair_ops(c, pi, vi, pc, vc, sc, kSelfListed && jc == i);
         tile_pair_add(sums, oc);
-        const TilePair od = tile_pair_ops(c, pi, vi, pd, vd, sd);
+        const TilePair od = tile_pair_ops(c, pi, vi, pd, vd, sd, kSelfListed && jd == i);
         tile_pair_add(sums, od);
         degenerate |= (sa < c.degenerate_s) | (sb < c.degenerate_s) | (sc < c.degenerate_s) | (sd < c.degenerate_s);
       }
@@ -735,8 +736,8 @@ k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ v
       const uint32_t ja = row[e], jb = row[e + 1];
       const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb];
       float sa, sb;
-      const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa);
-      const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb);
+      const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa, kSelfListed && ja == i);
+      const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb, kSelfListed && jb == i);
       degenerate |= (sa < c.degenerate_s) | (sb < c.degenerate_s);
       tile_pair_add(sums, oa);
       tile_pair_add(sums, ob);
@@ -744,7 +745,7 @@ k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ v
     if (e < mine) {
       const uint32_t j = row[e];
       float s;
-      const TilePair o = tile_pair_ops(c, pi, vi, pos[j], vel[j], s);
+      const TilePair o = tile_pair_ops(c, pi, vi, pos[j], vel[j], s, kSelfListed && j == i);
       degenerate |= s < c.degenerate_s;
       tile_pair_add(sums, o);
     }
@@ -752,16 +753,16 @@ k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ v
   }
   if (!(valid && listed)) return;
   if (!degenerate) {
-    accel[i] = tile_finish_force(sums, c, aux[i].x, vi.w);
+    accel[i] = tile_finish_force(sums, c, aux[i].x, vi.w, kSelfListed);
     return;
   }
   ForceSums exact;
   const uint32_t* mine = nlist + (size_t)i * list_rows;
   for (uint32_t e = 0; e < count; ++e) {
     const uint32_t j = mine[e];
-    add_pair(exact, c, false, pi, vi, pi.w, pos[j], vel[j]);
+    add_pair(exact, c, kSelfListed && j == i, pi, vi, pi.w, pos[j], vel[j]);
   }
-  add_pair(exact, c, true, pi, vi, pi.w, pi, vi);
+  if (!kSelfListed) add_pair(exact, c, true, pi, vi, pi.w, pi, vi);
   accel[i] = finish_force(exact, c, aux[i].x);
 }
 
@@ -807,19 +808,24 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
                    const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
-                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool tile_lists) {
+                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, int tile_lists) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
   if (lists.rows && tile_lists) {  // lists of the tile kernel: the particle itself is not listed
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
+    // (tile_lists: 1 = lists of the tile kernels, the particle itself not listed; 2 = lists of the per-particle / pair
+    // kernels, which contain it)
     static const int trip = [] { const char* e = getenv("CLSPH_FORCES_TRIP"); return e ? atoi(e) : 2; }();  // tuning
-    if (dense_occupancy && trip == 4)
-      k_forces_lists_tile<4, 4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    if (tile_lists == 2) {
+      if (dense_occupancy)
+        k_forces_lists_tile<4, 2, true><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+      else
+        k_forces_lists_tile<3, 2, true><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    } else if (dense_occupancy && trip == 4)
+      k_forces_lists_tile<4, 4, false><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     else if (dense_occupancy)
-      k_forces_lists_tile<4, 2><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
-    else if (trip == 4)
-      k_forces_lists_tile<3, 4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+      k_forces_lists_tile<4, 2, false><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     else
-      k_forces_lists_tile<3, 2><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+      k_forces_lists_tile<3, 2, false><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     if (launches) ++*launches;
   } else if (lists.rows) {
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);

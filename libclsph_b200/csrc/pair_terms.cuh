@@ -116,13 +116,15 @@ __device__ __forceinline__ float rsqrt_fast(float s) {
   return r;
 #endif
 }
+// is_self (lists that contain the particle itself): 1/r is taken as 0, which leaves exactly the particle's own term --
+// d = 0 and v_j - v_i = 0 wipe the three vector sums, (h^2 - 0)(3 h^2 - 0) m/rho_i is tile_self_lap.
 __device__ __forceinline__ TilePair tile_pair_ops(const SphConst& c, const float4& pi, const float4& vi, const float4& pj,
-                                                  const float4& vj, float& s_out) {
+                                                  const float4& vj, float& s_out, bool is_self = false) {
   TilePair o;
   o.dx = pi.x - pj.x; o.dy = pi.y - pj.y; o.dz = pi.z - pj.z;
   const float s = fmaf(o.dz, o.dz, fmaf(o.dy, o.dy, o.dx * o.dx));
-  s_out = s;
-  const float inv_r = rsqrt_fast(s);
+  s_out = is_self ? c.h2 : s;  // (never "degenerate")
+  const float inv_r = is_self ? 0.f : rsqrt_fast(s);
   const float hr = c.h - s * inv_r;
   o.kp = (pj.w + pi.w) * (hr * hr * inv_r);
   o.vc = vj.w * hr;
@@ -140,8 +142,8 @@ __device__ __forceinline__ void tile_pair_add(ForceSums& f, const TilePair& o) {
 }
 // The particle's own term (s = 0: only the laplacian of the colour field is non-zero), then the constants, then
 // finish_force. mor_i = m / rho_i.
-__device__ __forceinline__ float4 tile_finish_force(ForceSums f, const SphConst& c, float rho, float mor_i) {
-  f.lap += mor_i * (c.h2 * (3.f * c.h2));
+__device__ __forceinline__ float4 tile_finish_force(ForceSums f, const SphConst& c, float rho, float mor_i, bool self_listed = false) {
+  if (!self_listed) f.lap += mor_i * (c.h2 * (3.f * c.h2));
   const float kp = c.mass * c.c_spiky;
   f.px *= kp; f.py *= kp; f.pz *= kp;
   f.wx *= c.c_visc; f.wy *= c.c_visc; f.wz *= c.c_visc;
