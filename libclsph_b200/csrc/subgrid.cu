@@ -348,7 +348,7 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
 // kNoSelf: the particle itself is not listed (it still counts in the density and in the support tap): the form the
 // list force kernel with factored pair terms (k_forces_lists_tile) wants.
 template <bool kTaps, int kWalk, bool kStore2, bool kNoSelf>
-__global__ void __launch_bounds__(kSubThreads)
+__global__ void __launch_bounds__(kSubThreads, 8)  // 64 registers: eight CTAs of four warps per SM
 k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
                 const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
                 const SphConst c, float4* __restrict__ aux, uint32_t* __restrict__ nlist, uint32_t* __restrict__ ncount,
@@ -456,19 +456,28 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
       }
     }
   };
+  // Rows of sub-cells, z outermost. The index ranges of the NEXT row are looked up (four loads from the sub-cell
+  // table) before the current row is walked, so that a thread does not start every row waiting for them.
   const uint32_t cx_lo = xlo >> 1, cx_hi = xhi >> 1;
-  for (uint32_t fz = zlo; fz <= zhi; ++fz) {
-    const uint32_t kz = spread10(fz >> 1) << 2, oz = (fz & 1u) << 2;
-    for (uint32_t fy = ylo; fy <= yhi; ++fy) {
-      const uint32_t kzy = kz | (spread10(fy >> 1) << 1), ozy = oz | ((fy & 1u) << 1);
-      const uint2 a = sub_range(v, kzy | spread10(cx_lo), ozy | (xlo & 1u), ozy | (cx_hi == cx_lo ? (xhi & 1u) : 1u));
-      uint2 b = make_uint2(0u, 0u);
-      if (cx_hi > cx_lo) b = sub_range(v, kzy | spread10(cx_lo + 1u), ozy, ozy | (cx_hi == cx_lo + 1u ? (xhi & 1u) : 1u));
-      walk(a.x, a.y, b.x, b.y);
-      if (cx_hi > cx_lo + 1u) {  // rare third cell of the row
-        const uint2 e = sub_range(v, kzy | spread10(cx_hi), ozy, ozy | (xhi & 1u));
-        walk(e.x, e.y, 0u, 0u);
-      }
+  const uint32_t ny = yhi - ylo + 1u, n_rows = (zhi - zlo + 1u) * ny;
+  auto row_ranges = [&](uint32_t r, uint2& a, uint2& b) {
+    const uint32_t fz = zlo + r / ny, fy = ylo + r % ny;
+    const uint32_t kzy = (spread10(fz >> 1) << 2) | (spread10(fy >> 1) << 1), ozy = ((fz & 1u) << 2) | ((fy & 1u) << 1);
+    a = sub_range(v, kzy | spread10(cx_lo), ozy | (xlo & 1u), ozy | (cx_hi == cx_lo ? (xhi & 1u) : 1u));
+    b = make_uint2(0u, 0u);
+    if (cx_hi > cx_lo) b = sub_range(v, kzy | spread10(cx_lo + 1u), ozy, ozy | (cx_hi == cx_lo + 1u ? (xhi & 1u) : 1u));
+  };
+  uint2 na, nb;
+  row_ranges(0u, na, nb);
+  for (uint32_t r = 0; r < n_rows; ++r) {
+    const uint2 a = na, b = nb;
+    if (r + 1u < n_rows) row_ranges(r + 1u, na, nb);
+    walk(a.x, a.y, b.x, b.y);
+    if (cx_hi > cx_lo + 1u) {  // rare third cell of the row
+      const uint32_t fz = zlo + r / ny, fy = ylo + r % ny;
+      const uint32_t kzy = (spread10(fz >> 1) << 2) | (spread10(fy >> 1) << 1), ozy = ((fz & 1u) << 2) | ((fy & 1u) << 1);
+      const uint2 e = sub_range(v, kzy | spread10(cx_hi), ozy, ozy | (xhi & 1u));
+      walk(e.x, e.y, 0u, 0u);
     }
   }
   if (kStore2) {  // the last hit of an odd count is still held
