@@ -3,8 +3,9 @@
 // orders the kernels of sort.cu / grid.cu / neighbors.cu / integrate.cu on one stream.
 //
 // Sub-step launch sequence (all device resident, no host round trip):
-//   k_grid_setup -> memset(sort scratch) -> k_keys_hist -> k_scan_hist -> k_onesweep x4
-//   -> k_clear_cells -> k_reorder -> k_density -> k_forces -> k_integrate
+//   k_grid_setup -> memset(sort scratch) -> k_keys_hist (+ table clear, histogram scan) -> k_onesweep x4
+//   -> k_reorder_sub -> [k_rank on the side stream] k_density_pairs -> k_forces_lists(_tile) -> k_forces_sub -> k_integrate
+// (default organisation; sub_cell_order = 0: k_clear_cells -> k_reorder -> k_density_lists -> k_forces_lists -> k_integrate)
 // The reference's equivalent is libclsph/sph_simulation.cpp:173-344 with 17 blocking transfers.
 #include <cmath>
 #include <cstdarg>
@@ -81,7 +82,7 @@ struct clsph_context {
   bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
   bool merged_rows = true;      // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
   bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
-  bool factored_forces = true;      // option "factored_forces": k_forces_lists_tile on lists that leave the particle itself out
+  int factored_forces = -1;         // option "factored_forces": 1 k_forces_lists_tile, 0 k_forces_lists<fast>, -1 by the fluid (list rows)
   int pair_variant = 5;             // option "pair_variant" (tuning): walk 0/1/2 + 3 x (entries stored two at a time)
   uint32_t* pair_items = nullptr;   // [capacity] items written by k_reorder_sub
   uint32_t* pair_count = nullptr;
@@ -420,7 +421,7 @@ int enqueue_substep(clsph_context* ctx) {
 
   // sub-cell order: the pre-step keys tap is written by k_rank, in the reference's order
   launch_sort_keys(ctx->sort, src.pos, ctx->grid, n, ctx->sm_count, (ctx->debug && !sub) ? ctx->taps.keys_input : nullptr, sub,
-                   st, lc);
+                   sub ? ctx->sub_lb : nullptr, st, lc);  // (also clears the sub-cell table and scans the digit histograms)
   if (prof) next_event(ctx);
   launch_sort_passes(ctx->sort, ctx->grid, n, st, lc);
   if (prof) next_event(ctx);
@@ -428,10 +429,12 @@ int enqueue_substep(clsph_context* ctx) {
   bool join_side = false;  // the side stream has work of this sub-step
   // the list force kernel with factored pair terms on the lists of the per-particle / pair density kernels, which
   // contain the particle itself (option "factored_forces")
-  const bool factored = sub && !ctx->tiles && ctx->factored_forces && ctx->fast_pairs;
+  // Measured (profiles/r02_n_*): with ~25 neighbours per particle (water, 64 list rows) both kernels wait on the same
+  // gathers and the plain one is 1 % ahead; with ~45 (mucus, 112 rows) the factored one saves 0.10 of 0.91 ms.
+  const bool want_factored = ctx->factored_forces < 0 ? ctx->lists.rows >= 96u : ctx->factored_forces != 0;
+  const bool factored = sub && !ctx->tiles && want_factored && ctx->fast_pairs;
   const bool pairs = sub && ctx->pair_density && !ctx->tiles && !ctx->deferred_lists;
   if (sub) {
-    launch_clear_sub(ctx->sub_lb, ctx->grid, ctx->sub_capacity, ctx->sm_count, st, lc);
     launch_reorder_sub(src, dst, ctx->sort, ctx->skey, multi ? nullptr : ctx->rrank, ctx->rr_tmp, ctx->sub_lb, ctx->grid,
                        multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr,
                        multi ? ctx->ordk[ctx->cur] : nullptr, multi ? ctx->ordr[ctx->cur] : nullptr,
@@ -767,7 +770,7 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
   } else if (!std::strcmp(name, "pair_density")) {
     ctx->pair_density = value != 0;
   } else if (!std::strcmp(name, "factored_forces")) {
-    ctx->factored_forces = value != 0;
+    ctx->factored_forces = value < 0 ? -1 : (value != 0 ? 1 : 0);
   } else if (!std::strcmp(name, "pair_variant")) {
     if (value < 0 || value > 5) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: pair_variant must be in [0, 5]");
     ctx->pair_variant = (int)value;

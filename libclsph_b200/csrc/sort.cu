@@ -59,12 +59,23 @@ __device__ __forceinline__ uint32_t block256_exclusive_scan(uint32_t v, uint32_t
 // x, y, z): floor(2q) & 1 with q = (p - min) / (2h) as above; 2q is exact, and floor(2q) >> 1 ==
 // floor(q), so the cell part is unchanged and a stable sort by the longer key is a stable sort by
 // cell refined by octant.
+// Two chores ride along, each of which used to be a launch of its own (5 us apiece at 1 Mi particles, where the whole
+// sub-step is 520): the sub-cell table of the gather pass is cleared (sub_lb, nothing else touches it here), and the
+// last CTA to finish scans the histograms into digit_base (what k_scan_hist does; `done` counts the CTAs).
 template <bool kSub>
 __global__ void __launch_bounds__(256) k_keys_hist(const float4* __restrict__ pos, uint32_t* __restrict__ keys,
-                                                   const GridState* __restrict__ grid, uint32_t* __restrict__ hist) {
+                                                   const GridState* __restrict__ grid, uint32_t* __restrict__ hist,
+                                                   uint32_t* __restrict__ sub_lb, uint32_t* __restrict__ digit_base,
+                                                   uint32_t* __restrict__ done) {
   __shared__ uint32_t s_hist[kMaxSortPasses * kRadix];
+  __shared__ uint32_t s_scratch[8];
+  __shared__ bool s_last;
   for (int i = threadIdx.x; i < kMaxSortPasses * kRadix; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
+  if (kSub && sub_lb && grid->sub_dense) {
+    const size_t words = (size_t)grid->cell_count * 9u;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) sub_lb[w] = 0u;
+  }
 
   const float mnx = grid->min_x, mny = grid->min_y, mnz = grid->min_z, cell = grid->cell;
   const uint32_t n = grid->n;
@@ -96,6 +107,17 @@ __global__ void __launch_bounds__(256) k_keys_hist(const float4* __restrict__ po
   for (int i = threadIdx.x; i < kMaxSortPasses * kRadix; i += blockDim.x) {
     const uint32_t c = s_hist[i];
     if (c) atomicAdd(&hist[i], c);
+  }
+  if (!done) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int pass = 0; pass < passes; ++pass) {  // blockDim.x == kRadix
+    const uint32_t v = atomicAdd(&hist[pass * kRadix + threadIdx.x], 0u);
+    digit_base[pass * kRadix + threadIdx.x] = block256_exclusive_scan(v, s_scratch);
   }
 }
 
@@ -260,15 +282,16 @@ ScratchLayout layout_of(const SortBuffers& b) {
 
 // Zeroes the scratch, computes keys into keys_a and all digit histograms.
 void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* grid, uint32_t n_launch, int sm_count,
-                      uint32_t* keys_tap, bool sub_keys, cudaStream_t stream, uint64_t* launches) {
+                      uint32_t* keys_tap, bool sub_keys, uint32_t* sub_lb, cudaStream_t stream, uint64_t* launches) {
   const ScratchLayout l = layout_of(b);
   const uint32_t tiles = sort_tiles_for(n_launch);
   // histograms, tile counters and the look-back status words of the tiles in use start at zero
   const size_t zero_words = (size_t)2 * kMaxSortPasses * kRadix + 64 + (size_t)kMaxSortPasses * tiles * kRadix;
   cudaMemsetAsync(b.scratch, 0, zero_words * sizeof(uint32_t), stream);
   const unsigned hist_blocks = (unsigned)std::min<uint64_t>(((uint64_t)n_launch + 255) / 256, (uint64_t)sm_count * 8);
-  if (sub_keys) k_keys_hist<true><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist);
-  else k_keys_hist<false><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist);
+  uint32_t* done = l.tile_counter + 8;  // (words 0..3 are the tile counters of the passes; all zeroed above)
+  if (sub_keys) k_keys_hist<true><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist, sub_lb, l.digit_base, done);
+  else k_keys_hist<false><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist, nullptr, l.digit_base, done);
   if (launches) ++*launches;
   if (keys_tap) launch_copy_u32(b.keys_a, keys_tap, n_launch, stream, launches);
 }
@@ -278,7 +301,7 @@ void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_
                         uint64_t* launches) {
   const ScratchLayout l = layout_of(b);
   const uint32_t tiles = sort_tiles_for(n_launch);
-  k_scan_hist<<<1, 256, 0, stream>>>(l.hist, l.digit_base, grid);
+  // (the histogram scan is done by the last CTA of k_keys_hist)
   // pass 0: a -> b (identity payload), pass 1: b -> a, pass 2: a -> b, pass 3: b -> a
   for (int pass = 0; pass < kMaxSortPasses; ++pass) {
     const bool even = (pass & 1) == 0;
@@ -291,7 +314,7 @@ void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_
                                                          even ? b.keys_b : b.keys_a, even ? b.vals_b : b.vals_a, grid, l.digit_base,
                                                          l.tile_counter, l.status, pass);
   }
-  if (launches) *launches += 1 + kMaxSortPasses;
+  if (launches) *launches += kMaxSortPasses;
 }
 
 }  // namespace clsph

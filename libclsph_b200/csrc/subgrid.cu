@@ -525,18 +525,18 @@ k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, con
              const uint32_t* __restrict__ overflowed) {
   if (overflowed && *overflowed == 0u) return;  // the density pass found no list that overflowed
   const GridState g = *grid;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
-  if (!(ncount[i] > list_rows)) return;
-  const float4 pi = pos[i];
-  if (!owned_here(pi.x, skey[i], g)) return;  // multi-GPU: ghosts get no force
   const SubView v = make_view(g, sub_lb, keys_a, keys_b);
-  const float4 vi = vel[i];
-  ForceSums sums;
-  for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4& pj, float, bool inside) {
-    if (inside) add_pair(sums, c, j == i, pi, vi, pi.w, pj, vel[j]);  // rare path: the exact pair terms
-  });
-  accel[i] = finish_force(sums, c, aux[i].x);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
+    if (!(ncount[i] > list_rows)) continue;
+    const float4 pi = pos[i];
+    if (!owned_here(pi.x, skey[i], g)) continue;  // multi-GPU: ghosts get no force
+    const float4 vi = vel[i];
+    ForceSums sums;
+    for_each_neighbour(v, g, c, pos, pi, [&](uint32_t j, const float4& pj, float, bool inside) {
+      if (inside) add_pair(sums, c, j == i, pi, vi, pi.w, pj, vel[j]);  // rare path: the exact pair terms
+    });
+    accel[i] = finish_force(sums, c, aux[i].x);
+  }
 }
 
 // ---- the kernel behind the tile kernel (tiles.cu): the particles of TileLists::slow, one WARP each -------------
@@ -746,8 +746,10 @@ void launch_forces_sub_overflow(const float4* pos, const float4* vel, const floa
                                 const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, const SphConst& c,
                                 const NeighbourLists& lists, float4* accel, const uint32_t* overflowed, uint32_t n_launch,
                                 cudaStream_t stream, uint64_t* launches) {
-  k_forces_sub<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(
-      pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, lists.count, lists.rows, accel, overflowed);
+  // a resident grid striding over the particles: usually every CTA returns at its first instruction
+  const unsigned blocks = std::max(1u, std::min((n_launch + kSubThreads - 1) / kSubThreads, 148u * 16u));
+  k_forces_sub<<<blocks, kSubThreads, 0, stream>>>(pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, lists.count, lists.rows,
+                                                   accel, overflowed);
   if (launches) ++*launches;
 }
 
