@@ -375,6 +375,7 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
 #ifndef CLSPH_EMU
   asm volatile("" : "+l"(row1));
 #endif
+  const global_row_t grow0 = global_row(row0), grow1 = global_row(row1);
   // union of the two search windows
   uint32_t xlo, xhi, ylo, yhi, zlo, zhi;
   sub_bounds(p0.x, g.min_x, g.cell, c.h_margin, xlo, xhi);
@@ -403,13 +404,13 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
       // own (each lane writes its own row), so one 8-byte store per two hits halves that. The first hit of a pair
       // waits in a register (list_rows is even, rows are 8-byte aligned).
       const bool odd0 = (cnt0 & 1u) != 0u, odd1 = (cnt1 & 1u) != 0u;
-      store2_if(in0 && odd0 && cnt0 < list_rows, row0 + (cnt0 - 1u), held0, j);
-      held0 = (in0 && !odd0) ? j : held0;
-      store2_if(in1 && odd1 && cnt1 < list_rows, row1 + (cnt1 - 1u), held1, j);
-      held1 = (in1 && !odd1) ? j : held1;
+      row_store2_if(in0 && odd0 && cnt0 < list_rows, grow0, cnt0 - 1u, held0, j);
+      held0 = in0 ? j : held0;  // (after an odd hit the held value is not used again before the next even one replaces it)
+      row_store2_if(in1 && odd1 && cnt1 < list_rows, grow1, cnt1 - 1u, held1, j);
+      held1 = in1 ? j : held1;
     } else {
-      store_if(in0 && cnt0 < list_rows, row0 + cnt0, j);
-      store_if(in1 && cnt1 < list_rows, row1 + cnt1, j);
+      row_store_if(in0 && cnt0 < list_rows, grow0, cnt0, j);
+      row_store_if(in1 && cnt1 < list_rows, grow1, cnt1, j);
     }
     cnt0 += in0 ? 1u : 0u;
     cnt1 += in1 ? 1u : 0u;

@@ -78,6 +78,30 @@ __device__ __forceinline__ void store2_if(bool ok, uint32_t* addr, uint32_t a, u
 #endif
 }
 
+// The same on an address that is already in the global window (cvta once per row pointer, not once per store: the
+// conversion showed up as 6 % of the pair kernel's instructions). `words` = offset in 32-bit words.
+#ifdef CLSPH_EMU
+typedef uint32_t* global_row_t;
+__device__ __forceinline__ global_row_t global_row(uint32_t* row) { return row; }
+__device__ __forceinline__ void row_store_if(bool ok, global_row_t row, uint32_t words, uint32_t v) { if (ok) row[words] = v; }
+__device__ __forceinline__ void row_store2_if(bool ok, global_row_t row, uint32_t words, uint32_t a, uint32_t b) {
+  if (ok) { row[words] = a; row[words + 1] = b; }
+}
+#else
+typedef unsigned long long global_row_t;
+__device__ __forceinline__ global_row_t global_row(uint32_t* row) { return (global_row_t)__cvta_generic_to_global(row); }
+__device__ __forceinline__ void row_store_if(bool ok, global_row_t row, uint32_t words, uint32_t v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" ::"r"((uint32_t)ok),
+               "l"(row + 4ull * words), "r"(v)
+               : "memory");
+}
+__device__ __forceinline__ void row_store2_if(bool ok, global_row_t row, uint32_t words, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v2.u32 [%1], {%2, %3};\n\t}" ::"r"((uint32_t)ok),
+               "l"(row + 4ull * words), "r"(a), "r"(b)
+               : "memory");
+}
+#endif
+
 // for_each_range: calls range(begin, end) for every index range of candidates of the sub-cells around pi.
 // for_each_neighbour, on top of it:
 // Calls visit(j, pos[j], s, inside) for every candidate j of the sub-cells around pi, z outermost /
