@@ -468,11 +468,15 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(args.e2e_steps):
             e2e_step()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * (80 if world == 1 else 84),
+        zero_copy = world == 1 and os.environ.get("CLSPH_ZERO_COPY_UPLOAD", "1") != "0"
+        e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * ((48 if zero_copy else 80) if world == 1 else 84),
                "d2h_bytes_per_step": n * (80 if world == 1 else 84), "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "path": ("clsph_simulate_single_frame(host AoS in, host AoS out)" if world == 1 else
                         "clsph_dist_upload + clsph_step + clsph_dist_download per rank") + ", pinned buffers",
-               "cpus_near_gpu": near_cpus}
+               "cpus_near_gpu": near_cpus,
+               "h2d": ("the upload kernel reads position, velocity and half-step velocity (48 of the 80 bytes of a record; ~64 with "
+                       "32-byte sectors) straight from the pinned host array, inside the timed call" if zero_copy else
+                       "cudaMemcpyAsync of the 80-byte records into a staging area, then a conversion kernel")}
     else:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "steps": 0,
                "path": "skipped (--e2e-steps 0)"}

@@ -791,16 +791,32 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
   return ctx->have_params ? ensure_lists(ctx) : CLSPH_OK;
 }
 
-int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) {
+// step_follows: the caller enqueues a sub-step before anything reads density / pressure / key of the upload.
+static int upload_particles(clsph_context* ctx, const particle* aos, uint32_t n, bool step_follows) {
   if (!ctx) return CLSPH_EINVAL;
   if (!aos) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: aos is null");
   if (n < 128u) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: need at least 128 particles, got %u (sort.cl:9-20)", n);
   if (n > ctx->capacity) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: %u particles exceed the capacity %u", n, ctx->capacity);
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (ctx->frame_pending) CLSPH_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));  // the staging area is in use
-  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, aos, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, ctx->sub_order ? ctx->rrank : nullptr, n,
-                    ctx->stream, &ctx->launches);
+  // Page-locked host memory and a sub-step right behind: the kernel reads the 48 bytes per record it needs straight
+  // over the host link (CLSPH_ZERO_COPY_UPLOAD=0 keeps the staged copy of all 80).
+  const void* mapped = nullptr;
+  static const bool allow_zero_copy = [] { const char* e = std::getenv("CLSPH_ZERO_COPY_UPLOAD"); return !(e && std::atoi(e) == 0); }();
+  if (step_follows && allow_zero_copy && !ctx->dist.active) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, aos) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      mapped = attr.devicePointer;
+    cudaGetLastError();  // (pageable memory makes older drivers report an error here)
+  }
+  if (mapped) {
+    launch_aos_to_soa_host(mapped, ctx->state[ctx->cur], ctx->aux, ctx->skey, ctx->sub_order ? ctx->rrank : nullptr, n, ctx->stream,
+                           &ctx->launches);
+  } else {
+    CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->aos_stage, aos, sizeof(particle) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    launch_aos_to_soa(ctx->aos_stage, ctx->state[ctx->cur], ctx->aux, ctx->skey, nullptr, ctx->sub_order ? ctx->rrank : nullptr, n,
+                      ctx->stream, &ctx->launches);
+  }
   const uint32_t count_and_fresh[2] = {n, 1u};
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->n, &count_and_fresh[0], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->grid->fresh, &count_and_fresh[1], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -812,6 +828,8 @@ int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) 
   if (ctx->dist.active) dist_invalidate_bounds(&ctx->dist);
   return CLSPH_OK;
 }
+
+int clsph_upload_particles(clsph_context* ctx, const particle* aos, uint32_t n) { return upload_particles(ctx, aos, n, false); }
 
 /* ---- multi-GPU ---------------------------------------------------------------------------- */
 
@@ -996,7 +1014,7 @@ int clsph_simulate_single_frame(clsph_context* ctx, const particle* in, particle
   if (!in || !out || !params) return fail(ctx, CLSPH_EINVAL, "clsph_simulate_single_frame: null argument");
   int rc = clsph_set_parameters(ctx, params, terms);
   if (rc) return rc;
-  if ((rc = clsph_upload_particles(ctx, in, params->particles_count))) return rc;
+  if ((rc = upload_particles(ctx, in, params->particles_count, true))) return rc;
   if ((rc = clsph_step(ctx, 1))) return rc;
   if ((rc = clsph_download_particles(ctx, out))) return rc;
   return clsph_get_parameters(ctx, params);

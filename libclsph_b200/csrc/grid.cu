@@ -265,6 +265,38 @@ void launch_reorder(const StateArrays& src, const StateArrays& dst, const SortBu
   if (launches) ++*launches;
 }
 
+// Upload straight from page-locked HOST memory (zero copy): the three vectors a sub-step needs of each 80-byte record
+// -- position, velocity, half-step velocity, bytes [0, 48) -- read over the host link by the kernel itself, three
+// lanes per record so that a warp's loads are runs of 48 consecutive bytes. Density, pressure and key of the record
+// are not read (the sub-step that follows recomputes all three), which leaves one 32-byte sector in five untouched.
+__global__ void __launch_bounds__(256) k_aos_to_soa_host(const float4* __restrict__ aos, float4* __restrict__ pos,
+                                                         float4* __restrict__ vel, float4* __restrict__ ivel,
+                                                         float4* __restrict__ aux, uint32_t* __restrict__ skey,
+                                                         uint32_t* __restrict__ rrank, uint32_t n) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = t / 3u, part = t - i * 3u;
+  if (i >= n) return;
+  const float4 v = aos[(size_t)i * 5u + part];
+  if (part == 0u) {
+    pos[i] = v;
+    aux[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    skey[i] = 0u;
+    if (rrank) rrank[i] = i;  // the uploaded order is the reference's order
+  } else if (part == 1u) {
+    vel[i] = v;
+  } else {
+    ivel[i] = v;
+  }
+}
+
+void launch_aos_to_soa_host(const void* aos_host_mapped, const StateArrays& dst, float4* aux, uint32_t* skey, uint32_t* rrank,
+                            uint32_t n, cudaStream_t stream, uint64_t* launches) {
+  const uint64_t threads = (uint64_t)n * 3u;
+  k_aos_to_soa_host<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>((const float4*)aos_host_mapped, dst.pos, dst.vel, dst.ivel, aux,
+                                                                         skey, rrank, n);
+  if (launches) ++*launches;
+}
+
 void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uint32_t* skey, float4* accel,
                        uint32_t* rrank, uint32_t n, cudaStream_t stream, uint64_t* launches) {
   k_aos_to_soa<<<blocks_for(n, 256), 256, 0, stream>>>((const float4*)aos, dst.pos, dst.vel, dst.ivel, aux, skey, accel, rrank, n);

@@ -86,6 +86,9 @@ void launch_reorder(const StateArrays& src, const StateArrays& dst, const SortBu
 // record i goes to slot rrank[i] of the AoS array on download.
 void launch_aos_to_soa(const void* aos, const StateArrays& dst, float4* aux, uint32_t* skey, float4* accel,
                        uint32_t* rrank, uint32_t n, cudaStream_t stream, uint64_t* launches);
+// The same from page-locked host memory mapped into the device's address space, reading only what a sub-step needs.
+void launch_aos_to_soa_host(const void* aos_host_mapped, const StateArrays& dst, float4* aux, uint32_t* skey, uint32_t* rrank,
+                            uint32_t n, cudaStream_t stream, uint64_t* launches);
 void launch_soa_to_aos(const StateArrays& src, const float4* aux, const uint32_t* skey, const uint32_t* rrank, void* aos,
                        uint32_t n, cudaStream_t stream, uint64_t* launches);
 // Seven floats per particle (position, velocity, density) in the reference's order: what a frame file needs.

@@ -217,6 +217,13 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 enum { cudaHostAllocDefault = 0 };
+// every host pointer doubles as its own device pointer here, so the zero-copy upload kernel runs in the emulator too
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; void* devicePointer; void* hostPointer; int device; };
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  a->type = cudaMemoryTypeHost; a->devicePointer = const_cast<void*>(p); a->hostPointer = const_cast<void*>(p); a->device = 0;
+  return cudaSuccess;
+}
 inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { *p = std::malloc(bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s);

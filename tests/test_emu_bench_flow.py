@@ -84,7 +84,7 @@ def test_run_ours_single_gpu_prints_the_contract_line(options, monkeypatch, capf
     assert d["steps"] == 3 and d["warmup"] == 3 and d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["config"]["workload"] == "config3_mucus_labyrinth_4m" and d["config"]["particles_per_gpu"] == 1500
     assert d["config"]["options"] == list(options)
-    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 1500 * 80 and d["e2e"]["d2h_bytes_per_step"] == 1500 * 80
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] in (1500 * 80, 1500 * 48) and d["e2e"]["d2h_bytes_per_step"] == 1500 * 80
     assert d["gpu_launches"] > 0
     assert len(d["repeats"]["ms_per_step"]) == 3 and d["repeats"]["median_value"] > 0
     r = d["roofline"]
