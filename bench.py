@@ -468,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(args.e2e_steps):
             e2e_step()
         dt = max_over_ranks(time.perf_counter() - t0)
-        zero_copy = world == 1 and os.environ.get("CLSPH_ZERO_COPY_UPLOAD", "1") != "0"
+        zero_copy = world == 1 and os.environ.get("CLSPH_ZERO_COPY_UPLOAD", "0") not in ("0", "")
         e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * ((48 if zero_copy else 80) if world == 1 else 84),
                "d2h_bytes_per_step": n * (80 if world == 1 else 84), "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "path": ("clsph_simulate_single_frame(host AoS in, host AoS out)" if world == 1 else

@@ -799,10 +799,12 @@ static int upload_particles(clsph_context* ctx, const particle* aos, uint32_t n,
   if (n > ctx->capacity) return fail(ctx, CLSPH_EINVAL, "clsph_upload_particles: %u particles exceed the capacity %u", n, ctx->capacity);
   CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (ctx->frame_pending) CLSPH_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));  // the staging area is in use
-  // Page-locked host memory and a sub-step right behind: the kernel reads the 48 bytes per record it needs straight
-  // over the host link (CLSPH_ZERO_COPY_UPLOAD=0 keeps the staged copy of all 80).
+  // Page-locked host memory and a sub-step right behind: with CLSPH_ZERO_COPY_UPLOAD=1 the kernel reads the 48 bytes per
+  // record it needs straight over the host link instead of the copy engine moving all 80. OFF by default: measured on
+  // a B200 (profiles/r02_o_*) it is SLOWER end to end -- 3.79 vs 3.68 ms per step at 1 Mi particles, 15.4 vs 15.0 at
+  // 4 Mi: the copy engine streams at the link's rate, SM-issued reads of 48-byte runs do not.
   const void* mapped = nullptr;
-  static const bool allow_zero_copy = [] { const char* e = std::getenv("CLSPH_ZERO_COPY_UPLOAD"); return !(e && std::atoi(e) == 0); }();
+  static const bool allow_zero_copy = [] { const char* e = std::getenv("CLSPH_ZERO_COPY_UPLOAD"); return e && std::atoi(e) != 0; }();
   if (step_follows && allow_zero_copy && !ctx->dist.active) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, aos) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
