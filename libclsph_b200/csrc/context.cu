@@ -112,6 +112,7 @@ struct clsph_context {
   uint32_t* ordk[2] = {nullptr, nullptr};
   uint32_t* ordr[2] = {nullptr, nullptr};
   uint32_t* wrank = nullptr;
+  uint32_t* live_idx = nullptr;  // exchange in place (sub-cell order): indices of the sort's input, see k_dist_select
 
   DebugTaps taps{};
   uint32_t* ref_table = nullptr;
@@ -408,12 +409,19 @@ int enqueue_substep(clsph_context* ctx) {
                     multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, st, lc);
   if (prof) next_event(ctx);
 
+  const bool in_place = multi && sub && ctx->live_idx != nullptr;  // the owned particles stay where they are
   if (multi) {
-    if (dist_exchange(&ctx->dist, ctx->state[ctx->cur], ctx->pid[ctx->cur], ctx->skey, sub ? ctx->wrank : nullptr, ctx->grid,
-                      ctx->state[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], sub ? ctx->ordk[ctx->cur ^ 1] : nullptr,
-                      sub ? ctx->ordr[ctx->cur ^ 1] : nullptr, ctx->capacity, st, lc))
-      return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
-    ctx->cur ^= 1;  // the unsorted local array is the source of this step's sort
+    if (in_place) {
+      if (dist_exchange(&ctx->dist, ctx->state[ctx->cur], ctx->pid[ctx->cur], ctx->skey, ctx->wrank, ctx->grid, ctx->state[ctx->cur],
+                        ctx->pid[ctx->cur], ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->capacity, ctx->live_idx, st, lc))
+        return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
+    } else {
+      if (dist_exchange(&ctx->dist, ctx->state[ctx->cur], ctx->pid[ctx->cur], ctx->skey, sub ? ctx->wrank : nullptr, ctx->grid,
+                        ctx->state[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], sub ? ctx->ordk[ctx->cur ^ 1] : nullptr,
+                        sub ? ctx->ordr[ctx->cur ^ 1] : nullptr, ctx->capacity, nullptr, st, lc))
+        return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
+      ctx->cur ^= 1;  // the unsorted local array is the source of this step's sort
+    }
   }
   StateArrays& src = ctx->state[ctx->cur];
   StateArrays& dst = ctx->state[ctx->cur ^ 1];
@@ -421,9 +429,9 @@ int enqueue_substep(clsph_context* ctx) {
 
   // sub-cell order: the pre-step keys tap is written by k_rank, in the reference's order
   launch_sort_keys(ctx->sort, src.pos, ctx->grid, n, ctx->sm_count, (ctx->debug && !sub) ? ctx->taps.keys_input : nullptr, sub,
-                   sub ? ctx->sub_lb : nullptr, st, lc);  // (also clears the sub-cell table and scans the digit histograms)
+                   sub ? ctx->sub_lb : nullptr, in_place ? ctx->live_idx : nullptr, st, lc);  // (+ table clear, histogram scan)
   if (prof) next_event(ctx);
-  launch_sort_passes(ctx->sort, ctx->grid, n, st, lc);
+  launch_sort_passes(ctx->sort, ctx->grid, n, in_place ? ctx->live_idx : nullptr, st, lc);
   if (prof) next_event(ctx);
 
   bool join_side = false;  // the side stream has work of this sub-step
@@ -671,6 +679,7 @@ void clsph_destroy(clsph_context* ctx) {
     cudaFree(ctx->ordr[s]);
   }
   cudaFree(ctx->wrank);
+  cudaFree(ctx->live_idx);
   cudaFree(ctx->export_ids);
   cudaFree(ctx->lists.entries);
   cudaFree(ctx->lists.count);
@@ -861,6 +870,10 @@ int clsph_dist_init(clsph_context* ctx, int rank, int world, const void* unique_
   }
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->wrank, ctx->capacity));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->export_ids, ctx->capacity));
+  {  // CLSPH_DIST_IN_PLACE=0: the copying exchange (k_dist_classify) also in the sub-cell order
+    const char* e = std::getenv("CLSPH_DIST_IN_PLACE");
+    if (!(e && std::atoi(e) == 0)) CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->live_idx, ctx->capacity));
+  }
   return CLSPH_OK;
 }
 

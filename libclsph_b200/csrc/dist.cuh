@@ -40,7 +40,7 @@ void dist_invalidate_bounds(DistState* d);
 // wrank / u_ordk / u_ordr (all null or all set): order keys of the sub-cell order, see k_dist_classify.
 int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pid, const uint32_t* skey,
                   const uint32_t* wrank, GridState* grid, const StateArrays& u, uint32_t* u_pid, uint32_t* u_ordk,
-                  uint32_t* u_ordr, uint32_t capacity, cudaStream_t stream, uint64_t* launches);
+                  uint32_t* u_ordr, uint32_t capacity, uint32_t* live, cudaStream_t stream, uint64_t* launches);
 void launch_dist_export(const StateArrays& s, const float4* aux, const uint32_t* skey, const uint32_t* pid,
                         const uint32_t* wrank, const GridState* grid, void* aos, uint32_t* ids, uint32_t* out_count,
                         uint32_t capacity, cudaStream_t stream, uint64_t* launches);

@@ -65,8 +65,8 @@ uint32_t sort_tiles_for(uint32_t n);
 size_t sort_scratch_words(uint32_t max_particles);
 // sub_keys: keys are (cell key << 3 | octant) instead of the cell key (subgrid.cu).
 void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* grid, uint32_t n_launch, int sm_count,
-                      uint32_t* keys_tap, bool sub_keys, uint32_t* sub_lb, cudaStream_t stream, uint64_t* launches);
-void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_launch, cudaStream_t stream,
+                      uint32_t* keys_tap, bool sub_keys, uint32_t* sub_lb, const uint32_t* index, cudaStream_t stream, uint64_t* launches);
+void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_launch, const uint32_t* first_vals, cudaStream_t stream,
                         uint64_t* launches);
 
 // ---- grid.cu

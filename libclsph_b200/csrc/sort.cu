@@ -66,7 +66,7 @@ template <bool kSub>
 __global__ void __launch_bounds__(256) k_keys_hist(const float4* __restrict__ pos, uint32_t* __restrict__ keys,
                                                    const GridState* __restrict__ grid, uint32_t* __restrict__ hist,
                                                    uint32_t* __restrict__ sub_lb, uint32_t* __restrict__ digit_base,
-                                                   uint32_t* __restrict__ done) {
+                                                   uint32_t* __restrict__ done, const uint32_t* __restrict__ index) {
   __shared__ uint32_t s_hist[kMaxSortPasses * kRadix];
   __shared__ uint32_t s_scratch[8];
   __shared__ bool s_last;
@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(256) k_keys_hist(const float4* __restrict__ po
     const bool valid = i < n;
     const unsigned vmask = __ballot_sync(kFullMask, valid);
     if (!valid) continue;
-    const float4 p = pos[i];
+    // `index` (multi-GPU exchange in place): entry i of the sort's input is the particle at index[i]
+    const float4 p = pos[index ? index[i] : i];
     uint32_t key;
     if (kSub) {
       const uint32_t fx = sub_coord(p.x, mnx, cell), fy = sub_coord(p.y, mny, cell), fz = sub_coord(p.z, mnz, cell);
@@ -282,7 +283,8 @@ ScratchLayout layout_of(const SortBuffers& b) {
 
 // Zeroes the scratch, computes keys into keys_a and all digit histograms.
 void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* grid, uint32_t n_launch, int sm_count,
-                      uint32_t* keys_tap, bool sub_keys, uint32_t* sub_lb, cudaStream_t stream, uint64_t* launches) {
+                      uint32_t* keys_tap, bool sub_keys, uint32_t* sub_lb, const uint32_t* index, cudaStream_t stream,
+                      uint64_t* launches) {
   const ScratchLayout l = layout_of(b);
   const uint32_t tiles = sort_tiles_for(n_launch);
   // histograms, tile counters and the look-back status words of the tiles in use start at zero
@@ -290,15 +292,16 @@ void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* 
   cudaMemsetAsync(b.scratch, 0, zero_words * sizeof(uint32_t), stream);
   const unsigned hist_blocks = (unsigned)std::min<uint64_t>(((uint64_t)n_launch + 255) / 256, (uint64_t)sm_count * 8);
   uint32_t* done = l.tile_counter + 8;  // (words 0..3 are the tile counters of the passes; all zeroed above)
-  if (sub_keys) k_keys_hist<true><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist, sub_lb, l.digit_base, done);
-  else k_keys_hist<false><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist, nullptr, l.digit_base, done);
+  if (sub_keys) k_keys_hist<true><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist, sub_lb, l.digit_base, done, index);
+  else k_keys_hist<false><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist, nullptr, l.digit_base, done, index);
   if (launches) ++*launches;
   if (keys_tap) launch_copy_u32(b.keys_a, keys_tap, n_launch, stream, launches);
 }
 
 // Histogram scan + the four digit passes (those beyond grid->sort_passes return immediately).
-void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_launch, cudaStream_t stream,
-                        uint64_t* launches) {
+// first_vals: payload of the first pass (null: the identity) -- the index list of an exchange in place.
+void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_launch, const uint32_t* first_vals,
+                        cudaStream_t stream, uint64_t* launches) {
   const ScratchLayout l = layout_of(b);
   const uint32_t tiles = sort_tiles_for(n_launch);
   // (the histogram scan is done by the last CTA of k_keys_hist)
@@ -306,11 +309,11 @@ void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_
   for (int pass = 0; pass < kMaxSortPasses; ++pass) {
     const bool even = (pass & 1) == 0;
     if (sort_items_for(n_launch) == 8)
-      k_onesweep<8><<<tiles, kSortThreads, 0, stream>>>(even ? b.keys_a : b.keys_b, pass == 0 ? nullptr : (even ? b.vals_a : b.vals_b),
+      k_onesweep<8><<<tiles, kSortThreads, 0, stream>>>(even ? b.keys_a : b.keys_b, pass == 0 ? first_vals : (even ? b.vals_a : b.vals_b),
                                                         even ? b.keys_b : b.keys_a, even ? b.vals_b : b.vals_a, grid, l.digit_base,
                                                         l.tile_counter, l.status, pass);
     else
-      k_onesweep<16><<<tiles, kSortThreads, 0, stream>>>(even ? b.keys_a : b.keys_b, pass == 0 ? nullptr : (even ? b.vals_a : b.vals_b),
+      k_onesweep<16><<<tiles, kSortThreads, 0, stream>>>(even ? b.keys_a : b.keys_b, pass == 0 ? first_vals : (even ? b.vals_a : b.vals_b),
                                                          even ? b.keys_b : b.keys_a, even ? b.vals_b : b.vals_a, grid, l.digit_base,
                                                          l.tile_counter, l.status, pass);
   }

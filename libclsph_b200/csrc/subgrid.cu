@@ -110,7 +110,9 @@ reorder_sub_slot(uint32_t r, uint32_t n, const float4* __restrict__ src_pos, con
   }
   dst_pos[dest] = src_pos[from];
   dst_vel[dest] = src_vel[from];
-  dst_ivel[dest] = src_ivel[from];
+  float4 iv = src_ivel[from];
+  if (src_ordk) iv.w = 0.f;  // multi-GPU: the mark "advanced here" is k_integrate's to set again in this sub-step
+  dst_ivel[dest] = iv;
   const uint32_t key = fkey >> 3, oct = fkey & 7u;
   skey[r] = key;  // the same for the whole sub-cell, whichever slot
   // tile kernels (tiles.cu): a block is 8 consecutive Morton cells (2 x 2 x 2); the first particle of each

@@ -51,11 +51,15 @@ def by_id(parts, ids, n):
 
 
 # world 1: a slab that is not cut at all; transport: stores into the neighbours' mailboxes (default) or NCCL messages
-@pytest.mark.parametrize("world,copies,sub,transport", [(2, 2, 0, "peer"), (3, 3, 1, "peer"), (1, 2, 1, "peer"), (3, 3, 1, "nccl")])
+# "peer-copy": the exchange that copies the owned particles into a fresh array (CLSPH_DIST_IN_PLACE=0) instead of leaving them in place
+@pytest.mark.parametrize("world,copies,sub,transport", [(2, 2, 0, "peer"), (3, 3, 1, "peer"), (1, 2, 1, "peer"), (3, 3, 1, "nccl"),
+                                                        (3, 3, 1, "peer-copy")])
 def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub, transport, monkeypatch):
     steps = 3
     if transport == "nccl":
         monkeypatch.setenv("CLSPH_DIST_TRANSPORT", "nccl")
+    if transport == "peer-copy":
+        monkeypatch.setenv("CLSPH_DIST_IN_PLACE", "0")
     p, terms, state, scene_file = elongated_state(copies)
     n = state.size
     normals, vertices, indices = workloads.scene_arrays(scene_file)
@@ -75,7 +79,7 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub, t
             ctx.set_scene(normals, vertices, indices)
             ctx.set_parameters(p, terms)
             ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
-            assert ctx.dist_transport().startswith("peer stores" if transport == "peer" else "nccl")
+            assert ctx.dist_transport().startswith("nccl" if transport == "nccl" else "peer stores")
             ctx.dist_upload(np.ascontiguousarray(state[mine]), mine)
             for k in range(steps):
                 ctx.step(1)
