@@ -125,10 +125,9 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
  *                      one or two at a time; 5 (default) = four ahead, in twos.
  *   "merged_rows"      (pair_density = 0) 1 (default): the density pass walks the two index ranges of each row of
  *                      sub-cells in one loop, which evens out the loop lengths between the lanes of a warp.
- *   "deferred_lists"   (pair_density = 0) 1: hits of up to 32 consecutive candidates are collected in a bit mask
- *                      and the list entries written in a short loop afterwards. Same lists. Default 0.
- *   "tile_kernels"     1: density pass on blocks of 2 x 2 x 2 cells staged in shared memory by bulk copies
- *                      (tiles.cu). Correct, not faster than the default on a B200 (profiles/r02_b, r02_d). Default 0.
+ *   "factored_forces"  -1 (default): by the fluid -- the list force kernel with factored pair terms (per-run constants
+ *                      out of the sums, one MUFU.RSQ per pair) when the lists have 96 rows or more (~45 neighbours,
+ *                      mucus), k_forces_lists<fast> otherwise (~25, water); 1 / 0 force one of them. Needs fast_pairs.
  *   "neighbour_lists"  (sub_cell_order = 0) 1 (default): the density pass stores per-particle neighbour lists in HBM
  *                      and the force pass reads them; 0: both passes search on their own.
  *   "list_rows"        list entries kept per particle (0 = derive from the rest density; rounded up to even);

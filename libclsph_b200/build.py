@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libclsph_cuda.so")
-SOURCES = ["context.cu", "sort.cu", "grid.cu", "neighbors.cu", "subgrid.cu", "tiles.cu", "integrate.cu", "dist.cu"]
+SOURCES = ["context.cu", "sort.cu", "grid.cu", "neighbors.cu", "subgrid.cu", "integrate.cu", "dist.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "dist.cuh", "pair_terms.cuh", "subview.cuh"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

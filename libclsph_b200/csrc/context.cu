@@ -79,10 +79,9 @@ struct clsph_context {
   // sub-cell order (subgrid.cu): arrays sorted by (cell key << 3 | octant); rrank = index of each
   // particle in the reference's array, rr_tmp = the gathered ranks of the previous sub-step
   bool sub_order = true;        // option "sub_cell_order"
-  bool deferred_lists = false;  // k_density_sub<.., kDeferred>: list entries written per 32-candidate chunk
   bool merged_rows = true;      // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
   bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
-  int factored_forces = -1;         // option "factored_forces": 1 k_forces_lists_tile, 0 k_forces_lists<fast>, -1 by the fluid (list rows)
+  int factored_forces = -1;         // option "factored_forces": 1 k_forces_lists_factored, 0 k_forces_lists<fast>, -1 by the fluid (list rows)
   int pair_variant = 5;             // option "pair_variant" (tuning): walk 0/1/2 + 3 x (entries stored two at a time)
   uint32_t* pair_items = nullptr;   // [capacity] items written by k_reorder_sub
   uint32_t* pair_count = nullptr;
@@ -92,11 +91,6 @@ struct clsph_context {
   uint32_t* sub_lb = nullptr;
   uint32_t* rrank = nullptr;
   uint32_t* rr_tmp = nullptr;
-  // tile kernels (tiles.cu, option "tile_kernels"): the neighbour passes of the sub-cell order on blocks of 2 x 2 x 2 cells
-  bool tiles = false;
-  TileLists tl{};
-  TilePlan tile_plan{};
-
   // list mode (default): the density pass stores neighbour lists, the force pass reads them
   bool use_lists = true;
   uint32_t list_rows_override = 0;  // 0 = derive from the rest density
@@ -343,25 +337,7 @@ int ensure_sub(clsph_context* ctx) {
   return CLSPH_OK;
 }
 
-// Arrays of the tile kernels, allocated the first time they are selected; the staging plan follows the fluid.
-int ensure_tiles(clsph_context* ctx) {
-  if (!ctx->tiles || !ctx->sub_order) return CLSPH_OK;
-  if (!ctx->tl.blocks) {
-    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.blocks, ctx->capacity));
-    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.slow, ctx->capacity));
-    CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->tl.ctl, 1));
-    CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->tl.ctl, 0, sizeof(TileCtl), ctx->stream));
-  }
-  if (ctx->have_params) {
-    const simulation_parameters& p = ctx->params;
-    const double per_sub_cell = (double)p.fluid_density / (double)p.particle_mass * (double)p.h * p.h * p.h;
-    ctx->tile_plan = tiles_plan(per_sub_cell);
-  }
-  return CLSPH_OK;
-}
-
 int ensure_lists(clsph_context* ctx) {
-  if (int rc = ensure_tiles(ctx)) return rc;
   if (!ctx->use_lists && !ctx->sub_order) {
     ctx->lists.rows = 0;
     return CLSPH_OK;
@@ -440,14 +416,14 @@ int enqueue_substep(clsph_context* ctx) {
   // Measured (profiles/r02_n_*): with ~25 neighbours per particle (water, 64 list rows) both kernels wait on the same
   // gathers and the plain one is 1 % ahead; with ~45 (mucus, 112 rows) the factored one saves 0.10 of 0.91 ms.
   const bool want_factored = ctx->factored_forces < 0 ? ctx->lists.rows >= 96u : ctx->factored_forces != 0;
-  const bool factored = sub && !ctx->tiles && want_factored && ctx->fast_pairs;
-  const bool pairs = sub && ctx->pair_density && !ctx->tiles && !ctx->deferred_lists;
+  const bool factored = sub && want_factored && ctx->fast_pairs;
+  const bool pairs = sub && ctx->pair_density;
   if (sub) {
     launch_reorder_sub(src, dst, ctx->sort, ctx->skey, multi ? nullptr : ctx->rrank, ctx->rr_tmp, ctx->sub_lb, ctx->grid,
                        multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr,
                        multi ? ctx->ordk[ctx->cur] : nullptr, multi ? ctx->ordr[ctx->cur] : nullptr,
                        multi ? ctx->ordk[ctx->cur ^ 1] : nullptr, multi ? ctx->ordr[ctx->cur ^ 1] : nullptr,
-                       ctx->tiles ? ctx->tl.ctl : nullptr, ctx->tl.blocks, pairs ? ctx->pair_items : nullptr, ctx->pair_count, n, st, lc);
+                       pairs ? ctx->pair_items : nullptr, ctx->pair_count, n, st, lc);
     ctx->cur ^= 1;
     if (!multi) {  // one GPU: absolute index in the reference's array
       // Nothing in this sub-step reads the new ranks, and the pass (a count over the ~40 particles of each cell,
@@ -467,29 +443,16 @@ int enqueue_substep(clsph_context* ctx) {
       launch_rank_pair(dst.pos, ctx->skey, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->wrank, ctx->sub_lb, ctx->sort, ctx->grid, n,
                        st, lc);
     if (prof) next_event(ctx);
-    if (ctx->tiles) {
-      launch_density_tiles(dst.pos, dst.vel, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists, ctx->tl,
-                           ctx->tile_plan, ctx->sm_count, st, lc);
-      launch_density_slow(dst.pos, dst.vel, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists, ctx->tl,
-                          ctx->sm_count, st, lc);
-      if (ctx->debug)
-        launch_tile_taps(dst.pos, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->lists, ctx->taps.candidate_count,
-                         ctx->taps.support_count, n, st, lc);
-      if (prof) next_event(ctx);
-      launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
-                    false, true, ctx->forces_dense, ctx->accel, n, st, lc, 1);
-      launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
-                                 ctx->lists, ctx->accel, nullptr, n, st, lc);
-    } else {
+    {
       if (pairs)
         launch_density_pairs(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                             ctx->taps, ctx->debug, ctx->pair_variant, false, ctx->pair_items, ctx->pair_count, n, st, lc);
+                             ctx->taps, ctx->debug, ctx->pair_variant, ctx->pair_items, ctx->pair_count, n, st, lc);
       else
         launch_density_sub(dst.pos, dst.vel, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst, ctx->aux, ctx->lists,
-                           ctx->taps, ctx->debug, ctx->deferred_lists, ctx->merged_rows, n, st, lc);
+                           ctx->taps, ctx->debug, ctx->merged_rows, n, st, lc);
       if (prof) next_event(ctx);
       launch_forces(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->cell_start, ctx->cell_end, ctx->grid, ctx->konst, ctx->lists,
-                    false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc, factored ? 2 : 0);
+                    false, ctx->fast_pairs, ctx->forces_dense, ctx->accel, n, st, lc, factored);
       launch_forces_sub_overflow(dst.pos, dst.vel, ctx->aux, ctx->skey, ctx->sub_lb, ctx->sort, ctx->grid, ctx->konst,
                                  ctx->lists, ctx->accel, pairs ? ctx->pair_count + 1 : nullptr, n, st, lc);
     }
@@ -610,7 +573,6 @@ int clsph_create(clsph_context** out, int device, uint32_t max_particles, uint32
   CREATE_TRY(cudaMemset(ctx->cell_start, 0, sizeof(uint32_t) * ctx->cell_capacity));
   CREATE_TRY(cudaMemset(ctx->cell_end, 0, sizeof(uint32_t) * ctx->cell_capacity));
   neighbors_init();
-  tiles_init();
   CREATE_TRY(cudaGetLastError());
   if (ctx->sub_order && ensure_sub(ctx) != CLSPH_OK) {
     g_create_error = ctx->error;
@@ -692,9 +654,6 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->rr_tmp);
   cudaFree(ctx->pair_items);
   cudaFree(ctx->pair_count);
-  cudaFree(ctx->tl.blocks);
-  cudaFree(ctx->tl.slow);
-  cudaFree(ctx->tl.ctl);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->copy) cudaStreamSynchronize(ctx->copy);
   if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
@@ -770,10 +729,6 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     ctx->sub_order = value != 0;
     int rc = ensure_sub(ctx);
     if (rc) return rc;
-  } else if (!std::strcmp(name, "tile_kernels")) {
-    ctx->tiles = value != 0;
-  } else if (!std::strcmp(name, "deferred_lists")) {
-    ctx->deferred_lists = value != 0;
   } else if (!std::strcmp(name, "merged_rows")) {
     ctx->merged_rows = value != 0;
   } else if (!std::strcmp(name, "pair_density")) {

@@ -273,10 +273,10 @@ k_dist_classify(const float4* __restrict__ pos, const float4* __restrict__ vel, 
   if (!sig.done) return;
   // Peer transport: the records are in the neighbours' mailboxes once every CTA has passed this point; the last
   // one to arrive publishes the counts, then the sequence number the receivers wait for (release at system scope).
-  if (stored_remotely) __threadfence_system();
+  if (stored_remotely) __threadfence_system();  // the few threads that stored into a mailbox
   __syncthreads();
   if (threadIdx.x != 0) return;
-  __threadfence_system();
+  __threadfence();  // device scope is enough here (7500 CTAs: a system-scope fence in each cost ~25 us); the last CTA's is not
   if (atomicAdd(sig.done, 1u) != gridDim.x - 1u) return;
   __threadfence_system();
   if (sig.header_left) { store_flag(sig.header_left, atomicAdd(left.counts, 0u)); store_flag(sig.header_left + 1, atomicAdd(left.counts + 1, 0u)); }
@@ -361,10 +361,10 @@ k_dist_select(const float4* __restrict__ pos, const float4* __restrict__ vel, co
     }
   }
   if (!sig.done) return;
-  if (stored_remotely) __threadfence_system();
+  if (stored_remotely) __threadfence_system();  // the few threads that stored into a mailbox
   __syncthreads();
   if (threadIdx.x != 0) return;
-  __threadfence_system();
+  __threadfence();  // device scope is enough here (7500 CTAs: a system-scope fence in each cost ~25 us); the last CTA's is not
   if (atomicAdd(sig.done, 1u) != gridDim.x - 1u) return;
   __threadfence_system();
   if (sig.header_left) { store_flag(sig.header_left, atomicAdd(left.counts, 0u)); store_flag(sig.header_left + 1, atomicAdd(left.counts + 1, 0u)); }

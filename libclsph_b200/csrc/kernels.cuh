@@ -120,22 +120,21 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
                    const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
-                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, int tile_lists = 0);
+                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool factored = false);
 
-struct TileCtl;
 // ---- subgrid.cu: sub-cell order (arrays sorted by cell key << 3 | octant)
 void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capacity, int sm_count, cudaStream_t stream,
                       uint64_t* launches);
 void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                         const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,
-                        uint32_t* dst_ordk, uint32_t* dst_ordr, TileCtl* tile_ctl, uint32_t* tile_blocks, uint32_t* pair_items,
-                        uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+                        uint32_t* dst_ordk, uint32_t* dst_ordr, uint32_t* pair_items, uint32_t* pair_count, uint32_t n_launch,
+                        cudaStream_t stream, uint64_t* launches);
 // Density + pressure + neighbour lists, two particles of a sub-cell per thread (packed fp32: FADD2 / FFMA2).
 void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                           const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                          const DebugTaps& taps, bool debug, int variant, bool no_self, const uint32_t* pair_items,
-                          const uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
+                          const DebugTaps& taps, bool debug, int variant, const uint32_t* pair_items, const uint32_t* pair_count,
+                          uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 void launch_rank_pair(const float4* pos, const uint32_t* skey, const uint32_t* ordk, const uint32_t* ordr, uint32_t* wrank,
                       const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, uint32_t n_launch,
                       cudaStream_t stream, uint64_t* launches);
@@ -144,47 +143,14 @@ void launch_rank(const uint32_t* skey, const uint32_t* rr_old, uint32_t* rr_new,
                  uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 void launch_density_sub(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                         const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                        const DebugTaps& taps, bool debug, bool deferred, bool merged, uint32_t n_launch,
-                        cudaStream_t stream, uint64_t* launches);
+                        const DebugTaps& taps, bool debug, bool merged, uint32_t n_launch, cudaStream_t stream,
+                        uint64_t* launches);
 void launch_forces_sub_overflow(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                                 const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid, const SphConst& c,
                                 const NeighbourLists& lists, float4* accel, const uint32_t* overflowed, uint32_t n_launch,
                                 cudaStream_t stream, uint64_t* launches);
 void launch_scatter_words(const void* src, const uint32_t* rrank, void* dst, uint32_t n, uint32_t words,
                           cudaStream_t stream, uint64_t* launches);
-
-// ---- tiles.cu: the density pass of the sub-cell order as a tile kernel (blocks of 2 x 2 x 2 cells)
-// Device-side bookkeeping of one sub-step, zeroed before the gather kernel appends the block list.
-struct TileCtl {
-  uint32_t n_blocks;      // non-empty blocks, appended by k_reorder_sub
-  uint32_t next_density;  // work counter of the persistent tile kernel
-  uint32_t next_slow;     // work counter of k_density_slow
-  uint32_t n_slow;        // particles handed to k_density_slow (TileLists::slow)
-  uint32_t pad[4];
-};
-struct TileLists {
-  uint32_t* blocks = nullptr;           // [capacity] ids (cell key >> 3) of the non-empty blocks, any order
-  uint32_t* slow = nullptr;             // [capacity] particles for k_density_slow
-  TileCtl* ctl = nullptr;
-};
-struct TilePlan {
-  uint32_t density_slots = 0;  // staging capacity (particles of a region) per CTA
-  size_t density_smem = 0;     // dynamic shared memory per CTA
-};
-void tiles_init();
-TilePlan tiles_plan(double particles_per_sub_cell);
-// Densities, pressures and neighbour lists (the particle itself not listed; lists.count = neighbours found).
-void launch_density_tiles(float4* pos, float4* vel, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
-                          const SphConst& c, float4* aux, const NeighbourLists& lists, const TileLists& tl, const TilePlan& plan,
-                          int sm_count, cudaStream_t stream, uint64_t* launches);
-// subgrid.cu: the particles of TileLists::slow, one warp each, searching in global memory; same outputs, same bits
-void launch_density_slow(float4* pos, float4* vel, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
-                         const SphConst& c, float4* aux, const NeighbourLists& lists, const TileLists& tl, int sm_count,
-                         cudaStream_t stream, uint64_t* launches);
-// debug taps of the tile organisation: the reference's candidate count (27 cells) and the support count
-void launch_tile_taps(const float4* pos, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
-                      const GridState* grid, const SphConst& c, const NeighbourLists& lists, uint32_t* cand_count,
-                      uint32_t* supp_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches);
 
 // ---- integrate.cu
 void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,

@@ -667,17 +667,16 @@ k_forces_lists(const float4* __restrict__ pos, const float4* __restrict__ vel, c
   if (valid && listed) accel[i] = finish_force(sums, c, aux[i].x);
 }
 
-// The same pass for the lists of the tile kernel (tiles.cu): the particle itself is not listed (its own term is
-// added by tile_finish_force), and the pair terms are tile_pair_ops / tile_pair_add -- constants factored out of
-// the sums, one MUFU.RSQ per pair, no branch: ~46 instead of ~71 instructions per pair. A particle with a
-// degenerate pair (coincident particles, smoothing.cl:23; found by the exact test on s) is redone on the spot
-// with the reference's formulas.
-// kTrip neighbours per trip of the walk: 2 (four gathers in flight) or 4 (eight; the pass is bound by the latency
-// of those gathers, L1 hit rate ~60 %).
-// kSelfListed: the lists contain the particle itself (k_density_pairs / k_density_sub write them that way).
-template <int kBlocks, int kTrip, bool kSelfListed>
+// The same pass with the pair terms of pair_terms.cuh's second half: per-run constants factored out of the sums, one
+// MUFU.RSQ per pair, no branch -- ~46 instead of ~71 instructions per pair. The particle itself is in its list (the
+// density kernels write it there); for that entry 1/r is taken as 0, which leaves exactly its own term. A particle
+// with a degenerate pair (coincident particles, smoothing.cl:23; found by the exact test on s) is redone on the spot
+// with the reference's formulas. Measured against k_forces_lists<fast> (profiles/r02_c_summary.md): 59 M instead of
+// 88 M warp instructions at 1 Mi particles, the same 0.14 ms (both wait on the same gathers); 0.81 instead of 0.91 ms
+// at 4 Mi mucus with 45 neighbours per particle -- the library picks by the fluid (context.cu).
+template <int kBlocks>
 __global__ void __launch_bounds__(kFlWarps * 32, kBlocks)
-k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
+k_forces_lists_factored(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
                     const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
                     const uint32_t* __restrict__ skey, const GridState* __restrict__ grid, const SphConst c,
                     float4* __restrict__ accel) {
@@ -716,28 +715,12 @@ k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ v
     const uint32_t mine = count > e0 ? min(count - e0, 32u) : 0u;
     const uint32_t* row = tile + lane * kTileStride;
     uint32_t e = 0;
-    if (kTrip == 4) {
-      for (; e + 4 <= mine; e += 4) {  // four neighbours per trip: eight independent gathers in flight
-        const uint32_t ja = row[e], jb = row[e + 1], jc = row[e + 2], jd = row[e + 3];
-        const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb], pc = pos[jc], vc = vel[jc], pd = pos[jd], vd = vel[jd];
-        float sa, sb, sc, sd;
-        const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa, kSelfListed && ja == i);
-        tile_pair_add(sums, oa);
-        const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb, kSelfListed && jb == i);
-        tile_pair_add(sums, ob);
-        const TilePair oc = tile_pair_ops(c, pi, vi, pc, vc, sc, kSelfListed && jc == i);
-        tile_pair_add(sums, oc);
-        const TilePair od = tile_pair_ops(c, pi, vi, pd, vd, sd, kSelfListed && jd == i);
-        tile_pair_add(sums, od);
-        degenerate |= (sa < c.degenerate_s) | (sb < c.degenerate_s) | (sc < c.degenerate_s) | (sd < c.degenerate_s);
-      }
-    }
     for (; e + 2 <= mine; e += 2) {  // two neighbours per trip: four independent gathers in flight
       const uint32_t ja = row[e], jb = row[e + 1];
       const float4 pa = pos[ja], va = vel[ja], pb = pos[jb], vb = vel[jb];
       float sa, sb;
-      const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa, kSelfListed && ja == i);
-      const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb, kSelfListed && jb == i);
+      const TilePair oa = tile_pair_ops(c, pi, vi, pa, va, sa, ja == i);
+      const TilePair ob = tile_pair_ops(c, pi, vi, pb, vb, sb, jb == i);
       degenerate |= (sa < c.degenerate_s) | (sb < c.degenerate_s);
       tile_pair_add(sums, oa);
       tile_pair_add(sums, ob);
@@ -745,7 +728,7 @@ k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ v
     if (e < mine) {
       const uint32_t j = row[e];
       float s;
-      const TilePair o = tile_pair_ops(c, pi, vi, pos[j], vel[j], s, kSelfListed && j == i);
+      const TilePair o = tile_pair_ops(c, pi, vi, pos[j], vel[j], s, j == i);
       degenerate |= s < c.degenerate_s;
       tile_pair_add(sums, o);
     }
@@ -753,16 +736,15 @@ k_forces_lists_tile(const float4* __restrict__ pos, const float4* __restrict__ v
   }
   if (!(valid && listed)) return;
   if (!degenerate) {
-    accel[i] = tile_finish_force(sums, c, aux[i].x, vi.w, kSelfListed);
+    accel[i] = tile_finish_force(sums, c, aux[i].x, vi.w, true);
     return;
   }
   ForceSums exact;
   const uint32_t* mine = nlist + (size_t)i * list_rows;
   for (uint32_t e = 0; e < count; ++e) {
     const uint32_t j = mine[e];
-    add_pair(exact, c, kSelfListed && j == i, pi, vi, pi.w, pos[j], vel[j]);
+    add_pair(exact, c, j == i, pi, vi, pi.w, pos[j], vel[j]);
   }
-  if (!kSelfListed) add_pair(exact, c, true, pi, vi, pi.w, pi, vi);
   accel[i] = finish_force(exact, c, aux[i].x);
 }
 
@@ -808,24 +790,14 @@ void launch_density(float4* pos, float4* vel, const uint32_t* skey, const uint32
 void launch_forces(const float4* pos, const float4* vel, const float4* aux, const uint32_t* skey,
                    const uint32_t* cell_start, const uint32_t* cell_end, const GridState* grid, const SphConst& c,
                    const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
-                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, int tile_lists) {
+                   uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool factored) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
-  if (lists.rows && tile_lists) {  // lists of the tile kernel: the particle itself is not listed
+  if (lists.rows && factored) {  // pair terms with the constants factored out of the sums (sub-cell order, fast pairs)
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
-    // (tile_lists: 1 = lists of the tile kernels, the particle itself not listed; 2 = lists of the per-particle / pair
-    // kernels, which contain it)
-    static const int trip = [] { const char* e = getenv("CLSPH_FORCES_TRIP"); return e ? atoi(e) : 2; }();  // tuning
-    if (tile_lists == 2) {
-      if (dense_occupancy)
-        k_forces_lists_tile<4, 2, true><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
-      else
-        k_forces_lists_tile<3, 2, true><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
-    } else if (dense_occupancy && trip == 4)
-      k_forces_lists_tile<4, 4, false><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
-    else if (dense_occupancy)
-      k_forces_lists_tile<4, 2, false><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    if (dense_occupancy)
+      k_forces_lists_factored<4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     else
-      k_forces_lists_tile<3, 2, false><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+      k_forces_lists_factored<3><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     if (launches) ++*launches;
   } else if (lists.rows) {
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);

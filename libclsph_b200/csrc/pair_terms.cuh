@@ -93,7 +93,7 @@ __device__ __forceinline__ float4 finish_force(const ForceSums& f, const SphCons
   return make_float4(fx / rho + c.gx, fy / rho + c.gy, fz / rho + c.gz, 0.f);
 }
 
-// ---- pair terms of the tile kernels (tiles.cu) and of the per-particle kernels behind them (subgrid.cu) ----------
+// ---- factored pair terms (k_forces_lists_factored, neighbors.cu) --------------------------------------------------
 // Same formulas with the per-run constants factored out of the sums (they are applied once per particle in
 // tile_finish_force) and one MUFU.RSQ for r and 1/r: 36 floating-point instructions per pair, no branch.
 //   P += (p_j/rho_j^2 + p_i/rho_i^2) (h - r)^2 / r * d        pressure      x m c_spiky
@@ -150,14 +150,6 @@ __device__ __forceinline__ float4 tile_finish_force(ForceSums f, const SphConst&
   f.nx *= c.c_poly6_grad; f.ny *= c.c_poly6_grad; f.nz *= c.c_poly6_grad;
   f.lap *= c.c_poly6_lap;
   return finish_force(f, c, rho);
-}
-
-// The particle's own term of the density sum, added last by the tile kernel and the kernel behind it (s = 0; NaN
-// for a particle that has blown up, which then fails the support test as it does in the reference).
-__device__ __forceinline__ float tile_self_density(float acc, const float4& pi, const SphConst& c) {
-  const float s = dist2_contract(pi.x, pi.y, pi.z, pi.x, pi.y, pi.z);
-  const float t = s < c.support_s ? c.h2 - s : 0.f;
-  return fmaf(t * t, t, acc);
 }
 
 // forces.cl:33-36 / smoothing.cl:1-4: rho = sum m C6 (h^2 - r^2)^3; sph.cl:37-39: Tait pressure.

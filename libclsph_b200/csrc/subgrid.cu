@@ -61,7 +61,7 @@ reorder_sub_slot(uint32_t r, uint32_t n, const float4* __restrict__ src_pos, con
                  const uint32_t* __restrict__ rr_src, uint32_t* __restrict__ rr_dst, uint32_t* __restrict__ sub_lb,
                  const GridState* __restrict__ grid, const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid,
                  const uint32_t* __restrict__ src_ordk, const uint32_t* __restrict__ src_ordr, uint32_t* __restrict__ dst_ordk,
-                 uint32_t* __restrict__ dst_ordr, TileCtl* tile_ctl, uint32_t* __restrict__ tile_blocks, uint32_t* left_out) {
+                 uint32_t* __restrict__ dst_ordr, uint32_t* left_out) {
   const bool in_b = (grid->sort_passes & 1u) != 0u;
   const uint32_t* __restrict__ keys = in_b ? keys_b : keys_a;
   const uint32_t* __restrict__ vals = in_b ? vals_b : vals_a;
@@ -115,10 +115,6 @@ reorder_sub_slot(uint32_t r, uint32_t n, const float4* __restrict__ src_pos, con
   dst_ivel[dest] = iv;
   const uint32_t key = fkey >> 3, oct = fkey & 7u;
   skey[r] = key;  // the same for the whole sub-cell, whichever slot
-  // tile kernels (tiles.cu): a block is 8 consecutive Morton cells (2 x 2 x 2); the first particle of each
-  // non-empty block announces it. The list order is arbitrary and does not influence any result.
-  if (tile_ctl && key < grid->cell_count && (r == 0 || (keys[r - 1] >> 6) != (fkey >> 6)))
-    tile_blocks[atomicAdd(&tile_ctl->n_blocks, 1u)] = fkey >> 6;
   if (src_pid) dst_pid[dest] = src_pid[from];
   if (src_ordk) {  // multi-GPU: order keys (cell key and rank inside the cell of the previous sub-step)
     dst_ordk[dest] = src_ordk[from];
@@ -159,14 +155,13 @@ k_reorder_sub(const float4* __restrict__ src_pos, const float4* __restrict__ src
               uint32_t* __restrict__ rr_dst, uint32_t* __restrict__ sub_lb, const GridState* __restrict__ grid,
               const uint32_t* __restrict__ src_pid, uint32_t* __restrict__ dst_pid, const uint32_t* __restrict__ src_ordk,
               const uint32_t* __restrict__ src_ordr, uint32_t* __restrict__ dst_ordk, uint32_t* __restrict__ dst_ordr,
-              TileCtl* tile_ctl, uint32_t* __restrict__ tile_blocks, uint32_t* __restrict__ pair_items,
-              uint32_t* __restrict__ pair_count) {
+              uint32_t* __restrict__ pair_items, uint32_t* __restrict__ pair_count) {
   const uint32_t n = grid->n;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t left = 1u;
   if (r < n)
     reorder_sub_slot(r, n, src_pos, src_vel, src_ivel, dst_pos, dst_vel, dst_ivel, keys_a, keys_b, vals_a, vals_b, skey, rr_src,
-                     rr_dst, sub_lb, grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr, tile_ctl, tile_blocks, &left);
+                     rr_dst, sub_lb, grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr, &left);
   if (!pair_items) return;
   // one append per CTA: the items of 256 consecutive slots stay together and in order, which keeps the threads
   // of a density CTA on neighbouring sub-cells (L1 reuse of the candidate rows)
@@ -246,11 +241,8 @@ k_rank_pair(const float4* __restrict__ pos, const uint32_t* __restrict__ skey, c
 // nlist[i * list_rows + e] = e-th neighbour of particle i (indices into the sorted arrays);
 // ncount[i] = neighbours found, more than list_rows = list incomplete (k_forces_sub redoes it).
 // =============================================================================================
-// kDeferred: list entries are not stored candidate by candidate; the hits of up to 32 consecutive
-// candidates are collected in a bit mask (two instructions per candidate instead of six for the predicated
-// store, its address, the bound check and the counters) and written out by a short loop over the set bits.
 // kMerged: both index ranges of a row of sub-cells are walked in one loop (for_each_row).
-template <bool kTaps, bool kDeferred, bool kMerged>
+template <bool kTaps, bool kMerged>
 __global__ void __launch_bounds__(kSubThreads)
 k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
               const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
@@ -273,26 +265,7 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
 #endif
   float acc = 0.f;   // sum of (h^2 - s)^3 over the support
   uint32_t cnt = 0;
-  if (kDeferred) {
-    for_each_range(v, g, c, pi, [&](uint32_t begin, uint32_t end) {
-      for (uint32_t j0 = begin; j0 < end; j0 += 32u) {
-        const uint32_t chunk = min(end - j0, 32u);
-        uint32_t mask = 0u, bit = 1u;
-        for (uint32_t k = 0; k < chunk; ++k, bit <<= 1) {
-          const float4 pj = pos[j0 + k];
-          const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
-          const bool inside = s < c.support_s;
-          const float t = inside ? c.h2 - s : 0.f;
-          acc = fmaf(t * t, t, acc);
-          mask |= inside ? bit : 0u;
-        }
-        for (uint32_t m = mask; m; m &= m - 1u) {  // ascending bits: list order = candidate order, as without kDeferred
-          if (cnt < list_rows) row[cnt] = j0 + (uint32_t)__ffs((int)m) - 1u;
-          ++cnt;
-        }
-      }
-    });
-  } else if (kMerged) {
+  if (kMerged) {
     for_each_row(v, g, c, pi, [&](uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
       const uint32_t total = (a1 - a0) + (b1 - b0);
       uint32_t j = a0 < a1 ? a0 : b0;
@@ -347,9 +320,7 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
 // kWalk: how a thread walks a row's candidates -- 0: one after the other; 1: the same with the next candidate's
 // load issued before the current one is tested; 2: four loads issued, then four tests. kStore2: list entries are
 // stored two at a time (one 8-byte store per two hits) instead of one by one.
-// kNoSelf: the particle itself is not listed (it still counts in the density and in the support tap): the form the
-// list force kernel with factored pair terms (k_forces_lists_tile) wants.
-template <bool kTaps, int kWalk, bool kStore2, bool kNoSelf>
+template <bool kTaps, int kWalk, bool kStore2>
 __global__ void __launch_bounds__(kSubThreads, 8)  // 64 registers: eight CTAs of four warps per SM
 k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
                 const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
@@ -400,7 +371,7 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     const bool hit0 = f2_lo(s) < c.support_s, hit1 = f2_hi(s) < c.support_s;
     const f32x2 w = f2_make(hit0 ? f2_lo(d) : 0.f, hit1 ? f2_hi(d) : 0.f);
     acc = f2_fma(f2_mul(w, w), w, acc);
-    const bool in0 = kNoSelf ? (hit0 && j != i0) : hit0, in1 = kNoSelf ? (hit1 && j != i1) : hit1;  // what goes into the lists
+    const bool in0 = hit0, in1 = hit1;
     if (kStore2) {
       // List entries leave two at a time: every lane's store is an L1 wavefront and a 32-byte L2 sector write of its
       // own (each lane writes its own row), so one 8-byte store per two hits halves that. The first hit of a pair
@@ -511,11 +482,8 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
             total += r.y - r.x;
           }
     }
-    // the support count includes the particle itself (unless it has blown up: NaN fails the test as in the reference)
-    const uint32_t self0 = (kNoSelf && dist2_contract(p0.x, p0.y, p0.z, p0.x, p0.y, p0.z) < c.support_s) ? 1u : 0u;
-    const uint32_t self1 = (kNoSelf && dist2_contract(p1.x, p1.y, p1.z, p1.x, p1.y, p1.z) < c.support_s) ? 1u : 0u;
-    if (need0) { cand_count[i0] = total; supp_count[i0] = cnt0 + self0; }
-    if (need1) { cand_count[i1] = total; supp_count[i1] = cnt1 + self1; }
+    if (need0) { cand_count[i0] = total; supp_count[i0] = cnt0; }
+    if (need1) { cand_count[i1] = total; supp_count[i1] = cnt1; }
   }
 }
 
@@ -542,83 +510,6 @@ k_forces_sub(const float4* __restrict__ pos, const float4* __restrict__ vel, con
   }
 }
 
-// ---- the kernel behind the tile kernel (tiles.cu): the particles of TileLists::slow, one WARP each -------------
-// Density, pressure, neighbour list and count by the walk of k_density_sub (search window of sub_bounds, global
-// memory), lanes across the candidates of a range. The list entries and the density terms are taken in candidate
-// order (ballot + prefix count; the terms are broadcast one by one and every lane keeps the same running sum), and
-// the particle's own term comes last: the same order, hence the same bits, as k_density_tiles.
-__global__ void __launch_bounds__(kSubThreads)
-k_density_slow(float4* pos, float4* vel, const uint32_t* __restrict__ sub_lb, const uint32_t* __restrict__ keys_a,
-               const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid, const SphConst c, float4* __restrict__ aux,
-               uint32_t* __restrict__ nlist, uint32_t* __restrict__ ncount, uint32_t list_rows, const uint32_t* __restrict__ slow,
-               const TileCtl* __restrict__ ctl) {
-  const GridState g = *grid;
-  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
-  const uint32_t n_slow = ctl->n_slow;
-  const unsigned lane = lane_id();
-  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_slow; k += n_warps) {
-    const uint32_t i = slow[k];
-    const float4 pi = pos[i];
-    uint32_t* row = nlist + (size_t)i * list_rows;
-    float acc = 0.f;
-    uint32_t cnt = 0;
-    for_each_range(v, g, c, pi, [&](uint32_t begin, uint32_t end) {
-      for (uint32_t j0 = begin; j0 < end; j0 += 32u) {
-        const uint32_t j = j0 + lane;
-        const bool ok = j < end;
-        const float4 pj = pos[ok ? j : i];
-        const float s = dist2_contract(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
-        const bool inside = ok && j != i && s < c.support_s;
-        const float t = c.h2 - s;
-        unsigned m = __ballot_sync(kFullMask, inside);
-        const uint32_t at = cnt + (uint32_t)__popc(m & lanemask_lt());
-        if (inside && at < list_rows) row[at] = j;
-        cnt += (uint32_t)__popc(m);
-        while (m) {
-          const int src = __ffs((int)m) - 1;
-          m &= m - 1u;
-          const float tk = __shfl_sync(kFullMask, t, src);
-          acc = fmaf(tk * tk, tk, acc);
-        }
-      }
-    });
-    if (lane == 0u) {
-      finish_density(c, tile_self_density(acc, pi, c), i, aux, pos, vel);
-      ncount[i] = cnt;
-    }
-  }
-}
-
-// Debug taps of the tile organisation, in the internal order (the caller scatters through rrank).
-__global__ void __launch_bounds__(kSubThreads)
-k_tile_taps(const float4* __restrict__ pos, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
-            const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
-            const SphConst c, const uint32_t* __restrict__ ncount, uint32_t* __restrict__ cand_count,
-            uint32_t* __restrict__ supp_count) {
-  const GridState g = *grid;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
-  const SubView v = make_view(g, sub_lb, keys_a, keys_b);
-  const uint32_t key = skey[i];
-  // the reference's candidate count: every particle of the 27 cells around this one (forces.cl:25-40)
-  const uint32_t cx = compact10(key), cy = compact10(key >> 1), cz = compact10(key >> 2);
-  uint32_t total = 0;
-  if (cx != 0u && cy != 0u && cz != 0u) {  // with a 0 coordinate the reference's unsigned loop does not run
-    for (uint32_t z = cz - 1u; z <= cz + 1u; ++z)
-      for (uint32_t y = cy - 1u; y <= cy + 1u; ++y)
-        for (uint32_t x = cx - 1u; x <= cx + 1u; ++x) {
-          const uint2 r = sub_range(v, morton3(x, y, z), 0u, 7u);
-          total += r.y - r.x;
-        }
-  }
-  cand_count[i] = total;
-  // the support count includes the particle itself (unless it has blown up: NaN fails the test as in the reference)
-  const float4 pi = pos[i];
-  const bool self = dist2_contract(pi.x, pi.y, pi.z, pi.x, pi.y, pi.z) < c.support_s;
-  supp_count[i] = ncount[i] + (self ? 1u : 0u);
-}
-
 // dst[rrank[i]] = src[i], `words` 32-bit words per item: internal order -> the reference's order.
 __global__ void __launch_bounds__(256) k_scatter_words(const uint32_t* __restrict__ src, const uint32_t* __restrict__ rrank,
                                                        uint32_t* __restrict__ dst, uint32_t n, uint32_t words) {
@@ -640,14 +531,13 @@ void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capa
 void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                         const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,
-                        uint32_t* dst_ordk, uint32_t* dst_ordr, TileCtl* tile_ctl, uint32_t* tile_blocks, uint32_t* pair_items,
-                        uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
-  if (tile_ctl) cudaMemsetAsync(tile_ctl, 0, sizeof(TileCtl), stream);
+                        uint32_t* dst_ordk, uint32_t* dst_ordr, uint32_t* pair_items, uint32_t* pair_count, uint32_t n_launch,
+                        cudaStream_t stream, uint64_t* launches) {
   if (pair_items) cudaMemsetAsync(pair_count, 0, 2 * sizeof(uint32_t), stream);  // items, overflowing lists
   k_reorder_sub<<<(n_launch + 255) / 256, 256, 0, stream>>>(src.pos, src.vel, src.ivel, dst.pos, dst.vel, dst.ivel, sort.keys_a,
                                                             sort.keys_b, sort.vals_a, sort.vals_b, skey, rr_src, rr_dst, sub_lb,
                                                             grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr,
-                                                            tile_ctl, tile_blocks, pair_items, pair_count);
+                                                            pair_items, pair_count);
   if (launches) ++*launches;
 }
 
@@ -669,29 +559,23 @@ void launch_rank_pair(const float4* pos, const uint32_t* skey, const uint32_t* o
 
 void launch_density_sub(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                         const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                        const DebugTaps& taps, bool debug, bool deferred, bool merged, uint32_t n_launch,
-                        cudaStream_t stream, uint64_t* launches) {
+                        const DebugTaps& taps, bool debug, bool merged, uint32_t n_launch, cudaStream_t stream,
+                        uint64_t* launches) {
   const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
   uint32_t* cand = debug ? taps.candidate_count : nullptr;
   uint32_t* supp = debug ? taps.support_count : nullptr;
-if (debug && deferred)
-    k_density_sub<true, true, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
-                                                                         aux, lists.entries, lists.count, lists.rows, cand, supp);
-  else if (debug && merged)
-    k_density_sub<true, false, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
-                                                                         aux, lists.entries, lists.count, lists.rows, cand, supp);
+  if (debug && merged)
+    k_density_sub<true, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                                  lists.entries, lists.count, lists.rows, cand, supp);
   else if (debug)
-    k_density_sub<true, false, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
-                                                                          aux, lists.entries, lists.count, lists.rows, cand, supp);
-  else if (deferred)
-    k_density_sub<false, true, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
-                                                                          aux, lists.entries, lists.count, lists.rows, cand, supp);
+    k_density_sub<true, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                                   lists.entries, lists.count, lists.rows, cand, supp);
   else if (merged)
-    k_density_sub<false, false, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
-                                                                          aux, lists.entries, lists.count, lists.rows, cand, supp);
+    k_density_sub<false, true><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                                   lists.entries, lists.count, lists.rows, cand, supp);
   else
-    k_density_sub<false, false, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c,
-                                                                           aux, lists.entries, lists.count, lists.rows, cand, supp);
+    k_density_sub<false, false><<<blocks, kSubThreads, 0, stream>>>(pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux,
+                                                                    lists.entries, lists.count, lists.rows, cand, supp);
   if (launches) ++*launches;
 }
 
@@ -709,9 +593,9 @@ struct PairArgs {
   unsigned blocks;
   cudaStream_t stream;
 };
-template <bool kTaps, int kWalk, bool kStore2, bool kNoSelf>
+template <bool kTaps, int kWalk, bool kStore2>
 void launch_pairs_variant(const PairArgs& a) {
-  k_density_pairs<kTaps, kWalk, kStore2, kNoSelf><<<a.blocks, kSubThreads, 0, a.stream>>>(a.pos, a.vel, a.skey, a.sub_lb, a.keys_a, a.keys_b, a.grid, a.c, a.aux,
+  k_density_pairs<kTaps, kWalk, kStore2><<<a.blocks, kSubThreads, 0, a.stream>>>(a.pos, a.vel, a.skey, a.sub_lb, a.keys_a, a.keys_b, a.grid, a.c, a.aux,
                                                                                  a.nlist, a.ncount, a.list_rows, a.cand, a.supp, a.pair_items,
                                                                                  a.pair_count);
 }
@@ -719,27 +603,24 @@ void launch_pairs_variant(const PairArgs& a) {
 
 void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
                           const GridState* grid, const SphConst& c, float4* aux, const NeighbourLists& lists,
-                          const DebugTaps& taps, bool debug, int variant, bool no_self, const uint32_t* pair_items,
-                          const uint32_t* pair_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
+                          const DebugTaps& taps, bool debug, int variant, const uint32_t* pair_items, const uint32_t* pair_count,
+                          uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
   // the item count lives on the device (between n / 2 and n): sized for the worst case, surplus blocks leave at once
   const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
   uint32_t* cand = debug ? taps.candidate_count : nullptr;
   uint32_t* supp = debug ? taps.support_count : nullptr;
   const PairArgs a{pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries, lists.count, lists.rows, cand, supp,
                    pair_items, pair_count, blocks, stream};
-  if (no_self) {  // lists for k_forces_lists_tile; the measured-best walk only
-    if (debug) launch_pairs_variant<true, 2, true, true>(a);
-    else launch_pairs_variant<false, 2, true, true>(a);
-  } else if (debug) {
-    launch_pairs_variant<true, 2, true, false>(a);
+  if (debug) {
+    launch_pairs_variant<true, 2, true>(a);
   } else {
     switch (variant) {
-      case 0: launch_pairs_variant<false, 0, false, false>(a); break;
-      case 1: launch_pairs_variant<false, 1, false, false>(a); break;
-      case 2: launch_pairs_variant<false, 2, false, false>(a); break;
-      case 3: launch_pairs_variant<false, 0, true, false>(a); break;
-      case 4: launch_pairs_variant<false, 1, true, false>(a); break;
-      default: launch_pairs_variant<false, 2, true, false>(a); break;
+      case 0: launch_pairs_variant<false, 0, false>(a); break;
+      case 1: launch_pairs_variant<false, 1, false>(a); break;
+      case 2: launch_pairs_variant<false, 2, false>(a); break;
+      case 3: launch_pairs_variant<false, 0, true>(a); break;
+      case 4: launch_pairs_variant<false, 1, true>(a); break;
+      default: launch_pairs_variant<false, 2, true>(a); break;
     }
   }
   if (launches) ++*launches;
@@ -753,22 +634,6 @@ void launch_forces_sub_overflow(const float4* pos, const float4* vel, const floa
   const unsigned blocks = std::max(1u, std::min((n_launch + kSubThreads - 1) / kSubThreads, 148u * 16u));
   k_forces_sub<<<blocks, kSubThreads, 0, stream>>>(pos, vel, aux, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, lists.count, lists.rows,
                                                    accel, overflowed);
-  if (launches) ++*launches;
-}
-
-void launch_density_slow(float4* pos, float4* vel, const uint32_t* sub_lb, const SortBuffers& sort, const GridState* grid,
-                         const SphConst& c, float4* aux, const NeighbourLists& lists, const TileLists& tl, int sm_count,
-                         cudaStream_t stream, uint64_t* launches) {
-  k_density_slow<<<sm_count * 2, kSubThreads, 0, stream>>>(pos, vel, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries,
-                                                           lists.count, lists.rows, tl.slow, tl.ctl);
-  if (launches) ++*launches;
-}
-
-void launch_tile_taps(const float4* pos, const uint32_t* skey, const uint32_t* sub_lb, const SortBuffers& sort,
-                      const GridState* grid, const SphConst& c, const NeighbourLists& lists, uint32_t* cand_count,
-                      uint32_t* supp_count, uint32_t n_launch, cudaStream_t stream, uint64_t* launches) {
-  k_tile_taps<<<(n_launch + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(pos, skey, sub_lb, sort.keys_a, sort.keys_b, grid,
-                                                                                      c, lists.count, cand_count, supp_count);
   if (launches) ++*launches;
 }
 

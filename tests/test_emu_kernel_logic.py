@@ -90,8 +90,7 @@ SUB = dict(sub_cell_order=1)
 
 
 @pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=0, neighbour_lists=1, list_rows=8),
-                                     SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, deferred_lists=1),
-                                     dict(sub_cell_order=1, deferred_lists=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4),
+                                     SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4),
                                      dict(sub_cell_order=1, fast_pairs=1), dict(sub_cell_order=0, neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
                                      dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8),
                                      dict(factored_forces=0), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(list_rows=8)])
@@ -282,7 +281,7 @@ def test_sub_cell_order_reports_a_grid_too_large_for_its_keys(box_scene):
 
 @pytest.mark.parametrize("kind", H.EDGE_KINDS)
 @pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=1, face_grid=1),
-                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1),
+                                     dict(sub_cell_order=1, face_grid=1, pair_density=0),
                                      dict(sub_cell_order=1, face_grid=1, fast_pairs=1), dict(sub_cell_order=1, merged_rows=1)])
 def test_edge_states(kind, options, box_scene):
     """States sitting ON the path's decisions (tests/helpers.edge_state; the oracle is pinned against the
@@ -319,7 +318,7 @@ def test_blown_up_particles_do_not_hang_the_kernels(options, box_scene):
 
 
 @pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=1, face_grid=1, fast_pairs=1),
-                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4),
+                                     dict(sub_cell_order=1, face_grid=1, pair_density=0, forces_blocks=4),
                                      dict(sub_cell_order=1, face_grid=1, merged_rows=1, fast_pairs=1)])
 def test_developed_state(options):
     """State S2: fluid that has hit the floor of the box and spread -- free surface, wall
@@ -340,7 +339,7 @@ def test_option_validation():
         with pytest.raises(capi.ClsphError) as e:
             ctx.set_option(name, value)
         assert e.value.code == capi.E_INVAL, name
-    for name, value in (("forces_blocks", 4), ("forces_blocks", 3), ("fast_pairs", 1), ("merged_rows", 1), ("deferred_lists", 1),
+    for name, value in (("forces_blocks", 4), ("forces_blocks", 3), ("fast_pairs", 1), ("merged_rows", 1), ("pair_density", 0), ("pair_variant", 3), ("factored_forces", 1),
                         ("face_grid", 1), ("sub_cell_order", 1), ("sub_cell_order", 0), ("neighbour_lists", 0), ("list_rows", 48)):
         ctx.set_option(name, value)
     ctx.close()

@@ -33,7 +33,7 @@ def test_sub_cell_order_jittered(fluid, n, box_scene):
 
 
 @pytest.mark.parametrize("options", [SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, list_rows=24), BOTH,
-                                     dict(sub_cell_order=1, deferred_lists=1), dict(sub_cell_order=1, deferred_lists=1, list_rows=8),
+                                     
                                      dict(sub_cell_order=1, forces_blocks=4),
                                      dict(sub_cell_order=0, neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
                                      dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8),
@@ -210,7 +210,7 @@ def test_edge_states(kind, options, box_scene):
 
 
 @pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), BOTH,
-                                     dict(sub_cell_order=1, face_grid=1, deferred_lists=1, forces_blocks=4),
+                                     dict(sub_cell_order=1, face_grid=1, pair_density=0, forces_blocks=4),
                                      dict(sub_cell_order=1, face_grid=1, fast_pairs=1, merged_rows=1, forces_blocks=4)])
 def test_developed_state(options):
     """State S2 in small: fluid that has hit the floor of the box and spread (free surface, wall
