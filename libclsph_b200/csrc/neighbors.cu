@@ -748,6 +748,83 @@ k_forces_lists_factored(const float4* __restrict__ pos, const float4* __restrict
   accel[i] = finish_force(exact, c, aux[i].x);
 }
 
+// =============================================================================================
+// The same pass WITHOUT the shared-memory tile: every lane reads its own row four entries at a time (one 16-byte
+// load that does not allocate in L1: the lists are streamed once, the L1 is for the gathered positions and
+// velocities, and the 34 KB tile per CTA took a third of it) and gathers the four neighbours together -- eight
+// independent loads in flight per thread. kFactored: pair terms as in k_forces_lists_factored, else add_pair_fast.
+// =============================================================================================
+__device__ __forceinline__ uint4 load_list4(const uint32_t* p) {
+#ifdef CLSPH_EMU
+  return *reinterpret_cast<const uint4*>(p);
+#else
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#endif
+}
+
+template <bool kFactored, int kBlocks>
+__global__ void __launch_bounds__(128, kBlocks)
+k_forces_lists_direct(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
+                      const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
+                      const uint32_t* __restrict__ skey, const GridState* __restrict__ grid, const SphConst c,
+                      float4* __restrict__ accel) {
+  const GridState g = *grid;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const float4 pi = pos[i];
+  if (!owned_here(pi.x, skey[i], g)) return;  // multi-GPU: ghosts get no force
+  const uint32_t count = ncount[i];
+  if (count > list_rows) return;  // redone by k_forces_sub
+  const float4 vi = vel[i];
+  const uint32_t* row = nlist + (size_t)i * list_rows;  // 16-byte aligned: list_rows is a multiple of 8 (or even and >= 4 ...)
+  ForceSums sums;
+  bool degenerate = false;
+  auto pair = [&](uint32_t j, const float4& pj, const float4& vj) {
+    if (kFactored) {
+      float s;
+      const TilePair o = tile_pair_ops(c, pi, vi, pj, vj, s, j == i);
+      degenerate |= s < c.degenerate_s;
+      tile_pair_add(sums, o);
+    } else {
+      add_pair_sel<true>(sums, c, j == i, pi, vi, pi.w, pj, vj);
+    }
+  };
+  uint32_t e = 0;
+  for (; e + 4u <= count; e += 4u) {
+    const uint4 q = load_list4(row + e);
+    const float4 pa = pos[q.x], va = vel[q.x], pb = pos[q.y], vb = vel[q.y], pc = pos[q.z], vc = vel[q.z], pd = pos[q.w], vd = vel[q.w];
+    pair(q.x, pa, va);
+    pair(q.y, pb, vb);
+    pair(q.z, pc, vc);
+    pair(q.w, pd, vd);
+  }
+  if (e < count) {  // one to three entries left in the last quad
+    const uint4 q = load_list4(row + e);
+    const uint32_t left = count - e;
+    const uint32_t jb = left > 1u ? q.y : q.x, jc = left > 2u ? q.z : q.x;
+    const float4 pa = pos[q.x], va = vel[q.x], pb = pos[jb], vb = vel[jb], pc = pos[jc], vc = vel[jc];
+    pair(q.x, pa, va);
+    if (left > 1u) pair(jb, pb, vb);
+    if (left > 2u) pair(jc, pc, vc);
+  }
+  if (!kFactored) {
+    accel[i] = finish_force(sums, c, aux[i].x);
+    return;
+  }
+  if (!degenerate) {
+    accel[i] = tile_finish_force(sums, c, aux[i].x, vi.w, true);
+    return;
+  }
+  ForceSums exact;
+  for (uint32_t k = 0; k < count; ++k) {
+    const uint32_t j = row[k];
+    add_pair(exact, c, j == i, pi, vi, pi.w, pos[j], vel[j]);
+  }
+  accel[i] = finish_force(exact, c, aux[i].x);
+}
+
 // ---------------------------------------------------------------------------------------------
 void neighbors_init() {
   cudaFuncSetAttribute(k_density<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDensitySmem);
@@ -792,7 +869,16 @@ void launch_forces(const float4* pos, const float4* vel, const float4* aux, cons
                    const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool factored) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
-  if (lists.rows && factored) {  // pair terms with the constants factored out of the sums (sub-cell order, fast pairs)
+  // CLSPH_FORCES_DIRECT=1 (tuning): the variant without the shared-memory tile
+  static const int direct = [] { const char* e = getenv("CLSPH_FORCES_DIRECT"); return e ? atoi(e) : 0; }();
+  if (lists.rows && direct && fast_pairs && !search_fallback && (lists.rows % 4u) == 0u) {
+    const unsigned dblocks = (n_launch + 127) / 128;
+    if (factored && direct == 2) k_forces_lists_direct<true, 6><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    else if (factored) k_forces_lists_direct<true, 8><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    else if (direct == 2) k_forces_lists_direct<false, 6><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    else k_forces_lists_direct<false, 8><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    if (launches) ++*launches;
+  } else if (lists.rows && factored) {  // pair terms with the constants factored out of the sums (sub-cell order, fast pairs)
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);
     if (dense_occupancy)
       k_forces_lists_factored<4><<<lblocks, kFlWarps * 32, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
