@@ -413,12 +413,10 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     achieved = n * kb[dominant] / (per[dominant] * 1e-3) / 1e9
     pairs = sub and "pair_density=0" not in options
-    # the library picks the factored list force kernel by the fluid's neighbour count (list rows >= 96), context.cu
-    list_rows = (int(2.5 * float(p.fluid_density) / float(p.particle_mass) * 4.18879020478639 * float(p.h) ** 3 + 8.0) + 7) & ~7
-    factored = (sub and "factored_forces=0" not in options and "fast_pairs=0" not in options
-                and ("factored_forces=1" in options or list_rows >= 96))
+    factored = sub and "factored_forces=0" not in options and "fast_pairs=0" not in options
+    direct = sub and "fast_pairs=0" not in options and os.environ.get("CLSPH_FORCES_DIRECT", "1") != "0"
     kernel_name = {"density": ("k_density_pairs" if pairs else "k_density_sub") if sub else "k_density_lists",
-                   "forces": "k_forces_lists_factored" if factored else "k_forces_lists",
+                   "forces": "k_forces_lists_direct" if direct else ("k_forces_lists_factored" if factored else "k_forces_lists"),
                    "reorder": "k_reorder_sub" if sub else "k_reorder", "sort": "k_onesweep", "keys": "k_keys_hist",
                    "integrate": "k_integrate"}[dominant]
     # the committed ncu capture is of the default options

@@ -125,9 +125,8 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
  *                      one or two at a time; 5 (default) = four ahead, in twos.
  *   "merged_rows"      (pair_density = 0) 1 (default): the density pass walks the two index ranges of each row of
  *                      sub-cells in one loop, which evens out the loop lengths between the lanes of a warp.
- *   "factored_forces"  -1 (default): by the fluid -- the list force kernel with factored pair terms (per-run constants
- *                      out of the sums, one MUFU.RSQ per pair) when the lists have 96 rows or more (~45 neighbours,
- *                      mucus), k_forces_lists<fast> otherwise (~25, water); 1 / 0 force one of them. Needs fast_pairs.
+ *   "factored_forces"  1 (default): the list force kernel evaluates the pair terms with the per-run constants factored
+ *                      out of the sums and one MUFU.RSQ per pair (needs fast_pairs); 0: add_pair_fast.
  *   "neighbour_lists"  (sub_cell_order = 0) 1 (default): the density pass stores per-particle neighbour lists in HBM
  *                      and the force pass reads them; 0: both passes search on their own.
  *   "list_rows"        list entries kept per particle (0 = derive from the rest density; rounded up to even);

@@ -81,7 +81,7 @@ struct clsph_context {
   bool sub_order = true;        // option "sub_cell_order"
   bool merged_rows = true;      // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
   bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
-  int factored_forces = -1;         // option "factored_forces": 1 k_forces_lists_factored, 0 k_forces_lists<fast>, -1 by the fluid (list rows)
+  int factored_forces = 1;          // option "factored_forces": pair terms with the constants factored out of the sums (default) or add_pair_fast
   int pair_variant = 5;             // option "pair_variant" (tuning): walk 0/1/2 + 3 x (entries stored two at a time)
   uint32_t* pair_items = nullptr;   // [capacity] items written by k_reorder_sub
   uint32_t* pair_count = nullptr;
@@ -413,9 +413,9 @@ int enqueue_substep(clsph_context* ctx) {
   bool join_side = false;  // the side stream has work of this sub-step
   // the list force kernel with factored pair terms on the lists of the per-particle / pair density kernels, which
   // contain the particle itself (option "factored_forces")
-  // Measured (profiles/r02_n_*): with ~25 neighbours per particle (water, 64 list rows) both kernels wait on the same
-  // gathers and the plain one is 1 % ahead; with ~45 (mucus, 112 rows) the factored one saves 0.10 of 0.91 ms.
-  const bool want_factored = ctx->factored_forces < 0 ? ctx->lists.rows >= 96u : ctx->factored_forces != 0;
+  // (with the shared-memory tile kernels the factored terms only paid for ~45 neighbours per particle, profiles/r02_n_*;
+  // in the direct kernel, the default, they win for both fluids, profiles/r02_s_*)
+  const bool want_factored = ctx->factored_forces != 0;
   const bool factored = sub && want_factored && ctx->fast_pairs;
   const bool pairs = sub && ctx->pair_density;
   if (sub) {

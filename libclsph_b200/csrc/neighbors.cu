@@ -869,8 +869,10 @@ void launch_forces(const float4* pos, const float4* vel, const float4* aux, cons
                    const NeighbourLists& lists, bool search_fallback, bool fast_pairs, bool dense_occupancy, float4* accel,
                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool factored) {
   const unsigned blocks = (n_launch + kNbThreads - 1) / kNbThreads;
-  // CLSPH_FORCES_DIRECT=1 (tuning): the variant without the shared-memory tile
-  static const int direct = [] { const char* e = getenv("CLSPH_FORCES_DIRECT"); return e ? atoi(e) : 0; }();
+  // Default for the sub-cell order: the variant without the shared-memory tile (measured, profiles/r02_s_*: with the
+  // factored pair terms 0.125 instead of 0.137 ms at 1 Mi water, 0.753 instead of 0.793 at 4 Mi mucus).
+  // CLSPH_FORCES_DIRECT=0 selects the tile kernels, =2 the 72-register build.
+  static const int direct = [] { const char* e = getenv("CLSPH_FORCES_DIRECT"); return e ? atoi(e) : 1; }();
   if (lists.rows && direct && fast_pairs && !search_fallback && (lists.rows % 4u) == 0u) {
     const unsigned dblocks = (n_launch + 127) / 128;
     if (factored && direct == 2) k_forces_lists_direct<true, 6><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);

@@ -90,7 +90,7 @@ def test_run_ours_single_gpu_prints_the_contract_line(options, monkeypatch, capf
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["peak"] > 0 and r["achieved"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert set(r["stage_ms"]) >= {"keys", "sort", "reorder", "density", "forces", "integrate"}
-    assert r["kernel"] in ("k_density_pairs", "k_forces_lists_factored", "k_density_sub", "k_density_lists", "k_forces_lists", "k_integrate", "k_onesweep", "k_reorder_sub", "k_reorder",
+    assert r["kernel"] in ("k_density_pairs", "k_forces_lists_factored", "k_forces_lists_direct", "k_density_sub", "k_density_lists", "k_forces_lists", "k_integrate", "k_onesweep", "k_reorder_sub", "k_reorder",
                            "k_keys_hist")
 
 
