@@ -337,21 +337,33 @@ k_dist_select(const float4* __restrict__ pos, const float4* __restrict__ vel, co
       if (at < capacity) live[at] = i;
       else atomicOr(&grid->error, 2u);
     }
-    const bool remote = go_left || go_right || ghost_left || ghost_right;
-    if (__syncthreads_or(remote)) {  // few CTAs touch a plane: only they read the rest of the record and send
-      __shared__ float4 s_rec[256 * 4];
-      __shared__ uint32_t s_words[10];
+    stored_remotely = go_left || go_right || ghost_left || ghost_right;
+    if (__any_sync(kFullMask, stored_remotely)) {  // few warps touch a plane: only they read the rest of the record
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f), iv = v;
-      if (remote) { v = vel[i]; iv = ivel[i]; iv.w = 0.f; }
+      if (stored_remotely) { v = vel[i]; iv = ivel[i]; iv.w = 0.f; }
+      const float4 tag = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f);
+      uint32_t e = warp_append(go_left, left.counts);
+      if (go_left) {
+        if (e < emax) { float4* r = left.emigrants + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = tag; }
+        else atomicOr(&grid->error, 2u);
+      }
+      e = warp_append(go_right, right.counts);
+      if (go_right) {
+        if (e < emax) { float4* r = right.emigrants + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = tag; }
+        else atomicOr(&grid->error, 2u);
+      }
       float4 gp = p, gv = v;  // ghosts travel as (position, velocity) with the order keys in the two w lanes
       gp.w = __uint_as_float(ok_k); gv.w = __uint_as_float(ok_r);
-      const float4 emigrant[4] = {p, v, iv, make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f)};
-      const float4 ghost[4] = {gp, gv, v, v};
-      cta_send<4>(go_left, emigrant, left.counts, left.emigrants, emax, s_rec, s_words, grid);
-      cta_send<4>(go_right, emigrant, right.counts, right.emigrants, emax, s_rec, s_words, grid);
-      cta_send<2>(ghost_left, ghost, left.counts + 1, left.ghosts, gmax, s_rec, s_words, grid);
-      cta_send<2>(ghost_right, ghost, right.counts + 1, right.ghosts, gmax, s_rec, s_words, grid);
-      stored_remotely = true;  // (the copy-out is spread over all threads of the CTA)
+      e = warp_append(ghost_left, left.counts + 1);
+      if (ghost_left) {
+        if (e < gmax) { float4* r = left.ghosts + (size_t)e * 2; r[0] = gp; r[1] = gv; }
+        else atomicOr(&grid->error, 2u);
+      }
+      e = warp_append(ghost_right, right.counts + 1);
+      if (ghost_right) {
+        if (e < gmax) { float4* r = right.ghosts + (size_t)e * 2; r[0] = gp; r[1] = gv; }
+        else atomicOr(&grid->error, 2u);
+      }
     }
   }
   if (!sig.done) return;

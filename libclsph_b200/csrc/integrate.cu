@@ -258,21 +258,33 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
         else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
       }
       const bool remote = go_left || go_right || ghost_left || ghost_right;
-      if (__syncthreads_or(remote)) {  // few CTAs touch a plane; their records leave coalesced (cta_send)
-        __shared__ float4 s_rec[256 * 4];
-        __shared__ uint32_t s_words[10];
+      stored_remotely |= remote;
+      if (__any_sync(kFullMask, remote)) {
         const float4 p = make_float4(x_new.x, x_new.y, x_new.z, 0.f), v = make_float4(v_new.x, v_new.y, v_new.z, 0.f);
         const float4 iv = make_float4(vh_new.x, vh_new.y, vh_new.z, 0.f);
+        const float4 tag = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f);
+        uint32_t e = warp_append(go_left, sel.counts_left);
+        if (go_left) {
+          if (e < sel.emax) { float4* r = sel.emigrants_left + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = tag; }
+          else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
+        }
+        e = warp_append(go_right, sel.counts_right);
+        if (go_right) {
+          if (e < sel.emax) { float4* r = sel.emigrants_right + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = tag; }
+          else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
+        }
         float4 gp = p, gv = v;  // ghosts travel as (position, velocity) with the order keys in the two w lanes
         gp.w = __uint_as_float(ok_k); gv.w = __uint_as_float(ok_r);
-        const float4 emigrant[4] = {p, v, iv, make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f)};
-        const float4 ghost[4] = {gp, gv, v, v};
-        GridState* gw = const_cast<GridState*>(grid);
-        cta_send<4>(go_left, emigrant, sel.counts_left, sel.emigrants_left, sel.emax, s_rec, s_words, gw);
-        cta_send<4>(go_right, emigrant, sel.counts_right, sel.emigrants_right, sel.emax, s_rec, s_words, gw);
-        cta_send<2>(ghost_left, ghost, sel.counts_left + 1, sel.ghosts_left, sel.gmax, s_rec, s_words, gw);
-        cta_send<2>(ghost_right, ghost, sel.counts_right + 1, sel.ghosts_right, sel.gmax, s_rec, s_words, gw);
-        stored_remotely = true;  // (the copy-out is spread over all threads of the CTA)
+        e = warp_append(ghost_left, sel.counts_left + 1);
+        if (ghost_left) {
+          if (e < sel.gmax) { float4* r = sel.ghosts_left + (size_t)e * 2; r[0] = gp; r[1] = gv; }
+          else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
+        }
+        e = warp_append(ghost_right, sel.counts_right + 1);
+        if (ghost_right) {
+          if (e < sel.gmax) { float4* r = sel.ghosts_right + (size_t)e * 2; r[0] = gp; r[1] = gv; }
+          else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
+        }
       }
     }
   }

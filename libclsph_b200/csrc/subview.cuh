@@ -206,40 +206,4 @@ __device__ __forceinline__ uint32_t block256_append(bool want, uint32_t* counter
   return at;
 }
 
-// Records of a CTA to one destination, stored COALESCED. The boundary particles of a slab are scattered through the
-// Morton order, so a warp has only a few of them and their 16-byte stores into a neighbour's mailbox travelled over
-// NVLink as packets of their own: ~30 us per neighbour to drain 4.5 MB (measured: the same whether the pass ran as a
-// kernel of its own or inside the integrator). Here the CTA's records first go to shared memory in slot order, then
-// all 256 threads copy them out as one contiguous run (full 128-byte lines). All threads of the CTA must call it.
-template <int kRec16>  // 16-byte words per record: 4 emigrant, 2 ghost
-__device__ __forceinline__ void cta_send(bool want, const float4 (&rec)[4], uint32_t* count, float4* dst, uint32_t cap, float4* s_rec,
-                                         uint32_t* s_words, GridState* grid) {
-  // s_words: [0..7] per-warp counts -> offsets, [8] base, [9] total
-  const unsigned m = __ballot_sync(kFullMask, want);
-  const unsigned warp = threadIdx.x >> 5;
-  if (lane_id() == 0u) s_words[warp] = (uint32_t)__popc(m);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t total = 0;
-    for (int w = 0; w < 8; ++w) { const uint32_t c = s_words[w]; s_words[w] = total; total += c; }
-    s_words[9] = total;
-    s_words[8] = total ? atomicAdd(count, total) : 0u;
-  }
-  __syncthreads();
-  const uint32_t total = s_words[9], base = s_words[8];
-  if (total == 0u) { __syncthreads(); return; }
-  if (want) {
-    const uint32_t slot = s_words[warp] + (uint32_t)__popc(m & lanemask_lt());
-#pragma unroll
-    for (int k = 0; k < kRec16; ++k) s_rec[slot * kRec16 + k] = rec[k];
-  }
-  __syncthreads();
-  if (base + total > cap) {
-    if (threadIdx.x == 0) atomicOr(&grid->error, 2u);
-  }
-  const uint32_t room = base < cap ? min(total, cap - base) : 0u;
-  for (uint32_t k = threadIdx.x; k < room * kRec16; k += blockDim.x) dst[(size_t)base * kRec16 + k] = s_rec[k];
-  __syncthreads();  // the shared words are reused by the next call
-}
-
 }  // namespace clsph

@@ -31,13 +31,11 @@ struct Thread {
   int aux = 0;
   // block barrier
   bool at_barrier = false, barrier_released = false;
-  unsigned or_epoch = 0;  // __syncthreads_or calls made so far
 };
 
 struct Block {
   std::vector<Thread> threads;
   unsigned nthreads = 0, live = 0, barrier_count = 0;
-  int or_acc[4] = {0, 0, 0, 0};  // accumulators of __syncthreads_or, one per call modulo 4
   uint64_t progress = 0;
   ucontext_t sched;
   Thread* running = nullptr;
@@ -183,23 +181,6 @@ void block_barrier() {
   t->barrier_released = false;
 }
 
-}  // namespace emu (reopened below)
-// Barrier + OR of the predicate over the block. The slot of call e is cleared by every thread after the barrier of
-// call e - 2 ... no thread can reach call e before all have passed the barrier of call e - 1.
-int __syncthreads_or(int pred) {
-  using namespace emu;
-  Block* b = blk;
-  if (!b) fatal("__syncthreads_or outside a kernel");
-  Thread* t = b->running;
-  const unsigned e = t->or_epoch++;
-  if (pred) b->or_acc[e & 3u] = 1;
-  block_barrier();
-  const int r = b->or_acc[e & 3u];
-  b->or_acc[(e + 2u) & 3u] = 0;
-  return r;
-}
-namespace emu {
-
 void launch_raw(dim3 grid, dim3 block, size_t smem_bytes, void (*fn)(void*), void* arg) {
   if (blk) fatal("nested kernel launch");
   if (smem_bytes > kDynSmemBytes) fatal("dynamic shared memory request beyond the emulator's buffer");
@@ -218,11 +199,9 @@ void launch_raw(dim3 grid, dim3 block, size_t smem_bytes, void (*fn)(void*), voi
   for (unsigned bx = 0; bx < grid.x; ++bx) {
     b.live = nthreads;
     b.barrier_count = 0;
-    b.or_acc[0] = b.or_acc[1] = b.or_acc[2] = b.or_acc[3] = 0;
     for (unsigned i = 0; i < nthreads; ++i) {
       Thread& t = b.threads[i];
       t.done = t.waiting = t.released = t.at_barrier = t.barrier_released = false;
-      t.or_epoch = 0;
       t.ctx.tid = {i, 0u, 0u};
       t.ctx.bid = {bx, 0u, 0u};
       t.ctx.bdim = block;

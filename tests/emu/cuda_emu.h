@@ -124,7 +124,6 @@ inline unsigned __match_any_sync(unsigned mask, T v) {
 }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_collective(emu::kSyncWarp, mask, 0, 0); }
 inline void __syncthreads() { emu::block_barrier(); }
-int __syncthreads_or(int pred);  // cuda_emu.cpp
 
 // ---- arithmetic intrinsics (build with -ffp-contract=off: one rounding per operation) --------------
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
