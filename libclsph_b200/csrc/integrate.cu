@@ -73,8 +73,8 @@ __global__ void k_prepare_faces(const float* __restrict__ normals, const float* 
 // point: no hit is lost. A face may be met twice (two cells) and out of index order, so "ties go to
 // the later face" (collisions.cl:77-80, where faces come in ascending order) is applied as
 // "nearer wins; at equal distance the higher face index wins", which is the same thing.
-// kSelect: see SlabSelect (kernels.cuh). The loop runs CTA-uniformly (threads out of range or not advanced here skip
-// the body) so that the appends can be aggregated.
+// kSelect: see SlabSelect (kernels.cuh). The loop then runs warp-uniformly (lanes out of range or not advanced here
+// skip the body) so that the appends can be warp-aggregated.
 template <bool kGrid, bool kSelect>
 __global__ void __launch_bounds__(256)
 k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ ivel,
@@ -91,9 +91,8 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
   float hi[3] = {-2147483648.f, -2147483648.f, -2147483648.f};
 
   bool stored_remotely = false;
-  // (CTA-uniform trip count: kSelect appends with one atomic per CTA and iteration)
-  for (uint32_t bbase = blockIdx.x * blockDim.x; bbase < n; bbase += gridDim.x * blockDim.x) {
-    const uint32_t i = bbase + threadIdx.x;
+  for (uint32_t wbase = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < n; wbase += gridDim.x * blockDim.x) {
+    const uint32_t i = wbase + (threadIdx.x & 31u);
     float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
     bool advance = i < n;
     if (advance) {
@@ -252,7 +251,7 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
       const float depth = g.cell * 1.0009765625f;  // ghost depth 2h (1 + 2^-10), see k_dist_classify
       const bool ghost_left = stay && has_left && x_new.x < g.plane_lo + depth;
       const bool ghost_right = stay && has_right && x_new.x >= g.plane_hi - depth;
-      const uint32_t at = block256_append(advance, sel.live_count);  // (one atomic per warp was 40 k atomics on one word: ~50 us)
+      const uint32_t at = warp_append(advance, sel.live_count);
       if (advance) {
         if (at < sel.capacity) sel.live[at] = i;
         else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
