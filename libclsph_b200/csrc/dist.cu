@@ -653,10 +653,6 @@ int dist_init(DistState* d, int rank, int world, const void* id_bytes, float pla
   if (cudaMalloc(&d->counters, 64) != cudaSuccess) return 1;
   cudaMemset(d->counters, 0, 64);
   d->peer = setup_peer_transport(d);
-  {  // CLSPH_DIST_SELECT_AHEAD=0: the selection pass stays a kernel of its own at the start of every sub-step
-    const char* e = getenv("CLSPH_DIST_SELECT_AHEAD");
-    d->select_ahead = !(e && atoi(e) == 0);
-  }
   if (const char* t = getenv("CLSPH_DIST_TIMING")) {
     if (atoi(t) != 0 && !g_timing.on) {
       g_timing.on = true;
@@ -740,7 +736,8 @@ void dist_publish_bounds(DistState* d, const BoundsAcc* acc, cudaStream_t stream
 SlabSelect dist_next_select(DistState* d, uint32_t* live, const uint32_t* pid, const uint32_t* wrank, uint32_t* ordk, uint32_t* ordr,
                             uint32_t capacity) {
   SlabSelect sel;
-  if (!d->active || !d->peer || !live || !d->select_ahead) return sel;
+  static const bool allowed = [] { const char* e = getenv("CLSPH_DIST_SELECT_AHEAD"); return !(e && atoi(e) == 0); }();
+  if (!d->active || !d->peer || !live || !allowed) return sel;
   const bool has_left = d->rank > 0, has_right = d->rank + 1 < d->world;
   const uint32_t next = d->seq + 1u, par = next & 1u;
   void* lbox = has_left ? d->peer_mailbox[d->rank - 1] : d->mailbox;

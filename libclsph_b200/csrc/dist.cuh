@@ -25,7 +25,6 @@ struct DistState {
   void** peer_table = nullptr;           // the same table on the device
   uint32_t seq = 0;                      // sequence number of the current sub-step, the same on every rank
   bool bounds_published = false;         // the AABB for sub-step seq + 1 is already on its way
-  bool select_ahead = true;              // the integrator prepares the next exchange (dist_next_select)
   uint32_t selected_for = 0;             // sequence number the integrator has prepared the exchange for (0: none)
 };
 
