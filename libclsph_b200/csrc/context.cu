@@ -474,11 +474,8 @@ int enqueue_substep(clsph_context* ctx) {
   if (ctx->debug)  // the integrator consumes the acceleration; keep a copy for the tap
     CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->taps.acceleration, ctx->accel, sizeof(float4) * n,
                                         cudaMemcpyDeviceToDevice, st));
-  // multi-GPU, exchange in place over peer memory: the integrator also prepares the next sub-step's exchange
-  SlabSelect ahead;
-  if (in_place) ahead = dist_next_select(&ctx->dist, ctx->live_idx, ctx->pid[ctx->cur], ctx->wrank, ctx->ordk[ctx->cur], ctx->ordr[ctx->cur], ctx->capacity);
   launch_integrate(dst, ctx->accel, ctx->skey, ctx->faces, ctx->face_count, ctx->face_grid, ctx->grid, ctx->konst, ctx->bounds,
-                   ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, lc, &ahead);
+                   ctx->debug ? ctx->taps.collision_iters : nullptr, n, ctx->sm_count, st, lc);
   if (multi) dist_publish_bounds(&ctx->dist, ctx->bounds, st, lc);
   if (join_side) CLSPH_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));  // whatever follows sees the new ranks
   if (prof) next_event(ctx);

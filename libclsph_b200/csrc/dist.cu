@@ -141,10 +141,8 @@ struct MsgIn {
 
 // Mailbox of a rank (peer transport), mapped by every other rank:
 //   [0, 2048)     AABB slots [parity][source rank][8 words]: lo[3], hi[3], sequence number, pad
-//   [2048, 2176)  message headers [parity][side][8 words]: emigrants, ghosts, sequence number; side 0 = from the left neighbour
-//   [4096, ...)   records [parity][side]: emigrants (emax x 64 B), ghosts (gmax x 32 B)
-// parity = sequence number of the CONSUMING sub-step & 1: the integrator of sub-step k already stores the records of
-// sub-step k + 1 while a slow neighbour may still be unpacking those of k.
+//   [2048, 2112)  message headers [side][8 words]: emigrants, ghosts, sequence number; side 0 = from the left neighbour
+//   [4096, ...)   records of side 0, then of side 1: emigrants (emax x 64 B), ghosts (gmax x 32 B)
 constexpr int kMaxPeers = 32;
 constexpr size_t kMailboxRecords = 4096;
 __host__ __device__ inline uint32_t* mailbox_bounds(void* box, uint32_t parity, uint32_t rank) {
@@ -153,16 +151,12 @@ __host__ __device__ inline uint32_t* mailbox_bounds(void* box, uint32_t parity, 
 __host__ __device__ inline const uint32_t* mailbox_bounds(const void* box, uint32_t parity, uint32_t rank) {
   return static_cast<const uint32_t*>(box) + ((size_t)parity * kMaxPeers + rank) * 8u;
 }
-__host__ __device__ inline uint32_t* mailbox_header(void* box, int side, uint32_t parity) {
-  return static_cast<uint32_t*>(box) + 512 + (parity * 2u + (uint32_t)side) * 8u;
-}
+__host__ __device__ inline uint32_t* mailbox_header(void* box, int side) { return static_cast<uint32_t*>(box) + 512 + side * 8; }
 inline size_t side_bytes(uint32_t emax, uint32_t gmax) { return (size_t)emax * 64 + (size_t)gmax * 32; }
-inline float4* mailbox_emigrants(void* box, int side, uint32_t parity, uint32_t emax, uint32_t gmax) {
-  return reinterpret_cast<float4*>(static_cast<char*>(box) + kMailboxRecords + (size_t)(parity * 2u + (uint32_t)side) * side_bytes(emax, gmax));
+inline float4* mailbox_emigrants(void* box, int side, uint32_t emax, uint32_t gmax) {
+  return reinterpret_cast<float4*>(static_cast<char*>(box) + kMailboxRecords + (size_t)side * side_bytes(emax, gmax));
 }
-inline float4* mailbox_ghosts(void* box, int side, uint32_t parity, uint32_t emax, uint32_t gmax) {
-  return mailbox_emigrants(box, side, parity, emax, gmax) + (size_t)emax * 4;
-}
+inline float4* mailbox_ghosts(void* box, int side, uint32_t emax, uint32_t gmax) { return mailbox_emigrants(box, side, emax, gmax) + (size_t)emax * 4; }
 
 }  // namespace
 
@@ -492,7 +486,7 @@ k_dist_unpack(const MsgIn from_left, const MsgIn from_right, uint32_t wait_seq, 
   grid->n = min(atomicAdd(u_count, 0u), capacity);
   grid->fresh = 0u;
   counters[0] = 0u; counters[2] = 0u; counters[3] = 0u;
-  counters[4] = 0u; counters[5] = 0u; counters[6] = 0u; counters[7] = 0u; counters[8] = 0u; counters[9] = 0u;
+  counters[4] = 0u; counters[5] = 0u; counters[6] = 0u; counters[7] = 0u; counters[8] = 0u;
 }
 
 __global__ void k_dist_finish(GridState* grid, uint32_t* counters, uint32_t capacity) {
@@ -500,7 +494,7 @@ __global__ void k_dist_finish(GridState* grid, uint32_t* counters, uint32_t capa
     grid->n = min(counters[0], capacity);
     grid->fresh = 0u;
     counters[0] = 0u; counters[2] = 0u; counters[3] = 0u;
-    counters[4] = 0u; counters[5] = 0u; counters[6] = 0u; counters[7] = 0u; counters[8] = 0u; counters[9] = 0u;
+    counters[4] = 0u; counters[5] = 0u; counters[6] = 0u; counters[7] = 0u; counters[8] = 0u;
   }
 }
 
@@ -590,7 +584,7 @@ static bool setup_peer_transport(DistState* d) {
   const size_t table_words = words_per_rank * d->world;
   if (cudaMalloc(&table, (table_words + 1) * 4) != cudaSuccess) return false;
   cudaMemset(table, 0, (table_words + 1) * 4);
-  d->mailbox_bytes = kMailboxRecords + 4 * side_bytes(d->emax, d->gmax);
+  d->mailbox_bytes = kMailboxRecords + 2 * side_bytes(d->emax, d->gmax);
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
   if (want) {
@@ -731,52 +725,11 @@ void dist_publish_bounds(DistState* d, const BoundsAcc* acc, cudaStream_t stream
   if (launches) ++*launches;
 }
 
-// What the integrator of the current sub-step needs to prepare the exchange of the NEXT one (peer transport, exchange
-// in place): see SlabSelect in kernels.cuh. Returns a disabled record when that does not apply.
-SlabSelect dist_next_select(DistState* d, uint32_t* live, const uint32_t* pid, const uint32_t* wrank, uint32_t* ordk, uint32_t* ordr,
-                            uint32_t capacity) {
-  SlabSelect sel;
-  static const bool allowed = [] { const char* e = getenv("CLSPH_DIST_SELECT_AHEAD"); return !(e && atoi(e) == 0); }();
-  if (!d->active || !d->peer || !live || !allowed) return sel;
-  const bool has_left = d->rank > 0, has_right = d->rank + 1 < d->world;
-  const uint32_t next = d->seq + 1u, par = next & 1u;
-  void* lbox = has_left ? d->peer_mailbox[d->rank - 1] : d->mailbox;
-  void* rbox = has_right ? d->peer_mailbox[d->rank + 1] : d->mailbox;
-  sel.enabled = true;
-  sel.live = live;
-  sel.live_count = d->counters;
-  sel.capacity = capacity;
-  sel.pid = pid;
-  sel.wrank = wrank;
-  sel.ordk = ordk;
-  sel.ordr = ordr;
-  sel.counts_left = d->counters + 4;
-  sel.counts_right = d->counters + 6;
-  sel.emigrants_left = mailbox_emigrants(lbox, 1, par, d->emax, d->gmax);
-  sel.ghosts_left = mailbox_ghosts(lbox, 1, par, d->emax, d->gmax);
-  sel.emigrants_right = mailbox_emigrants(rbox, 0, par, d->emax, d->gmax);
-  sel.ghosts_right = mailbox_ghosts(rbox, 0, par, d->emax, d->gmax);
-  sel.emax = d->emax;
-  sel.gmax = d->gmax;
-  sel.done = d->counters + 9;
-  sel.header_left = has_left ? mailbox_header(lbox, 1, par) : nullptr;
-  sel.header_right = has_right ? mailbox_header(rbox, 0, par) : nullptr;
-  sel.seq = next;
-  d->selected_for = next;
-  return sel;
-}
-
 // The particles were replaced (upload): what was published for the next sub-step is stale. Skipping two
 // sequence numbers keeps the slot parity and makes every rank wait for the fresh values.
 void dist_invalidate_bounds(DistState* d) {
-  const bool prepared = d->selected_for > d->seq;  // the integrator has stored messages for a sub-step that will not come
-  if (d->bounds_published || prepared) d->seq += 2u;
+  if (d->bounds_published) d->seq += 2u;
   d->bounds_published = false;
-  d->selected_for = 0u;
-  if (prepared) {  // its appends: list length, message counts, CTA ticket
-    cudaDeviceSynchronize();
-    cudaMemset(d->counters, 0, 64);
-  }
 }
 
 // `live` != null: in place (k_dist_select): u must be prev, u_pid prev_pid; the sort then takes its input through `live`.
@@ -794,16 +747,12 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
   if (d->peer) {
     timing_mark(stream);
     // my left neighbour receives "from its right" (side 1), my right neighbour "from its left" (side 0)
-    const uint32_t par = d->seq & 1u;
     void* lbox = has_left ? d->peer_mailbox[d->rank - 1] : d->mailbox;  // (without a neighbour nothing is ever appended)
     void* rbox = has_right ? d->peer_mailbox[d->rank + 1] : d->mailbox;
-    const MsgOut left{d->counters + 4, mailbox_emigrants(lbox, 1, par, d->emax, d->gmax), mailbox_ghosts(lbox, 1, par, d->emax, d->gmax)};
-    const MsgOut right{d->counters + 6, mailbox_emigrants(rbox, 0, par, d->emax, d->gmax), mailbox_ghosts(rbox, 0, par, d->emax, d->gmax)};
-    const PeerSignal sig{d->counters + 2, has_left ? mailbox_header(lbox, 1, par) : nullptr, has_right ? mailbox_header(rbox, 0, par) : nullptr,
-                         d->seq};
-    if (live && d->selected_for == d->seq) {
-      // the integrator of the previous sub-step has done all of this already (dist_next_select): nothing to launch
-    } else if (live)
+    const MsgOut left{d->counters + 4, mailbox_emigrants(lbox, 1, d->emax, d->gmax), mailbox_ghosts(lbox, 1, d->emax, d->gmax)};
+    const MsgOut right{d->counters + 6, mailbox_emigrants(rbox, 0, d->emax, d->gmax), mailbox_ghosts(rbox, 0, d->emax, d->gmax)};
+    const PeerSignal sig{d->counters + 2, has_left ? mailbox_header(lbox, 1) : nullptr, has_right ? mailbox_header(rbox, 0) : nullptr, d->seq};
+    if (live)
       k_dist_select<<<blocks, 256, 0, stream>>>(prev.pos, prev.vel, prev.ivel, prev_pid, skey, wrank, grid, u_ordk, u_ordr, live, u_count,
                                                 capacity, left, right, d->emax, d->gmax, sig);
     else
@@ -811,12 +760,11 @@ int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pi
                                                   u_pid, u_ordk, u_ordr, u_count, capacity, left, right, d->emax, d->gmax, sig);
     timing_mark(stream);
     timing_mark(stream);
-    timing_mark(stream);
     if (has_left || has_right) {
-      const MsgIn from_left{has_left ? mailbox_header(d->mailbox, 0, par) : nullptr, mailbox_emigrants(d->mailbox, 0, par, d->emax, d->gmax),
-                            mailbox_ghosts(d->mailbox, 0, par, d->emax, d->gmax)};
-      const MsgIn from_right{has_right ? mailbox_header(d->mailbox, 1, par) : nullptr, mailbox_emigrants(d->mailbox, 1, par, d->emax, d->gmax),
-                             mailbox_ghosts(d->mailbox, 1, par, d->emax, d->gmax)};
+      const MsgIn from_left{has_left ? mailbox_header(d->mailbox, 0) : nullptr, mailbox_emigrants(d->mailbox, 0, d->emax, d->gmax),
+                            mailbox_ghosts(d->mailbox, 0, d->emax, d->gmax)};
+      const MsgIn from_right{has_right ? mailbox_header(d->mailbox, 1) : nullptr, mailbox_emigrants(d->mailbox, 1, d->emax, d->gmax),
+                             mailbox_ghosts(d->mailbox, 1, d->emax, d->gmax)};
       k_dist_unpack<<<2 * ublocks, 256, 0, stream>>>(from_left, from_right, d->seq, d->emax, d->gmax, grid, u.pos, u.vel, u.ivel, u_pid,
                                                      u_ordk, u_ordr, d->counters, capacity, live);
     } else {

@@ -25,7 +25,6 @@ struct DistState {
   void** peer_table = nullptr;           // the same table on the device
   uint32_t seq = 0;                      // sequence number of the current sub-step, the same on every rank
   bool bounds_published = false;         // the AABB for sub-step seq + 1 is already on its way
-  uint32_t selected_for = 0;             // sequence number the integrator has prepared the exchange for (0: none)
 };
 
 const char* dist_last_error();
@@ -37,8 +36,6 @@ const char* dist_transport(const DistState* d);
 int dist_reduce_bounds(DistState* d, BoundsAcc* acc, GridState* grid, cudaStream_t stream, uint64_t* launches);
 void dist_publish_bounds(DistState* d, const BoundsAcc* acc, cudaStream_t stream, uint64_t* launches);
 void dist_invalidate_bounds(DistState* d);
-SlabSelect dist_next_select(DistState* d, uint32_t* live, const uint32_t* pid, const uint32_t* wrank, uint32_t* ordk, uint32_t* ordr,
-                            uint32_t capacity);
 // prev (sorted by last step's keys, owned + ghosts) -> u (unsorted: owned + new ghosts); sets grid->n.
 // wrank / u_ordk / u_ordr (all null or all set): order keys of the sub-cell order, see k_dist_classify.
 int dist_exchange(DistState* d, const StateArrays& prev, const uint32_t* prev_pid, const uint32_t* skey,

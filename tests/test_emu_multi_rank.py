@@ -51,17 +51,15 @@ def by_id(parts, ids, n):
 
 
 # world 1: a slab that is not cut at all; transport: stores into the neighbours' mailboxes (default) or NCCL messages
-# "peer" = the default: exchange in place, prepared by the integrator of the previous sub-step. "peer-copy": the exchange that copies the owned particles into a fresh array (CLSPH_DIST_IN_PLACE=0) instead of leaving them in place
+# "peer-copy": the exchange that copies the owned particles into a fresh array (CLSPH_DIST_IN_PLACE=0) instead of leaving them in place
 @pytest.mark.parametrize("world,copies,sub,transport", [(2, 2, 0, "peer"), (3, 3, 1, "peer"), (1, 2, 1, "peer"), (3, 3, 1, "nccl"),
-                                                        (3, 3, 1, "peer-copy"), (3, 3, 1, "peer-select")])
+                                                        (3, 3, 1, "peer-copy")])
 def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub, transport, monkeypatch):
     steps = 3
     if transport == "nccl":
         monkeypatch.setenv("CLSPH_DIST_TRANSPORT", "nccl")
     if transport == "peer-copy":
         monkeypatch.setenv("CLSPH_DIST_IN_PLACE", "0")
-    if transport == "peer-select":  # the selection pass as a kernel of its own at the start of the sub-step, not inside the integrator
-        monkeypatch.setenv("CLSPH_DIST_SELECT_AHEAD", "0")
     p, terms, state, scene_file = elongated_state(copies)
     n = state.size
     normals, vertices, indices = workloads.scene_arrays(scene_file)
