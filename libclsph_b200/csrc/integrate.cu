@@ -13,7 +13,6 @@
 #include <cmath>
 
 #include "kernels.cuh"
-#include "subview.cuh"
 
 namespace clsph {
 
@@ -73,14 +72,12 @@ __global__ void k_prepare_faces(const float* __restrict__ normals, const float* 
 // point: no hit is lost. A face may be met twice (two cells) and out of index order, so "ties go to
 // the later face" (collisions.cl:77-80, where faces come in ascending order) is applied as
 // "nearer wins; at equal distance the higher face index wins", which is the same thing.
-// kSelect: see SlabSelect (kernels.cuh). The loop then runs warp-uniformly (lanes out of range or not advanced here
-// skip the body) so that the appends can be warp-aggregated.
-template <bool kGrid, bool kSelect>
+template <bool kGrid>
 __global__ void __launch_bounds__(256)
 k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ ivel,
             const float4* __restrict__ accel, const uint32_t* __restrict__ skey, const Face* __restrict__ faces,
             uint32_t face_count, const FaceGrid fg, const GridState* __restrict__ grid, const SphConst c,
-            BoundsAcc* next_bounds, uint32_t* __restrict__ iters_tap, const SlabSelect sel) {
+            BoundsAcc* next_bounds, uint32_t* __restrict__ iters_tap) {
   const GridState g = *grid;
   const uint32_t n = g.n;
   const bool sliced = slab_is_cut(g);  // multi-GPU: ghosts are not advanced
@@ -90,17 +87,9 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
   float lo[3] = {2147483648.f, 2147483648.f, 2147483648.f};
   float hi[3] = {-2147483648.f, -2147483648.f, -2147483648.f};
 
-  bool stored_remotely = false;
-  for (uint32_t wbase = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < n; wbase += gridDim.x * blockDim.x) {
-    const uint32_t i = wbase + (threadIdx.x & 31u);
-    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool advance = i < n;
-    if (advance) {
-      p4 = pos[i];
-      advance = !(sliced && !owned_here(p4.x, skey[i], g));
-    }
-    V3 x_new = mk(0.f, 0.f, 0.f), v_new = mk(0.f, 0.f, 0.f), vh_new = mk(0.f, 0.f, 0.f);
-    if (advance) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p4 = pos[i];
+    if (sliced && !owned_here(p4.x, skey[i], g)) continue;
     const float4 iv4 = ivel[i], a4 = accel[i];
     V3 x = mk(p4.x, p4.y, p4.z);
     V3 v = mk(iv4.x, iv4.y, iv4.z);
@@ -231,61 +220,6 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
     lo[0] = fminf(lo[0], x.x); hi[0] = fmaxf(hi[0], x.x);
     lo[1] = fminf(lo[1], x.y); hi[1] = fmaxf(hi[1], x.y);
     lo[2] = fminf(lo[2], x.z); hi[2] = fmaxf(hi[2], x.z);
-    x_new = x; v_new = v_out; vh_new = v;
-    }  // advance
-    if (kSelect) {
-      // the next exchange, prepared here (k_dist_select's decisions, on the NEW position)
-      uint32_t id = 0, ok_k = 0, ok_r = 0;
-      if (advance) {
-        id = sel.pid[i];
-        ok_k = skey[i];
-        ok_r = sel.wrank[i];
-        sel.ordk[i] = ok_k;
-        sel.ordr[i] = ok_r;
-      }
-      const float inf = __int_as_float(0x7f800000);
-      const bool has_left = g.plane_lo > -inf, has_right = g.plane_hi < inf;
-      const bool go_left = advance && has_left && x_new.x < g.plane_lo;
-      const bool go_right = advance && has_right && x_new.x >= g.plane_hi;
-      const bool stay = advance && !go_left && !go_right;
-      const float depth = g.cell * 1.0009765625f;  // ghost depth 2h (1 + 2^-10), see k_dist_classify
-      const bool ghost_left = stay && has_left && x_new.x < g.plane_lo + depth;
-      const bool ghost_right = stay && has_right && x_new.x >= g.plane_hi - depth;
-      const uint32_t at = warp_append(advance, sel.live_count);
-      if (advance) {
-        if (at < sel.capacity) sel.live[at] = i;
-        else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
-      }
-      const bool remote = go_left || go_right || ghost_left || ghost_right;
-      stored_remotely |= remote;
-      if (__any_sync(kFullMask, remote)) {
-        const float4 p = make_float4(x_new.x, x_new.y, x_new.z, 0.f), v = make_float4(v_new.x, v_new.y, v_new.z, 0.f);
-        const float4 iv = make_float4(vh_new.x, vh_new.y, vh_new.z, 0.f);
-        const float4 tag = make_float4(__uint_as_float(id), __uint_as_float(ok_k), __uint_as_float(ok_r), 0.f);
-        uint32_t e = warp_append(go_left, sel.counts_left);
-        if (go_left) {
-          if (e < sel.emax) { float4* r = sel.emigrants_left + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = tag; }
-          else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
-        }
-        e = warp_append(go_right, sel.counts_right);
-        if (go_right) {
-          if (e < sel.emax) { float4* r = sel.emigrants_right + (size_t)e * 4; r[0] = p; r[1] = v; r[2] = iv; r[3] = tag; }
-          else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
-        }
-        float4 gp = p, gv = v;  // ghosts travel as (position, velocity) with the order keys in the two w lanes
-        gp.w = __uint_as_float(ok_k); gv.w = __uint_as_float(ok_r);
-        e = warp_append(ghost_left, sel.counts_left + 1);
-        if (ghost_left) {
-          if (e < sel.gmax) { float4* r = sel.ghosts_left + (size_t)e * 2; r[0] = gp; r[1] = gv; }
-          else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
-        }
-        e = warp_append(ghost_right, sel.counts_right + 1);
-        if (ghost_right) {
-          if (e < sel.gmax) { float4* r = sel.ghosts_right + (size_t)e * 2; r[0] = gp; r[1] = gv; }
-          else atomicOr(const_cast<uint32_t*>(&grid->error), 2u);
-        }
-      }
-    }
   }
 
   // AABB of the new positions for the next sub-step's grid (sph_simulation.cpp:201-217)
@@ -303,23 +237,6 @@ k_integrate(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restri
     atomicMin(&next_bounds->lo[threadIdx.x], float_to_ordered(l));
     atomicMax(&next_bounds->hi[threadIdx.x], float_to_ordered(h));
   }
-  if (kSelect) {
-    // the records are in the neighbours' mailboxes once every CTA has passed this point; the last one publishes the
-    // counts, then the sequence number their unpack pass waits for (release at system scope; see k_dist_select)
-    if (stored_remotely) __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    __threadfence();
-    if (atomicAdd(sel.done, 1u) != gridDim.x - 1u) return;
-    __threadfence_system();
-    volatile uint32_t* hl = sel.header_left;
-    volatile uint32_t* hr = sel.header_right;
-    if (hl) { hl[0] = atomicAdd(sel.counts_left, 0u); hl[1] = atomicAdd(sel.counts_left + 1, 0u); }
-    if (hr) { hr[0] = atomicAdd(sel.counts_right, 0u); hr[1] = atomicAdd(sel.counts_right + 1, 0u); }
-    __threadfence_system();
-    if (hl) hl[2] = sel.seq;
-    if (hr) hr[2] = sel.seq;
-  }
 }
 
 void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,
@@ -332,22 +249,14 @@ void launch_prepare_faces(const float* normals, const float* vertices, const uin
 void launch_integrate(const StateArrays& s, const float4* accel, const uint32_t* skey, const Face* faces,
                       uint32_t face_count, const FaceGrid& face_grid, const GridState* grid, const SphConst& c,
                       BoundsAcc* next_bounds, uint32_t* iters_tap, uint32_t n_launch, int sm_count, cudaStream_t stream,
-                      uint64_t* launches, const SlabSelect* select) {
+                      uint64_t* launches) {
   const unsigned blocks = std::max(1u, std::min<unsigned>((n_launch + 255) / 256, (unsigned)sm_count * 8u));
-  const SlabSelect none;
-  if (select && select->enabled) {
-    if (face_grid.nx > 0 && face_count > 0)
-      k_integrate<true, true><<<blocks, 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, face_grid, grid, c,
-                                                          next_bounds, iters_tap, *select);
-    else
-      k_integrate<false, true><<<blocks, 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, face_grid, grid, c,
-                                                           next_bounds, iters_tap, *select);
-  } else if (face_grid.nx > 0 && face_count > 0)
-    k_integrate<true, false><<<blocks, 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, face_grid, grid, c,
-                                                         next_bounds, iters_tap, none);
+  if (face_grid.nx > 0 && face_count > 0)
+    k_integrate<true><<<blocks, 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, face_grid, grid, c,
+                                                  next_bounds, iters_tap);
   else
-    k_integrate<false, false><<<blocks, 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, face_grid, grid, c,
-                                                          next_bounds, iters_tap, none);
+    k_integrate<false><<<blocks, 256, 0, stream>>>(s.pos, s.vel, s.ivel, accel, skey, faces, face_count, face_grid, grid, c,
+                                                   next_bounds, iters_tap);
   if (launches) ++*launches;
 }
 

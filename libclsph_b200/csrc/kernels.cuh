@@ -153,38 +153,12 @@ void launch_scatter_words(const void* src, const uint32_t* rrank, void* dst, uin
                           cudaStream_t stream, uint64_t* launches);
 
 // ---- integrate.cu
-// Multi-GPU, sub-cell order, peer transport: the integrator, which produces the new positions, also prepares the NEXT
-// sub-step's exchange (dist.cu: what k_dist_select would do at the start of that sub-step) -- the list of the
-// particles it advanced, their order keys in place, and the emigrant / ghost records stored straight into the
-// neighbours' mailboxes while the rest of the kernel still computes; its last CTA publishes counts and sequence
-// number. enabled == false: nothing of this happens.
-struct SlabSelect {
-  bool enabled = false;
-  uint32_t* live = nullptr;         // indices of the particles advanced here (the sort's input list)
-  uint32_t* live_count = nullptr;
-  uint32_t capacity = 0;
-  const uint32_t* pid = nullptr;    // persistent ids, order keys of this sub-step (cell key = skey, rank in cell = wrank)
-  const uint32_t* wrank = nullptr;
-  uint32_t* ordk = nullptr;         // order keys written in place for the next gather pass
-  uint32_t* ordr = nullptr;
-  uint32_t* counts_left = nullptr;  // [0] emigrants, [1] ghosts appended so far
-  uint32_t* counts_right = nullptr;
-  float4* emigrants_left = nullptr; // record areas in the neighbours' mailboxes
-  float4* ghosts_left = nullptr;
-  float4* emigrants_right = nullptr;
-  float4* ghosts_right = nullptr;
-  uint32_t emax = 0, gmax = 0;
-  uint32_t* done = nullptr;         // CTA ticket
-  uint32_t* header_left = nullptr;  // my message headers in the neighbours' mailboxes (null: no such neighbour)
-  uint32_t* header_right = nullptr;
-  uint32_t seq = 0;                 // sequence number of the sub-step that will consume the messages
-};
 void launch_prepare_faces(const float* normals, const float* vertices, const uint32_t* indices, uint32_t face_count,
                           Face* faces, cudaStream_t stream, uint64_t* launches);
 void launch_integrate(const StateArrays& s, const float4* accel, const uint32_t* skey, const Face* faces,
                       uint32_t face_count, const FaceGrid& face_grid, const GridState* grid, const SphConst& c,
                       BoundsAcc* next_bounds, uint32_t* iters_tap, uint32_t n_launch, int sm_count, cudaStream_t stream,
-                      uint64_t* launches, const SlabSelect* select = nullptr);
+                      uint64_t* launches);
 // Host side: cell lists for the triangles (vertices 3V floats, indices 3F). Fills the three vectors
 // and the geometry of `out`; the caller uploads them and sets the pointers.
 void build_face_grid(const float* vertices, const uint32_t* indices, uint32_t face_count, FaceGrid* out,
