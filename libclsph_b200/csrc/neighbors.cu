@@ -791,17 +791,20 @@ k_forces_lists_direct(const float4* __restrict__ pos, const float4* __restrict__
       add_pair_sel<true>(sums, c, j == i, pi, vi, pi.w, pj, vj);
     }
   };
+  // the next four entries are requested before the current four neighbours are gathered: the list load (L2, the
+  // lists do not allocate in L1) is otherwise the head of every trip's dependency chain
   uint32_t e = 0;
+  uint4 q = count ? load_list4(row) : make_uint4(0u, 0u, 0u, 0u);
   for (; e + 4u <= count; e += 4u) {
-    const uint4 q = load_list4(row + e);
+    const uint4 qn = e + 4u < count ? load_list4(row + e + 4u) : q;
     const float4 pa = pos[q.x], va = vel[q.x], pb = pos[q.y], vb = vel[q.y], pc = pos[q.z], vc = vel[q.z], pd = pos[q.w], vd = vel[q.w];
     pair(q.x, pa, va);
     pair(q.y, pb, vb);
     pair(q.z, pc, vc);
     pair(q.w, pd, vd);
+    q = qn;
   }
-  if (e < count) {  // one to three entries left in the last quad
-    const uint4 q = load_list4(row + e);
+  if (e < count) {  // one to three entries left in the last quad (already in q)
     const uint32_t left = count - e;
     const uint32_t jb = left > 1u ? q.y : q.x, jc = left > 2u ? q.z : q.x;
     const float4 pa = pos[q.x], va = vel[q.x], pb = pos[jb], vb = vel[jb], pc = pos[jc], vc = vel[jc];
