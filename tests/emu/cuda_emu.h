@@ -177,7 +177,7 @@ struct cudaDeviceProp {
   char name[64];
 };
 
-enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaDevAttrMaxSharedMemoryPerMultiprocessor = 81 };
+enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaDevAttrMaxSharedMemoryPerMultiprocessor = 81, cudaDevAttrMultiProcessorCount = 16 };
 // ---- peer memory between ranks: in the emulator every rank is a thread of one process, a handle is the pointer
 struct cudaIpcMemHandle_t { char reserved[64]; };
 enum { cudaIpcMemLazyEnablePeerAccess = 1 };
@@ -198,7 +198,7 @@ inline T __ldcg(const T* p) { return *p; }
 long long clock64();  // nanoseconds (the product code only compares differences with a generous limit)
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {  // the B200's figures
-  *v = a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 227 * 1024 : 228 * 1024;
+  *v = a == cudaDevAttrMultiProcessorCount ? 4 : (a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 227 * 1024 : 228 * 1024);  // (4 SMs: small grids reach the persistent paths)
   return cudaSuccess;
 }
 cudaError_t cudaGetDeviceCount(int* n);
