@@ -769,20 +769,14 @@ __global__ void __launch_bounds__(128, kBlocks)
 k_forces_lists_direct(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ aux,
                       const uint32_t* __restrict__ nlist, const uint32_t* __restrict__ ncount, uint32_t list_rows,
                       const uint32_t* __restrict__ skey, const GridState* __restrict__ grid, const SphConst c,
-                      float4* __restrict__ accel, uint32_t sm_count) {
+                      float4* __restrict__ accel) {
   const GridState g = *grid;
-  // Persistent CTAs, one resident wave (gridDim.x = sm_count x CTAs per SM), each with ONE contiguous range of
-  // particles, numbered so that the CTAs that share an SM (block b lands on SM b % sm_count when a grid starts) hold
-  // neighbouring ranges: what they gather is then the same few hundred cells, and the L1 serves it.
-  const uint32_t per_sm = gridDim.x / sm_count;
-  const uint32_t range = blockIdx.x < per_sm * sm_count ? (blockIdx.x % sm_count) * per_sm + blockIdx.x / sm_count : blockIdx.x;
-  const uint32_t span = (g.n + gridDim.x - 1u) / gridDim.x;
-  const uint32_t begin = range * span, end = min(g.n, begin + span);
-  for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
   const float4 pi = pos[i];
-  if (!owned_here(pi.x, skey[i], g)) continue;  // multi-GPU: ghosts get no force
+  if (!owned_here(pi.x, skey[i], g)) return;  // multi-GPU: ghosts get no force
   const uint32_t count = ncount[i];
-  if (count > list_rows) continue;  // redone by k_forces_sub
+  if (count > list_rows) return;  // redone by k_forces_sub
   const float4 vi = vel[i];
   const uint32_t* row = nlist + (size_t)i * list_rows;  // 16-byte aligned: list_rows is a multiple of 8 (or even and >= 4 ...)
   ForceSums sums;
@@ -820,11 +814,11 @@ k_forces_lists_direct(const float4* __restrict__ pos, const float4* __restrict__
   }
   if (!kFactored) {
     accel[i] = finish_force(sums, c, aux[i].x);
-    continue;
+    return;
   }
   if (!degenerate) {
     accel[i] = tile_finish_force(sums, c, aux[i].x, vi.w, true);
-    continue;
+    return;
   }
   ForceSums exact;
   for (uint32_t k = 0; k < count; ++k) {
@@ -832,7 +826,6 @@ k_forces_lists_direct(const float4* __restrict__ pos, const float4* __restrict__
     add_pair(exact, c, j == i, pi, vi, pi.w, pos[j], vel[j]);
   }
   accel[i] = finish_force(exact, c, aux[i].x);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -884,18 +877,11 @@ void launch_forces(const float4* pos, const float4* vel, const float4* aux, cons
   // CLSPH_FORCES_DIRECT=0 selects the tile kernels, =2 the 72-register build.
   static const int direct = [] { const char* e = getenv("CLSPH_FORCES_DIRECT"); return e ? atoi(e) : 1; }();
   if (lists.rows && direct && fast_pairs && !search_fallback && (lists.rows % 4u) == 0u) {
-    // CLSPH_FORCES_PERSIST=0: one CTA per 128 particles in index order (tuning; the default is the resident wave)
-    static const int persist = [] { const char* e = getenv("CLSPH_FORCES_PERSIST"); return e ? atoi(e) : 1; }();
-    static const unsigned sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return (unsigned)std::max(n, 1); }();
-    const unsigned per_sm = direct == 2 ? 6u : 8u;
-    const unsigned needed = (n_launch + 127) / 128;
-    // (a grid that is not a multiple of sm_count makes the kernel fall back to ranges in index order)
-    const unsigned dblocks = persist ? std::min(needed, sms * per_sm) : needed;
-    const unsigned sm_arg = (persist && dblocks == sms * per_sm) ? sms : 1u;
-    if (factored && direct == 2) k_forces_lists_direct<true, 6><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel, sm_arg);
-    else if (factored) k_forces_lists_direct<true, 8><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel, sm_arg);
-    else if (direct == 2) k_forces_lists_direct<false, 6><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel, sm_arg);
-    else k_forces_lists_direct<false, 8><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel, sm_arg);
+    const unsigned dblocks = (n_launch + 127) / 128;
+    if (factored && direct == 2) k_forces_lists_direct<true, 6><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    else if (factored) k_forces_lists_direct<true, 8><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    else if (direct == 2) k_forces_lists_direct<false, 6><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
+    else k_forces_lists_direct<false, 8><<<dblocks, 128, 0, stream>>>(pos, vel, aux, lists.entries, lists.count, lists.rows, skey, grid, c, accel);
     if (launches) ++*launches;
   } else if (lists.rows && factored) {  // pair terms with the constants factored out of the sums (sub-cell order, fast pairs)
     const unsigned lblocks = (n_launch + kFlWarps * 32 - 1) / (kFlWarps * 32);

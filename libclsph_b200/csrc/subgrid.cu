@@ -25,8 +25,6 @@
 //
 // Replaces, like neighbors.cu, kernels/sph.cl:9-62 with forces.cl:15-112; the force pass proper is
 // k_forces_lists of neighbors.cu (it only consumes the lists written here).
-#include <cstdlib>
-
 #include "kernels.cuh"
 #include "pair_terms.cuh"
 #include "subview.cuh"
@@ -328,21 +326,11 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
                 const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
                 const SphConst c, float4* __restrict__ aux, uint32_t* __restrict__ nlist, uint32_t* __restrict__ ncount,
                 uint32_t list_rows, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ supp_count,
-                const uint32_t* __restrict__ pair_items, const uint32_t* __restrict__ pair_count, uint32_t sm_count) {
+                const uint32_t* __restrict__ pair_items, const uint32_t* __restrict__ pair_count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *pair_count) return;
   const GridState g = *grid;
   const SubView v = make_view(g, sub_lb, keys_a, keys_b);
-  // sm_count != 0: one resident wave of CTAs, each with a contiguous range of items, numbered so that the CTAs
-  // sharing an SM hold neighbouring ranges (see k_forces_lists_direct). sm_count == 0: one item per thread in index order.
-  const uint32_t n_items = *pair_count;
-  uint32_t begin = blockIdx.x * blockDim.x, end = min(n_items, begin + blockDim.x);
-  if (sm_count) {
-    const uint32_t per_sm = gridDim.x / sm_count;
-    const uint32_t range = (blockIdx.x % sm_count) * per_sm + blockIdx.x / sm_count;
-    const uint32_t span = (n_items + gridDim.x - 1u) / gridDim.x;
-    begin = range * span;
-    end = min(n_items, begin + span);
-  }
-  for (uint32_t t = begin + threadIdx.x; t < end; t += blockDim.x) {
   const uint32_t item = pair_items[t];
   const uint32_t i0 = item & 0x7FFFFFFFu;
   const bool two = (item >> 31) != 0u;
@@ -351,7 +339,7 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
   // multi-GPU: the particles of the slab and the ghosts within h of it get a density (k_density_sub)
   const bool need0 = p0.x >= g.plane_lo - c.h_margin && p0.x < g.plane_hi + c.h_margin;
   const bool need1 = two && p1.x >= g.plane_lo - c.h_margin && p1.x < g.plane_hi + c.h_margin;
-  if (!need0 && !need1) continue;
+  if (!need0 && !need1) return;
   uint32_t* row0 = nlist + (size_t)i0 * list_rows;
 #ifndef CLSPH_EMU
   asm volatile("" : "+l"(row0));  // keep the row address in registers (see k_density_sub)
@@ -497,7 +485,6 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     if (need0) { cand_count[i0] = total; supp_count[i0] = cnt0; }
     if (need1) { cand_count[i1] = total; supp_count[i1] = cnt1; }
   }
-  }  // items of this CTA
 }
 
 // Forces for the particles whose list overflowed: same traversal, pair terms evaluated in place.
@@ -605,13 +592,12 @@ struct PairArgs {
   const uint32_t *pair_items, *pair_count;
   unsigned blocks;
   cudaStream_t stream;
-  uint32_t sm_count;
 };
 template <bool kTaps, int kWalk, bool kStore2>
 void launch_pairs_variant(const PairArgs& a) {
   k_density_pairs<kTaps, kWalk, kStore2><<<a.blocks, kSubThreads, 0, a.stream>>>(a.pos, a.vel, a.skey, a.sub_lb, a.keys_a, a.keys_b, a.grid, a.c, a.aux,
                                                                                  a.nlist, a.ncount, a.list_rows, a.cand, a.supp, a.pair_items,
-                                                                                 a.pair_count, a.sm_count);
+                                                                                 a.pair_count);
 }
 }  // namespace
 
@@ -623,12 +609,8 @@ void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const 
   const unsigned blocks = (n_launch + kSubThreads - 1) / kSubThreads;
   uint32_t* cand = debug ? taps.candidate_count : nullptr;
   uint32_t* supp = debug ? taps.support_count : nullptr;
-  // CLSPH_DENSITY_PERSIST=0: one CTA per 128 items in index order (tuning; the default is the resident wave of 8 CTAs per SM)
-  static const int persist = [] { const char* e = getenv("CLSPH_DENSITY_PERSIST"); return e ? atoi(e) : 1; }();
-  static const unsigned sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return (unsigned)std::max(n, 1); }();
-  const bool wave = persist && blocks > sms * 8u;
   const PairArgs a{pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries, lists.count, lists.rows, cand, supp,
-                   pair_items, pair_count, wave ? sms * 8u : blocks, stream, wave ? sms : 0u};
+                   pair_items, pair_count, blocks, stream};
   if (debug) {
     launch_pairs_variant<true, 2, true>(a);
   } else {
