@@ -180,10 +180,15 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     key[k] = ok ? keys_in[idx] : 0xFFFFFFFFu;  // padding sorts to the very end of the tile
     val[k] = (vals_in != nullptr && ok) ? vals_in[idx] : idx;
   }
+  // the matches of the kItems rounds do not depend on each other: issued back to back (their latency is what a
+  // pass over a million keys -- one wave of tiles -- mostly consists of), then the short dependent part per round
+  unsigned match[kItems];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) match[k] = __match_any_sync(kFullMask, (key[k] >> shift) & 0xFFu);
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const uint32_t d = (key[k] >> shift) & 0xFFu;
-    const unsigned peers = __match_any_sync(kFullMask, d);
+    const unsigned peers = match[k];
     const int leader = __ffs(peers) - 1;
     uint32_t prev = 0;
     if ((int)lane == leader) {
