@@ -43,7 +43,7 @@
 // kernels that precede it in the other ranks' streams. Slots are double-buffered by the parity of the sequence
 // number (a rank two slabs away may run ahead by part of a sub-step); the record areas need no second buffer
 // because a neighbour can only store sub-step k's records after this rank has published its AABB for k, i.e. after
-// it has unpacked k - 1. Waits give up after ~10 s and flag CLSPH_ECOMM instead of hanging the GPU.
+// it has unpacked k - 1. Waits give up after ~30 s and flag CLSPH_ECOMM instead of hanging the GPU.
 // NCCL remains for the start-up (exchange of the IPC handles) and as the transport when peer access is unavailable
 // (CLSPH_DIST_TRANSPORT=nccl forces it).
 #include <dlfcn.h>
@@ -169,7 +169,7 @@ const char* dist_last_error() { return g_nccl_error; }
 __device__ __forceinline__ uint32_t load_flag(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void store_flag(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 // Waits until *flag == want. Gives up after kSpinLimit clock ticks (a peer that died must not hang this GPU).
-constexpr long long kSpinLimit = 20000000000ll;
+constexpr long long kSpinLimit = 60000000000ll;  // ~30 s of GPU clock: a rank may be busy on its host between sub-steps (tests compare on rank 0)
 __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t want, long long limit = kSpinLimit) {
   const long long t0 = clock64();
   while (load_flag(flag) != want)
