@@ -74,7 +74,7 @@ def test_run_ours_single_gpu_prints_the_contract_line(options, monkeypatch, capf
     monkeypatch.setitem(sys.modules, "torch", torch)
     monkeypatch.setitem(sys.modules, "torch.cuda", cuda)
     args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, impl="ours", config="config3_mucus_labyrinth_4m", particles=1500, e2e_steps=2,
-                                 no_cpu_baseline=True, cpu_sample=4096, option=list(options), repeats=2, no_parity=False)
+                                 no_cpu_baseline=True, cpu_sample=4096, option=list(options), repeats=2, no_parity=False, no_large_point=True)
     bench.run_ours(args, 0, 1, 0)
     out = capfd.readouterr().out
     lines = [ln for ln in out.splitlines() if ln.startswith("{")]
@@ -192,7 +192,7 @@ def test_run_ours_two_ranks_prints_the_contract_line(monkeypatch, capsys):
     def run_rank(rank):
         fdist.local.rank = rank
         args = types.SimpleNamespace(gpus=world, steps=3, warmup=3, impl="ours", config="config2_dambreak_1m", particles=12000, e2e_steps=2,
-                                     no_cpu_baseline=True, cpu_sample=4096, option=[], repeats=1, no_parity=False)
+                                     no_cpu_baseline=True, cpu_sample=4096, option=[], repeats=1, no_parity=False, no_large_point=True)
         try:
             bench.run_ours(args, rank, world, 0)
         except BaseException as exc:  # noqa: BLE001
