@@ -73,47 +73,15 @@ reorder_sub_slot(uint32_t r, uint32_t n, const float4* __restrict__ src_pos, con
   // the number of particles of the same sub-cell with a smaller rank, counted over the handful of equal
   // keys around r. The arrays, hence every floating-point sum, then depend on the state alone: k resident
   // sub-steps are bitwise equal to k host round trips, as in the established organisation.
-  // The walk over the equal keys around r is a chain of dependent loads (key -> index -> rank) per neighbour; a
-  // window of four slots on either side is therefore fetched at once -- keys and indices, then the ranks of those that
-  // matched, all independent -- and only a sub-cell reaching beyond the window (more than four particles on one side)
-  // continues one by one.
-  constexpr int kWin = 4;
-  uint32_t wl_v[kWin], wr_v[kWin];
-  bool wl_e[kWin], wr_e[kWin];
-  {
-    uint32_t wl_k[kWin], wr_k[kWin];
-#pragma unroll
-    for (int u = 0; u < kWin; ++u) {
-      const bool okl = r >= (uint32_t)(u + 1), okr = r + 1u + (uint32_t)u < n;
-      const uint32_t ql = okl ? r - 1u - (uint32_t)u : r, qr = okr ? r + 1u + (uint32_t)u : r;
-      wl_k[u] = keys[ql]; wl_v[u] = vals[ql];
-      wr_k[u] = keys[qr]; wr_v[u] = vals[qr];
-      wl_e[u] = okl && wl_k[u] == fkey && (u == 0 || wl_e[u - 1]);
-      wr_e[u] = okr && wr_k[u] == fkey && (u == 0 || wr_e[u - 1]);
-    }
-  }
-  uint32_t left = 0;
-#pragma unroll
-  for (int u = 0; u < kWin; ++u) left += wl_e[u] ? 1u : 0u;
   uint32_t dest = r;
   if (rr_src) {
     const uint32_t mine = rr_src[from];
-    uint32_t smaller = 0;
-    uint32_t rl[kWin], rrv[kWin];
-#pragma unroll
-    for (int u = 0; u < kWin; ++u) {
-      rl[u] = wl_e[u] ? rr_src[wl_v[u]] : 0xFFFFFFFFu;
-      rrv[u] = wr_e[u] ? rr_src[wr_v[u]] : 0xFFFFFFFFu;
+    uint32_t left = 0, smaller = 0;
+    for (uint32_t q = r; q > 0 && keys[q - 1] == fkey; --q) {
+      ++left;
+      smaller += rr_src[vals[q - 1]] < mine ? 1u : 0u;
     }
-#pragma unroll
-    for (int u = 0; u < kWin; ++u) smaller += (rl[u] < mine ? 1u : 0u) + (rrv[u] < mine ? 1u : 0u);
-    if (wl_e[kWin - 1])
-      for (uint32_t q = r - kWin; q > 0 && keys[q - 1] == fkey; --q) {
-        ++left;
-        smaller += rr_src[vals[q - 1]] < mine ? 1u : 0u;
-      }
-    if (wr_e[kWin - 1])
-      for (uint32_t q = r + 1 + kWin; q < n && keys[q] == fkey; ++q) smaller += rr_src[vals[q]] < mine ? 1u : 0u;
+    for (uint32_t q = r + 1; q < n && keys[q] == fkey; ++q) smaller += rr_src[vals[q]] < mine ? 1u : 0u;
     dest = r - left + smaller;
     rr_dst[dest] = mine;
     *left_out = left;
@@ -123,34 +91,21 @@ reorder_sub_slot(uint32_t r, uint32_t n, const float4* __restrict__ src_pos, con
     // particles of a sub-cell in the order a single GPU would, all sums run in the same order, and the
     // decomposition is bitwise transparent.
     const uint32_t mk = src_ordk[from], mr = src_ordr[from];
-    uint32_t smaller = 0;
-    uint32_t lk[kWin], lr[kWin], rk[kWin], rq[kWin];
-#pragma unroll
-    for (int u = 0; u < kWin; ++u) {
-      lk[u] = wl_e[u] ? src_ordk[wl_v[u]] : 0xFFFFFFFFu; lr[u] = wl_e[u] ? src_ordr[wl_v[u]] : 0xFFFFFFFFu;
-      rk[u] = wr_e[u] ? src_ordk[wr_v[u]] : 0xFFFFFFFFu; rq[u] = wr_e[u] ? src_ordr[wr_v[u]] : 0xFFFFFFFFu;
+    uint32_t left = 0, smaller = 0;
+    for (uint32_t q = r; q > 0 && keys[q - 1] == fkey; --q) {
+      ++left;
+      const uint32_t o = vals[q - 1], jk = src_ordk[o], jr = src_ordr[o];
+      smaller += (jk < mk || (jk == mk && jr < mr)) ? 1u : 0u;
     }
-#pragma unroll
-    for (int u = 0; u < kWin; ++u) {
-      smaller += (wl_e[u] && (lk[u] < mk || (lk[u] == mk && lr[u] < mr))) ? 1u : 0u;
-      smaller += (wr_e[u] && (rk[u] < mk || (rk[u] == mk && rq[u] < mr))) ? 1u : 0u;
+    for (uint32_t q = r + 1; q < n && keys[q] == fkey; ++q) {
+      const uint32_t o = vals[q], jk = src_ordk[o], jr = src_ordr[o];
+      smaller += (jk < mk || (jk == mk && jr < mr)) ? 1u : 0u;
     }
-    if (wl_e[kWin - 1])
-      for (uint32_t q = r - kWin; q > 0 && keys[q - 1] == fkey; --q) {
-        ++left;
-        const uint32_t o = vals[q - 1], jk = src_ordk[o], jr = src_ordr[o];
-        smaller += (jk < mk || (jk == mk && jr < mr)) ? 1u : 0u;
-      }
-    if (wr_e[kWin - 1])
-      for (uint32_t q = r + 1 + kWin; q < n && keys[q] == fkey; ++q) {
-        const uint32_t o = vals[q], jk = src_ordk[o], jr = src_ordr[o];
-        smaller += (jk < mk || (jk == mk && jr < mr)) ? 1u : 0u;
-      }
     dest = r - left + smaller;
     *left_out = left;
   } else {
-    if (wl_e[kWin - 1])
-      for (uint32_t q = r - kWin; q > 0 && keys[q - 1] == fkey; --q) ++left;
+    uint32_t left = 0;
+    for (uint32_t q = r; q > 0 && keys[q - 1] == fkey; --q) ++left;
     *left_out = left;
   }
   dst_pos[dest] = src_pos[from];
