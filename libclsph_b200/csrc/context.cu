@@ -736,7 +736,7 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
   } else if (!std::strcmp(name, "factored_forces")) {
     ctx->factored_forces = value < 0 ? -1 : (value != 0 ? 1 : 0);
   } else if (!std::strcmp(name, "pair_variant")) {
-    if (value < 0 || value > 6) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: pair_variant must be in [0, 6]");
+    if (value < 0 || value > 5) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: pair_variant must be in [0, 5]");
     ctx->pair_variant = (int)value;
   } else if (!std::strcmp(name, "fast_pairs")) {
     ctx->fast_pairs = value != 0;

@@ -320,12 +320,7 @@ k_density_sub(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const
 // kWalk: how a thread walks a row's candidates -- 0: one after the other; 1: the same with the next candidate's
 // load issued before the current one is tested; 2: four loads issued, then four tests. kStore2: list entries are
 // stored two at a time (one 8-byte store per two hits) instead of one by one.
-// kStaged (with kWalk == 2): the hits of a thread are first written to shared memory -- one unconditional store per
-// target and candidate at slot [hits so far], which a miss leaves to be overwritten -- and flushed to the list rows
-// every ~8 hits, two entries per store. The hot loop then spends 3 instead of 11 instructions per target and
-// candidate on the lists (they were more than half of it).
-constexpr int kStageSlots = 12;
-template <bool kTaps, int kWalk, bool kStore2, bool kStaged = false>
+template <bool kTaps, int kWalk, bool kStore2>
 __global__ void __launch_bounds__(kSubThreads, 8)  // 64 registers: eight CTAs of four warps per SM
 k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, const uint32_t* __restrict__ sub_lb,
                 const uint32_t* __restrict__ keys_a, const uint32_t* __restrict__ keys_b, const GridState* __restrict__ grid,
@@ -369,25 +364,6 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
   const f32x2 H2 = f2_bcast(c.h2);
   f32x2 acc = f2_make(0.f, 0.f);  // sums of (h^2 - s)^3 over the two supports
   uint32_t cnt0 = 0, cnt1 = 0, held0 = 0, held1 = 0;
-  extern __shared__ uint32_t s_stage[];  // kStaged: [2 targets][kStageSlots][blockDim.x]
-  uint32_t* const st0 = s_stage + threadIdx.x;
-  uint32_t* const st1 = st0 + kStageSlots * kSubThreads;
-  uint32_t rc0 = 0, rc1 = 0;  // staged hits not yet in the rows
-  // staged entries [0, rc) of one target -> its row at [cnt, cnt + rc), pairs of entries where the row position is even
-  auto flush_one = [&](const uint32_t* st, uint32_t rc, global_row_t grow, uint32_t& cnt) {
-    uint32_t e = 0, at = cnt;
-    if ((at & 1u) && e < rc) {
-      row_store_if(at < list_rows, grow, at, st[0]);
-      ++e; ++at;
-    }
-    for (; e + 2u <= rc; e += 2u, at += 2u) row_store2_if(at < list_rows, grow, at, st[e * kSubThreads], st[(e + 1u) * kSubThreads]);
-    if (e < rc) row_store_if(at < list_rows, grow, at, st[e * kSubThreads]);
-    cnt += rc;
-  };
-  auto maybe_flush = [&](uint32_t limit) {  // keeps room for the next four candidates
-    if (rc0 > limit) { flush_one(st0, rc0, grow0, cnt0); rc0 = 0; }
-    if (rc1 > limit) { flush_one(st1, rc1, grow1, cnt1); rc1 = 0; }
-  };
   auto test = [&](const float4& pj, uint32_t j) {
     const f32x2 dx = f2_sub(X, f2_bcast(pj.x)), dy = f2_sub(Y, f2_bcast(pj.y)), dz = f2_sub(Z, f2_bcast(pj.z));
     const f32x2 s = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
@@ -396,13 +372,6 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
     const f32x2 w = f2_make(hit0 ? f2_lo(d) : 0.f, hit1 ? f2_hi(d) : 0.f);
     acc = f2_fma(f2_mul(w, w), w, acc);
     const bool in0 = hit0, in1 = hit1;
-    if (kStaged) {
-      st0[rc0 * kSubThreads] = j;
-      rc0 += in0 ? 1u : 0u;
-      st1[rc1 * kSubThreads] = j;
-      rc1 += in1 ? 1u : 0u;
-      return;
-    }
     if (kStore2) {
       // List entries leave two at a time: every lane's store is an L1 wavefront and a 32-byte L2 sector write of its
       // own (each lane writes its own row), so one 8-byte store per two hits halves that. The first hit of a pair
@@ -434,13 +403,11 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
         test(q1, j1);
         test(q2, j2);
         test(q3, j3);
-        if (kStaged) maybe_flush(kStageSlots - 4u);
       }
       for (; k < total; ++k) {
         const uint32_t j = k < la ? a0 + k : k + shift;
         test(pos[j], j);
       }
-      if (kStaged) maybe_flush(kStageSlots - 4u - 3u);  // (the next row may end in up to three single tests before the next check)
     } else if (kWalk == 1) {
       if (total == 0u) return;
       uint32_t j = a0 < a1 ? a0 : b0;
@@ -487,8 +454,7 @@ k_density_pairs(float4* pos, float4* vel, const uint32_t* __restrict__ skey, con
       walk(e.x, e.y, 0u, 0u);
     }
   }
-  if (kStaged) maybe_flush(0u);
-  if (kStore2 && !kStaged) {  // the last hit of an odd count is still held
+  if (kStore2) {  // the last hit of an odd count is still held
     if ((cnt0 & 1u) && cnt0 - 1u < list_rows) row0[cnt0 - 1u] = held0;
     if (two && (cnt1 & 1u) && cnt1 - 1u < list_rows) row1[cnt1 - 1u] = held1;
   }
@@ -627,10 +593,9 @@ struct PairArgs {
   unsigned blocks;
   cudaStream_t stream;
 };
-template <bool kTaps, int kWalk, bool kStore2, bool kStaged = false>
+template <bool kTaps, int kWalk, bool kStore2>
 void launch_pairs_variant(const PairArgs& a) {
-  const size_t smem = kStaged ? sizeof(uint32_t) * 2u * kStageSlots * kSubThreads : 0u;
-  k_density_pairs<kTaps, kWalk, kStore2, kStaged><<<a.blocks, kSubThreads, smem, a.stream>>>(a.pos, a.vel, a.skey, a.sub_lb, a.keys_a, a.keys_b, a.grid, a.c, a.aux,
+  k_density_pairs<kTaps, kWalk, kStore2><<<a.blocks, kSubThreads, 0, a.stream>>>(a.pos, a.vel, a.skey, a.sub_lb, a.keys_a, a.keys_b, a.grid, a.c, a.aux,
                                                                                  a.nlist, a.ncount, a.list_rows, a.cand, a.supp, a.pair_items,
                                                                                  a.pair_count);
 }
@@ -646,9 +611,7 @@ void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const 
   uint32_t* supp = debug ? taps.support_count : nullptr;
   const PairArgs a{pos, vel, skey, sub_lb, sort.keys_a, sort.keys_b, grid, c, aux, lists.entries, lists.count, lists.rows, cand, supp,
                    pair_items, pair_count, blocks, stream};
-  if (debug && variant == 6) {
-    launch_pairs_variant<true, 2, true, true>(a);
-  } else if (debug) {
+  if (debug) {
     launch_pairs_variant<true, 2, true>(a);
   } else {
     switch (variant) {
@@ -657,7 +620,6 @@ void launch_density_pairs(float4* pos, float4* vel, const uint32_t* skey, const 
       case 2: launch_pairs_variant<false, 2, false>(a); break;
       case 3: launch_pairs_variant<false, 0, true>(a); break;
       case 4: launch_pairs_variant<false, 1, true>(a); break;
-      case 6: launch_pairs_variant<false, 2, true, true>(a); break;
       default: launch_pairs_variant<false, 2, true>(a); break;
     }
   }

@@ -93,8 +93,7 @@ SUB = dict(sub_cell_order=1)
                                      SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4),
                                      dict(sub_cell_order=1, fast_pairs=1), dict(sub_cell_order=0, neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
                                      dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8),
-                                     dict(factored_forces=0), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(list_rows=8),
-                                     dict(pair_variant=6), dict(pair_variant=6, list_rows=8), dict(pair_variant=3)])
+                                     dict(factored_forces=0), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(list_rows=8)])
 def test_neighbour_organisations(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
@@ -193,14 +192,14 @@ def test_pair_density_is_bitwise_the_per_particle_kernel(fluid, n, box_scene):
     s = H.state_s1(p, vol)
     s["intermediate_velocity"][:, 0] += (2.5 * np.sign(s["position"][:, 2])).astype(np.float32)
     outs = []
-    for pair, variant in ((1, 5), (1, 6), (0, 5)):  # pairs in twos, pairs staged in shared memory, one particle per thread
-        ctx = G.make_ctx(s.size, box_scene, p, terms, debug=True, options=dict(pair_density=pair, pair_variant=variant, merged_rows=1, factored_forces=0))
+    for pair in (1, 0):
+        ctx = G.make_ctx(s.size, box_scene, p, terms, debug=True, options=dict(pair_density=pair, merged_rows=1, factored_forces=0))
         ctx.upload(s)
         ctx.step(3)
         outs.append((ctx.download().tobytes(), ctx.fetch(capi.TAP_SUPPORT_COUNT).tobytes(), ctx.fetch(capi.TAP_CANDIDATE_COUNT).tobytes(),
                      ctx.fetch(capi.TAP_ACCELERATION).tobytes()))
         ctx.close()
-    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == outs[1]
 
 
 def test_sub_cell_order_host_round_trip_and_option_rules(box_scene):
