@@ -462,7 +462,7 @@ def run_ours(args, rank, world, local_rank):
                                "frac": value / world * step_bytes(passes) / 1e9 / peak,
                                "frac_of_nominal_8TBs": value / world * step_bytes(passes) / 1e9 / 8000.0},
                 "stage_ms": per,
-                "note": "density/force passes are FP32-issue / shared-memory bound at the reference's 2h cell geometry (SURVEY 8d)"}
+                "note": "density/force passes are instruction-issue / L1-gather / latency bound at the reference's 2h cell geometry, not HBM bound (SURVEY 8d, DESIGN 7)"}
 
     # ---- end to end through the host-buffer calls, pinned host memory: every step uploads the 80-byte AoS
     # array, runs one sub-step and downloads the result (the reference's call shape when a callback is installed)

@@ -39,9 +39,6 @@ struct GridState {
   uint32_t sub;                      // 1: this sub-step sorts by sub-cell keys
   uint32_t sub_dense;                // 1: cell_count fits the dense sub-cell table; 0: binary search
   float plane_hi;
-  // Tile kernels (tiles.cu): a particle within sub_delta (in units of h) of a boundary of its sub-cell may have
-  // neighbours two sub-cells away once rounding is counted; such particles go to the per-particle kernel.
-  float sub_delta;
 };
 
 // AABB accumulators: floats mapped to order-preserving unsigned so atomicMin/Max apply.

@@ -109,11 +109,6 @@ __global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t 
   grid->dense = (count <= cell_capacity) ? 1u : 0u;
   grid->sub = sub_mode ? 1u : 0u;
   grid->sub_dense = (sub_mode && count <= sub_capacity) ? 1u : 0u;
-  // Sub-cell coordinates are floor(f), f = 2 fl(fl(p - min) / cell): two roundings, relative error below 2^-23,
-  // absolute below F 2^-23 with F = the largest f of the grid. For a pair inside the support |dx| < h (1 + 2^-21)
-  // exactly, so |f_i - f_j| < 1 + 2^-21 + F 2^-22. sub_delta is twice that excess.
-  const float f_max = 2.f * (float)min(max(max(gs[0], gs[1]), gs[2]), 1024) + 4.f;
-  grid->sub_delta = 9.5367431640625e-07f + f_max * 4.76837158203125e-07f;  // 2^-20 + F 2^-21
   grid->error |= err;  // sticky until the host reads and clears it
 }
 

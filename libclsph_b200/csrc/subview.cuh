@@ -1,6 +1,6 @@
 // subview.cuh -- index ranges of the sub-cell order: from (cell, octant range) to a range of the sorted
 // arrays, and the per-particle traversal of the sub-cells around a particle (global memory). Shared by
-// subgrid.cu (sort-order bookkeeping, per-particle kernels) and tiles.cu (staging of the tile kernels).
+// subgrid.cu (sort-order bookkeeping, density kernels) and dist.cu (order keys of the multi-GPU exchange).
 // See the header comment of subgrid.cu for the organisation itself.
 #pragma once
 
