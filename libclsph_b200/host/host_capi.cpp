@@ -4,6 +4,7 @@
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <vector>
 
 #include "file_save_delegates/houdini_file_saver.h"
 #include "sph_simulation.h"
@@ -58,6 +59,28 @@ int clsph_host_scene_load(const char* name, unsigned int* face_count, size_t* n_
 int clsph_host_write_frames(const char* prefix, particle* particles, const simulation_parameters* p, int frames) {
   houdini_file_saver saver(prefix);
   for (int k = 0; k < frames; ++k) saver.writeFrameToFile(particles, *p);
+  return 0;
+}
+
+// The same with the format chosen (0 geo, 1 bgeo) and, with packed != 0, through writeFramePoints from the seven
+// floats per particle (position, velocity, density) that clsph_frame_begin packs.
+int clsph_host_write_frames_as(const char* prefix, particle* particles, const simulation_parameters* p, int frames, int format,
+                               int packed) {
+  houdini_file_saver saver(prefix);
+  saver.format = format ? houdini_file_saver::bgeo : houdini_file_saver::geo;
+  std::vector<float> points;
+  if (packed) {
+    points.resize(static_cast<size_t>(p->particles_count) * 7);
+    for (unsigned int i = 0; i < p->particles_count; ++i) {
+      float* o = &points[static_cast<size_t>(i) * 7];
+      for (int k = 0; k < 3; ++k) o[k] = particles[i].position.s[k], o[3 + k] = particles[i].velocity.s[k];
+      o[6] = particles[i].density;
+    }
+  }
+  for (int k = 0; k < frames; ++k) {
+    if (packed) saver.writeFramePoints(points.data(), p->particles_count, p->particle_mass, p->h);
+    else saver.writeFrameToFile(particles, *p);
+  }
   return 0;
 }
 

@@ -12,6 +12,18 @@
 // below: exact integer formatting, ~5x faster than snprintf) and writes the file. At most two frames are in flight; wait() or the
 // destructor blocks until everything is on disk. `asynchronous = false` restores the reference's
 // "written when the call returns".
+//
+// The reference's other output, chosen there at compile time with USE_PARTIO (:78-88 through
+// util/partio/PartioFunctions.h:5-65): a binary Houdini "Bgeo V5" file written by libpartio's writer
+// with the attributes position, velocity, color, id, mass, pscale. libpartio is not vendored by the
+// reference (headers only), so write_job_bgeo below restates the layout of Partio's published BGEO
+// writer (partio 1.1, src/lib/io/BGEO.cpp: everything big-endian; header of the magic, 'V', 5 and
+// nine counts; one definition per attribute other than position; per point x y z 1 and the
+// attribute words; the "generator"/"papi" primitive attribute; one particle-system primitive
+// 0x8000 listing every point; 0x00 0xff). PARITY UNPINNED: there is no libpartio here to compare
+// bytes with; tests/test_bgeo.py reads the file back with an independent parser of that layout.
+// One deliberate difference: the reference fills velocity[0] three times and
+// leaves [1] and [2] as libpartio's allocator left them; all three components are written here.
 #include "file_save_delegates/houdini_file_saver.h"
 
 #include <algorithm>
@@ -203,6 +215,8 @@ struct FramePoint {  // what a frame needs of a particle: 28 of its 80 bytes
 struct FrameJob {
   std::string file_name;
   float mass = 0.f;
+  float pscale = 0.f;   // support radius h (.bgeo only)
+  bool bgeo = false;
   std::vector<FramePoint> points;
 };
 
@@ -285,6 +299,114 @@ void write_job(const FrameJob& job, int threads) {
   std::fclose(f);
 }
 
+// ---- "Bgeo V5", big-endian ---------------------------------------------------------------------------
+struct Bytes {
+  std::string s;
+  void u8(unsigned v) { s.push_back(static_cast<char>(v)); }
+  void u16(unsigned v) { u8(v >> 8); u8(v); }
+  void u32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
+  void str(const char* t) {  // Houdini string: 16-bit length, then the characters
+    const size_t n = std::strlen(t);
+    u16(static_cast<unsigned>(n));
+    s.append(t, n);
+  }
+};
+
+inline char* put_be32(char* p, uint32_t v) {
+  p[0] = static_cast<char>(v >> 24); p[1] = static_cast<char>(v >> 16); p[2] = static_cast<char>(v >> 8); p[3] = static_cast<char>(v);
+  return p + 4;
+}
+inline char* put_be32(char* p, float f) {
+  uint32_t v;
+  std::memcpy(&v, &f, 4);
+  return put_be32(p, v);
+}
+
+constexpr size_t kBgeoPointWords = 4 + 3 + 3 + 1 + 1 + 1;  // position xyzw, velocity, color, id, mass, pscale
+
+void write_job_bgeo(const FrameJob& job, int threads) {
+  const size_t n = job.points.size();
+  Bytes head;
+  head.u32(0x4267656fu);  // "Bgeo"
+  head.u8('V');
+  head.u32(5);
+  head.u32(static_cast<uint32_t>(n));  // points
+  head.u32(1);                         // primitives
+  head.u32(0);                         // point groups
+  head.u32(0);                         // primitive groups
+  head.u32(5);                         // point attributes (all but position)
+  head.u32(0);                         // vertex attributes
+  head.u32(1);                         // primitive attributes
+  head.u32(0);                         // detail attributes
+  // definitions in the order PartioFunctions.h:8-13 adds them; Houdini types: 0 float, 1 int, 5 vector
+  const struct { const char* name; unsigned size; uint32_t type; } attrs[5] = {
+      {"velocity", 3, 5}, {"color", 3, 5}, {"id", 1, 1}, {"mass", 1, 0}, {"pscale", 1, 0}};
+  for (const auto& a : attrs) {
+    head.str(a.name);
+    head.u16(a.size);
+    head.u32(a.type);
+    for (unsigned k = 0; k < a.size; ++k) head.u32(0);  // default values
+  }
+
+  const bool wide = n > (1u << 16);  // vertex numbers: 32 bits above 65536 points, else 16
+  const size_t index_bytes = wide ? 4 : 2;
+  std::unique_ptr<char[]> points(new char[n * kBgeoPointWords * 4 + 4]);
+  std::unique_ptr<char[]> indices(new char[n * index_bytes + 4]);
+  const size_t parts = std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(std::max(1, threads)), (n + 65535) / 65536));
+  auto work = [&](size_t k) {
+    const size_t i0 = n * k / parts, i1 = n * (k + 1) / parts;
+    char* p = points.get() + i0 * kBgeoPointWords * 4;
+    char* x = indices.get() + i0 * index_bytes;
+    for (size_t i = i0; i < i1; ++i) {
+      const FramePoint& q = job.points[i];
+      float r, g, b;
+      density_colour(q.rho, &r, &g, &b);
+      p = put_be32(p, q.px); p = put_be32(p, q.py); p = put_be32(p, q.pz); p = put_be32(p, 1.f);
+      p = put_be32(p, q.vx); p = put_be32(p, q.vy); p = put_be32(p, q.vz);
+      p = put_be32(p, r); p = put_be32(p, g); p = put_be32(p, b);
+      p = put_be32(p, static_cast<uint32_t>(i));
+      p = put_be32(p, job.mass);
+      p = put_be32(p, job.pscale);
+      if (wide) x = put_be32(x, static_cast<uint32_t>(i));
+      else { x[0] = static_cast<char>(i >> 8); x[1] = static_cast<char>(i); x += 2; }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (size_t k = 1; k < parts; ++k) pool.emplace_back(work, k);
+  work(0);
+  for (std::thread& t : pool) t.join();
+
+  Bytes mid;  // the primitive attribute table and the head of the one primitive
+  mid.str("generator");
+  mid.u16(1);   // one value
+  mid.u32(4);   // type: index into a string table
+  mid.u32(1);   // one string
+  mid.str("papi");
+  mid.u32(0x8000);  // particle system
+  mid.u32(static_cast<uint32_t>(n));
+  Bytes tail;
+  tail.u32(0);  // the primitive's "generator" value: string 0
+  tail.u8(0x00);
+  tail.u8(0xff);
+
+  std::FILE* f = std::fopen(job.file_name.c_str(), "wb");
+  if (!f) {
+    std::cerr << "Error while writing to " << job.file_name << std::endl;
+    return;
+  }
+  std::fwrite(head.s.data(), 1, head.s.size(), f);
+  std::fwrite(points.get(), 1, n * kBgeoPointWords * 4, f);
+  std::fwrite(mid.s.data(), 1, mid.s.size(), f);
+  std::fwrite(indices.get(), 1, n * index_bytes, f);
+  std::fwrite(tail.s.data(), 1, tail.s.size(), f);
+  std::fclose(f);
+}
+
+void write_frame(const FrameJob& job, int threads) {
+  if (job.bgeo) write_job_bgeo(job, threads);
+  else write_job(job, threads);
+}
+
 }  // namespace
 
 // Background writer: one thread taking jobs in order; each job is formatted on `threads` cores.
@@ -321,7 +443,7 @@ struct houdini_file_saver::writer {
         busy = true;
       }
       cv.notify_all();
-      write_job(job, threads);
+      write_frame(job, threads);
       {
         std::lock_guard<std::mutex> lk(m);
         busy = false;
@@ -349,18 +471,25 @@ extern "C" int clsph_host_format_g(float v, char* out) {
   return static_cast<int>(end - out);
 }
 
+#ifdef USE_PARTIO  // the reference's compile-time switch (houdini_file_saver.cpp:8, :27)
+static const houdini_file_saver::frame_format kDefaultFormat = houdini_file_saver::bgeo;
+#else
+static const houdini_file_saver::frame_format kDefaultFormat = houdini_file_saver::geo;
+#endif
+
 houdini_file_saver::houdini_file_saver(std::string prefix)
-    : frames_folder_prefix(prefix), asynchronous(true), frame_count(0), writer_(nullptr) {}
+    : frames_folder_prefix(prefix), asynchronous(true), format(kDefaultFormat), frame_count(0), writer_(nullptr) {}
 
 houdini_file_saver::houdini_file_saver(const houdini_file_saver& other)
-    : frames_folder_prefix(other.frames_folder_prefix), asynchronous(other.asynchronous), frame_count(other.frame_count),
-      writer_(nullptr) {}
+    : frames_folder_prefix(other.frames_folder_prefix), asynchronous(other.asynchronous), format(other.format),
+      frame_count(other.frame_count), writer_(nullptr) {}
 
 houdini_file_saver& houdini_file_saver::operator=(const houdini_file_saver& other) {
   if (this != &other) {
     wait();
     frames_folder_prefix = other.frames_folder_prefix;
     asynchronous = other.asynchronous;
+    format = other.format;
     frame_count = other.frame_count;
   }
   return *this;
@@ -374,8 +503,10 @@ void houdini_file_saver::wait() {
 
 int houdini_file_saver::writeFrameToFile(particle* particles, const simulation_parameters& parameters) {
   FrameJob job;
-  job.file_name = frames_folder_prefix + "frames/frame" + frame_suffix(++frame_count) + ".geo";
+  job.bgeo = format == bgeo;
+  job.file_name = frames_folder_prefix + "frames/frame" + frame_suffix(++frame_count) + (job.bgeo ? ".bgeo" : ".geo");
   job.mass = parameters.particle_mass;
+  job.pscale = parameters.h;
   const unsigned int n = parameters.particles_count;
   job.points.resize(n);
   for (unsigned int i = 0; i < n; ++i) {
@@ -388,11 +519,13 @@ int houdini_file_saver::writeFrameToFile(particle* particles, const simulation_p
   return submit_job(&job);
 }
 
-int houdini_file_saver::writeFramePoints(const float* points, unsigned int count, float particle_mass) {
+int houdini_file_saver::writeFramePoints(const float* points, unsigned int count, float particle_mass, float support_radius) {
   static_assert(sizeof(FramePoint) == 7 * sizeof(float), "FramePoint is the packed record of clsph_frame_begin");
   FrameJob job;
-  job.file_name = frames_folder_prefix + "frames/frame" + frame_suffix(++frame_count) + ".geo";
+  job.bgeo = format == bgeo;
+  job.file_name = frames_folder_prefix + "frames/frame" + frame_suffix(++frame_count) + (job.bgeo ? ".bgeo" : ".geo");
   job.mass = particle_mass;
+  job.pscale = support_radius;
   job.points.resize(count);
   if (count) std::memcpy(job.points.data(), points, sizeof(FramePoint) * static_cast<size_t>(count));
   return submit_job(&job);
@@ -402,7 +535,7 @@ int houdini_file_saver::submit_job(void* job_ptr) {
   FrameJob& job = *static_cast<FrameJob*>(job_ptr);
   if (!asynchronous) {
     const unsigned hw = std::thread::hardware_concurrency();
-    write_job(job, static_cast<int>(hw ? hw : 4));
+    write_frame(job, static_cast<int>(hw ? hw : 4));
     return 0;
   }
   if (!writer_) writer_ = new writer();

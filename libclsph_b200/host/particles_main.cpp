@@ -25,13 +25,14 @@ int main(int argc, char** argv) {
   std::string positional[4];
   int n_positional = 0, frames = 0;
   bool assume_yes = false;
-  std::string sync = "", frame_export = "";
+  std::string sync = "", frame_export = "", format = "";
   std::vector<std::string> device_options;
   for (int a = 1; a < argc; ++a) {
     if (!std::strcmp(argv[a], "--yes")) assume_yes = true;
     else if (!std::strcmp(argv[a], "--frames") && a + 1 < argc) frames = std::atoi(argv[++a]);
     else if (!std::strcmp(argv[a], "--sync") && a + 1 < argc) sync = argv[++a];
     else if (!std::strcmp(argv[a], "--frame-export") && a + 1 < argc) frame_export = argv[++a];
+    else if (!std::strcmp(argv[a], "--format") && a + 1 < argc) format = argv[++a];  // geo | bgeo
     else if (!std::strcmp(argv[a], "--option") && a + 1 < argc) device_options.push_back(argv[++a]);  // name=value
     else if (n_positional < 4) positional[n_positional++] = argv[a];
   }
@@ -51,6 +52,12 @@ int main(int argc, char** argv) {
     simulation.device_options.push_back(std::make_pair(device_options[k].substr(0, eq), std::atoll(device_options[k].c_str() + eq + 1)));
   }
   houdini_file_saver saver = houdini_file_saver(positional[3]);
+  if (format == "bgeo") saver.format = houdini_file_saver::bgeo;
+  else if (format == "geo") saver.format = houdini_file_saver::geo;
+  else if (!format.empty()) {
+    std::cerr << "--format expects geo or bgeo, got " << format << std::endl;
+    return -1;
+  }
   try {
     simulation.load_settings("fluid_properties/" + positional[0] + ".json", "simulation_properties/" + positional[1] + ".json");
   } catch (const std::exception& ex) {

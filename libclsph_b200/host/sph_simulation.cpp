@@ -141,7 +141,7 @@ void sph_simulation::simulate(int frame_count) {
     }
   auto collect_frame = [&](int buffer) {
     check_cuda_abi(ctx, clsph_frame_end(ctx));
-    frame_saver->writeFramePoints(frame_points[buffer], n, parameters.particle_mass);
+    frame_saver->writeFramePoints(frame_points[buffer], n, parameters.particle_mass, parameters.h);
     frame_in_flight = false;
   };
 

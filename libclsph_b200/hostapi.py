@@ -19,6 +19,8 @@ def build(force=False):
     """make -C libclsph_b200/host (g++): libclsph_host.so and the clsphparticles driver."""
     _build.build()
     srcs = [os.path.join(_HERE, "host", f) for f in os.listdir(os.path.join(_HERE, "host"))]
+    for folder, _, files in os.walk(os.path.join(os.path.dirname(_HERE), "include", "clsph")):
+        srcs += [os.path.join(folder, f) for f in files]
     newest = max(os.path.getmtime(f) for f in srcs)
     if force or not os.path.exists(LIB_PATH) or not os.path.exists(CLI_PATH) or os.path.getmtime(LIB_PATH) < newest:
         subprocess.run(["make", "-C", os.path.join(_HERE, "host"), "-B"], check=True, stdout=subprocess.DEVNULL)
@@ -35,6 +37,7 @@ def lib():
         L.clsph_host_load_settings.argtypes = [ctypes.c_char_p, ctypes.c_char_p, vp, vp, vp, vp, vp, ctypes.c_char_p]
         L.clsph_host_scene_load.argtypes = [ctypes.c_char_p, vp, vp, vp, vp, vp, vp]
         L.clsph_host_write_frames.argtypes = [ctypes.c_char_p, vp, vp, ctypes.c_int]
+        L.clsph_host_write_frames_as.argtypes = [ctypes.c_char_p, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.clsph_host_simulate.argtypes = [vp, vp, ctypes.c_float, vp, vp, ctypes.c_size_t, vp, ctypes.c_uint32,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]
         _lib = L
@@ -74,8 +77,14 @@ def scene_load(name, cwd):
         os.chdir(old)
 
 
-def write_frames(prefix, particles, params, frames=1):
-    lib().clsph_host_write_frames(prefix.encode(), particle_ptr(particles), ctypes.byref(params), frames)
+def write_frames(prefix, particles, params, frames=1, fmt=None, packed=False):
+    """houdini_file_saver::writeFrameToFile `frames` times. fmt "geo" / "bgeo" sets houdini_file_saver::format;
+    packed=True goes through writeFramePoints (the seven floats per particle that clsph_frame_begin packs)."""
+    if fmt is None and not packed:
+        lib().clsph_host_write_frames(prefix.encode(), particle_ptr(particles), ctypes.byref(params), frames)
+    else:
+        lib().clsph_host_write_frames_as(prefix.encode(), particle_ptr(particles), ctypes.byref(params), frames,
+                                         1 if fmt == "bgeo" else 0, 1 if packed else 0)
 
 
 def simulate(params, terms, initial_volume, normals, vertices, indices, frames, policy=0, callbacks=True, cwd=None):

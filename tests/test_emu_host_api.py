@@ -74,3 +74,27 @@ def test_frames_packed_on_the_device_are_byte_identical_under_the_emulator(tmp_p
     for name in dev:
         assert dev[name] == host[name], name
     assert dev["frame0000001.geo"] != dev["frame0000003.geo"]  # the fluid moved
+
+
+def test_cli_bgeo_frames_under_the_emulator(tmp_path):
+    """clsphparticles --format bgeo (the reference's USE_PARTIO build): the device-packed and the callback path write
+    the same binary files, and the points are those of the .geo run (positions to the 6 digits the text keeps)."""
+    from tests.test_bgeo import read_bgeo
+    hostapi.build()
+    dev = _cli_frames(tmp_path, "device", ["--format", "bgeo"], frames=2)
+    host = _cli_frames(tmp_path, "host", ["--format", "bgeo", "--frame-export", "host"], frames=2)
+    text = _cli_frames(tmp_path, "text", [], frames=2)
+    assert sorted(dev) == sorted(host) == ["frame0000001.bgeo", "frame0000002.bgeo"]
+    for name in dev:
+        assert dev[name] == host[name], name
+    attributes, _ = read_bgeo(dev["frame0000002.bgeo"])
+    lines = text["frame0000002.geo"].decode().splitlines()
+    first = lines.index("mass 1 float 1") + 1
+    for i in (0, 1, 1000, 2047):
+        want = [float(v) for v in lines[first + i].split(" ")[:3]]
+        got = attributes["position"][i]
+        assert all(abs(g - w) <= 1e-5 * max(1.0, abs(w)) for g, w in zip(got, want)), (i, got, want)
+    assert len(attributes["position"]) == 2048
+    bad = subprocess.run([hostapi.CLI_PATH, "water", "small", "box.obj", "", "--yes", "--format", "obj"], cwd=os.path.join(str(tmp_path), "text"),
+                         env=_env(), capture_output=True, text=True, timeout=600)
+    assert bad.returncode != 0 and "--format expects" in bad.stderr

@@ -182,6 +182,31 @@ def test_frames_packed_on_the_device_are_byte_identical(tmp_path):
         assert out["device"][name] == out["host"][name], name
 
 
+@pytest.mark.gpu
+def test_bgeo_frames_from_the_device_hold_the_simulated_state(tmp_path):
+    """clsphparticles --format bgeo on the GPU (100 000 particles, so 32-bit vertex numbers): device-packed and callback
+    paths write the same bytes; the file parses; densities in the colour ramp's range."""
+    from tests.test_bgeo import read_bgeo
+    hostapi.build()
+    out = {}
+    for mode, extra in (("device", []), ("host", ["--frame-export", "host"])):
+        wd = _workdir(tmp_path / mode)
+        sim = open(os.path.join(wd, "simulation_properties", "default.json")).read()
+        open(os.path.join(wd, "simulation_properties", "small.json"), "w").write(sim.replace('"particles_count" : 32000', '"particles_count" : 100000'))
+        r = subprocess.run([hostapi.CLI_PATH, "water", "small", "box.obj", "", "--yes", "--frames", "2", "--format", "bgeo"] + extra, cwd=wd,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        names = sorted(os.listdir(os.path.join(wd, "frames")))
+        out[mode] = {n: open(os.path.join(wd, "frames", n), "rb").read() for n in names}
+    assert sorted(out["device"]) == sorted(out["host"]) == ["frame0000001.bgeo", "frame0000002.bgeo"]
+    for name in out["device"]:
+        assert out["device"][name] == out["host"][name], name
+    attributes, _ = read_bgeo(out["device"]["frame0000002.bgeo"])
+    assert len(attributes["position"]) == 100000 and np.all(np.isfinite(attributes["position"]))
+    assert np.all(attributes["color"] >= 0) and np.all(attributes["color"] <= 1) and attributes["color"].max() > 0
+    assert np.any(attributes["velocity"][:, 1] != 0)  # all three velocity components are written (SURVEY E11)
+
+
 def test_geo_numbers_match_printf_g_on_adversarial_values(tmp_path):
     """The frame writer formats with std::to_chars on worker threads; every number must still read
     exactly like the reference's iostream output (printf %g): checked against Python's %g over
