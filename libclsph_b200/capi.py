@@ -17,7 +17,7 @@ SYMBOLS = [
     "clsph_set_parameters", "clsph_set_option", "clsph_upload_particles", "clsph_step", "clsph_synchronize",
     "clsph_get_parameters", "clsph_download_particles", "clsph_simulate_single_frame", "clsph_set_debug",
     "clsph_debug_fetch", "clsph_kernel_advection_collision", "clsph_comm_unique_id", "clsph_dist_init",
-    "clsph_dist_upload", "clsph_dist_download", "clsph_dist_transport", "clsph_frame_begin", "clsph_frame_end", "clsph_host_alloc", "clsph_host_free", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_stream",
+    "clsph_dist_upload", "clsph_dist_download", "clsph_dist_transport", "clsph_frame_begin", "clsph_frame_end", "clsph_host_alloc", "clsph_host_free", "clsph_profile_enable", "clsph_profile_read", "clsph_particle_count", "clsph_sort_passes", "clsph_stream",
 ]
 
 TAP_SORTED_KEYS, TAP_PERMUTATION, TAP_CELL_TABLE, TAP_KEYS_INPUT, TAP_CANDIDATE_COUNT = 0, 1, 2, 3, 4
@@ -79,6 +79,7 @@ def load_library(path=None):
     L.clsph_profile_enable.argtypes = [vp, ctypes.c_int]
     L.clsph_profile_read.argtypes = [vp, vp]
     L.clsph_particle_count.argtypes = [vp, ctypes.POINTER(u32)]
+    L.clsph_sort_passes.argtypes = [vp, ctypes.POINTER(u32)]
     L.clsph_stream.argtypes = [vp]
     L.clsph_stream.restype = vp
     L.clsph_frame_begin.argtypes = [vp, vp, u32]
@@ -169,6 +170,12 @@ class Context:
     def particle_count(self):
         n = ctypes.c_uint32()
         self._check(self._lib.clsph_particle_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def sort_passes(self):
+        """Radix passes of the last sub-step; 0 = counting sort on the dense sub-cell table."""
+        n = ctypes.c_uint32()
+        self._check(self._lib.clsph_sort_passes(self._h, ctypes.byref(n)))
         return n.value
 
     def download(self, out=None):

@@ -25,7 +25,7 @@ struct GridState {
   int gx, gy, gz;                    // grid_size_*
   uint32_t cell_count;               // morton(gx, gy, gz)
   uint32_t n;                        // particles on this device
-  uint32_t sort_passes;              // ceil(bits(cell_count - 1) / 8), 1..4
+  uint32_t sort_passes;              // ceil(bits(cell_count - 1) / 8), 1..4; 0: counting sort on the dense sub-cell table (sort.cu)
   uint32_t dense;                    // 1: cell_count fits the dense table; 0: binary-search fallback
   uint32_t error;                    // bit 0: a grid axis reached 1024 cells; bit 1: a multi-GPU buffer overflowed;
                                      // bit 2: sub-cell keys need more than 32 bits (Morton cell count beyond 2^29: z axis of 512+ cells)
@@ -39,6 +39,9 @@ struct GridState {
   uint32_t sub;                      // 1: this sub-step sorts by sub-cell keys
   uint32_t sub_dense;                // 1: cell_count fits the dense sub-cell table; 0: binary search
   float plane_hi;
+  // Words of the dense sub-cell table that the last sub-step wrote (9 per cell of its grid). Set by k_keys_hist, never
+  // by k_grid_setup, whose launch zeroes exactly that range: the table is all zero whenever a sub-step starts.
+  uint32_t table_words;
 };
 
 // AABB accumulators: floats mapped to order-preserving unsigned so atomicMin/Max apply.

@@ -3,8 +3,10 @@
 // orders the kernels of sort.cu / grid.cu / neighbors.cu / integrate.cu on one stream.
 //
 // Sub-step launch sequence (all device resident, no host round trip):
-//   k_grid_setup -> memset(sort scratch) -> k_keys_hist (+ table clear, histogram scan) -> k_onesweep x4
-//   -> k_reorder_sub -> [k_rank on the side stream] k_density_pairs -> k_forces_lists(_tile) -> k_forces_sub -> k_integrate
+//   k_grid_setup (+ zeroing of the sub-cell table and the sort's scratch) -> k_keys_hist (keys + counts) -> k_scan_table
+//   -> k_onesweep x4 (the first one scatters, the others return: counting sort; or the radix passes when the grid does not
+//   fit the sub-cell table) -> k_reorder_sub -> [k_rank on the side stream] k_density_pairs -> k_forces_lists_direct
+//   -> k_forces_sub -> k_integrate
 // (default organisation; sub_cell_order = 0: k_clear_cells -> k_reorder -> k_density_lists -> k_forces_lists -> k_integrate)
 // The reference's equivalent is libclsph/sph_simulation.cpp:173-344 with 17 blocking transfers.
 #include <cmath>
@@ -83,6 +85,8 @@ struct clsph_context {
   bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
   int factored_forces = 1;          // option "factored_forces": pair terms with the constants factored out of the sums (default) or add_pair_fast
   int pair_variant = 5;             // option "pair_variant" (tuning): walk 0/1/2 + 3 x (entries stored two at a time)
+  bool count_sort = true;           // option "count_sort": counting sort on the dense sub-cell table instead of radix passes (sort.cu)
+  uint32_t* scan_state = nullptr;   // kScanStateWords words: chunk ticket and look-back words of the table scan
   uint32_t* pair_items = nullptr;   // [capacity] items written by k_reorder_sub
   uint32_t* pair_count = nullptr;
   bool forces_dense = true;     // k_forces_lists<.., 4>: four resident CTAs per SM (option forces_blocks = 4)
@@ -328,6 +332,8 @@ int refresh_face_grid(clsph_context* ctx) {
 int ensure_sub(clsph_context* ctx) {
   if (!ctx->sub_order || ctx->sub_lb) return CLSPH_OK;
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->sub_lb, (size_t)ctx->sub_capacity * 9u));
+  CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->scan_state, scan_state_words(ctx->sub_capacity)));
+  CLSPH_CUDA_TRY(ctx, cudaMemsetAsync(ctx->scan_state, 0, sizeof(uint32_t) * scan_state_words(ctx->sub_capacity), ctx->stream));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->rrank, ctx->capacity));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->rr_tmp, ctx->capacity));
   CLSPH_CUDA_TRY(ctx, dev_alloc(&ctx->pair_items, ctx->capacity));
@@ -382,7 +388,8 @@ int enqueue_substep(clsph_context* ctx) {
   if (multi && dist_reduce_bounds(&ctx->dist, ctx->bounds, ctx->grid, st, lc)) return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
   const bool sub = ctx->sub_order;
   launch_grid_setup(ctx->bounds, ctx->grid, ctx->params.h, ctx->n, ctx->cell_capacity, multi ? ctx->dist.plane_lo : -inf,
-                    multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, st, lc);
+                    multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, ctx->count_sort, sub ? ctx->sub_lb : nullptr,
+                    ctx->scan_state, scan_state_words(ctx->sub_capacity), ctx->sort.scratch, sort_scratch_zero_words(n), ctx->sm_count, st, lc);
   if (prof) next_event(ctx);
 
   const bool in_place = multi && sub && ctx->live_idx != nullptr;  // the owned particles stay where they are
@@ -407,7 +414,8 @@ int enqueue_substep(clsph_context* ctx) {
   launch_sort_keys(ctx->sort, src.pos, ctx->grid, n, ctx->sm_count, (ctx->debug && !sub) ? ctx->taps.keys_input : nullptr, sub,
                    sub ? ctx->sub_lb : nullptr, in_place ? ctx->live_idx : nullptr, st, lc);  // (+ table clear, histogram scan)
   if (prof) next_event(ctx);
-  launch_sort_passes(ctx->sort, ctx->grid, n, in_place ? ctx->live_idx : nullptr, st, lc);
+  if (sub) launch_scan_table(ctx->sub_lb, ctx->grid, ctx->scan_state, ctx->sub_capacity, ctx->sm_count, st, lc);  // (counting sort only)
+  launch_sort_passes(ctx->sort, ctx->grid, n, in_place ? ctx->live_idx : nullptr, sub ? ctx->sub_lb : nullptr, st, lc);
   if (prof) next_event(ctx);
 
   bool join_side = false;  // the side stream has work of this sub-step
@@ -650,6 +658,7 @@ void clsph_destroy(clsph_context* ctx) {
   cudaFree(ctx->fg_ids);
   cudaFree(ctx->fg_global);
   cudaFree(ctx->sub_lb);
+  cudaFree(ctx->scan_state);
   cudaFree(ctx->rrank);
   cudaFree(ctx->rr_tmp);
   cudaFree(ctx->pair_items);
@@ -735,6 +744,8 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
     ctx->pair_density = value != 0;
   } else if (!std::strcmp(name, "factored_forces")) {
     ctx->factored_forces = value < 0 ? -1 : (value != 0 ? 1 : 0);
+  } else if (!std::strcmp(name, "count_sort")) {
+    ctx->count_sort = value != 0;
   } else if (!std::strcmp(name, "pair_variant")) {
     if (value < 0 || value > 5) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: pair_variant must be in [0, 5]");
     ctx->pair_variant = (int)value;
@@ -1119,6 +1130,14 @@ int clsph_profile_read(clsph_context* ctx, clsph_stage_times* out) {
 int clsph_particle_count(clsph_context* ctx, uint32_t* n) {
   if (!ctx || !n) return CLSPH_EINVAL;
   *n = ctx->n;
+  return CLSPH_OK;
+}
+
+int clsph_sort_passes(clsph_context* ctx, uint32_t* passes) {
+  if (!ctx || !passes) return CLSPH_EINVAL;
+  CLSPH_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CLSPH_CUDA_TRY(ctx, cudaMemcpyAsync(passes, &ctx->grid->sort_passes, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CLSPH_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return CLSPH_OK;
 }
 

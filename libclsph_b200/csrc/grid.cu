@@ -67,9 +67,22 @@ __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ pos, 
 // same on every rank because the AABB was all-reduced. keep_n: the particle count lives on the
 // device (it changes with migration) and must not be overwritten.
 // sub_mode: sort by sub-cell keys (cell key << 3 | octant), which need 3 more key bits; sub_capacity =
-// cells the dense sub-cell table can hold.
-__global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity,
-                             float plane_lo, float plane_hi, int keep_n, uint32_t sub_mode, uint32_t sub_capacity) {
+// cells the dense sub-cell table can hold. count_sort: when the grid fits that table the sub-step sorts by counting
+// on it (sort_passes = 0, see sort.cu) instead of by radix passes.
+// The other threads of the launch zero what the previous sub-step left in the sub-cell table (grid->table_words, which
+// thread 0 does not touch), the state words of the table scan and the sort's histograms and look-back words: every later
+// kernel of the step is ordered behind this launch, and nothing before it in the step reads any of them.
+__global__ void __launch_bounds__(256) k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity,
+                                                    float plane_lo, float plane_hi, int keep_n, uint32_t sub_mode, uint32_t sub_capacity,
+                                                    uint32_t count_sort, uint32_t* __restrict__ sub_lb, uint32_t* __restrict__ scan_state,
+                                                    uint32_t scan_words, uint32_t* __restrict__ sort_scratch, size_t sort_scratch_words) {
+  if (sub_lb) {
+    const size_t words = grid->table_words;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t w = first; w < words; w += stride) sub_lb[w] = 0u;
+    for (size_t w = first; w < scan_words; w += stride) scan_state[w] = 0u;
+    for (size_t w = first; w < sort_scratch_words; w += stride) sort_scratch[w] = 0u;
+  }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float cell = __fmul_rn(h, 2.f);
   const float pad = __fmul_rn(cell, 2.f);
@@ -105,10 +118,11 @@ __global__ void k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t 
   // largest sort key: count - 1, or 8 * count - 1 with the octant bits appended
   const uint32_t top = sub_mode ? (count >= (1u << 29) ? 0xFFFFFFFFu : max(count * 8u, 2u) - 1u) : (count > 1u ? count - 1u : 1u);
   const uint32_t bits = 32u - (uint32_t)__clz((int)top);
-  grid->sort_passes = err ? 4u : max(1u, (bits + 7u) / 8u);
   grid->dense = (count <= cell_capacity) ? 1u : 0u;
   grid->sub = sub_mode ? 1u : 0u;
   grid->sub_dense = (sub_mode && count <= sub_capacity) ? 1u : 0u;
+  const bool counting = count_sort && sub_mode && !err && count <= sub_capacity;
+  grid->sort_passes = err ? 4u : counting ? 0u : max(1u, (bits + 7u) / 8u);
   grid->error |= err;  // sticky until the host reads and clears it
 }
 
@@ -236,10 +250,17 @@ void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, 
 }
 
 void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
-                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, cudaStream_t stream,
-                       uint64_t* launches) {
-  k_grid_setup<<<1, 32, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0, sub_mode,
-                                     sub_capacity);
+                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, bool count_sort, uint32_t* sub_lb,
+                       uint32_t* scan_state, uint32_t scan_words, uint32_t* sort_scratch, size_t sort_scratch_words, int sm_count,
+                       cudaStream_t stream, uint64_t* launches) {
+  // with a sub-cell table to zero: enough threads to stream a few MB; without: the one thread that does the set-up
+  if (sub_lb)
+    k_grid_setup<<<(unsigned)sm_count * 4u, 256, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0, sub_mode,
+                                                             sub_capacity, count_sort ? 1u : 0u, sub_lb, scan_state, scan_words, sort_scratch,
+                                                             sort_scratch_words);
+  else
+    k_grid_setup<<<1, 32, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0, sub_mode, sub_capacity, 0u,
+                                       nullptr, nullptr, 0u, nullptr, 0);
   if (launches) ++*launches;
 }
 

@@ -66,15 +66,21 @@ size_t sort_scratch_words(uint32_t max_particles);
 // sub_keys: keys are (cell key << 3 | octant) instead of the cell key (subgrid.cu).
 void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* grid, uint32_t n_launch, int sm_count,
                       uint32_t* keys_tap, bool sub_keys, uint32_t* sub_lb, const uint32_t* index, cudaStream_t stream, uint64_t* launches);
-void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_launch, const uint32_t* first_vals, cudaStream_t stream,
-                        uint64_t* launches);
+void launch_sort_passes(const SortBuffers& b, const GridState* grid, uint32_t n_launch, const uint32_t* first_vals, const uint32_t* table,
+                        cudaStream_t stream, uint64_t* launches);
+// counting sort on the dense sub-cell table (grid->sort_passes == 0): scan state words, scan of the table
+uint32_t scan_state_words(uint32_t sub_capacity);
+size_t sort_scratch_zero_words(uint32_t n);  // leading words of SortBuffers::scratch that must be zero before a sort of n keys
+void launch_scan_table(uint32_t* sub_lb, const GridState* grid, uint32_t* scan_state, uint32_t sub_capacity, int sm_count,
+                       cudaStream_t stream, uint64_t* launches);
 
 // ---- grid.cu
 void launch_bounds_reset(BoundsAcc* acc, cudaStream_t stream, uint64_t* launches);
 void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, cudaStream_t stream, uint64_t* launches);
 void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
-                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, cudaStream_t stream,
-                       uint64_t* launches);
+                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, bool count_sort, uint32_t* sub_lb,
+                       uint32_t* scan_state, uint32_t scan_words, uint32_t* sort_scratch, size_t sort_scratch_words, int sm_count,
+                       cudaStream_t stream, uint64_t* launches);
 void launch_clear_cells(uint32_t* cell_start, uint32_t* cell_end, const GridState* grid, uint32_t cell_capacity,
                         int sm_count, cudaStream_t stream, uint64_t* launches);
 // Gathers `src` into `dst` through the sort permutation, writes sorted keys and the cell table.
@@ -123,8 +129,6 @@ void launch_forces(const float4* pos, const float4* vel, const float4* aux, cons
                    uint32_t n_launch, cudaStream_t stream, uint64_t* launches, bool factored = false);
 
 // ---- subgrid.cu: sub-cell order (arrays sorted by cell key << 3 | octant)
-void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capacity, int sm_count, cudaStream_t stream,
-                      uint64_t* launches);
 void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                         const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,

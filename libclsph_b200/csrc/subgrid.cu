@@ -38,15 +38,9 @@ constexpr int kSubThreads = 128;
 }  // namespace
 
 // =============================================================================================
-// Sub-cell table: cleared, then written by the gather kernel from the sorted keys.
+// Sub-cell table: zero at the start of a sub-step (k_grid_setup), then either the counting sort's own table
+// (sort.cu) or written by the gather kernel from the sorted keys.
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_clear_sub(uint32_t* __restrict__ sub_lb, const GridState* __restrict__ grid) {
-  if (!grid->sub_dense) return;
-  const size_t words = (size_t)grid->cell_count * 9u;
-  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x)
-    sub_lb[w] = 0u;
-}
-
 // Sorted slot r takes the particle that sat at vals[r]. skey gets the CELL key (what every other
 // kernel and the exported grid_index expect); rr_dst the particle's reference rank of the previous
 // sub-step. Slots where the sub-cell key changes fill the octant boundaries of the dense table:
@@ -120,7 +114,7 @@ reorder_sub_slot(uint32_t r, uint32_t n, const float4* __restrict__ src_pos, con
     dst_ordk[dest] = src_ordk[from];
     dst_ordr[dest] = src_ordr[from];
   }
-  if (!grid->sub_dense) return;
+  if (!grid->sub_dense || grid->sort_passes == 0u) return;  // (a counting sort has left the finished table, sort.cu)
   const uint32_t count = grid->cell_count;  // keys are < count whenever the grid fits (see k_reorder)
   uint32_t* row = sub_lb + (size_t)key * 9u;
   if (r == 0) {
@@ -520,14 +514,6 @@ __global__ void __launch_bounds__(256) k_scatter_words(const uint32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-void launch_clear_sub(uint32_t* sub_lb, const GridState* grid, uint32_t sub_capacity, int sm_count, cudaStream_t stream,
-                      uint64_t* launches) {
-  const uint64_t words = (uint64_t)sub_capacity * 9u;
-  const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1u, (words + 255) / 256), (uint64_t)sm_count * 8u);
-  k_clear_sub<<<blocks, 256, 0, stream>>>(sub_lb, grid);
-  if (launches) ++*launches;
-}
-
 void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const SortBuffers& sort, uint32_t* skey,
                         const uint32_t* rr_src, uint32_t* rr_dst, uint32_t* sub_lb, const GridState* grid,
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,

@@ -93,7 +93,7 @@ SUB = dict(sub_cell_order=1)
                                      SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4),
                                      dict(sub_cell_order=1, fast_pairs=1), dict(sub_cell_order=0, neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
                                      dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8),
-                                     dict(factored_forces=0), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(list_rows=8)])
+                                     dict(factored_forces=0), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(list_rows=8), dict(count_sort=0)])
 def test_neighbour_organisations(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
@@ -200,6 +200,11 @@ def test_pair_density_is_bitwise_the_per_particle_kernel(fluid, n, box_scene):
                      ctx.fetch(capi.TAP_ACCELERATION).tobytes()))
         ctx.close()
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("fluid,n", [("water", 6000), ("mucus", 3000)])
+def test_counting_sort_is_bitwise_the_radix_sort(fluid, n, box_scene):
+    G.check_counting_sort_against_radix(fluid, n, box_scene)
 
 
 def test_sub_cell_order_host_round_trip_and_option_rules(box_scene):
@@ -339,7 +344,7 @@ def test_option_validation():
         with pytest.raises(capi.ClsphError) as e:
             ctx.set_option(name, value)
         assert e.value.code == capi.E_INVAL, name
-    for name, value in (("forces_blocks", 4), ("forces_blocks", 3), ("fast_pairs", 1), ("merged_rows", 1), ("pair_density", 0), ("pair_variant", 3), ("factored_forces", 1),
+    for name, value in (("forces_blocks", 4), ("forces_blocks", 3), ("fast_pairs", 1), ("merged_rows", 1), ("pair_density", 0), ("pair_variant", 3), ("factored_forces", 1), ("count_sort", 0),
                         ("face_grid", 1), ("sub_cell_order", 1), ("sub_cell_order", 0), ("neighbour_lists", 0), ("list_rows", 48)):
         ctx.set_option(name, value)
     ctx.close()

@@ -99,6 +99,32 @@ def check_resident_steps_against_oracle(state, params, terms, scene, steps, what
     ctx.close()
 
 
+def check_counting_sort_against_radix(fluid, n, scene, steps=4):
+    """Sorting by counting on the sub-cell table (default while the grid fits it) against the radix passes: the order
+    inside a sub-cell is set by the reference rank either way, so every byte of the state and of the taps is the same
+    after several resident sub-steps; clsph_sort_passes tells which sort ran."""
+    p, terms, vol = H.config(fluid, n)
+    s = H.state_s1(p, vol)
+    s["intermediate_velocity"][:, 0] += (2.5 * np.sign(s["position"][:, 2])).astype(np.float32)  # shear: sub-cells change
+    outs, passes = [], []
+    for counting in (1, 0):
+        ctx = make_ctx(s.size, scene, p, terms, debug=True, options=dict(count_sort=counting))
+        ctx.upload(s)
+        ctx.step(steps)
+        passes.append(ctx.sort_passes())
+        outs.append((ctx.download().tobytes(),) + tuple(ctx.fetch(t).tobytes() for t in (
+            capi.TAP_SORTED_KEYS, capi.TAP_PERMUTATION, capi.TAP_CELL_TABLE, capi.TAP_SUPPORT_COUNT, capi.TAP_CANDIDATE_COUNT,
+            capi.TAP_ACCELERATION)))
+        ctx.close()
+    assert passes[0] == 0 and passes[1] >= 1, passes
+    assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("fluid,n", [("water", 200000), ("mucus", 60000)])
+def test_counting_sort_is_bitwise_the_radix_sort(fluid, n, box_scene):
+    check_counting_sort_against_radix(fluid, n, box_scene)
+
+
 @pytest.mark.parametrize("n", [128, 1000, 4096, 32000])
 def test_lattice_state_s0(n, box_scene):
     p, terms, vol = H.config("water", n)
