@@ -387,9 +387,17 @@ int enqueue_substep(clsph_context* ctx) {
   }
   if (multi && dist_reduce_bounds(&ctx->dist, ctx->bounds, ctx->grid, st, lc)) return fail(ctx, CLSPH_ECOMM, "%s", dist_last_error());
   const bool sub = ctx->sub_order;
+  StepZero zero{};
+  if (sub) {
+    zero.sub_lb = ctx->sub_lb;
+    zero.scan_state = ctx->scan_state;
+    zero.scan_words = scan_state_words(ctx->sub_capacity);
+    zero.sort_scratch = ctx->sort.scratch;
+    zero.sort_scratch_words = sort_scratch_zero_words(n);
+    zero.pair_count = ctx->pair_count;
+  }
   launch_grid_setup(ctx->bounds, ctx->grid, ctx->params.h, ctx->n, ctx->cell_capacity, multi ? ctx->dist.plane_lo : -inf,
-                    multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, ctx->count_sort, sub ? ctx->sub_lb : nullptr,
-                    ctx->scan_state, scan_state_words(ctx->sub_capacity), ctx->sort.scratch, sort_scratch_zero_words(n), ctx->sm_count, st, lc);
+                    multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, ctx->count_sort, zero, ctx->sm_count, st, lc);
   if (prof) next_event(ctx);
 
   const bool in_place = multi && sub && ctx->live_idx != nullptr;  // the owned particles stay where they are

@@ -74,14 +74,14 @@ __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ pos, 
 // kernel of the step is ordered behind this launch, and nothing before it in the step reads any of them.
 __global__ void __launch_bounds__(256) k_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity,
                                                     float plane_lo, float plane_hi, int keep_n, uint32_t sub_mode, uint32_t sub_capacity,
-                                                    uint32_t count_sort, uint32_t* __restrict__ sub_lb, uint32_t* __restrict__ scan_state,
-                                                    uint32_t scan_words, uint32_t* __restrict__ sort_scratch, size_t sort_scratch_words) {
-  if (sub_lb) {
+                                                    uint32_t count_sort, const StepZero zero) {
+  if (zero.sub_lb) {
     const size_t words = grid->table_words;
     const size_t stride = (size_t)gridDim.x * blockDim.x, first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t w = first; w < words; w += stride) sub_lb[w] = 0u;
-    for (size_t w = first; w < scan_words; w += stride) scan_state[w] = 0u;
-    for (size_t w = first; w < sort_scratch_words; w += stride) sort_scratch[w] = 0u;
+    for (size_t w = first; w < words; w += stride) zero.sub_lb[w] = 0u;
+    for (size_t w = first; w < zero.scan_words; w += stride) zero.scan_state[w] = 0u;
+    for (size_t w = first; w < zero.sort_scratch_words; w += stride) zero.sort_scratch[w] = 0u;
+    if (first < 2 && zero.pair_count) zero.pair_count[first] = 0u;  // pair items, overflowing lists (subgrid.cu)
   }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float cell = __fmul_rn(h, 2.f);
@@ -250,17 +250,15 @@ void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, 
 }
 
 void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
-                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, bool count_sort, uint32_t* sub_lb,
-                       uint32_t* scan_state, uint32_t scan_words, uint32_t* sort_scratch, size_t sort_scratch_words, int sm_count,
-                       cudaStream_t stream, uint64_t* launches) {
+                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, bool count_sort, const StepZero& zero,
+                       int sm_count, cudaStream_t stream, uint64_t* launches) {
   // with a sub-cell table to zero: enough threads to stream a few MB; without: the one thread that does the set-up
-  if (sub_lb)
+  if (zero.sub_lb)
     k_grid_setup<<<(unsigned)sm_count * 4u, 256, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0, sub_mode,
-                                                             sub_capacity, count_sort ? 1u : 0u, sub_lb, scan_state, scan_words, sort_scratch,
-                                                             sort_scratch_words);
+                                                             sub_capacity, count_sort ? 1u : 0u, zero);
   else
     k_grid_setup<<<1, 32, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0, sub_mode, sub_capacity, 0u,
-                                       nullptr, nullptr, 0u, nullptr, 0);
+                                       StepZero{});
   if (launches) ++*launches;
 }
 

@@ -29,6 +29,16 @@ struct SortBuffers {
   uint32_t* scratch;  // sort_scratch_words() words
 };
 
+// Device words zeroed by the launch of k_grid_setup at the start of a sub-step (sub-cell order).
+struct StepZero {
+  uint32_t* sub_lb;            // the range the last sub-step wrote (GridState::table_words)
+  uint32_t* scan_state;
+  uint32_t scan_words;
+  uint32_t* sort_scratch;
+  size_t sort_scratch_words;
+  uint32_t* pair_count;        // 2 words (nullable)
+};
+
 // Precomputed triangle record for the collision pass (5 x float4).
 struct Face {
   float nx, ny, nz, nlen;   // scene normal and its length()
@@ -78,9 +88,8 @@ void launch_scan_table(uint32_t* sub_lb, const GridState* grid, uint32_t* scan_s
 void launch_bounds_reset(BoundsAcc* acc, cudaStream_t stream, uint64_t* launches);
 void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, cudaStream_t stream, uint64_t* launches);
 void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
-                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, bool count_sort, uint32_t* sub_lb,
-                       uint32_t* scan_state, uint32_t scan_words, uint32_t* sort_scratch, size_t sort_scratch_words, int sm_count,
-                       cudaStream_t stream, uint64_t* launches);
+                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, bool count_sort, const StepZero& zero,
+                       int sm_count, cudaStream_t stream, uint64_t* launches);
 void launch_clear_cells(uint32_t* cell_start, uint32_t* cell_end, const GridState* grid, uint32_t cell_capacity,
                         int sm_count, cudaStream_t stream, uint64_t* launches);
 // Gathers `src` into `dst` through the sort permutation, writes sorted keys and the cell table.

@@ -519,7 +519,7 @@ void launch_reorder_sub(const StateArrays& src, const StateArrays& dst, const So
                         const uint32_t* src_pid, uint32_t* dst_pid, const uint32_t* src_ordk, const uint32_t* src_ordr,
                         uint32_t* dst_ordk, uint32_t* dst_ordr, uint32_t* pair_items, uint32_t* pair_count, uint32_t n_launch,
                         cudaStream_t stream, uint64_t* launches) {
-  if (pair_items) cudaMemsetAsync(pair_count, 0, 2 * sizeof(uint32_t), stream);  // items, overflowing lists
+  // (pair_count -- items, overflowing lists -- was zeroed by the launch of k_grid_setup)
   k_reorder_sub<<<(n_launch + 255) / 256, 256, 0, stream>>>(src.pos, src.vel, src.ivel, dst.pos, dst.vel, dst.ivel, sort.keys_a,
                                                             sort.keys_b, sort.vals_a, sort.vals_b, skey, rr_src, rr_dst, sub_lb,
                                                             grid, src_pid, dst_pid, src_ordk, src_ordr, dst_ordk, dst_ordr,
