@@ -462,6 +462,9 @@ def run_ours(args, rank, world, local_rank):
                                "frac": value / world * step_bytes(passes) / 1e9 / peak,
                                "frac_of_nominal_8TBs": value / world * step_bytes(passes) / 1e9 / 8000.0},
                 "stage_ms": per,
+                # what the library's sort did in the last sub-step: 0 = counting sort on the sub-cell table, else 8-bit radix passes
+                # (the algorithmic bytes above keep SURVEY 8d's figure, 16 bytes per radix pass the keys need)
+                "sort_passes_run": ctx.sort_passes(),
                 "note": "density/force passes are instruction-issue / L1-gather / latency bound at the reference's 2h cell geometry, not HBM bound (SURVEY 8d, DESIGN 7)"}
 
     # ---- end to end through the host-buffer calls, pinned host memory: every step uploads the 80-byte AoS

@@ -39,9 +39,13 @@ struct GridState {
   uint32_t sub;                      // 1: this sub-step sorts by sub-cell keys
   uint32_t sub_dense;                // 1: cell_count fits the dense sub-cell table; 0: binary search
   float plane_hi;
-  // Words of the dense sub-cell table that the last sub-step wrote (9 per cell of its grid). Set by k_keys_hist, never
-  // by k_grid_setup, whose launch zeroes exactly that range: the table is all zero whenever a sub-step starts.
-  uint32_t table_words;
+  // What the last sub-step left in the dense sub-cell table, so that the launch of the next k_grid_setup can zero it
+  // again (the table is all zero whenever a sub-step starts). Set by k_keys_hist, never by k_grid_setup itself.
+  // table_words: 9 per cell of that step's grid (0: no table was written). table_full: a counting sort scanned the whole
+  // range; otherwise k_reorder_sub wrote only rows of cells that hold particles -- those of the table_n sorted keys the
+  // sort left in its "a" (table_in_b: "b") buffer -- and only these are zeroed: on a grid much larger than the fluid
+  // (a slab of a long multi-GPU domain: 600 MB of table for 1 Mi particles) that is the difference between 100 and 3 us.
+  uint32_t table_words, table_full, table_n, table_in_b;
 };
 
 // AABB accumulators: floats mapped to order-preserving unsigned so atomicMin/Max apply.

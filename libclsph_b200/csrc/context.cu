@@ -390,6 +390,8 @@ int enqueue_substep(clsph_context* ctx) {
   StepZero zero{};
   if (sub) {
     zero.sub_lb = ctx->sub_lb;
+    zero.keys_a = ctx->sort.keys_a;
+    zero.keys_b = ctx->sort.keys_b;
     zero.scan_state = ctx->scan_state;
     zero.scan_words = scan_state_words(ctx->sub_capacity);
     zero.sort_scratch = ctx->sort.scratch;

@@ -78,7 +78,20 @@ __global__ void __launch_bounds__(256) k_grid_setup(BoundsAcc* acc, GridState* g
   if (zero.sub_lb) {
     const size_t words = grid->table_words;
     const size_t stride = (size_t)gridDim.x * blockDim.x, first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t w = first; w < words; w += stride) zero.sub_lb[w] = 0u;
+    if (grid->table_full) {
+      for (size_t w = first; w < words; w += stride) zero.sub_lb[w] = 0u;
+    } else if (words) {  // the rows of the cells that held particles: where the sorted keys change cell
+      const uint32_t* __restrict__ keys = grid->table_in_b ? zero.keys_b : zero.keys_a;
+      const uint32_t n_old = grid->table_n;
+      for (size_t r = first; r < n_old; r += stride) {
+        const uint32_t key = keys[r] >> 3;
+        if ((r == 0 || (keys[r - 1] >> 3) != key) && ((size_t)key + 1u) * 9u <= words) {
+          uint32_t* row = zero.sub_lb + (size_t)key * 9u;
+#pragma unroll
+          for (int o = 0; o < 9; ++o) row[o] = 0u;
+        }
+      }
+    }
     for (size_t w = first; w < zero.scan_words; w += stride) zero.scan_state[w] = 0u;
     for (size_t w = first; w < zero.sort_scratch_words; w += stride) zero.sort_scratch[w] = 0u;
     if (first < 2 && zero.pair_count) zero.pair_count[first] = 0u;  // pair items, overflowing lists (subgrid.cu)
@@ -121,7 +134,11 @@ __global__ void __launch_bounds__(256) k_grid_setup(BoundsAcc* acc, GridState* g
   grid->dense = (count <= cell_capacity) ? 1u : 0u;
   grid->sub = sub_mode ? 1u : 0u;
   grid->sub_dense = (sub_mode && count <= sub_capacity) ? 1u : 0u;
-  const bool counting = count_sort && sub_mode && !err && count <= sub_capacity;
+  // A counting sort scans (and the next sub-step zeroes) the whole table, so it only pays while the table is small beside
+  // the particles. Measured on B200s (profiles/r02_ak_*, r02_am_*): 48 us against the radix passes' 77 at 2 table words
+  // per particle (1 Mi particles, one GPU), 119 against 90 at 15 (one slab of eight): break-even near 7.
+  const uint32_t n_now = keep_n ? grid->n : n;
+  const bool counting = count_sort && sub_mode && !err && count <= sub_capacity && (uint64_t)count * 9u <= (uint64_t)n_now * 6u;
   grid->sort_passes = err ? 4u : counting ? 0u : max(1u, (bits + 7u) / 8u);
   grid->error |= err;  // sticky until the host reads and clears it
 }

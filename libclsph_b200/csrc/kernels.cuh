@@ -31,7 +31,9 @@ struct SortBuffers {
 
 // Device words zeroed by the launch of k_grid_setup at the start of a sub-step (sub-cell order).
 struct StepZero {
-  uint32_t* sub_lb;            // the range the last sub-step wrote (GridState::table_words)
+  uint32_t* sub_lb;            // what the last sub-step wrote (GridState::table_words ...)
+  const uint32_t* keys_a;      // the sort's key buffers: the sorted keys of the last sub-step are still in one of them
+  const uint32_t* keys_b;
   uint32_t* scan_state;
   uint32_t scan_words;
   uint32_t* sort_scratch;

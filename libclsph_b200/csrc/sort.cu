@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) k_keys_hist(const float4* __restrict__ po
                                                    uint32_t* __restrict__ sub_lb, uint32_t* __restrict__ digit_base,
                                                    uint32_t* __restrict__ done, const uint32_t* __restrict__ index,
                                                    uint32_t* __restrict__ keys_count, uint32_t* __restrict__ arrival,
-                                                   uint32_t* __restrict__ table_words) {
+                                                   GridState* __restrict__ table_note) {
   __shared__ uint32_t s_hist[kMaxSortPasses * kRadix];
   __shared__ uint32_t s_scratch[8];
   __shared__ bool s_last;
@@ -89,8 +89,14 @@ __global__ void __launch_bounds__(256) k_keys_hist(const float4* __restrict__ po
   const uint32_t n = grid->n;
   const int passes = (int)grid->sort_passes;
   const uint32_t stride = gridDim.x * blockDim.x;
-  // the table is written in this sub-step (here or by k_reorder_sub): the next k_grid_setup zeroes that much of it
-  if (kSub && sub_lb && blockIdx.x == 0 && threadIdx.x == 0) *table_words = grid->sub_dense ? grid->cell_count * 9u : 0u;
+  // the table is written in this sub-step (here or by k_reorder_sub): a note for the next k_grid_setup, which zeroes it
+  // (table_note is `grid` itself; these four words are read by nothing else, see common.cuh)
+  if (kSub && sub_lb && blockIdx.x == 0 && threadIdx.x == 0) {
+    table_note->table_words = grid->sub_dense ? grid->cell_count * 9u : 0u;
+    table_note->table_full = passes == 0 ? 1u : 0u;
+    table_note->table_n = n;
+    table_note->table_in_b = (uint32_t)passes & 1u;
+  }
   if (kSub && passes == 0) {
     const uint32_t last_key = grid->cell_count * 8u - 1u;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
@@ -475,7 +481,7 @@ void launch_sort_keys(const SortBuffers& b, const float4* pos, const GridState* 
   uint32_t* done = l.tile_counter + 8;  // (words 0..3 are the tile counters of the passes; all zeroed above)
   if (sub_keys)
     k_keys_hist<true><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist, sub_lb, l.digit_base, done, index, b.keys_b,
-                                                                    b.vals_b, const_cast<uint32_t*>(&grid->table_words));
+                                                                    b.vals_b, const_cast<GridState*>(grid));
   else
     k_keys_hist<false><<<std::max(1u, hist_blocks), 256, 0, stream>>>(pos, b.keys_a, grid, l.hist, nullptr, l.digit_base, done, index, nullptr,
                                                                      nullptr, nullptr);

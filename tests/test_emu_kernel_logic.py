@@ -152,7 +152,7 @@ def test_sub_cell_order_binary_search_fallback(box_scene):
     G.check_against_oracle(s, p, terms, box_scene, "sub, binary search", cell_table_capacity=8, options=SUB)
 
 
-@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=1), SUB])
+@pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=1), SUB, dict(count_sort=0)])
 def test_resident_steps_keep_the_reference_order(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     s = H.state_s1(p, vol)
