@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_grid_setup(BoundsAcc* acc, GridState* g
   grid->sub_dense = (sub_mode && count <= sub_capacity) ? 1u : 0u;
   // A counting sort scans (and the next sub-step zeroes) the whole table, so it only pays while the table is small beside
   // the particles. Measured on B200s (profiles/r02_ak_*, r02_am_*): 48 us against the radix passes' 77 at 2 table words
-  // per particle (1 Mi particles, one GPU), 119 against 90 at 15 (one slab of eight): break-even near 7.
+  // per particle (1 Mi particles, one GPU), 119 against 90 at 13 (one slab of eight, whose table spans the whole domain): break-even near 7.
   const uint32_t n_now = keep_n ? grid->n : n;
   const bool counting = count_sort && sub_mode && !err && count <= sub_capacity && (uint64_t)count * 9u <= (uint64_t)n_now * 6u;
   grid->sort_passes = err ? 4u : counting ? 0u : max(1u, (bits + 7u) / 8u);
