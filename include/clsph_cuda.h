@@ -118,9 +118,10 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
  *                      Needs a grid whose Morton cell count stays below 2^29 (z axis < 512 cells; larger grids
  *                      report CLSPH_EGRID and want 0); set it before particles are uploaded.
  *                      0: the established organisation on whole cells (k_density_lists / k_forces_lists).
- *   "count_sort"       (with sub_cell_order) 1 (default): while the grid fits the dense sub-cell table, particles are
- *                      sorted by counting on that table (count, scan the table in place, scatter) instead of by
- *                      8-bit radix passes; the arrays come out bit for bit the same. 0: radix passes always.
+ *   "count_sort"       (with sub_cell_order) 1 (default): while the grid fits the dense sub-cell table and that table
+ *                      has at most 6 words per particle, particles are sorted by counting on it (count, scan the
+ *                      table in place, scatter) instead of by 8-bit radix passes; the arrays come out bit for bit
+ *                      the same. 0: radix passes always. 2: counting whenever the grid fits the table (A/B runs).
  *   "pair_density"     (with sub_cell_order) 1 (default): the density pass handles two particles of a sub-cell per
  *                      thread with packed fp32 arithmetic (FADD2 / FFMA2), bitwise the same results as 0
  *                      (one particle per thread). "pair_variant" 0..5 selects how a thread walks its candidates

@@ -85,7 +85,7 @@ struct clsph_context {
   bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
   int factored_forces = 1;          // option "factored_forces": pair terms with the constants factored out of the sums (default) or add_pair_fast
   int pair_variant = 5;             // option "pair_variant" (tuning): walk 0/1/2 + 3 x (entries stored two at a time)
-  bool count_sort = true;           // option "count_sort": counting sort on the dense sub-cell table instead of radix passes (sort.cu)
+  int count_sort = 1;               // option "count_sort": counting sort on the dense sub-cell table instead of radix passes (sort.cu); 0 never, 1 by k_grid_setup's rule, 2 whenever the grid fits the table
   uint32_t* scan_state = nullptr;   // kScanStateWords words: chunk ticket and look-back words of the table scan
   uint32_t* pair_items = nullptr;   // [capacity] items written by k_reorder_sub
   uint32_t* pair_count = nullptr;
@@ -399,7 +399,7 @@ int enqueue_substep(clsph_context* ctx) {
     zero.pair_count = ctx->pair_count;
   }
   launch_grid_setup(ctx->bounds, ctx->grid, ctx->params.h, ctx->n, ctx->cell_capacity, multi ? ctx->dist.plane_lo : -inf,
-                    multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, ctx->count_sort, zero, ctx->sm_count, st, lc);
+                    multi ? ctx->dist.plane_hi : inf, multi, sub ? 1u : 0u, ctx->sub_capacity, (uint32_t)ctx->count_sort, zero, ctx->sm_count, st, lc);
   if (prof) next_event(ctx);
 
   const bool in_place = multi && sub && ctx->live_idx != nullptr;  // the owned particles stay where they are
@@ -755,7 +755,8 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
   } else if (!std::strcmp(name, "factored_forces")) {
     ctx->factored_forces = value < 0 ? -1 : (value != 0 ? 1 : 0);
   } else if (!std::strcmp(name, "count_sort")) {
-    ctx->count_sort = value != 0;
+    if (value < 0 || value > 2) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: count_sort must be 0, 1 or 2");
+    ctx->count_sort = (int)value;
   } else if (!std::strcmp(name, "pair_variant")) {
     if (value < 0 || value > 5) return fail(ctx, CLSPH_EINVAL, "clsph_set_option: pair_variant must be in [0, 5]");
     ctx->pair_variant = (int)value;

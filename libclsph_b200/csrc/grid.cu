@@ -67,8 +67,9 @@ __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ pos, 
 // same on every rank because the AABB was all-reduced. keep_n: the particle count lives on the
 // device (it changes with migration) and must not be overwritten.
 // sub_mode: sort by sub-cell keys (cell key << 3 | octant), which need 3 more key bits; sub_capacity =
-// cells the dense sub-cell table can hold. count_sort: when the grid fits that table the sub-step sorts by counting
-// on it (sort_passes = 0, see sort.cu) instead of by radix passes.
+// cells the dense sub-cell table can hold. count_sort (0 / 1 / 2, the option): when the grid fits that table -- and,
+// with 1, the table is small beside the particles -- the sub-step sorts by counting on it (sort_passes = 0, see sort.cu)
+// instead of by radix passes.
 // The other threads of the launch zero what the previous sub-step left in the sub-cell table (grid->table_words, which
 // thread 0 does not touch), the state words of the table scan and the sort's histograms and look-back words: every later
 // kernel of the step is ordered behind this launch, and nothing before it in the step reads any of them.
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(256) k_grid_setup(BoundsAcc* acc, GridState* g
   // the particles. Measured on B200s (profiles/r02_ak_*, r02_am_*): 48 us against the radix passes' 77 at 2 table words
   // per particle (1 Mi particles, one GPU), 119 against 90 at 13 (one slab of eight, whose table spans the whole domain): break-even near 7.
   const uint32_t n_now = keep_n ? grid->n : n;
-  const bool counting = count_sort && sub_mode && !err && count <= sub_capacity && (uint64_t)count * 9u <= (uint64_t)n_now * 6u;
+  const bool counting = count_sort && sub_mode && !err && count <= sub_capacity &&
+                        (count_sort == 2u || (uint64_t)count * 9u <= (uint64_t)n_now * 6u);  // (option count_sort = 2: whenever it fits)
   grid->sort_passes = err ? 4u : counting ? 0u : max(1u, (bits + 7u) / 8u);
   grid->error |= err;  // sticky until the host reads and clears it
 }
@@ -267,12 +269,12 @@ void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, 
 }
 
 void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
-                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, bool count_sort, const StepZero& zero,
+                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, uint32_t count_sort, const StepZero& zero,
                        int sm_count, cudaStream_t stream, uint64_t* launches) {
   // with a sub-cell table to zero: enough threads to stream a few MB; without: the one thread that does the set-up
   if (zero.sub_lb)
     k_grid_setup<<<(unsigned)sm_count * 4u, 256, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0, sub_mode,
-                                                             sub_capacity, count_sort ? 1u : 0u, zero);
+                                                             sub_capacity, count_sort, zero);
   else
     k_grid_setup<<<1, 32, 0, stream>>>(acc, grid, h, n, cell_capacity, plane_lo, plane_hi, keep_n ? 1 : 0, sub_mode, sub_capacity, 0u,
                                        StepZero{});

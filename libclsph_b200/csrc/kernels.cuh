@@ -90,7 +90,7 @@ void launch_scan_table(uint32_t* sub_lb, const GridState* grid, uint32_t* scan_s
 void launch_bounds_reset(BoundsAcc* acc, cudaStream_t stream, uint64_t* launches);
 void launch_bounds(const float4* pos, uint32_t n, BoundsAcc* acc, int sm_count, cudaStream_t stream, uint64_t* launches);
 void launch_grid_setup(BoundsAcc* acc, GridState* grid, float h, uint32_t n, uint32_t cell_capacity, float plane_lo,
-                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, bool count_sort, const StepZero& zero,
+                       float plane_hi, bool keep_n, uint32_t sub_mode, uint32_t sub_capacity, uint32_t count_sort, const StepZero& zero,
                        int sm_count, cudaStream_t stream, uint64_t* launches);
 void launch_clear_cells(uint32_t* cell_start, uint32_t* cell_end, const GridState* grid, uint32_t cell_capacity,
                         int sm_count, cudaStream_t stream, uint64_t* launches);

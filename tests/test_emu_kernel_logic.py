@@ -344,7 +344,7 @@ def test_option_validation():
         with pytest.raises(capi.ClsphError) as e:
             ctx.set_option(name, value)
         assert e.value.code == capi.E_INVAL, name
-    for name, value in (("forces_blocks", 4), ("forces_blocks", 3), ("fast_pairs", 1), ("merged_rows", 1), ("pair_density", 0), ("pair_variant", 3), ("factored_forces", 1), ("count_sort", 0),
+    for name, value in (("forces_blocks", 4), ("forces_blocks", 3), ("fast_pairs", 1), ("merged_rows", 1), ("pair_density", 0), ("pair_variant", 3), ("factored_forces", 1), ("count_sort", 0), ("count_sort", 2),
                         ("face_grid", 1), ("sub_cell_order", 1), ("sub_cell_order", 0), ("neighbour_lists", 0), ("list_rows", 48)):
         ctx.set_option(name, value)
     ctx.close()

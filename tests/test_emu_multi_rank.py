@@ -52,10 +52,14 @@ def by_id(parts, ids, n):
 
 # world 1: a slab that is not cut at all; transport: stores into the neighbours' mailboxes (default) or NCCL messages
 # "peer-copy": the exchange that copies the owned particles into a fresh array (CLSPH_DIST_IN_PLACE=0) instead of leaving them in place
+# "peer-radix" / "peer-count": the ranks sort by radix passes (sub-cell table zeroed row by row) / by counting on the table
+# whatever its size (zeroed as a range), the single rank they are compared with bitwise keeps the default rule
 @pytest.mark.parametrize("world,copies,sub,transport", [(2, 2, 0, "peer"), (3, 3, 1, "peer"), (1, 2, 1, "peer"), (3, 3, 1, "nccl"),
-                                                        (3, 3, 1, "peer-copy")])
+                                                        (3, 3, 1, "peer-copy"), (3, 3, 1, "peer-radix"), (3, 3, 1, "peer-count")])
 def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub, transport, monkeypatch):
     steps = 3
+    sort_option = {"peer-radix": 0, "peer-count": 2}.get(transport)
+    sort_seen = []
     if transport == "nccl":
         monkeypatch.setenv("CLSPH_DIST_TRANSPORT", "nccl")
     if transport == "peer-copy":
@@ -76,6 +80,8 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub, t
             mine = np.nonzero(owner == rank)[0].astype(np.uint32)
             ctx = capi.Context(int(n * (1.0 / world + 0.5)) + 4096)
             ctx.set_option("sub_cell_order", sub)
+            if sort_option is not None:
+                ctx.set_option("count_sort", sort_option)
             ctx.set_scene(normals, vertices, indices)
             ctx.set_parameters(p, terms)
             ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
@@ -85,6 +91,7 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub, t
                 ctx.step(1)
                 ctx.synchronize()
                 results[rank][k] = ctx.dist_download()
+                sort_seen.append(ctx.sort_passes())
             barrier.wait(timeout=600)
             ctx.close()
         except BaseException as exc:  # noqa: BLE001 - reported by the main thread
@@ -147,6 +154,10 @@ def test_slab_decomposition_matches_single_rank_and_oracle(world, copies, sub, t
             w = wants[k][f][:, :3] if wants[k][f].ndim == 2 else wants[k][f]
             assert rel(g, w) <= (1e-4 if k == 0 else 2e-3), (k, f, rel(g, w))
     assert moved_total > 0 or world == 1, "the shear should have moved particles across a slab plane"
+    if sort_option == 0:
+        assert all(v >= 1 for v in sort_seen), sort_seen
+    if sort_option == 2:
+        assert all(v == 0 for v in sort_seen), sort_seen
 
 
 def test_buffer_overflow_is_reported_and_nobody_hangs():
