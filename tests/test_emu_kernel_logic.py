@@ -207,6 +207,10 @@ def test_counting_sort_is_bitwise_the_radix_sort(fluid, n, box_scene):
     G.check_counting_sort_against_radix(fluid, n, box_scene)
 
 
+def test_counting_sort_on_a_table_much_larger_than_the_fluid(box_scene):
+    G.check_counting_sort_on_a_sparse_table(3000, box_scene)
+
+
 def test_sub_cell_order_host_round_trip_and_option_rules(box_scene):
     p, terms, vol = H.config("water", 2048)
     s = H.state_s1(p, vol)

@@ -125,6 +125,32 @@ def test_counting_sort_is_bitwise_the_radix_sort(fluid, n, box_scene):
     check_counting_sort_against_radix(fluid, n, box_scene)
 
 
+def check_counting_sort_on_a_sparse_table(n, scene, steps=3):
+    """Two halves of the fluid 40 cells apart: many table words per particle, so the device's rule picks the radix passes
+    (and zeroes the table row by row afterwards); count_sort = 2 forces the counting sort, whose scan then runs over
+    many chunks with a ragged last one and whose table is zeroed as a range. Same bytes either way, over several sub-steps."""
+    p, terms, vol = H.config("water", n)
+    s = H.state_s1(p, vol)
+    s["position"][: s.size // 2, 2] += np.float32(40 * 2 * p.h)
+    s["intermediate_velocity"][:, 0] += (2.5 * np.sign(s["position"][:, 1])).astype(np.float32)
+    outs, passes = [], []
+    for mode in (2, 1, 0):
+        ctx = make_ctx(s.size, scene, p, terms, debug=True, options=dict(count_sort=mode))
+        ctx.upload(s)
+        ctx.step(steps)
+        passes.append(ctx.sort_passes())
+        outs.append((ctx.download().tobytes(),) + tuple(ctx.fetch(t).tobytes() for t in (
+            capi.TAP_SORTED_KEYS, capi.TAP_PERMUTATION, capi.TAP_CELL_TABLE, capi.TAP_SUPPORT_COUNT, capi.TAP_CANDIDATE_COUNT)))
+        assert ctx.parameters().grid_cell_count * 9 > 6 * s.size
+        ctx.close()
+    assert passes[0] == 0 and passes[1] >= 1 and passes[2] >= 1, passes
+    assert outs[0] == outs[1] == outs[2]
+
+
+def test_counting_sort_on_a_table_much_larger_than_the_fluid(box_scene):
+    check_counting_sort_on_a_sparse_table(100000, box_scene)
+
+
 @pytest.mark.parametrize("n", [128, 1000, 4096, 32000])
 def test_lattice_state_s0(n, box_scene):
     p, terms, vol = H.config("water", n)
