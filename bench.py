@@ -444,7 +444,7 @@ def run_ours(args, rank, world, local_rank):
     dominant = max((k for k in kb), key=lambda k: per.get(k, 0.0))
     peak, peak_src = measured_peak()
     achieved = n * kb[dominant] / (per[dominant] * 1e-3) / 1e9
-    pairs = sub and "pair_density=0" not in options
+    pairs = sub and "pair_density=0" not in options and ("pair_density=1" in options or n >= 160000)  # the library's size rule
     factored = sub and "factored_forces=0" not in options and "fast_pairs=0" not in options
     direct = sub and "fast_pairs=0" not in options and os.environ.get("CLSPH_FORCES_DIRECT", "1") != "0"
     kernel_name = {"density": ("k_density_pairs" if pairs else "k_density_sub") if sub else "k_density_lists",

@@ -122,9 +122,10 @@ int clsph_set_parameters(clsph_context* ctx, const simulation_parameters* params
  *                      has at most 6 words per particle, particles are sorted by counting on it (count, scan the
  *                      table in place, scatter) instead of by 8-bit radix passes; the arrays come out bit for bit
  *                      the same. 0: radix passes always. 2: counting whenever the grid fits the table (A/B runs).
- *   "pair_density"     (with sub_cell_order) 1 (default): the density pass handles two particles of a sub-cell per
+ *   "pair_density"     (with sub_cell_order) 1: the density pass handles two particles of a sub-cell per
  *                      thread with packed fp32 arithmetic (FADD2 / FFMA2), bitwise the same results as 0
- *                      (one particle per thread). "pair_variant" 0..5 selects how a thread walks its candidates
+ *                      (one particle per thread). -1 (default): 1 from 160 000 particles, 0 below (where the GPU is
+ *                      not full and the shorter walk of a one-particle thread wins). "pair_variant" 0..5 selects how a thread walks its candidates
  *                      (one by one / next load ahead / four loads ahead) and whether list entries are stored
  *                      one or two at a time; 5 (default) = four ahead, in twos.
  *   "merged_rows"      (pair_density = 0) 1 (default): the density pass walks the two index ranges of each row of

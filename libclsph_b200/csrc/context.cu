@@ -82,7 +82,7 @@ struct clsph_context {
   // particle in the reference's array, rr_tmp = the gathered ranks of the previous sub-step
   bool sub_order = true;        // option "sub_cell_order"
   bool merged_rows = true;      // k_density_sub<.., kMerged>: the two index ranges of a sub-cell row in one loop
-  bool pair_density = true;     // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density")
+  int pair_density = -1;        // k_density_pairs: two particles of a sub-cell per thread, packed fp32 (option "pair_density"); -1: by size
   int factored_forces = 1;          // option "factored_forces": pair terms with the constants factored out of the sums (default) or add_pair_fast
   int pair_variant = 5;             // option "pair_variant" (tuning): walk 0/1/2 + 3 x (entries stored two at a time)
   int count_sort = 1;               // option "count_sort": counting sort on the dense sub-cell table instead of radix passes (sort.cu); 0 never, 1 by k_grid_setup's rule, 2 whenever the grid fits the table
@@ -435,7 +435,10 @@ int enqueue_substep(clsph_context* ctx) {
   // in the direct kernel, the default, they win for both fluids, profiles/r02_s_*)
   const bool want_factored = ctx->factored_forces != 0;
   const bool factored = sub && want_factored && ctx->fast_pairs;
-  const bool pairs = sub && ctx->pair_density;
+  // Two particles per thread halve the threads: below ~150 k particles the GPU is not full either way and the pass lasts
+  // as long as one thread's walk, which is shorter with one particle per thread (100 k: 0.113 against 0.117 ms per
+  // sub-step; 256 k: 0.175 against 0.171, profiles/r02_as_*). Same results, bit for bit.
+  const bool pairs = sub && (ctx->pair_density < 0 ? n >= 160000u : ctx->pair_density != 0);
   if (sub) {
     launch_reorder_sub(src, dst, ctx->sort, ctx->skey, multi ? nullptr : ctx->rrank, ctx->rr_tmp, ctx->sub_lb, ctx->grid,
                        multi ? ctx->pid[ctx->cur] : nullptr, multi ? ctx->pid[ctx->cur ^ 1] : nullptr,
@@ -751,7 +754,7 @@ int clsph_set_option(clsph_context* ctx, const char* name, long long value) {
   } else if (!std::strcmp(name, "merged_rows")) {
     ctx->merged_rows = value != 0;
   } else if (!std::strcmp(name, "pair_density")) {
-    ctx->pair_density = value != 0;
+    ctx->pair_density = value < 0 ? -1 : (value != 0 ? 1 : 0);
   } else if (!std::strcmp(name, "factored_forces")) {
     ctx->factored_forces = value < 0 ? -1 : (value != 0 ? 1 : 0);
   } else if (!std::strcmp(name, "count_sort")) {

@@ -81,6 +81,8 @@ def main():
     ctx = capi.Context(cap, device=local)
     if not sub:
         ctx.set_option("sub_cell_order", 0)
+    else:
+        ctx.set_option("pair_density", 1)  # the kernel of the large runs, whatever the size rule says for this block
     ctx.set_scene(normals, vertices, indices)
     ctx.set_parameters(p, terms)
     ctx.dist_init(rank, world, uid, float(planes[rank]), float(planes[rank + 1]))
@@ -93,6 +95,8 @@ def main():
         single = capi.Context(n, device=local)
         if not sub:
             single.set_option("sub_cell_order", 0)
+        else:
+            single.set_option("pair_density", 1)
         single.set_scene(normals, vertices, indices)
         single.set_parameters(p, terms)
         single.upload(state)

@@ -31,6 +31,13 @@ def test_every_abi_symbol_is_exported_by_the_emulator_build(emulator_library):
         assert hasattr(emulator_library, name), name
 
 
+def test_smoke_entry_point_under_the_emulator(capsys):
+    """__graft_entry__.smoke() is what the driver runs on the GPU box; here its logic (options, taps, oracle comparison)."""
+    import __graft_entry__ as entry
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
+
+
 @pytest.mark.parametrize("n", [128, 1000, 4096])
 def test_lattice_state_s0(n, box_scene):
     G.test_lattice_state_s0(n, box_scene)
@@ -86,14 +93,15 @@ def test_binary_search_fallback_matches_dense_table(box_scene):
     assert dense.tobytes() == sparse.tobytes()
 
 
-SUB = dict(sub_cell_order=1)
+# (the pair density kernel is the default from 160 000 particles; the small states here ask for it explicitly)
+SUB = dict(sub_cell_order=1, pair_density=1)
 
 
 @pytest.mark.parametrize("options", [dict(sub_cell_order=0, neighbour_lists=0), dict(sub_cell_order=0, neighbour_lists=1), dict(sub_cell_order=0, neighbour_lists=1, list_rows=8),
                                      SUB, dict(sub_cell_order=1, list_rows=8), dict(sub_cell_order=1, forces_blocks=4),
                                      dict(sub_cell_order=1, fast_pairs=1), dict(sub_cell_order=0, neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
                                      dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8),
-                                     dict(factored_forces=0), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(list_rows=8), dict(count_sort=0)])
+                                     dict(factored_forces=0, pair_density=1), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(pair_density=1, list_rows=8), dict(count_sort=0), dict()])
 def test_neighbour_organisations(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 3000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)

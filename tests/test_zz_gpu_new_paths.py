@@ -15,9 +15,9 @@ from tests import test_gpu_parity as G
 
 pytestmark = pytest.mark.gpu
 
-SUB = dict(sub_cell_order=1)
+SUB = dict(sub_cell_order=1, pair_density=1)  # (the pair kernel is the default only from 160 000 particles)
 GRID = dict(face_grid=1)
-BOTH = dict(sub_cell_order=1, face_grid=1, fast_pairs=1)
+BOTH = dict(sub_cell_order=1, face_grid=1, fast_pairs=1, pair_density=1)
 
 
 @pytest.mark.parametrize("n", [128, 1000, 4096, 32000])
@@ -37,7 +37,7 @@ def test_sub_cell_order_jittered(fluid, n, box_scene):
                                      dict(sub_cell_order=1, forces_blocks=4),
                                      dict(sub_cell_order=0, neighbour_lists=1, fast_pairs=1, forces_blocks=4, face_grid=1),
                                      dict(sub_cell_order=1, merged_rows=1), dict(sub_cell_order=1, merged_rows=1, list_rows=8),
-                                     dict(factored_forces=0), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(list_rows=8)])
+                                     dict(factored_forces=0, pair_density=1), dict(factored_forces=0, list_rows=8), dict(pair_density=0), dict(pair_density=1, list_rows=8), dict()])
 def test_sub_cell_order_crowded_and_overflowing_lists(options, box_scene, plane_scene):
     p, terms, vol = H.config("water", 20000)
     G.check_against_oracle(H.state_s1(p, vol), p, terms, box_scene, "water %r" % (options,), options=options)
